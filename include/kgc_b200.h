@@ -1,0 +1,183 @@
+/*
+ * kgc_b200.h - C ABI of libkgc_b200.so, the B200 (sm_100a) implementation of the M-GCN
+ * hot path (weilonghu/KGC-GCN).  The reference is pure Python and has no FFI of its own;
+ * each entry point below names the reference code (file:line under the reference root) whose
+ * arithmetic it replaces.  The Python host layer (kgc_gcn_b200/*.py) binds these with ctypes
+ * and keeps the reference's module API (MGCN / MGCNConv / ConvE / DataLoader); INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C"; every function returns int: 0 = OK, non-zero = failure, text in
+ *     kgc_last_error() (thread-local).  No torch types, plain device pointers and sizes.
+ *   - The CALLER allocates every input, output and workspace buffer (device memory) and
+ *     passes the CUDA stream (a cudaStream_t cast to void*); nothing is synchronised
+ *     internally except where a function says so; no hidden global state.
+ *   - Matrices are row-major and dense unless a stride is given.  D (= gcn_in_dim) must be
+ *     a multiple of 4 and <= 256; Dout a multiple of 4 and <= 1024 (float4 paths).
+ *   - Index dtypes: the reference's int64 edge lists are consumed as they are by
+ *     kgc_csr_build; everything downstream is int32 (node, edge and type ids < 2^31).
+ *   - There is NO CPU fallback: every entry point launches sm_100a kernels.
+ */
+#ifndef KGC_B200_H_
+#define KGC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define KGC_ABI_VERSION 1
+
+/* Work item of a segmented reduction: rows [beg, end) of the input record / partial array are
+ * summed; the result goes to row `out` of the final output (flags & 1) or of the partial
+ * buffer of this level (flags & 1 == 0).  Built by the host plan (kgc_gcn_b200/plan.py). */
+typedef struct { int32_t beg, end, out, flags; } kgc_item_t;
+
+/* Edge record of a sorted CSR: 16 bytes, one 128-bit load per edge.
+ *   dst-sorted : a = src,  b = type      src-sorted : a = dst, b = type
+ *   type-sorted: a = src,  b = dst       eid is the GLOBAL edge id (0..2E-1); norm is fp32 */
+typedef struct { int32_t eid, a, b; float norm; } kgc_edge_rec_t;
+
+const char* kgc_last_error(void);
+int kgc_abi_version(void);
+
+/* ---- K1: CSR / permutation builder + per-half degree normalisation -------------------------
+ * Replaces MGCNConv.compute_norm (model.py:72-80) and the gather/scatter index handling of PyG
+ * propagate (model.py:99-101).  Input is the reference's edge list: src = edge_index[0],
+ * dst = edge_index[1], type = edge_attr[0], all int64 [n_edges2]; the first n_edges2/2 edges
+ * are the "in" half, the rest the "out" half (model.py:84-90).
+ *   deg[h*N + v]  = #{e in half h : src_e = v}                       (int32, exact)
+ *   norm[e]       = deg_h^-1/2[src_e] * deg_h^-1/2[dst_e], 0 where a degree is 0   (fp32)
+ *   perm_K / rowptr_K / rec_K for K in {dst, src, type}: STABLE sort of all n_edges2 edges by
+ *   key K (ties keep ascending edge id, so within a row the in-half edges come first);
+ *   rowptr_K[r] = first sorted position with key >= r; rowmid_dst[r] = first position in
+ *   row r whose edge belongs to the out half.
+ * Synchronises the stream once (to validate ids); ids out of range are an error. */
+size_t kgc_csr_workspace_bytes(int64_t n_edges2, int64_t n_nodes, int64_t n_types);
+int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type,
+                  int64_t n_edges2, int64_t n_nodes, int64_t n_types,
+                  int32_t* deg, float* norm,
+                  int32_t* perm_dst, int32_t* rowptr_dst, int32_t* rowmid_dst, kgc_edge_rec_t* rec_dst,
+                  int32_t* perm_src, int32_t* rowptr_src, kgc_edge_rec_t* rec_src,
+                  int32_t* perm_type, int32_t* rowptr_type, kgc_edge_rec_t* rec_type,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: aggregation forward -----------------------------------------------------------------
+ * Replaces the gather + MGCNConv.message product + norm + scatter-add of the "in" and "out"
+ * propagations (model.py:99-100,111-118) in the aggregate-then-transform order:
+ *   out[row] = sum over the item's records of  norm_e * x[a_e] (.) rel[b_e] (.) ee[eid_e]
+ * over dst-sorted records; deterministic (fixed order, no float atomics).
+ * x [n_nodes,D], rel [n_types,D], ee [n_edges2,D], out_final [*,D], out_part [*,D]. */
+int kgc_agg_fwd(const float* x, const float* rel, const float* ee,
+                const kgc_edge_rec_t* rec_dst, const kgc_item_t* items, int64_t n_items,
+                float* out_final, float* out_part, int32_t D, void* stream);
+
+/* Higher reduction levels shared by K2/K3: out[row] = sum of rows [beg,end) of `part_in`
+ * (+ addend[row] on final rows when addend != NULL), in a fixed order. */
+int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items,
+                    float* out_final, float* out_part, const float* addend, int32_t D, void* stream);
+
+/* ---- K3: aggregation backward ------------------------------------------------------------------
+ * Autograd of the same three lines (model.py:114-118 + aggr='add').  g3 is [3,n_nodes,D]:
+ * plane 0/1 = d(agg_in)/d(agg_out) = d(res_h) @ W_h^T, plane 2 = the self-loop term added to d_x.
+ * Over src-sorted records (row j = source node):
+ *   p_e      = norm_e * g3[half_e][a_e] (.) rel[b_e]
+ *   d_ee[e]  = p_e (.) x[j]                                  (one row per edge, no reduction)
+ *   d_x[j]   = sum_e p_e (.) ee[e]   (+ g3[2][j] on final rows)
+ * half_e = (eid_e >= n_edges2/2). */
+int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
+                    const kgc_edge_rec_t* rec_src, const kgc_item_t* items, int64_t n_items,
+                    int64_t n_nodes, int64_t n_edges2,
+                    float* d_ee, float* dx_final, float* dx_part, int32_t D, void* stream);
+
+/* Over type-sorted records (row t = relation type):
+ *   d_rel[t] = sum_e norm_e * g3[half_e][b_e] (.) x[a_e] (.) ee[e] */
+int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
+                    const kgc_edge_rec_t* rec_type, const kgc_item_t* items, int64_t n_items,
+                    int64_t n_nodes, int64_t n_edges2,
+                    float* drel_final, float* drel_part, int32_t D, void* stream);
+
+/* ---- K4: layer tail ------------------------------------------------------------------------------
+ * Replaces model.py:103-106: out = (drop(in_res) + drop(out_res) + loop_res) / 3 [+ bias];
+ * BatchNorm1d over the n_rows rows; tanh.  res3 is [3,n_rows,Dout] (in, out, loop planes).
+ * mask_in / mask_out: uint8 keep masks [n_rows,Dout] or NULL (no dropout); keep_scale = 1/(1-p).
+ * kgc_tail_fwd writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares, fp64);
+ * kgc_colstats_finalize reduces them in a fixed order into stats[0]=mean, [1]=biased var,
+ * [2]=rstd=1/sqrt(var+eps) (training) - or fills them from running stats (training == 0);
+ * kgc_tail_apply writes all_ent = tanh((pre - mean) * rstd * gamma + beta). */
+int64_t kgc_tail_num_blocks(int64_t n_rows);
+int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, float keep_scale,
+                 const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials, void* stream);
+int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
+                          int32_t training, const float* running_mean, const float* running_var,
+                          float* stats, void* stream);
+int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
+                   int64_t n_rows, int32_t Dout, float* all_ent, void* stream);
+/* Backward of the tail.  kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and
+ * dz*xhat; kgc_colsum_finalize -> sums[0]=sum dz (= d beta), sums[1]=sum dz*xhat (= d gamma);
+ * kgc_tail_bwd_apply: d_pre (BatchNorm backward, batch statistics when training) spread to the
+ * three planes d_res3[3,n_rows,Dout] with the dropout masks and the 1/3. */
+int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
+                        int64_t n_rows, int32_t Dout, double* partials, void* stream);
+int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, float* sums, void* stream);
+int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
+                       const float* gamma, const float* sums, const uint8_t* mask_in, const uint8_t* mask_out,
+                       float keep_scale, int32_t training, int64_t n_rows, int32_t Dout,
+                       float* d_res3, void* stream);
+
+/* ---- K5: label / batch builder ---------------------------------------------------------------------
+ * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's
+ * query ids qid[B] (int64) and the query->objects CSR (ptr int64 [Q+1], idx int32 [nnz]):
+ *   label[b, :] = add;  label[b, idx[k]] = pos   with the host passing pos = (1-ls)*1 + 1/N and
+ *   add = 1/N when smoothing (data_loader.py:41-43), else pos = 1, add = 0.
+ * triple_out[b,:] = triples[qid[b],:] (int64 [Q,3]). */
+int kgc_label_build(const int64_t* qid, int64_t B, const int64_t* triples, const int64_t* ptr,
+                    const int32_t* idx, int64_t n_entity, float pos, float add,
+                    int64_t* triple_out, float* label, void* stream);
+
+/* Extension with NO reference counterpart (the reference trains 1-N and ships no sampler,
+ * SURVEY.md fact 2; "parity unpinned"): k negatives per query as a pure function of the caller's
+ * uint32 draws.  neg[b,j] = first of draws[b,j,0..tries) mapped to [0,N) by (u * N) >> 32 that is
+ * not a positive of query qid[b]; -1 if every try collides. */
+int kgc_neg_sample(const int64_t* qid, int64_t B, const int64_t* ptr, const int32_t* idx, int64_t n_entity,
+                   const uint32_t* draws, int32_t k, int32_t tries, int32_t* neg, void* stream);
+
+/* ---- K6: fused 1-N scoring + filter + rank (tcgen05 / TMA) --------------------------------------------
+ * Replaces model.py:177-178 (X @ all_ent^T + bias) and main.py:122-126 (filter, rank) without
+ * materialising the [B,N] score matrix.  Ranking is on the logit (sigmoid is monotone, SURVEY.md
+ * section 7 "Tie semantics").
+ * kgc_score_pack_*: fp32 rows -> bf16 rows of pitch KGC_SCORE_KPAD with the bias folded into three
+ * extra K columns (entity side: bf16 hi/mid/lo split of bias[j]; query side: 1,1,1).
+ * kgc_score_rank: for every query q, count over all entities j of  s[q,j] > thr[q]  (count_gt) and
+ * == (count_eq), where s is the bf16 x bf16 -> fp32 tensor-core product.  kgc_score_pairs evaluates
+ * s for explicit (q, j) pairs through the SAME MMA path (targets and filtered positives), so the
+ * host-side correction  gt -= #{j in filter(q)\{o} : s[q,j] > thr[q]}  is bit-consistent. */
+#define KGC_SCORE_KPAD 208
+int kgc_score_pack_entities(const float* all_ent, const float* bias, int64_t n, int32_t d,
+                            uint16_t* e_bf16, void* stream);
+int kgc_score_pack_queries(const float* xq, int64_t b, int32_t d, uint16_t* q_bf16, void* stream);
+size_t kgc_score_workspace_bytes(int64_t b, int64_t n);
+int kgc_score_pairs(const uint16_t* q_bf16, const uint16_t* e_bf16, const int32_t* pair_q, const int32_t* pair_e,
+                    int64_t n_pairs, int64_t b, int64_t n, float* s_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, int64_t b, int64_t n, int64_t n_begin,
+                   int64_t n_end, const float* thr, int32_t* count_gt, int32_t* count_eq,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Filter correction + rank + metric sums (main.py:128-133): ranks[q] = 1 + gt[q] - sum over the
+ * query's filtered pairs of (s_pair > thr[q]); sums = {count, sum rank, sum 1/rank, hits@1..10}. */
+int kgc_rank_finalize(const int32_t* count_gt, const float* thr, const float* s_filt, const int64_t* filt_ptr,
+                      const int32_t* filt_idx, const int64_t* obj, int64_t b, int32_t* ranks, double* sums13,
+                      void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGC_B200_H_ */

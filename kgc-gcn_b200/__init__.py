@@ -1,0 +1,15 @@
+"""kgc_gcn_b200: B200-native hot path of M-GCN (weilonghu/KGC-GCN) behind the reference's module API.
+
+    from kgc_gcn_b200 import MGCN, MGCNConv, ConvE, DataLoader, KBDataset
+
+Compute runs in libkgc_b200.so (hand-written sm_100a CUDA behind the C ABI of include/kgc_b200.h);
+there is no CPU fallback.
+"""
+from .conv import MGCNConv, get_param            # noqa: F401
+from .model import MGCN, ConvE                   # noqa: F401
+from .data_loader import DataLoader, KBDataset, GraphData, BatchIterator, epoch_permutation   # noqa: F401
+from .plan import GraphPlan, get_plan, build_levels   # noqa: F401
+from . import _lib                               # noqa: F401
+
+__all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
+           'get_plan', 'build_levels', 'get_param', 'epoch_permutation']

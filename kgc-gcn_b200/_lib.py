@@ -1,0 +1,79 @@
+"""ctypes binding of libkgc_b200.so (the C ABI declared in include/kgc_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a call
+fails, a RuntimeError is raised.  PyTorch is used only for device memory, streams and
+torch.distributed; every pointer handed to the library is a raw device address.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libkgc_b200.so')
+_LIB = None
+
+_vp, _i64, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/kgc_b200.h declares (tests check this)
+SIGNATURES = {
+    'kgc_last_error': (ctypes.c_char_p, []),
+    'kgc_abi_version': (ctypes.c_int, []),
+    'kgc_csr_workspace_bytes': (_sz, [_i64, _i64, _i64]),
+    'kgc_csr_build': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _sz, _vp]),
+    'kgc_agg_fwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    'kgc_agg_bwd_src': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
+    'kgc_agg_bwd_rel': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
+    'kgc_tail_num_blocks': (_i64, [_i64]),
+    'kgc_tail_fwd': (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    'kgc_colstats_finalize': (ctypes.c_int, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    'kgc_tail_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    'kgc_tail_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    'kgc_colsum_finalize': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i32, _vp, _vp]),
+    'kgc_label_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
+    'kgc_neg_sample': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+}
+
+
+def lib():
+    """Load libkgc_b200.so once; fail loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('{} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(nvcc, sm_100a). There is no CPU or PyTorch fallback.'.format(LIB_PATH))
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)       # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.kgc_abi_version() != 1:
+            raise RuntimeError('libkgc_b200.so ABI version mismatch')
+        _LIB = handle
+    return _LIB
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise RuntimeError with kgc_last_error() on failure."""
+    h = lib()
+    rc = getattr(h, name)(*args)
+    if rc != 0:
+        raise RuntimeError('{} failed: {}'.format(name, h.kgc_last_error().decode('utf-8', 'replace')))
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, dtype, name):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError('{} must be a CUDA tensor: the M-GCN hot path runs on the GPU only (no CPU fallback)'.format(name))
+    if t.dtype != dtype:
+        raise TypeError('{} must be {}, got {}'.format(name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()

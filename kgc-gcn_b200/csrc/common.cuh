@@ -1,0 +1,54 @@
+// Shared helpers for libkgc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "kgc_b200.h"
+
+namespace kgc {
+
+void set_error(const std::string& msg);
+
+inline int fail(const char* where, const std::string& what) {
+  set_error(std::string(where) + ": " + what);
+  return 1;
+}
+
+#define KGC_CUDA_TRY(expr)                                                          \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) return ::kgc::fail(__func__, std::string(#expr) + " -> " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define KGC_REQUIRE(cond, msg)                          \
+  do {                                                  \
+    if (!(cond)) return ::kgc::fail(__func__, (msg));   \
+  } while (0)
+
+#define KGC_LAUNCH_CHECK() KGC_CUDA_TRY(cudaGetLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// 128-bit streaming load that does not allocate in L1 (the edge-embedding stream is read once).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w));
+}
+__device__ __forceinline__ int4 ld_rec(const kgc_edge_rec_t* p) {
+  return __ldg(reinterpret_cast<const int4*>(p));
+}
+
+}  // namespace kgc

@@ -1,0 +1,276 @@
+// K4: layer tail - dropout combine, /3, BatchNorm1d over the node rows, tanh - and its backward.
+// Replaces reference model.py:103-106.  Elementwise + column reductions over [n_rows, Dout]; the
+// column statistics are accumulated in fp64 per thread, reduced per block in a fixed order and
+// finalised by one small kernel, so the result is deterministic and accurate (no atomics).
+#include "common.cuh"
+
+namespace kgc {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 4 * kNumSMs;
+
+struct Stripe {
+  int64_t row_beg, row_end;
+};
+__device__ __forceinline__ Stripe block_stripe(int64_t n_rows) {
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  Stripe s;
+  s.row_beg = blockIdx.x * per;
+  s.row_end = s.row_beg + per < n_rows ? s.row_beg + per : n_rows;
+  return s;
+}
+
+__device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t idx4, float s) {
+  const uchar4 v = *reinterpret_cast<const uchar4*>(m + idx4 * 4);
+  return make_float4(v.x ? s : 0.f, v.y ? s : 0.f, v.z ? s : 0.f, v.w ? s : 0.f);
+}
+
+// Sum the per-thread double4 accumulators of the RL row-lanes of a block, in lane order, and store
+// them as partials[block][which][col].
+__device__ __forceinline__ void block_store_partials(double4 a, double4 b, int rl, int c, int RL, int Do4,
+                                                     double* partials, double4* sm) {
+  // sm holds 2 * RL * Do4 double4
+  const bool active = rl < RL;
+  if (active) {
+    sm[(0 * RL + rl) * Do4 + c] = a;
+    sm[(1 * RL + rl) * Do4 + c] = b;
+  }
+  __syncthreads();
+  if (active && rl == 0) {
+    double4 sa = sm[c], sb = sm[RL * Do4 + c];
+    for (int k = 1; k < RL; ++k) {
+      const double4 ta = sm[(0 * RL + k) * Do4 + c], tb = sm[(1 * RL + k) * Do4 + c];
+      sa.x += ta.x; sa.y += ta.y; sa.z += ta.z; sa.w += ta.w;
+      sb.x += tb.x; sb.y += tb.y; sb.z += tb.z; sb.w += tb.w;
+    }
+    double4* out = reinterpret_cast<double4*>(partials) + (int64_t)blockIdx.x * 2 * Do4;
+    out[c] = sa;
+    out[Do4 + c] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_fwd_kernel(const float4* __restrict__ res3, const uint8_t* __restrict__ mask_in,
+                const uint8_t* __restrict__ mask_out, float keep_scale, const float4* __restrict__ bias,
+                int64_t n_rows, int Do4, float4* __restrict__ pre, double* __restrict__ partials) {
+  extern __shared__ double4 sm[];
+  const int RL = kThreads / Do4;
+  const int rl = threadIdx.x / Do4, c = threadIdx.x % Do4;
+  const Stripe s = block_stripe(n_rows);
+  const int64_t plane = n_rows * (int64_t)Do4;
+  double4 sum = make_double4(0, 0, 0, 0), sq = make_double4(0, 0, 0, 0);
+  if (rl < RL) {
+    const float4 bv = bias ? __ldg(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = s.row_beg + rl; r < s.row_end; r += RL) {
+      const int64_t i = r * Do4 + c;
+      float4 a = __ldg(res3 + i), b = __ldg(res3 + plane + i);
+      const float4 l = __ldg(res3 + 2 * plane + i);
+      if (mask_in) { const float4 m = mask4(mask_in, i, keep_scale); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; }
+      if (mask_out) { const float4 m = mask4(mask_out, i, keep_scale); b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w; }
+      float4 o;   // (drop(in) + drop(out) + loop) / 3 [+ bias]   (model.py:103-105)
+      o.x = (a.x + b.x + l.x) / 3.0f + bv.x;
+      o.y = (a.y + b.y + l.y) / 3.0f + bv.y;
+      o.z = (a.z + b.z + l.z) / 3.0f + bv.z;
+      o.w = (a.w + b.w + l.w) / 3.0f + bv.w;
+      pre[i] = o;
+      sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+      sq.x += (double)o.x * o.x; sq.y += (double)o.y * o.y; sq.z += (double)o.z * o.z; sq.w += (double)o.w * o.w;
+    }
+  }
+  block_store_partials(sum, sq, rl, c, RL, Do4, partials, sm);
+}
+
+// stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
+__global__ void colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int64_t n_rows,
+                                         int Dout, float eps, int training, const float* __restrict__ rmean,
+                                         const float* __restrict__ rvar, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Dout) return;
+  double mean, var;
+  if (training) {
+    double s = 0, q = 0;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      s += partials[(b * 2 + 0) * Dout + c];
+      q += partials[(b * 2 + 1) * Dout + c];
+    }
+    mean = s / (double)n_rows;
+    var = q / (double)n_rows - mean * mean;
+    if (var < 0) var = 0;
+  } else {
+    mean = rmean[c];
+    var = rvar[c];
+  }
+  stats[c] = (float)mean;
+  stats[Dout + c] = (float)var;
+  stats[2 * Dout + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout,
+                                       float* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Dout) return;
+  double s = 0, q = 0;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    s += partials[(b * 2 + 0) * Dout + c];
+    q += partials[(b * 2 + 1) * Dout + c];
+  }
+  sums[c] = (float)s;
+  sums[Dout + c] = (float)q;
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_apply_kernel(const float4* __restrict__ pre, const float4* __restrict__ stats, const float4* __restrict__ gamma,
+                  const float4* __restrict__ beta, int64_t n4, int Do4, float4* __restrict__ all_ent) {
+  const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % Do4);
+  const float4 v = __ldg(pre + i), m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c);
+  const float4 ga = __ldg(gamma + c), be = __ldg(beta + c);
+  float4 o;   // tanh(BatchNorm(out))   (model.py:106)
+  o.x = tanhf((v.x - m.x) * rs.x * ga.x + be.x);
+  o.y = tanhf((v.y - m.y) * rs.y * ga.y + be.y);
+  o.z = tanhf((v.z - m.z) * rs.z * ga.z + be.z);
+  o.w = tanhf((v.w - m.w) * rs.w * ga.w + be.w);
+  all_ent[i] = o;
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
+                       const float4* __restrict__ pre, const float4* __restrict__ stats, int64_t n_rows, int Do4,
+                       double* __restrict__ partials) {
+  extern __shared__ double4 sm[];
+  const int RL = kThreads / Do4;
+  const int rl = threadIdx.x / Do4, c = threadIdx.x % Do4;
+  const Stripe s = block_stripe(n_rows);
+  double4 s1 = make_double4(0, 0, 0, 0), s2 = make_double4(0, 0, 0, 0);
+  if (rl < RL) {
+    const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c);
+    for (int64_t r = s.row_beg + rl; r < s.row_end; r += RL) {
+      const int64_t i = r * Do4 + c;
+      const float4 g = __ldg(g_ent + i), t = __ldg(all_ent + i), v = __ldg(pre + i);
+      const float dzx = g.x * (1.f - t.x * t.x), dzy = g.y * (1.f - t.y * t.y);
+      const float dzz = g.z * (1.f - t.z * t.z), dzw = g.w * (1.f - t.w * t.w);
+      s1.x += dzx; s1.y += dzy; s1.z += dzz; s1.w += dzw;
+      s2.x += (double)dzx * ((v.x - m.x) * rs.x);
+      s2.y += (double)dzy * ((v.y - m.y) * rs.y);
+      s2.z += (double)dzz * ((v.z - m.z) * rs.z);
+      s2.w += (double)dzw * ((v.w - m.w) * rs.w);
+    }
+  }
+  block_store_partials(s1, s2, rl, c, RL, Do4, partials, sm);
+}
+
+__global__ void __launch_bounds__(kThreads)
+tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
+                      const float4* __restrict__ pre, const float4* __restrict__ stats,
+                      const float4* __restrict__ gamma, const float4* __restrict__ sums,
+                      const uint8_t* __restrict__ mask_in, const uint8_t* __restrict__ mask_out, float keep_scale,
+                      int training, int64_t n_rows, int Do4, float4* __restrict__ d_res3) {
+  const int64_t n4 = n_rows * (int64_t)Do4;
+  const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % Do4);
+  const float4 g = __ldg(g_ent + i), t = __ldg(all_ent + i), v = __ldg(pre + i);
+  const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c);
+  float4 dz = make_float4(g.x * (1.f - t.x * t.x), g.y * (1.f - t.y * t.y), g.z * (1.f - t.z * t.z),
+                          g.w * (1.f - t.w * t.w));
+  float4 dp;
+  if (training) {   // BatchNorm backward with batch statistics
+    const float inv_n = 1.0f / (float)n_rows;
+    const float4 s1 = __ldg(sums + c), s2 = __ldg(sums + Do4 + c);
+    dp.x = ga.x * rs.x * (dz.x - s1.x * inv_n - (v.x - m.x) * rs.x * s2.x * inv_n);
+    dp.y = ga.y * rs.y * (dz.y - s1.y * inv_n - (v.y - m.y) * rs.y * s2.y * inv_n);
+    dp.z = ga.z * rs.z * (dz.z - s1.z * inv_n - (v.z - m.z) * rs.z * s2.z * inv_n);
+    dp.w = ga.w * rs.w * (dz.w - s1.w * inv_n - (v.w - m.w) * rs.w * s2.w * inv_n);
+  } else {
+    dp = make_float4(ga.x * rs.x * dz.x, ga.y * rs.y * dz.y, ga.z * rs.z * dz.z, ga.w * rs.w * dz.w);
+  }
+  const float4 third = make_float4(dp.x / 3.0f, dp.y / 3.0f, dp.z / 3.0f, dp.w / 3.0f);
+  float4 a = third, b = third;
+  if (mask_in) { const float4 k = mask4(mask_in, i, keep_scale); a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w; }
+  if (mask_out) { const float4 k = mask4(mask_out, i, keep_scale); b.x *= k.x; b.y *= k.y; b.z *= k.z; b.w *= k.w; }
+  d_res3[i] = a;
+  d_res3[n4 + i] = b;
+  d_res3[2 * n4 + i] = third;
+}
+
+inline int check_dout(int32_t Dout) { return (Dout <= 0 || Dout % 4 != 0 || Dout > 1024) ? 1 : 0; }
+inline size_t partial_smem(int Do4) { return size_t(2) * (kThreads / Do4) * Do4 * sizeof(double4); }
+
+}  // namespace
+}  // namespace kgc
+
+using namespace kgc;
+
+extern "C" int64_t kgc_tail_num_blocks(int64_t n_rows) {
+  int64_t nb = ceil_div(n_rows > 0 ? n_rows : 1, 32);
+  return nb < kMaxBlocks ? nb : kMaxBlocks;
+}
+
+extern "C" int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, float keep_scale,
+                            const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials,
+                            void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  KGC_REQUIRE(n_rows > 0, "n_rows must be positive");
+  const int Do4 = Dout / 4;
+  const size_t smem = partial_smem(Do4);   // <= 16 KB
+  tail_fwd_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
+      (const float4*)res3, mask_in, mask_out, keep_scale, (const float4*)bias, n_rows, Do4, (float4*)pre, partials);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
+                                     int32_t training, const float* running_mean, const float* running_var,
+                                     float* stats, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  KGC_REQUIRE(training || (running_mean && running_var), "eval mode needs running statistics");
+  colstats_finalize_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, as_stream(stream)>>>(
+      partials, n_blocks, n_rows, Dout, eps, training, running_mean, running_var, stats);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
+                              int64_t n_rows, int32_t Dout, float* all_ent, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  const int Do4 = Dout / 4;
+  const int64_t n4 = n_rows * Do4;
+  tail_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
+      (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, n4, Do4, (float4*)all_ent);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
+                                   int64_t n_rows, int32_t Dout, double* partials, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  const int Do4 = Dout / 4;
+  const size_t smem = partial_smem(Do4);   // <= 16 KB
+  tail_bwd_reduce_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
+      (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, n_rows, Do4, partials);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, float* sums, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, as_stream(stream)>>>(partials, n_blocks, Dout, sums);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
+                                  const float* gamma, const float* sums, const uint8_t* mask_in,
+                                  const uint8_t* mask_out, float keep_scale, int32_t training, int64_t n_rows,
+                                  int32_t Dout, float* d_res3, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  const int Do4 = Dout / 4;
+  const int64_t n4 = n_rows * Do4;
+  tail_bwd_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
+      (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma,
+      (const float4*)sums, mask_in, mask_out, keep_scale, training, n_rows, Do4, (float4*)d_res3);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}

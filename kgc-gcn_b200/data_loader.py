@@ -1,0 +1,262 @@
+"""DataLoader / KBDataset: drop-in mirrors of the reference data layer (data_loader.py:17-192).
+
+Host side (Python, as in the reference): vocabulary + id assignment, (s, r) -> objects grouping, query
+lists, the bi-directional edge list.  Device side: the per-step work - epoch permutation, the dense
+multi-hot [B, N] label with the reference's label smoothing, the [B, 3] triple gather - runs in K5
+(kgc_label_build) straight into device memory from a query -> objects CSR, replacing the per-query
+Python loop of KBDataset.get_label and the B*N*4-byte host-to-device copy of every step.
+Sparse (CSR) batches for the fused scorer are offered next to the dense reference-compatible ones.
+"""
+import logging
+import os
+from collections import OrderedDict, defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class GraphData(object):
+    """Stand-in for torch_geometric.data.Data as the reference uses it (data_loader.py:151-155):
+    tensor attributes ``edge_index``, ``edge_attr`` (unpackable as edge_type, edge_ids - model.py:26),
+    ``entity``, ``edge_norm``, plus ``num_nodes``; ``.to(device)`` moves them IN PLACE because
+    main.py:206 ignores the return value."""
+
+    def __init__(self, edge_index=None, edge_attr=None, **kwargs):
+        self.edge_index, self.edge_attr = edge_index, edge_attr
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+    @property
+    def device(self):
+        return self.edge_index.device
+
+
+class KBDataset(object):
+    """Query set in CSR form.  ``triplets`` is the reference's list of {'triple': (s, r, o), 'label': [objs]}."""
+
+    def __init__(self, triplets, num_entity, params, training=False):
+        self.triplets = triplets
+        self.num_entity = int(num_entity)
+        self.params = params
+        self.training = training
+        q = len(triplets)
+        self.triples = np.asarray([t['triple'] for t in triplets], dtype=np.int64).reshape(q, 3)
+        self.ptr = np.zeros(q + 1, dtype=np.int64)
+        idx = []
+        for i, t in enumerate(triplets):
+            objs = sorted(int(o) for o in t['label'])
+            idx.extend(objs)
+            self.ptr[i + 1] = len(idx)
+        self.idx = np.asarray(idx, dtype=np.int32)
+        self._dev = {}
+
+    def label_values(self):
+        """(pos, add): label = add everywhere, pos on the positives.  Training with lbl_smooth != 0 gives
+        (1 - ls) * y + 1 / N (data_loader.py:41-43 - note 1/N, not ls/N), evaluated in float32 like numpy does."""
+        ls = float(getattr(self.params, 'lbl_smooth', 0.0) or 0.0)
+        if self.training and ls != 0.0:
+            add = np.float32(1.0 / self.num_entity)
+            pos = np.float32(np.float32(1.0 - ls) * np.float32(1.0) + add)
+            return float(pos), float(add)
+        return 1.0, 0.0
+
+    def device_csr(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(torch.from_numpy(a).to(device) for a in (self.triples, self.ptr, self.idx))
+        return self._dev[key]
+
+    def build_batch(self, qid, device):
+        """K5: (triple[B,3] int64, label[B,N] float32) on ``device`` for the query ids ``qid``."""
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('label/batch build runs on the GPU only (no CPU fallback); move the graph with '
+                               'graph.to("cuda") before get_data_loaders')
+        triples, ptr, idx = self.device_csr(device)
+        qid = torch.as_tensor(qid, dtype=torch.int64).to(device, non_blocking=True)
+        b = int(qid.numel())
+        triple = torch.empty((b, 3), dtype=torch.int64, device=device)
+        label = torch.empty((b, self.num_entity), dtype=torch.float32, device=device)
+        pos, add = self.label_values()
+        p = _lib.ptr
+        with torch.cuda.device(device):
+            _lib.call('kgc_label_build', p(qid), b, p(triples), p(ptr), p(idx), self.num_entity, pos, add, p(triple),
+                      p(label), _lib.stream())
+        return triple, label
+
+    def sparse_batch(self, qid):
+        """Host CSR slice for the fused scorer: (triple[B,3], filt_ptr[B+1] int64, filt_idx[nnz] int32), numpy."""
+        qid = np.asarray(qid, dtype=np.int64)
+        lens = self.ptr[qid + 1] - self.ptr[qid]
+        fptr = np.zeros(qid.shape[0] + 1, dtype=np.int64)
+        np.cumsum(lens, out=fptr[1:])
+        fidx = np.concatenate([self.idx[self.ptr[q]:self.ptr[q + 1]] for q in qid]) if qid.size else self.idx[:0]
+        return self.triples[qid], fptr, fidx.astype(np.int32)
+
+    def collate_fn(self, batch):
+        return torch.stack([b[0] for b in batch], dim=0), torch.stack([b[1] for b in batch], dim=0)
+
+    def __len__(self):
+        return len(self.triplets)
+
+    def __getitem__(self, idx):
+        raise RuntimeError('KBDataset is batch-built on the GPU; iterate the loaders from get_data_loaders() '
+                           'or call build_batch(qid, device)')
+
+
+def epoch_permutation(n, shuffle=True):
+    """Order of one epoch.  Restates torch.utils.data.RandomSampler (what the reference's shuffle=True
+    DataLoaders use, data_loader.py:169-176): one int64 seed drawn from the global torch generator, then
+    torch.randperm under a fresh generator seeded with it - so under the same torch.manual_seed the batches
+    come out in the reference's order."""
+    if not shuffle:
+        return np.arange(n, dtype=np.int64)
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    return torch.randperm(n, generator=gen).numpy()
+
+
+class BatchIterator(object):
+    """Re-iterable, has len(); yields (triple[B,3] int64, label[B,N] float32) like the reference's torch
+    DataLoader (data_loader.py:180-192) but already on the graph's device."""
+
+    def __init__(self, dataset, batch_size, shuffle=True, drop_last=False, device='cuda'):
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.device = torch.device(device)
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def batches(self):
+        """Query-id batches of one epoch (host integers)."""
+        perm = epoch_permutation(len(self.dataset), self.shuffle)
+        for i in range(len(self)):
+            yield perm[i * self.batch_size:(i + 1) * self.batch_size]
+
+    def __iter__(self):
+        for qid in self.batches():
+            yield self.dataset.build_batch(qid, self.device)
+
+    def sparse(self):
+        """Same epoch order, CSR labels on the device: (triple, filt_ptr, filt_idx) for MGCN.rank / predict."""
+        for qid in self.batches():
+            trip, fptr, fidx = self.dataset.sparse_batch(qid)
+            yield (torch.from_numpy(trip).to(self.device), torch.from_numpy(fptr).to(self.device),
+                   torch.from_numpy(fidx).to(self.device))
+
+
+class DataLoader(object):
+
+    def __init__(self, dataset, params):
+        self.data_dir = os.path.join('data', dataset)
+        self.params = params
+        self.graph = self._load_data()
+
+    def _load_data(self):
+        # pass 1 (data_loader.py:64-74): ids in first-appearance order over train, valid, test; tokens lower-cased
+        ent2id, rel2id = OrderedDict(), OrderedDict()
+        splits = ('train', 'valid', 'test')
+        for split in splits:
+            with open(os.path.join(self.data_dir, split + '.txt'), 'r') as f:
+                for line in f:
+                    if not line.strip():
+                        continue
+                    sub, rel, obj = (tok.lower() for tok in line.strip().split())
+                    ent2id.setdefault(sub, len(ent2id))
+                    rel2id.setdefault(rel, len(rel2id))
+                    ent2id.setdefault(obj, len(ent2id))
+        n_rel = len(rel2id)
+        for name, idx in list(rel2id.items()):
+            rel2id[name + '_reverse'] = idx + n_rel
+        self.entity2id, self.relation2id = dict(ent2id), dict(rel2id)
+        self.num_entity, self.num_relation = len(ent2id), n_rel
+
+        # pass 2 (data_loader.py:80-96): tokens NOT lower-cased here - a mixed-case dataset raises KeyError
+        # exactly as the reference does; (s, r) -> {o} in both directions, snapshot after the train split
+        data = {}
+        known = defaultdict(set)
+        known_train = None
+        for split in splits:
+            rows = []
+            with open(os.path.join(self.data_dir, split + '.txt'), 'r') as f:
+                for line in f:
+                    if not line.strip():
+                        continue
+                    head, relation, tail = line.strip().split()
+                    s, r, o = self.entity2id[head], self.relation2id[relation], self.entity2id[tail]
+                    rows.append((s, r, o))
+                    known[(s, r)].add(o)
+                    known[(o, r + n_rel)].add(s)
+            data[split] = rows
+            if split == 'train':
+                known_train = OrderedDict((k, sorted(v)) for k, v in known.items())
+        known_all = {k: sorted(v) for k, v in known.items()}
+        self.num_edge = len(data['train'])
+
+        # query lists (data_loader.py:98-111)
+        trip = {'train': [{'triple': (s, r, -1), 'label': objs, 'sub_samp': 1} for (s, r), objs in known_train.items()]}
+        for split in ('valid', 'test'):
+            tails, heads = [], []
+            for s, r, o in data[split]:
+                tails.append({'triple': (s, r, o), 'label': known_all[(s, r)]})
+                heads.append({'triple': (o, r + n_rel, s), 'label': known_all[(o, r + n_rel)]})
+            trip[split + '_tail'], trip[split + '_head'] = tails, heads
+        self.triplets = trip
+
+        graph = self._build_graph(np.arange(self.num_entity, dtype=np.int64),
+                                  np.asarray(data['train'], dtype=np.int64).reshape(-1, 3), bi_direction=True)
+        logging.info('entity={}, relation={}, train_triplets={}, valid_triplets={}, test_triplets={}'.format(
+            self.num_entity, self.num_relation, len(data['train']), len(data['valid']), len(data['test'])))
+        return graph
+
+    def _edge_normal(self, edge_type, edge_index, num_entity):
+        """1 / in-degree(dst), inf -> 0 (data_loader.py:122-130).  Kept for API compatibility only: the
+        convolution never reads it."""
+        dst = np.asarray(edge_index[1], dtype=np.int64)
+        deg = np.bincount(dst, minlength=num_entity).astype(np.float32)
+        with np.errstate(divide='ignore'):
+            norm = (np.float32(1.0) / deg[dst]).astype(np.float32)
+        norm[np.isinf(norm)] = 0
+        return torch.from_numpy(norm)
+
+    def _build_graph(self, graph_nodes, triplets, bi_direction=True):
+        """Bi-directional edge list (data_loader.py:132-157): columns 0..E-1 = (s -> o, r), E..2E-1 = (o -> s, r + R)."""
+        src, rel, dst = triplets.transpose()
+        if bi_direction is True:
+            src, dst = np.concatenate((src, dst)), np.concatenate((dst, src))
+            rel = np.concatenate((rel, rel + self.num_relation))
+        edge_index = np.stack((src, dst))
+        edge_attr = np.stack((rel, np.arange(edge_index.shape[1])))
+        data = GraphData(edge_index=torch.from_numpy(edge_index), edge_attr=torch.from_numpy(edge_attr))
+        data.entity = torch.from_numpy(graph_nodes)
+        data.num_nodes = len(graph_nodes)
+        data.edge_norm = self._edge_normal(rel, edge_index, len(graph_nodes))
+        return data
+
+    def _get_dataset(self, data_type, params):
+        if data_type == 'train':
+            return KBDataset(self.triplets['train'], len(self.entity2id), params, training=True)
+        elif data_type in ['valid_head', 'valid_tail', 'test_head', 'test_tail']:
+            return KBDataset(self.triplets[data_type], len(self.entity2id), params)
+        else:
+            raise ValueError('Unkown data type')
+
+    def _create_data_loader(self, dataset, batch_size, num_workers, shuffle, drop_last=False):
+        # num_workers is accepted for signature compatibility; batches are built by one CUDA kernel per step
+        return BatchIterator(dataset, batch_size, shuffle=shuffle, drop_last=drop_last, device=self.graph.device)
+
+    def get_data_loaders(self, batch_size, num_workers, params):
+        marks = ['train', 'valid_head', 'valid_tail', 'test_head', 'test_tail']
+        return {mark: self._create_data_loader(self._get_dataset(mark, params), batch_size=batch_size,
+                                               num_workers=num_workers, shuffle=True, drop_last=False)
+                for mark in marks}

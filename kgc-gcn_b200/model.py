@@ -1,0 +1,100 @@
+"""MGCN and ConvE: drop-in mirrors of the reference classes (model.py:10-44, 130-181).
+
+Same constructors, forward signatures, parameter / state-dict names, so a checkpoint
+written by the reference loads here and vice versa.  The encoder is the CUDA MGCNConv; the ConvE front
+end (bn0 -> 7x7 conv -> bn1 -> relu -> fc -> bn2 -> relu, model.py:161-175) is SURVEY.md "next" row N2 and
+stays on torch/cuDNN; the 1-N scoring tail is torch.addmm + sigmoid in ``forward`` (which must return
+the dense [B,N] matrix to stay call-compatible) and the fused tensor-core kernel in ``rank``.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .conv import MGCNConv, get_param
+
+
+class ConvE(nn.Module):
+
+    def __init__(self, params, num_entities):
+        super(ConvE, self).__init__()
+        self.params = params
+        self.bn0 = nn.BatchNorm2d(1)
+        self.bn1 = nn.BatchNorm2d(params.num_filter)
+        self.bn2 = nn.BatchNorm1d(params.gcn_out_dim)
+        self.hidden_drop = nn.Dropout(params.hidden_drop)
+        self.feature_drop = nn.Dropout(params.feat_drop)
+        self.conv_e = nn.Conv2d(in_channels=1, out_channels=params.num_filter,
+                                kernel_size=(params.kernel_size, params.kernel_size), stride=1, padding=0,
+                                bias=params.bias)
+        flat_sz_h = int(2 * params.k_w) - params.kernel_size + 1
+        flat_sz_w = params.k_h - params.kernel_size + 1
+        self.flat_sz = flat_sz_h * flat_sz_w * params.num_filter
+        self.fc = nn.Linear(self.flat_sz, params.gcn_out_dim)
+        self.register_parameter('bias', nn.Parameter(torch.zeros(num_entities)))
+
+    def query(self, src_emb, rel_emb):
+        """Front end: (src_emb, rel_emb) -> query matrix X[B, Dout] (model.py:161-175)."""
+        d = self.params.gcn_out_dim
+        stack_inp = torch.cat([src_emb.view(-1, 1, d), rel_emb.view(-1, 1, d)], dim=1)
+        x = torch.transpose(stack_inp, 2, 1).reshape(-1, 1, 2 * self.params.k_w, self.params.k_h)
+        x = self.bn0(x)
+        x = self.conv_e(x)
+        x = F.relu(self.bn1(x))
+        x = self.feature_drop(x)
+        x = self.fc(x.view(-1, self.flat_sz))
+        x = self.hidden_drop(x)
+        return F.relu(self.bn2(x))
+
+    def forward(self, src_emb, rel_emb, all_ent):
+        x = self.query(src_emb, rel_emb)
+        # model.py:177-179: mm, += bias, sigmoid
+        return torch.sigmoid(torch.addmm(self.bias, x, all_ent.transpose(1, 0)))
+
+
+class MGCN(nn.Module):
+
+    def __init__(self, num_entities, num_relations, num_edges, params):
+        super(MGCN, self).__init__()
+        self.params = params
+        self.entity_embedding = get_param((num_entities, params.gcn_in_dim))
+        self.relation_embedding = get_param((2 * num_relations, params.gcn_in_dim))
+        self.edge_embeddings = get_param((2 * num_edges, params.gcn_in_dim))
+        self.conv1 = MGCNConv(params.gcn_in_dim, params.gcn_out_dim, num_relations * 2)
+        self.conv2 = ConvE(params, num_entities)
+        self.loss_fn = nn.BCELoss()
+        self._arange_cache = {}
+
+    def _is_arange(self, idx, n):
+        """data.entity / edge_ids are arange in every graph the reference builds (data_loader.py:145-153);
+        the identity gathers of model.py:29-30 are then skipped (they copy 16 MB + 70 MB per WN18RR step).
+        The check costs one device sync, so it is cached on the identity + version of the index tensor."""
+        key = (idx.data_ptr(), idx._version, idx.numel(), n, str(idx.device))
+        ok = self._arange_cache.get(key)
+        if ok is None:
+            ok = idx.numel() == n and bool((idx == torch.arange(n, device=idx.device)).all())
+            if len(self._arange_cache) > 16:
+                self._arange_cache.clear()
+            self._arange_cache[key] = ok
+        return ok
+
+    def encode(self, data):
+        """GCN encoder (model.py:25-34): returns (all_ent after gcn_drop, all_rel)."""
+        entity, edge_index, edge_norm = data.entity, data.edge_index, data.edge_norm
+        edge_type, edge_ids = data.edge_attr
+        ent = self.entity_embedding
+        if not self._is_arange(entity, ent.size(0)):
+            ent = torch.index_select(ent, 0, entity)
+        edge = self.edge_embeddings
+        if not self._is_arange(edge_ids, edge.size(0)):
+            edge = torch.index_select(edge, 0, edge_ids)
+        all_ent, all_rel = self.conv1(ent, edge_index, edge_type, edge_norm, edge, self.relation_embedding)
+        all_ent = F.dropout(all_ent, p=self.params.gcn_drop, training=self.training)
+        return all_ent, all_rel
+
+    def forward(self, src, rel, data):
+        all_ent, all_rel = self.encode(data)
+        src_emb, rel_emb = torch.index_select(all_ent, 0, src), torch.index_select(all_rel, 0, rel)
+        return self.conv2(src_emb, rel_emb, all_ent)
+
+    def loss(self, pred, label):
+        return self.loss_fn(pred, label)
