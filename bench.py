@@ -1,0 +1,462 @@
+"""bench.py - headline benchmark of the M-GCN hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload wn18rr|fb15k237]
+
+Metric (BASELINE.json): edges/sec of the relation-aware graph convolution, forward + backward, where an
+"edge" is one directed edge of edge_index (2E per pass).  One JSON line on stdout:
+  value        MGCNConv.forward + backward with every input resident in HBM (CUDA-event time, L2 flushed
+               between steps, dropout p=0.1 drawn inside the timed region, CUDA-graph launch)
+  e2e          the same metric through the reference-facing API for a whole training step
+               (loader batch from host ids -> model(src, rel, graph) -> loss -> backward -> clip -> Adam ->
+               loss.item()), host<->device copies inside the timed region
+  roofline     the dominant kernel, timed alone with CUDA events: algorithmic bytes / time vs measured HBM peak
+  cpu_baseline the oracle port of the reference (CPU torch, all host threads) on the same graph
+  aux          filtered-rank queries/sec of the fused tcgen05 scorer (second half of BASELINE.json's metric)
+`--impl reference` times the oracle port's full training step on the host cores (the reference is pure
+Python and cannot travel to the GPU box; oracle/ is its pinned restatement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N entities, R relations, E train triples, synthetic seed)        SURVEY.md 8(d)
+    'wn18rr': (40943, 11, 86835, 0),
+    'fb15k237': (14541, 237, 272115, 1),
+}
+D_IN, D_OUT, BATCH = 100, 200, 128
+
+
+def params_ns():
+    from types import SimpleNamespace
+    return SimpleNamespace(gcn_in_dim=D_IN, gcn_out_dim=D_OUT, gcn_drop=0.3, hidden_drop=0.3, feat_drop=0.3, k_w=10,
+                           k_h=20, num_filter=200, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=BATCH)
+
+
+def oracle():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import mgcn_oracle
+    return mgcn_oracle
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def algorithmic_bytes(N, R, E, D=D_IN):
+    """compulsory traffic, each tensor once, fp32, int32 indices."""
+    T = 2 * R + 1
+    fwd = 2 * E * (4 * D + 12) + 2 * N * (4 * D + 4) + N * 4 * D + T * 4 * D
+    bwd = 2 * E * (8 * D + 12) + 2 * N * 4 * D + N * 4 * D + N * 4 * D + 2 * T * 4 * D
+    return fwd, bwd
+
+
+class ClockSampler(object):
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def synthetic_queries(orc, tri, R):
+    """(s, r) -> objects grouping of the train triples in both directions (data_loader.py:86-102)."""
+    from collections import OrderedDict
+    known = OrderedDict()
+    for s, r, o in tri.tolist():
+        known.setdefault((s, r), set()).add(o)
+        known.setdefault((o, r + R), set()).add(s)
+    return [{'triple': (s, r, -1), 'label': sorted(v)} for (s, r), v in known.items()]
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_conv_baseline(orc, N, R, E, seed, budget_s=12.0):
+    """Oracle port of MGCNConv fwd+bwd (reference operation order) on the host cores; bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    tri = orc.synthetic_triples(N, R, E, seed)
+    g = orc.build_graph(tri, N, R)
+    p = orc.conv_params(N, R, E, D_IN, D_OUT, seed=0)
+    ei, et = torch.from_numpy(g['edge_index']), torch.from_numpy(g['edge_attr'][0])
+    gen = torch.Generator().manual_seed(1)
+    g_ent, g_rel = torch.randn(N, D_OUT, generator=gen), torch.randn(2 * R, D_OUT, generator=gen)
+    times = []
+    t_end = time.time() + budget_s
+    it = 0
+    while it < 2 or (time.time() < t_end and it < 40):
+        m_in = torch.empty(N, D_OUT).bernoulli_(0.9)
+        m_out = torch.empty(N, D_OUT).bernoulli_(0.9)
+        t0 = time.perf_counter()
+        orc.conv_fwd_bwd(p['x'], ei, et, p['edge_embs'], p['rels'], p['w'], g_ent, g_rel, mask_in=m_in, mask_out=m_out)
+        times.append(time.perf_counter() - t0)
+        it += 1
+    t = float(np.median(times[1:]))
+    return {'value': 2 * E / t, 'unit': 'edges/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': 'oracle port of MGCNConv fwd+bwd (reference op order, fp32, dropout masks pre-drawn), full '
+                      'graph, median of {} steps, {:.3f} s/step'.format(len(times) - 1, t)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the oracle port's FULL training step on the host cores (same scope as our e2e)."""
+    if rank != 0:
+        return
+    orc = oracle()
+    N, R, E, seed = WORKLOADS[args.workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    tri = orc.synthetic_triples(N, R, E, seed)
+    g = orc.build_graph(tri, N, R)
+    prm = params_ns()
+    qs = synthetic_queries(orc, tri, R)
+    model = orc.OracleMGCN(N, R, E, prm)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ei, et = torch.from_numpy(g['edge_index']), torch.from_numpy(g['edge_attr'][0])
+    rng = np.random.default_rng(0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        qid = rng.integers(0, len(qs), BATCH)
+        t0 = time.perf_counter()
+        trip, lab = orc.make_batch(qs, qid, N, prm.lbl_smooth, True)          # KBDataset + collate (data_loader.py:25-51)
+        trip, lab = torch.from_numpy(trip), torch.from_numpy(lab)
+        opt.zero_grad()
+        pred = model(trip[:, 0], trip[:, 1], ei, et)
+        loss = torch.nn.functional.binary_cross_entropy(pred, lab)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        loss.item()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    val = 2 * E * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': 'edges/sec GCN fwd+bwd', 'value': val, 'unit': 'edges/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload + '_shape', 'N': N, 'R': R, 'E': E, 'd_in': D_IN, 'd_out': D_OUT,
+                   'batch': BATCH, 'scope': 'full training step on the host CPU'},
+        'cpu_baseline': {'value': val, 'unit': 'edges/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': 'oracle port (oracle/mgcn_oracle.py OracleMGCN) full train step: label build, GCN, '
+                                   'ConvE, BCE, backward, clip, Adam; whole graph each step'},
+        'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def time_kernel(fn, flush, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        flush()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def run_ours(args, rank, world, local_rank):
+    import kgc_gcn_b200 as k
+    L = k._lib
+    L.lib()
+    orc = oracle()                       # synthetic-workload generators + the cpu_baseline leg only
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    N, R, E, seed = WORKLOADS[args.workload]
+    # N > 1: every rank owns an independent, equally shaped graph partition (weak scaling; seeds differ per rank)
+    tri = orc.synthetic_triples(N, R, E, seed + 1000 * rank)
+    g = orc.build_graph(tri, N, R)
+    p = orc.conv_params(N, R, E, D_IN, D_OUT, seed=0)
+    ei, et = torch.from_numpy(g['edge_index']).to(dev), torch.from_numpy(g['edge_attr'][0]).to(dev)
+    torch.manual_seed(0)
+
+    conv = k.MGCNConv(D_IN, D_OUT, 2 * R).to(dev)          # dropout p = 0.1, the reference default (model.py:49)
+    with torch.no_grad():
+        for name in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge'):
+            getattr(conv, name).copy_(p['w'][name])
+    conv.train()
+    x = p['x'].to(dev).requires_grad_(True)
+    ee = p['edge_embs'].to(dev).requires_grad_(True)
+    rl = p['rels'].to(dev).requires_grad_(True)
+    gen = torch.Generator().manual_seed(1)
+    g_ent, g_rel = torch.randn(N, D_OUT, generator=gen).to(dev), torch.randn(2 * R, D_OUT, generator=gen).to(dev)
+    leaves = [x, ee, rl] + list(conv.parameters())
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        ent, rel = conv(x, ei, et, None, ee, rl)
+        torch.autograd.backward([ent, rel], [g_ent, g_rel])
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.zero_()
+
+    # ---- launch mode: CUDA graph of the whole fwd+bwd (falls back to eager launches if capture fails)
+    launch_mode = 'eager'
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    L.LAUNCHES = 0
+    step()
+    launches_per_step = L.LAUNCHES
+    run_step = step
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            for t in leaves:
+                t.grad = None
+            with torch.cuda.graph(graph):
+                step()
+            run_step = graph.replay
+            launch_mode = 'cuda_graph'
+        except Exception as exc:                      # pragma: no cover
+            sys.stderr.write('graph capture failed, timing eager launches: {}\n'.format(exc))
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        run_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for a, b in ev:
+            flush()
+            a.record()
+            run_step()
+            b.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        # ---- e2e: the whole training step through the reference-facing API, host ids in, loss out
+        e2e = e2e_train_step(k, orc, tri, g, N, R, E, dev, args)
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e['ms_total']], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e['ms_total'] = float(t[0]), float(t[1])
+    value = world * 2 * E * args.steps / (total_ms * 1e-3)
+    e2e_value = world * 2 * E * e2e['steps'] / (e2e['ms_total'] * 1e-3)
+
+    # ---- roofline of the dominant kernel, timed alone through the C ABI (rank 0)
+    roof, kernels = None, None
+    if rank == 0:
+        roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    fwd_b, bwd_b = algorithmic_bytes(N, R, E)
+    peak, peak_src = measured_peaks()
+    line = {
+        'metric': 'edges/sec GCN fwd+bwd', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload + '_shape', 'N': N, 'R': R, 'E': E, 'directed_edges': 2 * E, 'd_in': D_IN,
+                   'd_out': D_OUT, 'dropout': 'p=0.1 keep masks drawn inside the timed region (training mode)',
+                   'l2': 'flushed between steps (256 MiB memset outside the timed events)', 'launch': launch_mode,
+                   'parallelism': 'single GPU' if world == 1 else 'one equally shaped graph partition per GPU, no exchange'},
+        'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
+                'ms_per_step': e2e['ms_total'] / e2e['steps'],
+                'scope': 'full training step: loader batch (K5) + MGCN forward + BCE + backward + clip + Adam + loss.item()'},
+        'gpu_launches': launches_per_step * args.steps,
+        'clocks': clocks.summary(),
+        'roofline': roof,
+        'kernels': kernels,
+        'step_hbm': {'algorithmic_bytes_fwd_bwd': fwd_b + bwd_b, 'achieved_gbs': (fwd_b + bwd_b) / (total_ms / args.steps * 1e-3) / 1e9,
+                     'frac_of_peak': (fwd_b + bwd_b) / (total_ms / args.steps * 1e-3) / 1e9 / peak, 'peak_gbs': peak,
+                     'peak_source': peak_src, 'note': 'whole layer incl. the dense GEMMs and the BN/tanh tail, SURVEY.md 8(d) bytes'},
+    }
+    if not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_conv_baseline(orc, N, R, E, seed)
+    aux = aux_filtered_rank(k, dev, args)
+    if aux is not None:
+        line['aux'] = aux
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
+    prm = params_ns()
+    graph = k.GraphData(edge_index=torch.from_numpy(g['edge_index']), edge_attr=torch.from_numpy(g['edge_attr']))
+    graph.entity = torch.from_numpy(g['entity'])
+    graph.edge_norm = torch.from_numpy(g['edge_norm'])
+    graph.num_nodes = N
+    graph.to(dev)
+    ds = k.KBDataset(synthetic_queries(orc, tri, R), N, prm, training=True)
+    loader = k.BatchIterator(ds, BATCH, shuffle=True, device=dev)
+    model = k.MGCN(N, R, E, prm).to(dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    steps, warm = args.steps, max(3, args.warmup)
+    batches = loader.batches()
+    ms, n = 0.0, 0
+    for i in range(warm + steps):
+        qid = next(batches)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        trip, lab = ds.build_batch(qid, dev)                         # H2D: the batch's query ids
+        opt.zero_grad()
+        pred = model(trip[:, 0], trip[:, 1], graph)
+        loss = model.loss(pred, lab)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        loss.item()                                                   # D2H: the loss
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ms += a.elapsed_time(b)
+            n += 1
+    del model, opt
+    return {'ms_total': ms, 'steps': n, 'h2d': BATCH * 8, 'd2h': 4}
+
+
+def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
+    """Each level-0 aggregation kernel alone through the C ABI, CUDA events, L2 flushed before every launch."""
+    L = k._lib
+    p, st = L.ptr, L.stream
+    plan = k.get_plan(ei, et, N, 2 * R + 1)
+    D, T = D_IN, 2 * R + 1
+    relp = torch.cat([rl.detach(), conv.loop_rel.detach()], 0).contiguous()
+    xd, eed = x.detach(), ee.detach()
+    agg = torch.empty((2, N, D), device=x.device)
+    g3 = torch.randn((3, N, D), device=x.device)
+    d_ee, d_x, d_rel = torch.empty_like(eed), torch.empty((N, D), device=x.device), torch.empty((T, D), device=x.device)
+
+    def part(rp):
+        n = rp.levels[0][2]
+        return torch.empty((max(n, 1), D), device=x.device)
+    pf, ps, pr = part(plan.fwd), part(plan.bwd_src), part(plan.bwd_rel)
+    it_f, n_f, _ = plan.fwd.levels[0]
+    it_s, n_s, _ = plan.bwd_src.levels[0]
+    it_r, n_r, _ = plan.bwd_rel.levels[0]
+    fns = {
+        'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), p(eed), p(plan.rec_dst), p(it_f), n_f, p(agg), p(pf), D, st()),
+        'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), p(eed), p(g3), p(plan.rec_src), p(it_s), n_s, N,
+                                      2 * E, p(d_ee), p(d_x), p(ps), D, st()),
+        'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(it_r), n_r, N, 2 * E,
+                                      p(d_rel), p(pr), D, st()),
+    }
+    row = 4 * D
+    bytes_ = {   # per launch: edge-embedding stream + 16-byte records + each dense operand once + outputs once
+        'agg_fwd': 2 * E * (row + 16) + N * row + T * row + 2 * N * row + 16 * n_f,
+        'agg_bwd_src': 2 * E * (2 * row + 16) + N * row + 3 * N * row + T * row + N * row + 16 * n_s,
+        'agg_bwd_rel': 2 * E * (row + 16) + N * row + 2 * N * row + T * row + 16 * n_r,
+    }
+    peak, peak_src = measured_peaks()
+    out = {}
+    for name, fn in fns.items():
+        ms = time_kernel(fn, flush)
+        gbs = bytes_[name] / (ms * 1e-3) / 1e9
+        out[name] = {'ms': ms, 'algorithmic_bytes': bytes_[name], 'achieved_gbs': gbs, 'frac': gbs / peak}
+    top = max(out, key=lambda n: out[n]['ms'])
+    roof = {'kernel': top, 'bound': 'hbm', 'achieved': out[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+            'frac': out[top]['frac'], 'traffic': None, 'peak_source': peak_src,
+            'how': 'kernel launched alone through the C ABI, CUDA events on the launch stream, L2 flushed before each launch'}
+    return roof, out
+
+
+def aux_filtered_rank(k, dev, args):
+    if not hasattr(k, 'bench_filtered_rank'):
+        return None
+    try:
+        return k.bench_filtered_rank(dev, quick=args.quick_aux)
+    except Exception as exc:                           # pragma: no cover
+        return {'error': repr(exc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='wn18rr', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick-aux', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

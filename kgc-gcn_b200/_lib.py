@@ -55,9 +55,15 @@ def lib():
     return _LIB
 
 
+LAUNCHES = 0     # kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
+_KERNELS_PER_CALL = {'kgc_csr_build': 16}
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise RuntimeError with kgc_last_error() on failure."""
+    global LAUNCHES
     h = lib()
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     rc = getattr(h, name)(*args)
     if rc != 0:
         raise RuntimeError('{} failed: {}'.format(name, h.kgc_last_error().decode('utf-8', 'replace')))

@@ -1,0 +1,175 @@
+"""CPU tests of the host logic: reduction plan scheduling, loader, epoch permutation, C-ABI exports.
+No kernel is launched here (there is no GPU in the authoring container and no CPU fallback)."""
+import ctypes
+import json
+import os
+import re
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import mgcn_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def simulate(levels, values, n_out):
+    """Execute a reduction plan in numpy: what kgc_agg_fwd (level 0) + kgc_rows_reduce (levels >= 1) do."""
+    out = np.full(n_out, np.nan)
+    cur = values
+    for items, n_part in levels:
+        part = np.full(n_part, np.nan)
+        for beg, end, o, flags in items.tolist():
+            s = cur[beg:end].sum()
+            if flags & 1:
+                assert o == flags >> 1
+                out[o] = s
+            else:
+                part[o] = s
+        cur = part
+    return out
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_build_levels_exact(seed):
+    from kgc_gcn_b200 import build_levels
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, 5, 400)
+    lens[7], lens[100], lens[399] = 70000, 33, 1025 * 32 + 1      # hubs -> 3 levels
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    rows = rng.permutation(400)
+    levels = build_levels(ptr[:-1], ptr[1:], rows, 32, 1024)
+    assert len(levels) == 3 and levels[-1][1] == 0
+    vals = rng.integers(-5, 6, ptr[-1]).astype(np.float64)
+    out = simulate(levels, vals, 400)
+    exp = np.array([vals[ptr[i]:ptr[i + 1]].sum() for i in range(400)])
+    np.testing.assert_array_equal(out[rows], exp)
+    for items, _ in levels[:1]:
+        assert (items[:, 1] - items[:, 0]).max() <= 32
+    for items, _ in levels[1:]:
+        assert (items[:, 1] - items[:, 0]).max() <= 1024
+
+
+def test_build_levels_empty_rows_write_zero():
+    from kgc_gcn_b200 import build_levels
+    levels = build_levels(np.array([0, 0, 2]), np.array([0, 2, 2]), np.array([0, 1, 2]))
+    assert len(levels) == 1
+    assert levels[0][0].tolist() == [[0, 0, 0, 1], [0, 2, 1, 3], [2, 2, 2, 5]]
+
+
+def params(**kw):
+    base = dict(gcn_in_dim=20, gcn_out_dim=200, gcn_drop=0.0, hidden_drop=0.0, feat_drop=0.0, k_w=10, k_h=20,
+                num_filter=2, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=128)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+@pytest.fixture()
+def toy_loader(golden_dir):
+    import kgc_gcn_b200 as k
+    cwd = os.getcwd()
+    os.chdir(golden_dir)
+    try:
+        yield k.DataLoader('Toy', params())
+    finally:
+        os.chdir(cwd)
+
+
+def test_loader_host_side(toy_loader, golden_dir):
+    dl = toy_loader
+    with open(os.path.join(golden_dir, 'toy_loader.json')) as f:
+        gold = json.load(f)
+    assert dl.entity2id == gold['entity2id'] and dl.relation2id == gold['relation2id']
+    assert dl.graph.edge_index.tolist() == gold['edge_index']
+    assert dl.graph.edge_attr.tolist() == gold['edge_attr']
+    et, eid = dl.graph.edge_attr                      # unpackable like model.py:26
+    assert eid.tolist() == list(range(20))
+    np.testing.assert_array_equal(dl.graph.edge_norm.numpy(), np.asarray(gold['edge_norm'], dtype=np.float32))
+    for key in gold['triplets']:
+        got = [{'triple': list(q['triple']), 'label': sorted(q['label'])} for q in dl.triplets[key]]
+        assert got == gold['triplets'][key]
+    assert dl.graph.to('cpu') is dl.graph              # in-place .to (main.py:206 ignores the return value)
+
+
+def test_dataset_csr_and_label_values(toy_loader):
+    import kgc_gcn_b200 as k
+    dl = toy_loader
+    ds = dl._get_dataset('train', params())
+    assert len(ds) == 17
+    assert ds.ptr.tolist()[:4] == [0, 3, 4, 5] and ds.idx.tolist()[:5] == [1, 2, 3, 0, 0]
+    pos, add = ds.label_values()
+    ref = orc.make_label([2], 7, 0.1, True)
+    assert np.float32(pos) == ref[2] and np.float32(add) == ref[0] and pos > 1.0      # the reference's quirk
+    assert dl._get_dataset('valid_tail', params()).label_values() == (1.0, 0.0)
+    trip, fptr, fidx = ds.sparse_batch([9, 0])
+    assert trip.tolist() == [[6, 8, -1], [0, 0, -1]] and fptr.tolist() == [0, 2, 5] and fidx.tolist() == [0, 2, 1, 2, 3]
+    with pytest.raises(ValueError):
+        dl._get_dataset('bogus', params())
+    with pytest.raises(RuntimeError, match='GPU only'):
+        ds.build_batch([0, 1], 'cpu')                  # no CPU fallback
+
+
+def test_epoch_permutation_matches_torch_random_sampler():
+    """Under the same torch.manual_seed the batch order equals the reference's shuffle=True DataLoader order."""
+    from kgc_gcn_b200 import epoch_permutation
+    n = 17
+    torch.manual_seed(123)
+    ref = [list(torch.utils.data.RandomSampler(range(n))) for _ in range(2)]
+    torch.manual_seed(123)
+    got = [epoch_permutation(n).tolist() for _ in range(2)]
+    assert got == ref
+    assert sorted(got[0]) == list(range(n))
+
+
+def test_batch_iterator_lengths(toy_loader):
+    dl = toy_loader
+    it = dl.get_data_loaders(4, 0, params())
+    assert len(it['train']) == 5 and len(it['valid_head']) == 2
+    sizes = [len(b) for b in it['train'].batches()]
+    assert sizes == [4, 4, 4, 4, 1]
+
+
+def test_state_dict_names():
+    import kgc_gcn_b200 as k
+    m = k.MGCN(7, 5, 10, params(gcn_in_dim=8))
+    keys = set(m.state_dict().keys())
+    expect = {'entity_embedding', 'relation_embedding', 'edge_embeddings', 'conv1.loop_weight', 'conv1.in_weight',
+              'conv1.out_weight', 'conv1.rels_weight', 'conv1.loop_rel', 'conv1.loop_edge', 'conv2.bias',
+              'conv2.conv_e.weight', 'conv2.fc.weight', 'conv2.fc.bias'}
+    for bn in ('conv1.ent_bn', 'conv2.bn0', 'conv2.bn1', 'conv2.bn2'):
+        expect |= {bn + s for s in ('.weight', '.bias', '.running_mean', '.running_var', '.num_batches_tracked')}
+    assert keys == expect
+    assert m.entity_embedding.shape == (7, 8) and m.relation_embedding.shape == (10, 8)
+    assert m.edge_embeddings.shape == (20, 8) and m.conv2.fc.weight.shape == (200, 14 * 14 * 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'kgc-gcn_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'mgcn_oracle' not in src and 'oracle' not in re.findall(r'^\s*(?:from|import)\s+(\w+)', src, re.M), fn
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libkgc_b200.so loads and exports every function include/kgc_b200.h declares (no compute calls here)."""
+    import kgc_gcn_b200 as k
+    hdr = open(os.path.join(ROOT, 'include', 'kgc_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(kgc_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 17
+    h = ctypes.CDLL(k._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(h, name), 'missing export ' + name
+    assert declared == set(k._lib.SIGNATURES), declared ^ set(k._lib.SIGNATURES)
+    assert k._lib.lib().kgc_abi_version() == 1
+
+
+def test_cpu_tensors_fail_loudly():
+    import kgc_gcn_b200 as k
+    conv = k.MGCNConv(8, 8, 4)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        conv(torch.zeros(2, 8), ei, torch.tensor([0, 2]), None, torch.zeros(2, 8), torch.zeros(4, 8))
