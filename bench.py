@@ -301,13 +301,14 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
         # ---- e2e: the whole training step through the reference-facing API, host ids in, loss out
-        e2e = e2e_train_step(k, orc, tri, g, N, R, E, dev, args)
+        e2e = {'ms_total': float('nan'), 'steps': 0, 'h2d': 0, 'd2h': 0} if args.no_e2e else \
+            e2e_train_step(k, orc, tri, g, N, R, E, dev, args)
     if dist is not None:
         t = torch.tensor([total_ms, e2e['ms_total']], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e['ms_total'] = float(t[0]), float(t[1])
     value = world * 2 * E * args.steps / (total_ms * 1e-3)
-    e2e_value = world * 2 * E * e2e['steps'] / (e2e['ms_total'] * 1e-3)
+    e2e_value = world * 2 * E * e2e['steps'] / (e2e['ms_total'] * 1e-3) if e2e['steps'] else None
 
     # ---- roofline of the dominant kernel, timed alone through the C ABI (rank 0)
     roof, kernels = None, None
@@ -328,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
                    'l2': 'flushed between steps (256 MiB memset outside the timed events)', 'launch': launch_mode,
                    'parallelism': 'single GPU' if world == 1 else 'one equally shaped graph partition per GPU, no exchange'},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
-                'ms_per_step': e2e['ms_total'] / e2e['steps'],
+                'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1),
                 'scope': 'full training step: loader batch (K5) + MGCN forward + BCE + backward + clip + Adam + loss.item()'},
         'gpu_launches': launches_per_step * args.steps,
         'clocks': clocks.summary(),
@@ -448,6 +449,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick-aux', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
