@@ -149,30 +149,33 @@ int kgc_neg_sample(const int64_t* qid, int64_t B, const int64_t* ptr, const int3
 
 /* ---- K6: fused 1-N scoring + filter + rank (tcgen05 / TMA) --------------------------------------------
  * Replaces model.py:177-178 (X @ all_ent^T + bias) and main.py:122-126 (filter, rank) without
- * materialising the [B,N] score matrix.  Ranking is on the logit (sigmoid is monotone, SURVEY.md
- * section 7 "Tie semantics").
- * kgc_score_pack_*: fp32 rows -> bf16 rows of pitch KGC_SCORE_KPAD with the bias folded into three
- * extra K columns (entity side: bf16 hi/mid/lo split of bias[j]; query side: 1,1,1).
- * kgc_score_rank: for every query q, count over all entities j of  s[q,j] > thr[q]  (count_gt) and
- * == (count_eq), where s is the bf16 x bf16 -> fp32 tensor-core product.  kgc_score_pairs evaluates
- * s for explicit (q, j) pairs through the SAME MMA path (targets and filtered positives), so the
- * host-side correction  gt -= #{j in filter(q)\{o} : s[q,j] > thr[q]}  is bit-consistent. */
-#define KGC_SCORE_KPAD 208
+ * materialising the [B,N] score matrix.  Ranking is on the logit (sigmoid is monotone and saturates,
+ * SURVEY.md section 7 "Tie semantics").
+ *   kpad = kgc_score_kpad(d): padded K (multiple of 16, >= d + 3, <= 256; 208 for d = 200), -1 if d is too large.
+ *   kgc_score_pack_*: fp32 rows -> bf16 rows of pitch kpad with the bias folded into three extra K columns
+ *     (entity side: bf16 hi/mid/lo split of bias[j]; query side: 1, 1, 1), zero padded.
+ *   kgc_score_rank: for every query q, ADD to count_gt[q] the number of entities j in [0, n) with
+ *     s[q,j] > thr[q] (and to count_eq[q], when not NULL, those with s == thr), s being the
+ *     bf16 x bf16 -> fp32 tensor-core product.  The caller zeroes the counters; entity-sharded callers
+ *     call it once per shard and all-reduce the integers.
+ *   kgc_score_pairs: s for explicit (query row, entity row) pairs through the SAME MMA path (the target
+ *     score thr[q] and the scores of the filtered positives), so the correction below is bit-consistent.
+ *   kgc_rank_finalize (main.py:122-133): ranks[q] = 1 + count_gt[q] - #{k in filter(q), idx[k] != obj[q],
+ *     s_filt[k] > thr[q]}; eq_out likewise (minus the target itself); sums13 = {count, sum rank,
+ *     sum 1/rank (fp32 division as main.py:131), hits@1..10} reduced in a fixed order. */
+int32_t kgc_score_kpad(int32_t d);
 int kgc_score_pack_entities(const float* all_ent, const float* bias, int64_t n, int32_t d,
                             uint16_t* e_bf16, void* stream);
 int kgc_score_pack_queries(const float* xq, int64_t b, int32_t d, uint16_t* q_bf16, void* stream);
-size_t kgc_score_workspace_bytes(int64_t b, int64_t n);
+size_t kgc_score_pairs_workspace_bytes(int64_t n_pairs, int32_t kpad);
 int kgc_score_pairs(const uint16_t* q_bf16, const uint16_t* e_bf16, const int32_t* pair_q, const int32_t* pair_e,
-                    int64_t n_pairs, int64_t b, int64_t n, float* s_out, void* workspace, size_t workspace_bytes,
+                    int64_t n_pairs, int32_t kpad, float* s_out, void* workspace, size_t workspace_bytes,
                     void* stream);
-int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, int64_t b, int64_t n, int64_t n_begin,
-                   int64_t n_end, const float* thr, int32_t* count_gt, int32_t* count_eq,
-                   void* workspace, size_t workspace_bytes, void* stream);
-/* Filter correction + rank + metric sums (main.py:128-133): ranks[q] = 1 + gt[q] - sum over the
- * query's filtered pairs of (s_pair > thr[q]); sums = {count, sum rank, sum 1/rank, hits@1..10}. */
-int kgc_rank_finalize(const int32_t* count_gt, const float* thr, const float* s_filt, const int64_t* filt_ptr,
-                      const int32_t* filt_idx, const int64_t* obj, int64_t b, int32_t* ranks, double* sums13,
-                      void* stream);
+int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, int64_t b, int64_t n, int32_t kpad,
+                   const float* thr, int32_t* count_gt, int32_t* count_eq, void* stream);
+int kgc_rank_finalize(const int32_t* count_gt, const int32_t* count_eq, const float* thr, const float* s_filt,
+                      const int64_t* filt_ptr, const int32_t* filt_idx, const int64_t* obj, int64_t b,
+                      int32_t* ranks, int32_t* eq_out, double* sums13, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

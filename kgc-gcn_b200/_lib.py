@@ -35,6 +35,13 @@ SIGNATURES = {
     'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i32, _vp, _vp]),
     'kgc_label_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
     'kgc_neg_sample': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    'kgc_score_kpad': (_i32, [_i32]),
+    'kgc_score_pack_entities': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    'kgc_score_pack_queries': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    'kgc_score_pairs_workspace_bytes': (_sz, [_i64, _i32]),
+    'kgc_score_pairs': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    'kgc_score_rank': (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'kgc_rank_finalize': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -56,7 +63,7 @@ def lib():
 
 
 LAUNCHES = 0     # kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {'kgc_csr_build': 16}
+_KERNELS_PER_CALL = {'kgc_csr_build': 16, 'kgc_score_pairs': 3, 'kgc_rank_finalize': 2}
 
 
 def call(name, *args):

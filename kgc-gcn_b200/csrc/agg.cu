@@ -254,7 +254,26 @@ rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restr
   float4 acc[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = it.x + grp; r < it.y; r += kThreads / kGroup) {
+  constexpr int kStride = kThreads / kGroup;
+  int r = it.x + grp;
+  for (; r + 3 * kStride < it.y; r += 4 * kStride) {      // 4 independent rows in flight, added in row order
+    float4 v[4][NF];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const int c = g + f * kGroup;
+        if (c < D4) v[u][f] = __ldg(part_in + (int64_t)(r + u * kStride) * D4 + c);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const int c = g + f * kGroup;
+        if (c < D4) add4(acc[f], v[u][f]);
+      }
+  }
+  for (; r < it.y; r += kStride) {
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int c = g + f * kGroup;

@@ -81,19 +81,49 @@ tail_fwd_kernel(const float4* __restrict__ res3, const uint8_t* __restrict__ mas
   block_store_partials(sum, sq, rl, c, RL, Do4, partials, sm);
 }
 
-// stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
-__global__ void colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int64_t n_rows,
-                                         int Dout, float eps, int training, const float* __restrict__ rmean,
-                                         const float* __restrict__ rvar, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Dout) return;
-  double mean, var;
-  if (training) {
-    double s = 0, q = 0;
-    for (int64_t b = 0; b < n_blocks; ++b) {
+// Column finalisers: one block per 8 columns; 32 row-lanes stride over the per-block partials, then the
+// 32 lane sums are added in lane order - fixed order, deterministic, and ~100x less serial than one
+// thread per column.
+constexpr int kFinCols = 8, kFinLanes = 32;
+
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int64_t n_blocks, int Dout,
+                                                int c, int lane, double (*sm)[kFinLanes][kFinCols], double* s_out,
+                                                double* q_out) {
+  double s = 0, q = 0;
+  if (c < Dout) {
+    for (int64_t b = lane; b < n_blocks; b += kFinLanes) {
       s += partials[(b * 2 + 0) * Dout + c];
       q += partials[(b * 2 + 1) * Dout + c];
     }
+  }
+  const int cc = threadIdx.x % kFinCols;
+  sm[0][lane][cc] = s;
+  sm[1][lane][cc] = q;
+  __syncthreads();
+  if (lane == 0) {
+    s = sm[0][0][cc];
+    q = sm[1][0][cc];
+    for (int k = 1; k < kFinLanes; ++k) {
+      s += sm[0][k][cc];
+      q += sm[1][k][cc];
+    }
+  }
+  *s_out = s;
+  *q_out = q;
+}
+
+// stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int64_t n_rows, int Dout, float eps,
+                         int training, const float* __restrict__ rmean, const float* __restrict__ rvar,
+                         float* __restrict__ stats) {
+  __shared__ double sm[2][kFinLanes][kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
+  double s = 0, q = 0;
+  if (training) reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
+  if (lane != 0 || c >= Dout) return;
+  double mean, var;
+  if (training) {
     mean = s / (double)n_rows;
     var = q / (double)n_rows - mean * mean;
     if (var < 0) var = 0;
@@ -106,15 +136,13 @@ __global__ void colstats_finalize_kernel(const double* __restrict__ partials, in
   stats[2 * Dout + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout,
-                                       float* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Dout) return;
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout, float* __restrict__ sums) {
+  __shared__ double sm[2][kFinLanes][kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
   double s = 0, q = 0;
-  for (int64_t b = 0; b < n_blocks; ++b) {
-    s += partials[(b * 2 + 0) * Dout + c];
-    q += partials[(b * 2 + 1) * Dout + c];
-  }
+  reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
+  if (lane != 0 || c >= Dout) return;
   sums[c] = (float)s;
   sums[Dout + c] = (float)q;
 }
@@ -226,7 +254,7 @@ extern "C" int kgc_colstats_finalize(const double* partials, int64_t n_blocks, i
                                      float* stats, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   KGC_REQUIRE(training || (running_mean && running_var), "eval mode needs running statistics");
-  colstats_finalize_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, as_stream(stream)>>>(
+  colstats_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
       partials, n_blocks, n_rows, Dout, eps, training, running_mean, running_var, stats);
   KGC_LAUNCH_CHECK();
   return 0;
@@ -256,7 +284,7 @@ extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, con
 
 extern "C" int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, float* sums, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
-  colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, as_stream(stream)>>>(partials, n_blocks, Dout, sums);
+  colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(partials, n_blocks, Dout, sums);
   KGC_LAUNCH_CHECK();
   return 0;
 }

@@ -98,3 +98,11 @@ class MGCN(nn.Module):
 
     def loss(self, pred, label):
         return self.loss_fn(pred, label)
+
+    def rank(self, src, rel, obj, filt_ptr, filt_idx, data, count_eq=False):
+        """Filtered rank of obj among all entities for the queries (src, rel) without materialising the
+        [B, N] scores (K6): what main.py:121-126 computes from model(sub, rel, graph)."""
+        from .scoring import filtered_rank
+        all_ent, all_rel = self.encode(data)
+        xq = self.conv2.query(torch.index_select(all_ent, 0, src), torch.index_select(all_rel, 0, rel))
+        return filtered_rank(xq, all_ent, self.conv2.bias, obj, filt_ptr, filt_idx, count_eq=count_eq)

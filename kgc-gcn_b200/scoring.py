@@ -1,0 +1,149 @@
+"""Fused 1-N scoring + filtered ranking (K6) and the reference-facing evaluation helpers.
+
+Replaces ConvE's scoring tail (model.py:177-179) + predict's filter / double argsort (main.py:117-133)
+for evaluation.  The [B, N] score matrix is never written: a tcgen05 / TMA kernel sweeps the bf16 entity
+table once per pair of 128-query tiles and counts, per query, the entities whose logit beats the target's.
+
+Tie semantics: rank = 1 + count_gt on the LOGIT (sigmoid is monotone but saturates
+in fp32, which manufactures ties the reference then breaks arbitrarily); count_eq is reported so that
+callers can check reference_rank in [1 + gt, 1 + gt + eq].
+"""
+import torch
+
+from . import _lib
+
+
+def score_kpad(d):
+    kpad = int(_lib.lib().kgc_score_kpad(int(d)))
+    if kpad < 0:
+        raise ValueError('scoring dimension {} too large (d + 3 <= 256)'.format(d))
+    return kpad
+
+
+class EntityTable(object):
+    """bf16 copy of all_ent [N, d] with the decoder bias folded into three extra K columns (pitch kpad)."""
+
+    def __init__(self, all_ent, bias=None):
+        all_ent = _lib.require_cuda(all_ent.detach(), torch.float32, 'all_ent')
+        self.n, self.d = int(all_ent.shape[0]), int(all_ent.shape[1])
+        self.kpad = score_kpad(self.d)
+        if bias is not None:
+            bias = _lib.require_cuda(bias.detach(), torch.float32, 'bias')
+        self.data = torch.empty((self.n, self.kpad), dtype=torch.bfloat16, device=all_ent.device)
+        _lib.call('kgc_score_pack_entities', _lib.ptr(all_ent), _lib.ptr(bias), self.n, self.d, _lib.ptr(self.data),
+                  _lib.stream())
+
+
+def pack_queries(xq):
+    xq = _lib.require_cuda(xq.detach(), torch.float32, 'xq')
+    b, d = int(xq.shape[0]), int(xq.shape[1])
+    out = torch.empty((b, score_kpad(d)), dtype=torch.bfloat16, device=xq.device)
+    _lib.call('kgc_score_pack_queries', _lib.ptr(xq), b, d, _lib.ptr(out), _lib.stream())
+    return out
+
+
+def pair_scores(q_bf16, table, pair_q, pair_e):
+    """s[p] = <Q[pair_q[p]], E[pair_e[p]]> (+ bias) through the same tcgen05 path as the sweep."""
+    n_pairs = int(pair_q.numel())
+    out = torch.empty((n_pairs,), dtype=torch.float32, device=q_bf16.device)
+    if n_pairs == 0:
+        return out
+    ws_bytes = int(_lib.lib().kgc_score_pairs_workspace_bytes(n_pairs, table.kpad))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q_bf16.device)
+    p = _lib.ptr
+    _lib.call('kgc_score_pairs', p(q_bf16), p(table.data), p(pair_q), p(pair_e), n_pairs, table.kpad, p(out), p(ws),
+              ws_bytes, _lib.stream())
+    return out
+
+
+def filtered_rank(xq, all_ent, bias, obj, filt_ptr, filt_idx, count_eq=False, table=None, n_offset=0, group=None):
+    """Filtered rank of obj[q] among all entities for every query row of ``xq`` [B, d].
+
+    filt_ptr [B+1] int64 / filt_idx [nnz] int32: the known positives of each query (CSR, the all-split filter
+    of data_loader.py:108-110; may or may not contain the target).  Returns a dict with ranks [B] int32,
+    count_gt [B] int32 (already filter-corrected), count_eq (if asked), thr [B] (target logits) and
+    sums [13] float64 = {count, sum rank, sum 1/rank, hits@1..10} (main.py:128-133).
+
+    Entity-sharded use (one process per GPU): pass this rank's ``table`` shard (rows n_offset .. n_offset+n)
+    and the process ``group``; target / filter logits are computed by the owning rank and summed (each entry
+    is non-zero on exactly one rank, so the sum is exact), integer counts are all-reduced (bit-exact).
+    """
+    dev = xq.device
+    if table is None:
+        table = EntityTable(all_ent, bias)
+    b = int(xq.shape[0])
+    obj = _lib.require_cuda(obj, torch.int64, 'obj')
+    filt_ptr = _lib.require_cuda(filt_ptr, torch.int64, 'filt_ptr')
+    filt_idx = _lib.require_cuda(filt_idx, torch.int32, 'filt_idx')
+    q_bf16 = pack_queries(xq)
+    # (query, entity) pairs whose logits are needed exactly: the targets, then every filtered positive
+    lens = (filt_ptr[1:] - filt_ptr[:-1])
+    rows = torch.arange(b, device=dev, dtype=torch.int32)
+    pair_q = torch.cat([rows, torch.repeat_interleave(rows, lens)])
+    pair_e = torch.cat([obj.to(torch.int32), filt_idx])
+    if group is None:
+        s_pairs = pair_scores(q_bf16, table, pair_q, pair_e)
+    else:
+        import torch.distributed as dist
+        local = (pair_e >= n_offset) & (pair_e < n_offset + table.n)
+        sel = torch.nonzero(local).squeeze(1)
+        s_pairs = torch.zeros((pair_q.numel(),), dtype=torch.float32, device=dev)
+        s_pairs[sel] = pair_scores(q_bf16, table, pair_q[sel].contiguous(), (pair_e[sel] - n_offset).contiguous())
+        dist.all_reduce(s_pairs, group=group)
+    thr = s_pairs[:b].contiguous()
+    s_filt = s_pairs[b:].contiguous()
+    gt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    eq = torch.zeros((b,), dtype=torch.int32, device=dev) if count_eq else None
+    p = _lib.ptr
+    _lib.call('kgc_score_rank', p(q_bf16), p(table.data), b, table.n, table.kpad, p(thr), p(gt), p(eq), _lib.stream())
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(gt, group=group)
+        if eq is not None:
+            dist.all_reduce(eq, group=group)
+    ranks = torch.empty((b,), dtype=torch.int32, device=dev)
+    eq_out = torch.empty((b,), dtype=torch.int32, device=dev) if count_eq else None
+    sums = torch.empty((13,), dtype=torch.float64, device=dev)
+    _lib.call('kgc_rank_finalize', p(gt), p(eq), p(thr), p(s_filt), p(filt_ptr), p(filt_idx), p(obj), b, p(ranks),
+              p(eq_out), p(sums), _lib.stream())
+    out = {'ranks': ranks, 'count_gt': ranks - 1, 'thr': thr, 'sums': sums}
+    if count_eq:
+        out['count_eq'] = eq_out
+    return out
+
+
+SUM_KEYS = ['count', 'mr', 'mrr'] + ['hits@{}'.format(k) for k in range(1, 11)]
+
+
+def predict(model, data_iters, graph, data_type, device, mode='tail_batch'):
+    """Drop-in for main.py:105-135: same signature and result dict (count, mr, mrr, hits@1..10 sums).
+    The encoder runs ONCE per call (in eval mode all_ent / all_rel do not depend on the batch: SURVEY.md
+    "next" row N3, results identical); every batch then goes through the fused scorer."""
+    model.eval()
+    with torch.no_grad():
+        all_ent, all_rel = model.encode(graph)
+        table = EntityTable(all_ent, model.conv2.bias)
+        total = torch.zeros((13,), dtype=torch.float64, device=all_ent.device)
+        for trip, fptr, fidx in data_iters['{}_{}'.format(data_type, mode.split('_')[0])].sparse():
+            sub, rel, obj = trip[:, 0], trip[:, 1], trip[:, 2]
+            xq = model.conv2.query(all_ent.index_select(0, sub), all_rel.index_select(0, rel))
+            out = filtered_rank(xq, None, None, obj, fptr, fidx, table=table)
+            total += out['sums']
+        total = total.cpu().tolist()
+    return {k: float(v) for k, v in zip(SUM_KEYS, total)}
+
+
+def evaluate(model, data_iters, graph, params, data_type, mark='Val', hits=(1, 3, 10)):
+    """Drop-in for main.py:80-102: (tail + head) / (2 * count), rounded to 5 places."""
+    import logging
+    import numpy as np
+    tail = predict(model, data_iters, graph, data_type, params.device, mode='tail_batch')
+    head = predict(model, data_iters, graph, data_type, params.device, mode='head_batch')
+    count = float(tail['count'])
+    results = {'mr': np.round((tail['mr'] + head['mr']) / (2 * count), 5),
+               'mrr': np.round((tail['mrr'] + head['mrr']) / (2 * count), 5)}
+    for k in hits:
+        key = 'hits@{}'.format(k)
+        results[key] = np.round((tail[key] + head[key]) / (2 * count), 5)
+    logging.info('- {} metrics: {}  '.format(mark, '; '.join('{}: {:05.3f}'.format(k, v) for k, v in results.items())))
+    return results

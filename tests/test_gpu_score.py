@@ -1,0 +1,197 @@
+"""GPU parity tests of the fused scoring + filtered-rank path (K6, tcgen05/TMA) through the C ABI.
+
+Bit-exact gate: integer rank counts given identical scores.  Inputs made of small integers are exactly
+representable in bf16 and their dot products are exact in fp32 whatever the accumulation order, so the
+tensor-core scores equal the oracle's and count_gt / count_eq / ranks must match bit for bit (ties are
+frequent with integer scores, which exercises the == path).
+Tolerance gate (bf16 operands): scores within 2^-7 relative of the fp32 product, and rank counts inside
+the interval the oracle gives when the target margin is widened by that tolerance.
+"""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import mgcn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def k():
+    import kgc_gcn_b200
+    kgc_gcn_b200._lib.lib()
+    return kgc_gcn_b200
+
+
+def int_case(B, N, d, seed, nfilt=3):
+    g = torch.Generator().manual_seed(seed)
+    xq = torch.randint(-3, 4, (B, d), generator=g).float()
+    tab = torch.randint(-3, 4, (N, d), generator=g).float()
+    bias = torch.randint(-2, 3, (N,), generator=g).float()
+    obj = torch.randint(0, N, (B,), generator=g)
+    lens = torch.randint(0, 2 * nfilt + 1, (B,), generator=g).tolist()
+    lists = []
+    for q in range(B):          # sorted, unique; the target is in the list for half of the queries (as the reference's labels are)
+        cand = set(torch.randperm(N, generator=g)[:min(lens[q], N)].tolist())
+        if q % 2 == 0:
+            cand.add(int(obj[q]))
+        lists.append(sorted(cand))
+    fptr = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in lists], out=fptr[1:])
+    fidx = np.asarray([v for x in lists for v in x], dtype=np.int32)
+    return xq, tab, bias, obj, fptr, fidx
+
+
+def run_rank(k, xq, tab, bias, obj, fptr, fidx, count_eq=True):
+    return k.filtered_rank(xq.cuda(), tab.cuda(), None if bias is None else bias.cuda(), obj.cuda(),
+                           torch.from_numpy(fptr).cuda(), torch.from_numpy(fidx).cuda(), count_eq=count_eq)
+
+
+@pytest.mark.parametrize('B,N,d', [(96, 400, 200), (300, 1000, 200), (1, 127, 200), (129, 129, 100), (257, 5000, 61),
+                                   (640, 20000, 200)])
+def test_rank_counts_bit_exact(k, B, N, d):
+    xq, tab, bias, obj, fptr, fidx = int_case(B, N, d, seed=B + N)
+    scores = (xq.double() @ tab.double().t() + bias.double()).numpy()
+    gt, eq = orc.rank_counts(scores, fptr, fidx, obj.numpy())
+    out = run_rank(k, xq, tab, bias, obj, fptr, fidx)
+    np.testing.assert_array_equal(out['thr'].cpu().numpy(), scores[np.arange(B), obj.numpy()].astype(np.float32))
+    np.testing.assert_array_equal(out['count_gt'].cpu().numpy(), gt)
+    np.testing.assert_array_equal(out['count_eq'].cpu().numpy(), eq)
+    np.testing.assert_array_equal(out['ranks'].cpu().numpy(), 1 + gt)
+    sums = orc.metric_sums(1 + gt)
+    got = dict(zip(k.scoring.SUM_KEYS, out['sums'].cpu().tolist()))
+    for key, v in sums.items():
+        assert abs(got[key] - v) <= 1e-4 * max(1.0, abs(v)), key
+    # the reference's own dense formulation lands inside [1 + gt, 1 + gt + eq] (ties are implementation-defined there)
+    lab = torch.zeros(B, N)
+    for q in range(B):
+        lab[q, torch.from_numpy(fidx[fptr[q]:fptr[q + 1]]).long()] = 1
+    ref = orc.filtered_ranks_dense(torch.from_numpy(scores).float(), lab, obj).numpy()
+    assert ((ref >= 1 + gt) & (ref <= 1 + gt + eq)).all()
+
+
+def test_gt_only_variant_matches(k):
+    xq, tab, bias, obj, fptr, fidx = int_case(200, 3000, 200, seed=5)
+    a = run_rank(k, xq, tab, bias, obj, fptr, fidx, count_eq=True)
+    b = run_rank(k, xq, tab, bias, obj, fptr, fidx, count_eq=False)
+    assert torch.equal(a['ranks'], b['ranks'])
+
+
+def test_pair_scores_exact_and_bias_split(k):
+    g = torch.Generator().manual_seed(3)
+    B, N, d = 200, 333, 200
+    xq = torch.randint(-3, 4, (B, d), generator=g).float()
+    tab = torch.randint(-3, 4, (N, d), generator=g).float()
+    bias = torch.randn(N, generator=g) * 3                      # arbitrary fp32 bias: hi + mid + lo split must be exact
+    table = k.EntityTable(tab.cuda(), bias.cuda())
+    q16 = k.pack_queries(xq.cuda())
+    pq = torch.randint(0, B, (1000,), generator=g).int()
+    pe = torch.randint(0, N, (1000,), generator=g).int()
+    s = k.pair_scores(q16, table, pq.cuda(), pe.cuda()).cpu()
+    dots = (xq[pq.long()].double() * tab[pe.long()].double()).sum(1)
+    ref = (dots + bias[pe.long()].double())
+    # the dot is an exact integer; the three bias pieces add in fp32: error <= a few ulp of the sum
+    assert float((s.double() - ref).abs().max()) <= 4e-7 * float(ref.abs().max())
+
+
+def test_rank_random_floats_within_tolerance(k):
+    g = torch.Generator().manual_seed(9)
+    B, N, d = 512, 30000, 200
+    xq = torch.randn(B, d, generator=g).abs()
+    tab = torch.rand(N, d, generator=g) * 2 - 1
+    bias = torch.randn(N, generator=g) * 0.1
+    obj = torch.randint(0, N, (B,), generator=g)
+    fptr = np.arange(0, 4 * B + 1, 4, dtype=np.int64)
+    fidx = np.sort(torch.randint(0, N, (B, 4), generator=g).numpy().astype(np.int32), axis=1).reshape(-1)
+    out = run_rank(k, xq, tab, bias, obj, fptr, fidx)
+    x16, t16 = xq.bfloat16().double(), tab.bfloat16().double()
+    scores = (x16 @ t16.t() + bias.double()).numpy()               # exact product of the bf16-rounded operands
+    so = scores[np.arange(B), obj.numpy()]
+    thr = out['thr'].cpu().double().numpy()
+    tol = 2e-6 * np.abs(scores).max()                               # fp32 accumulation of 203 terms
+    assert np.abs(thr - so).max() <= tol
+    # operands rounded to bf16: scores within 2^-7 relative of the fp32 ones (stated tolerance of the bf16 path)
+    full = (xq.double() @ tab.double().t() + bias.double()).numpy()
+    assert np.abs(scores - full).max() <= 2.0 ** -7 * np.abs(full).max()
+    keep = np.ones((B, N), dtype=bool)
+    for q in range(B):
+        keep[q, fidx[fptr[q]:fptr[q + 1]]] = False
+        keep[q, obj[q]] = False
+    lo = ((scores > (so + tol)[:, None]) & keep).sum(1)
+    hi = ((scores > (so - tol)[:, None]) & keep).sum(1)
+    gt = out['count_gt'].cpu().numpy()
+    assert ((gt >= lo) & (gt <= hi)).all()
+    assert (gt == ((scores > so[:, None]) & keep).sum(1)).mean() > 0.97
+
+
+def test_full_sweep_properties_at_scale(k):
+    """Size-independent properties at a BASELINE-like size (16k queries x 1M entities, d = 200):
+    thr = -inf counts every entity exactly once for every query, thr = +inf counts none, and the
+    integer-input counts equal an exact fp32 matmul of the same integers."""
+    g = torch.Generator().manual_seed(1)
+    B, N, d = 16384, 1000003, 200
+    xq = torch.randint(-2, 3, (B, d), generator=g).float().cuda()
+    tab = torch.randint(-2, 3, (N, d), generator=g, dtype=torch.int8).float().cuda()
+    table = k.EntityTable(tab, None)
+    q16 = k.pack_queries(xq)
+    L = k._lib
+    for thr_val, expect in ((-float('inf'), N), (float('inf'), 0)):
+        thr = torch.full((B,), thr_val, device='cuda')
+        gt = torch.zeros(B, dtype=torch.int32, device='cuda')
+        L.call('kgc_score_rank', L.ptr(q16), L.ptr(table.data), B, N, table.kpad, L.ptr(thr), L.ptr(gt), None, L.stream())
+        assert int(gt.min()) == expect and int(gt.max()) == expect
+    thr = torch.randint(-20, 21, (B,), generator=g).float().cuda()
+    gt = torch.zeros(B, dtype=torch.int32, device='cuda')
+    eq = torch.zeros(B, dtype=torch.int32, device='cuda')
+    L.call('kgc_score_rank', L.ptr(q16), L.ptr(table.data), B, N, table.kpad, L.ptr(thr), L.ptr(gt), L.ptr(eq), L.stream())
+    ref_gt = torch.zeros(B, dtype=torch.int64, device='cuda')
+    ref_eq = torch.zeros(B, dtype=torch.int64, device='cuda')
+    for lo in range(0, N, 65536):                                # exact: small integers, |sum| < 2^24
+        s = xq[:2048] @ tab[lo:lo + 65536].t()
+        ref_gt[:2048] += (s > thr[:2048, None]).sum(1)
+        ref_eq[:2048] += (s == thr[:2048, None]).sum(1)
+    assert torch.equal(gt[:2048].long(), ref_gt[:2048]) and torch.equal(eq[:2048].long(), ref_eq[:2048])
+
+
+def test_toy_predict_identical_metrics(k, golden_dir):
+    """BASELINE.json north_star: bf16 scoring 'with identical MRR/hits@k on data/Toy' - our predict()/evaluate()
+    against the sums the reference's own predict()/evaluate() produced for the same state dict."""
+    prm = SimpleNamespace(gcn_in_dim=20, gcn_out_dim=200, gcn_drop=0.0, hidden_drop=0.0, feat_drop=0.0, k_w=10, k_h=20,
+                          num_filter=2, kernel_size=7, bias=False, lbl_smooth=0.0, batch_size=128, device='cuda')
+    cwd = os.getcwd()
+    os.chdir(golden_dir)
+    try:
+        dl = k.DataLoader('Toy', prm)
+    finally:
+        os.chdir(cwd)
+    dl.graph.to('cuda')
+    z = np.load(os.path.join(golden_dir, 'toy_model.npz'))
+    m = k.MGCN(dl.num_entity, dl.num_relation, dl.num_edge, prm)
+    m.load_state_dict({kk[3:]: torch.from_numpy(z[kk]) for kk in z.files if kk.startswith('sd.')})
+    m = m.cuda()
+    with open(os.path.join(golden_dir, 'toy_metrics.json')) as f:
+        gold = json.load(f)
+    torch.manual_seed(5)
+    iters = dl.get_data_loaders(4, 0, prm)
+    for mode in ('tail', 'head'):
+        res = k.predict(m, iters, dl.graph, 'valid', 'cuda', mode=mode + '_batch')
+        for key, v in gold[mode].items():
+            assert abs(res[key] - v) <= 1e-4 * max(1.0, abs(v)), (mode, key, res[key], v)
+    ev = k.evaluate(m, iters, dl.graph, prm, 'valid')
+    for key, v in gold['evaluate'].items():
+        assert abs(float(ev[key]) - v) < 1e-5, (key, ev[key], v)
+    # and through MGCN.rank for one explicit batch
+    trip = torch.from_numpy(z['eval.tail.triple']).cuda()
+    ds = dl._get_dataset('valid_tail', prm)
+    _, fptr, fidx = ds.sparse_batch(np.arange(len(ds)))
+    with torch.no_grad():
+        m.eval()
+        out = m.rank(trip[:, 0], trip[:, 1], trip[:, 2], torch.from_numpy(fptr).cuda(), torch.from_numpy(fidx).cuda(), dl.graph,
+                     count_eq=True)
+    lab = torch.from_numpy(np.stack([orc.make_label(q['label'], 7) for q in dl.triplets['valid_tail']]))
+    ref = orc.filtered_ranks_dense(torch.from_numpy(z['eval.tail.score.f32']), lab, trip[:, 2].cpu()).numpy()
+    np.testing.assert_array_equal(out['ranks'].cpu().numpy(), ref)
