@@ -341,9 +341,11 @@ def run_ours(args, rank, world, local_rank):
     }
     if not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_conv_baseline(orc, N, R, E, seed)
-    aux = aux_filtered_rank(k, dev, args)
-    if aux is not None:
-        line['aux'] = aux
+    if not args.no_aux:
+        try:
+            line['aux'] = aux_filtered_rank(k, dev, args)
+        except Exception as exc:                       # pragma: no cover
+            line['aux'] = {'error': repr(exc)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -431,12 +433,59 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
 
 
 def aux_filtered_rank(k, dev, args):
-    if not hasattr(k, 'bench_filtered_rank'):
-        return None
-    try:
-        return k.bench_filtered_rank(dev, quick=args.quick_aux)
-    except Exception as exc:                           # pragma: no cover
-        return {'error': repr(exc)}
+    """Second half of BASELINE.json's metric: filtered-rank queries/sec of the fused tcgen05 scorer
+    (B = 65,536 queries, d = 200, N entities; X = |N(0,1)|, E ~ U(-1,1), bias ~ N(0,0.1),
+    mean 4 filtered positives per query, seed 3)."""
+    L = k._lib
+    out = []
+    sizes = [1000000] if not args.aux_full else [1000000, 2000000, 4594485]
+    B, d = 65536, D_OUT
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+        pk = json.load(f)
+    for N in sizes:
+        g = torch.Generator(device=dev).manual_seed(3)
+        xq = torch.randn(B, d, generator=g, device=dev).abs_()
+        tab = torch.rand(N, d, generator=g, device=dev).mul_(2).sub_(1)
+        bias = torch.randn(N, generator=g, device=dev).mul_(0.1)
+        obj = torch.randint(0, N, (B,), generator=g, device=dev)
+        fptr = torch.arange(0, 4 * B + 1, 4, device=dev, dtype=torch.int64)
+        fidx = torch.randint(0, N, (B, 4), generator=g, device=dev).sort(1).values.reshape(-1).to(torch.int32)
+
+        def whole():
+            return k.filtered_rank(xq, tab, bias, obj, fptr, fidx)
+        for _ in range(2):
+            res = whole()
+        torch.cuda.synchronize()
+        reps = 3
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b_ in ev:
+            a.record()
+            res = whole()
+            b_.record()
+        torch.cuda.synchronize()
+        ms_whole = float(np.mean([a.elapsed_time(b_) for a, b_ in ev]))
+        # the sweep kernel alone (dominant): packed operands resident, thresholds given
+        table = k.EntityTable(tab, bias)
+        q16 = k.pack_queries(xq)
+        thr = res['thr']
+        gt = torch.zeros(B, dtype=torch.int32, device=dev)
+
+        def sweep():
+            L.call('kgc_score_rank', L.ptr(q16), L.ptr(table.data), B, N, table.kpad, L.ptr(thr), L.ptr(gt), None, L.stream())
+        ms_sweep = time_kernel(sweep, lambda: None, iters=3, warm=1)
+        flops = 2.0 * B * N * d
+        tf = flops / (ms_sweep * 1e-3) / 1e12
+        out.append({'B': B, 'N': N, 'd': d, 'queries_per_s': B / (ms_whole * 1e-3), 'ms_whole_call': ms_whole,
+                    'ms_sweep_kernel': ms_sweep, 'sweep_tflops_unpadded': tf,
+                    'frac_of_bf16_sustained': tf / pk['bf16_tflops_sustained'], 'frac_of_bf16_burst': tf / pk['bf16_tflops'],
+                    'mean_rank': float(res['sums'][1] / res['sums'][0])})
+        del tab, table, xq
+        torch.cuda.empty_cache()
+    return {'metric': 'filtered-rank queries/sec (fused tcgen05 scoring, bf16 operands, fp32 accumulate)', 'unit': 'queries/s',
+            'value': out[0]['queries_per_s'], 'sweeps': out,
+            'roofline': {'bound': 'tensor', 'achieved': out[-1]['sweep_tflops_unpadded'], 'peak': pk['bf16_tflops_sustained'],
+                         'unit': 'TFLOP/s', 'frac': out[-1]['frac_of_bf16_sustained'],
+                         'note': 'un-padded flops 2*B*N*200 / sweep-kernel CUDA-event time vs measured sustained cuBLAS bf16'}}
 
 
 def main():
@@ -448,7 +497,8 @@ def main():
     ap.add_argument('--workload', default='wn18rr', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--quick-aux', action='store_true')
+    ap.add_argument('--no-aux', action='store_true', help='skip the filtered-rank scoring sweep')
+    ap.add_argument('--aux-full', action='store_true', help='scoring sweep at N = 1M, 2M and 4,594,485')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

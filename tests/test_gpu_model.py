@@ -80,7 +80,8 @@ def test_train_step_grads(toy):
         truth = z['train.grad.' + name]
         scale = max(float(np.abs(truth).max()), 1e-30)
         err = float(np.abs(prm.grad.cpu().numpy().astype(np.float64) - truth).max())
-        if err > 5e-5 * scale:
+        # + absolute floor: gradients that are mathematically zero (a BN bias feeding another BN) are pure fp32 noise
+        if err > 5e-5 * scale + 2e-7:
             bad[name] = (err, scale)
     assert not bad, bad
 
