@@ -59,9 +59,14 @@ int kgc_abi_version(void);
  *   row r whose edge belongs to the out half.
  * Synchronises the stream once (to validate ids); ids out of range are an error. */
 size_t kgc_csr_workspace_bytes(int64_t n_edges2, int64_t n_nodes, int64_t n_types);
+/* Partitioned graphs (nodes range-partitioned by destination): a rank passes only the
+ * edges it owns, in-half edges first (n_edges_in of them), src as GLOBAL node ids in [0, n_nodes), dst
+ * as LOCAL row ids in [0, n_dst_rows) with global id = dst + dst_offset, and the GLOBAL per-half degrees
+ * (deg_given = 1; deg is then an input).  The single-GPU case is n_edges_in = n_edges2 / 2,
+ * n_dst_rows = n_nodes, dst_offset = 0, deg_given = 0. */
 int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type,
-                  int64_t n_edges2, int64_t n_nodes, int64_t n_types,
-                  int32_t* deg, float* norm,
+                  int64_t n_edges2, int64_t n_edges_in, int64_t n_nodes, int64_t n_dst_rows, int64_t dst_offset,
+                  int64_t n_types, int32_t deg_given, int32_t* deg, float* norm,
                   int32_t* perm_dst, int32_t* rowptr_dst, int32_t* rowmid_dst, kgc_edge_rec_t* rec_dst,
                   int32_t* perm_src, int32_t* rowptr_src, kgc_edge_rec_t* rec_src,
                   int32_t* perm_type, int32_t* rowptr_type, kgc_edge_rec_t* rec_type,
@@ -83,51 +88,52 @@ int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_ite
                     float* out_final, float* out_part, const float* addend, int32_t D, void* stream);
 
 /* ---- K3: aggregation backward ------------------------------------------------------------------
- * Autograd of the same three lines (model.py:114-118 + aggr='add').  g3 is [3,n_nodes,D]:
- * plane 0/1 = d(agg_in)/d(agg_out) = d(res_h) @ W_h^T, plane 2 = the self-loop term added to d_x.
- * Over src-sorted records (row j = source node):
+ * Autograd of the same three lines (model.py:114-118 + aggr='add').  g3 is [2,n_dst_rows,D]:
+ * plane 0/1 = d(agg_in)/d(agg_out) = d(res_h) @ W_h^T, indexed by the (local) destination row.
+ * Over src-sorted records (row j = source node, global id):
  *   p_e      = norm_e * g3[half_e][a_e] (.) rel[b_e]
  *   d_ee[e]  = p_e (.) x[j]                                  (one row per edge, no reduction)
- *   d_x[j]   = sum_e p_e (.) ee[e]   (+ g3[2][j] on final rows)
- * half_e = (eid_e >= n_edges2/2). */
+ *   d_x[j]   = sum_e p_e (.) ee[e]   (+ loop_addend[j], the self-loop term, on final rows when not NULL)
+ * half_e = (eid_e >= n_edges_in). */
 int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
                     const kgc_edge_rec_t* rec_src, const kgc_item_t* items, int64_t n_items,
-                    int64_t n_nodes, int64_t n_edges2,
+                    int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend,
                     float* d_ee, float* dx_final, float* dx_part, int32_t D, void* stream);
 
 /* Over type-sorted records (row t = relation type):
  *   d_rel[t] = sum_e norm_e * g3[half_e][b_e] (.) x[a_e] (.) ee[e] */
 int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
                     const kgc_edge_rec_t* rec_type, const kgc_item_t* items, int64_t n_items,
-                    int64_t n_nodes, int64_t n_edges2,
+                    int64_t n_dst_rows, int64_t n_edges_in,
                     float* drel_final, float* drel_part, int32_t D, void* stream);
 
 /* ---- K4: layer tail ------------------------------------------------------------------------------
  * Replaces model.py:103-106: out = (drop(in_res) + drop(out_res) + loop_res) / 3 [+ bias];
- * BatchNorm1d over the n_rows rows; tanh.  res3 is [3,n_rows,Dout] (in, out, loop planes).
+ * BatchNorm1d over the node rows; tanh.  res3 is [3,n_rows,Dout] (in, out, loop planes).
  * mask_in / mask_out: uint8 keep masks [n_rows,Dout] or NULL (no dropout); keep_scale = 1/(1-p).
- * kgc_tail_fwd writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares, fp64);
- * kgc_colstats_finalize reduces them in a fixed order into stats[0]=mean, [1]=biased var,
- * [2]=rstd=1/sqrt(var+eps) (training) - or fills them from running stats (training == 0);
- * kgc_tail_apply writes all_ent = tanh((pre - mean) * rstd * gamma + beta). */
+ *   kgc_tail_fwd           writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares; fp64)
+ *   kgc_colsum_finalize    reduces the partials in a fixed order into sums[2,Dout] (fp64).  A partitioned
+ *                          graph all-reduces these 2*Dout doubles across ranks here.
+ *   kgc_colstats_from_sums stats[0]=mean, [1]=biased var, [2]=rstd=1/sqrt(var+eps) over n_rows (GLOBAL) rows
+ *                          when training, or from the running statistics (training == 0)
+ *   kgc_tail_apply         all_ent = tanh((pre - mean) * rstd * gamma + beta) */
 int64_t kgc_tail_num_blocks(int64_t n_rows);
 int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, float keep_scale,
                  const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials, void* stream);
-int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
-                          int32_t training, const float* running_mean, const float* running_var,
-                          float* stats, void* stream);
+int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, void* stream);
+int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_t Dout, float eps, int32_t training,
+                           const float* running_mean, const float* running_var, float* stats, void* stream);
 int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
                    int64_t n_rows, int32_t Dout, float* all_ent, void* stream);
 /* Backward of the tail.  kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and
- * dz*xhat; kgc_colsum_finalize -> sums[0]=sum dz (= d beta), sums[1]=sum dz*xhat (= d gamma);
- * kgc_tail_bwd_apply: d_pre (BatchNorm backward, batch statistics when training) spread to the
- * three planes d_res3[3,n_rows,Dout] with the dropout masks and the 1/3. */
+ * dz*xhat; kgc_colsum_finalize -> sums[0] = sum dz (= d beta), sums[1] = sum dz*xhat (= d gamma), all-reduced
+ * by a partitioned caller; kgc_tail_bwd_apply: d_pre (BatchNorm backward over n_rows_global rows when
+ * training) spread to the three planes d_res3[3,n_rows,Dout] with the dropout masks and the 1/3. */
 int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
                         int64_t n_rows, int32_t Dout, double* partials, void* stream);
-int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, float* sums, void* stream);
 int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
-                       const float* gamma, const float* sums, const uint8_t* mask_in, const uint8_t* mask_out,
-                       float keep_scale, int32_t training, int64_t n_rows, int32_t Dout,
+                       const float* gamma, const double* sums, const uint8_t* mask_in, const uint8_t* mask_out,
+                       float keep_scale, int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout,
                        float* d_res3, void* stream);
 
 /* ---- K5: label / batch builder ---------------------------------------------------------------------

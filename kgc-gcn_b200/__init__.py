@@ -11,8 +11,9 @@ from .data_loader import DataLoader, KBDataset, GraphData, BatchIterator, epoch_
 from .plan import GraphPlan, get_plan, build_levels   # noqa: F401
 from .scoring import (EntityTable, filtered_rank, pack_queries, pair_scores, predict, evaluate,   # noqa: F401
                       score_kpad)
+from .partition import GraphPartition, partition_edges   # noqa: F401
 from . import _lib                               # noqa: F401
 
 __all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
            'get_plan', 'build_levels', 'get_param', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
-           'pair_scores', 'predict', 'evaluate', 'score_kpad']
+           'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges']

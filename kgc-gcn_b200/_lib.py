@@ -20,19 +20,19 @@ SIGNATURES = {
     'kgc_last_error': (ctypes.c_char_p, []),
     'kgc_abi_version': (ctypes.c_int, []),
     'kgc_csr_workspace_bytes': (_sz, [_i64, _i64, _i64]),
-    'kgc_csr_build': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _sz, _vp]),
+    'kgc_csr_build': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'kgc_agg_fwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
-    'kgc_agg_bwd_src': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
+    'kgc_agg_bwd_src': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     'kgc_agg_bwd_rel': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     'kgc_tail_num_blocks': (_i64, [_i64]),
     'kgc_tail_fwd': (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp, _i64, _i32, _vp, _vp, _vp]),
-    'kgc_colstats_finalize': (ctypes.c_int, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    'kgc_colsum_finalize': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    'kgc_colstats_from_sums': (ctypes.c_int, [_vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
     'kgc_tail_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     'kgc_tail_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
-    'kgc_colsum_finalize': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
-    'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i32, _vp, _vp]),
+    'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i64, _i32, _vp, _vp]),
     'kgc_label_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
     'kgc_neg_sample': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

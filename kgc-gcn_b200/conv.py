@@ -29,60 +29,101 @@ def _mm(a, b, out):
     return torch.mm(a, b, out=out)
 
 
+class _Collectives(object):
+    """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
+
+    def __init__(self, group, world, n_global):
+        self.group, self.world, self.n_global = group, int(world), int(n_global)
+
+    def all_gather_rows(self, x_local):
+        import torch.distributed as dist
+        out = torch.empty((self.world * x_local.shape[0],) + tuple(x_local.shape[1:]), dtype=x_local.dtype,
+                          device=x_local.device)
+        dist.all_gather_into_tensor(out, x_local.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter_rows(self, full):
+        import torch.distributed as dist
+        rows = full.shape[0] // self.world
+        if dist.get_backend(self.group) == 'gloo':       # gloo (CPU tests of the host logic) has no reduce-scatter
+            dist.all_reduce(full, group=self.group)
+            r = dist.get_rank(self.group)
+            return full[r * rows:(r + 1) * rows].clone()
+        out = torch.empty((rows,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group)
+        return out
+
+    def all_reduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
+        return t
+
+
 class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, rels, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, bias,
-                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps):
-        N, D = x.shape
+                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll):
+        # x: this rank's node rows [Nl, D] (all rows on one GPU); ee: the rows of the edges this rank owns
+        Nl, D = x.shape
         Dout = w_in.shape[1]
         p, st = _lib.ptr, _lib.stream
         x = _lib.require_cuda(x, torch.float32, 'x')
         ee = _lib.require_cuda(ee, torch.float32, 'edge_embs')
-        if ee.shape[0] != plan.num_edges2 or N != plan.num_nodes:
+        n_global = Nl if coll is None else coll.n_global
+        if ee.shape[0] != plan.num_edges2 or Nl != plan.num_dst_rows or n_global != plan.num_nodes:
             raise ValueError('edge_embs / x do not match the graph plan')
         relp = torch.cat([rels, loop_rel], 0).contiguous()          # model.py:86
         if relp.shape[0] != plan.num_types:
             raise ValueError('rels_embs rows + 1 must equal the number of edge types of the plan')
+        # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition)
+        x_full = x if coll is None else coll.all_gather_rows(x)
 
-        agg = torch.empty((2, N, D), dtype=torch.float32, device=x.device)
+        agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(items, n_items, out_final, part):
-            _lib.call('kgc_agg_fwd', p(x), p(relp), p(ee), p(plan.rec_dst), p(items), n_items, p(out_final), p(part),
-                      D, st())
+            _lib.call('kgc_agg_fwd', p(x_full), p(relp), p(ee), p(plan.rec_dst), p(items), n_items, p(out_final),
+                      p(part), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
 
         v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
         w_loop_s = v * w_loop
-        res3 = plan.scratch('res3', (3, N, Dout))
+        res3 = plan.scratch('res3', (3, Nl, Dout))
         _mm(agg[0], w_in, res3[0])
         _mm(agg[1], w_out, res3[1])
         _mm(x, w_loop_s, res3[2])
 
-        nb = int(_lib.lib().kgc_tail_num_blocks(N))
+        nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
-        pre = torch.empty((N, Dout), dtype=torch.float32, device=x.device)
+        sums = torch.empty((2, Dout), dtype=torch.float64, device=x.device)
+        pre = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
         stats = torch.empty((3, Dout), dtype=torch.float32, device=x.device)
-        all_ent = torch.empty((N, Dout), dtype=torch.float32, device=x.device)
-        _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), float(keep_scale), p(bias), N, Dout, p(pre),
+        all_ent = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
+        _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), float(keep_scale), p(bias), Nl, Dout, p(pre),
                   p(partials), st())
-        _lib.call('kgc_colstats_finalize', p(partials), nb, N, Dout, float(eps), int(training), p(running_mean),
+        if training:
+            _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
+            if coll is not None:
+                coll.all_reduce(sums)                                # BatchNorm statistics over ALL node rows
+        _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
                   p(running_var), p(stats), st())
-        _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), N, Dout, p(all_ent), st())
+        _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), st())
         all_rel = torch.mm(relp, w_rel)[:-1]                          # model.py:107
 
-        ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias = plan, bool(training), float(keep_scale), bias is not None
-        ctx.save_for_backward(x, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent,
-                              stats, mask_in, mask_out, w_loop_s)
+        ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias, ctx.coll = plan, bool(training), float(keep_scale), \
+            bias is not None, coll
+        ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre,
+                              all_ent, stats, mask_in, mask_out, w_loop_s)
         ctx.mark_non_differentiable(stats)
         return all_ent, all_rel, stats
 
     @staticmethod
     def backward(ctx, g_ent, g_rel, _g_stats):
-        (x, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent, stats, mask_in,
+        (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent, stats, mask_in,
          mask_out, w_loop_s) = ctx.saved_tensors
-        plan = ctx.plan
-        N, D = x.shape
+        plan, coll = ctx.plan, ctx.coll
+        Nl, D = x.shape
+        n_global = plan.num_nodes
         Dout = w_in.shape[1]
         T = relp.shape[0]
         p, st = _lib.ptr, _lib.stream
@@ -92,47 +133,63 @@ class _ConvFn(torch.autograd.Function):
         g_ent = g_ent.contiguous()
 
         # ---- K4 backward: tanh, BatchNorm, /3, dropout
-        nb = int(_lib.lib().kgc_tail_num_blocks(N))
+        nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
-        sums = torch.empty((2, Dout), dtype=torch.float32, device=dev)
-        d_res3 = plan.scratch('d_res3', (3, N, Dout))
-        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(all_ent), p(pre), p(stats), N, Dout, p(partials), st())
+        sums = torch.empty((2, Dout), dtype=torch.float64, device=dev)
+        d_res3 = plan.scratch('d_res3', (3, Nl, Dout))
+        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(all_ent), p(pre), p(stats), Nl, Dout, p(partials), st())
         _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
+        if coll is not None:
+            coll.all_reduce(sums)
         _lib.call('kgc_tail_bwd_apply', p(g_ent), p(all_ent), p(pre), p(stats), p(gamma), p(sums), p(mask_in),
-                  p(mask_out), ctx.keep_scale, int(ctx.training), N, Dout, p(d_res3), st())
-        d_beta, d_gamma = sums[0], sums[1]
-        d_bias = d_res3[2].sum(0) * 3.0 if ctx.has_bias else None
+                  p(mask_out), ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
+        sums32 = sums.float()
+        d_beta, d_gamma = sums32[0], sums32[1]
 
         # ---- dense transforms (fp32 GEMMs)
-        g3 = plan.scratch('g3', (3, N, D))
+        g3 = plan.scratch('g3', (3, Nl, D))
         _mm(d_res3[0], w_in.t(), g3[0])
         _mm(d_res3[1], w_out.t(), g3[1])
         _mm(d_res3[2], w_loop_s.t(), g3[2])
-        d_w_in = torch.mm(agg[0].t(), d_res3[0])
-        d_w_out = torch.mm(agg[1].t(), d_res3[1])
-        m_loop = torch.mm(x.t(), d_res3[2])                           # [D, Dout]
+        # replicated-parameter gradients: one flat buffer so that a partitioned run needs ONE all-reduce
+        flat = torch.empty((3 * D * Dout + T * D + (Dout if ctx.has_bias else 0),), dtype=torch.float32, device=dev)
+        d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
+        d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
+        _mm(agg[0].t(), d_res3[0], d_w_in)
+        _mm(agg[1].t(), d_res3[1], d_w_out)
+        _mm(x.t(), d_res3[2], m_loop)                                  # [D, Dout]
+        if ctx.has_bias:
+            torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
+
+        # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
+        d_x_full = torch.empty((n_global, D), dtype=torch.float32, device=dev)
+        d_ee = torch.empty_like(ee)
+        loop_addend = g3[2] if coll is None else None
+
+        def level0_src(items, n_items, out_final, part):
+            _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), p(ee), p(g3), p(plan.rec_src), p(items), n_items,
+                      plan.num_dst_rows, plan.num_edges_in, p(loop_addend), p(d_ee), p(out_final), p(part), D, st())
+        plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
+
+        def level0_rel(items, n_items, out_final, part):
+            _lib.call('kgc_agg_bwd_rel', p(x_full), p(ee), p(g3), p(plan.rec_type), p(items), n_items,
+                      plan.num_dst_rows, plan.num_edges_in, p(out_final), p(part), D, st())
+        plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
+
+        if coll is None:
+            d_x = d_x_full
+        else:
+            d_x = coll.reduce_scatter_rows(d_x_full)                 # every rank contributed to every source row
+            d_x += g3[2]
+            coll.all_reduce(flat)
         v = (loop_rel * loop_edge).reshape(D, 1)
         d_w_loop = v * m_loop
         d_v = (m_loop * w_loop).sum(1).reshape(1, D)
         d_loop_edge = d_v * loop_rel
         d_loop_rel = d_v * loop_edge
+        d_bias = flat[3 * D * Dout + T * D:] * 3.0 if ctx.has_bias else None
 
-        # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
-        d_x = torch.empty((N, D), dtype=torch.float32, device=dev)
-        d_ee = torch.empty_like(ee)
-        d_relp = torch.empty((T, D), dtype=torch.float32, device=dev)
-
-        def level0_src(items, n_items, out_final, part):
-            _lib.call('kgc_agg_bwd_src', p(x), p(relp), p(ee), p(g3), p(plan.rec_src), p(items), n_items, N,
-                      plan.num_edges2, p(d_ee), p(out_final), p(part), D, st())
-        plan.run_reduction(plan.bwd_src, level0_src, d_x, D, addend=g3[2], tag='s')
-
-        def level0_rel(items, n_items, out_final, part):
-            _lib.call('kgc_agg_bwd_rel', p(x), p(ee), p(g3), p(plan.rec_type), p(items), n_items, N, plan.num_edges2,
-                      p(out_final), p(part), D, st())
-        plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
-
-        # ---- relation transform (model.py:107)
+        # ---- relation transform (model.py:107): replicated inputs, identical on every rank
         if g_rel is not None:
             g_rel_pad = torch.cat([g_rel, g_rel.new_zeros((1, Dout))], 0)
             d_relp = d_relp + torch.mm(g_rel_pad, w_rel.t())
@@ -142,7 +199,7 @@ class _ConvFn(torch.autograd.Function):
         d_rels = d_relp[:-1]
         d_loop_rel = d_loop_rel + d_relp[-1:]
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 class MGCNConv(nn.Module):
@@ -206,14 +263,34 @@ class MGCNConv(nn.Module):
         all_ent, all_rel, stats = _ConvFn.apply(
             x, rels_embs, edge_embs, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, plan, m_in, m_out, keep_scale,
-            use_batch_stats, bn.running_mean, bn.running_var, bn.eps)
+            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None)
+        self._update_running_stats(stats, num_ent)
+        return all_ent, all_rel
+
+    def _update_running_stats(self, stats, n_rows):
+        bn = self.ent_bn
         if self.training and bn.track_running_stats and bn.running_mean is not None:
             with torch.no_grad():           # nn.BatchNorm1d bookkeeping: momentum update with the UNBIASED variance
                 bn.num_batches_tracked += 1
                 mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                unbias = float(num_ent) / float(max(num_ent - 1, 1))
+                unbias = float(n_rows) / float(max(n_rows - 1, 1))
                 bn.running_mean.mul_(1.0 - mom).add_(stats[0], alpha=mom)
                 bn.running_var.mul_(1.0 - mom).add_(stats[1], alpha=mom * unbias)
+
+    def forward_partitioned(self, x_local, part, edge_embs_local, rels_embs):
+        """The same layer on a dst-partitioned graph: ``x_local`` = this rank's node rows,
+        ``edge_embs_local`` = the rows of the edges it owns (``part.owned_eids`` order), ``part`` = a
+        GraphPartition.  Exchanges: all-gather of x (forward), reduce-scatter of d_x (backward), all-reduce of the
+        BatchNorm column sums (2 x Dout doubles, both ways) and of the replicated-parameter gradients."""
+        m_in, m_out, keep_scale = self._masks(x_local.size(0), x_local.device)
+        bn = self.ent_bn
+        use_batch_stats = self.training or bn.running_mean is None
+        coll = _Collectives(part.group, part.world, part.num_nodes)
+        all_ent, all_rel, stats = _ConvFn.apply(
+            x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
+            self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,
+            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, coll)
+        self._update_running_stats(stats, part.num_nodes)
         return all_ent, all_rel
 
     def __repr__(self):

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kThreads)
 agg_bwd_src_kernel(const float4* __restrict__ x, const float4* __restrict__ rel, const float4* __restrict__ ee,
                    const float4* __restrict__ g3, const kgc_edge_rec_t* __restrict__ rec,
                    const kgc_item_t* __restrict__ items, int64_t n_items, int64_t n_nodes, int32_t half_edges,
-                   float4* __restrict__ d_ee, float4* __restrict__ dx_final, float4* __restrict__ dx_part, int D4) {
+                   const float4* __restrict__ loop_addend, float4* __restrict__ d_ee, float4* __restrict__ dx_final,
+                   float4* __restrict__ dx_part, int D4) {
   const int64_t item = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / kGroup;
   const int g = threadIdx.x % kGroup;
   if (item >= n_items) return;
@@ -160,14 +161,13 @@ agg_bwd_src_kernel(const float4* __restrict__ x, const float4* __restrict__ rel,
     }
   }
   if (final_row) {
-    const float4* loop = g3 + 2 * plane + j * D4;     // self-loop term of d_x
     float4* out = dx_final + j * D4;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int c = g + f * kGroup;
       if (c < D4) {
         float4 v = acc[f];
-        add4(v, __ldg(loop + c));
+        if (loop_addend != nullptr) add4(v, __ldg(loop_addend + j * D4 + c));     // self-loop term of d_x
         out[c] = v;
       }
     }
@@ -351,30 +351,30 @@ extern "C" int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, in
 
 extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
                                const kgc_edge_rec_t* rec_src, const kgc_item_t* items, int64_t n_items,
-                               int64_t n_nodes, int64_t n_edges2, float* d_ee, float* dx_final, float* dx_part,
-                               int32_t D, void* stream) {
+                               int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend, float* d_ee,
+                               float* dx_final, float* dx_part, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   if (n_items == 0) return 0;
   const unsigned grid = (unsigned)ceil_div(n_items * kGroup, kThreads);
   KGC_DISPATCH_NF(nf, (agg_bwd_src_kernel<NF><<<grid, kThreads, 0, as_stream(stream)>>>(
                           (const float4*)x, (const float4*)rel, (const float4*)ee, (const float4*)g3, rec_src, items,
-                          n_items, n_nodes, (int32_t)(n_edges2 / 2), (float4*)d_ee, (float4*)dx_final,
-                          (float4*)dx_part, D4)));
+                          n_items, n_dst_rows, (int32_t)n_edges_in, (const float4*)loop_addend, (float4*)d_ee,
+                          (float4*)dx_final, (float4*)dx_part, D4)));
   KGC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3, const kgc_edge_rec_t* rec_type,
-                               const kgc_item_t* items, int64_t n_items, int64_t n_nodes, int64_t n_edges2,
+                               const kgc_item_t* items, int64_t n_items, int64_t n_dst_rows, int64_t n_edges_in,
                                float* drel_final, float* drel_part, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   if (n_items == 0) return 0;
   const unsigned grid = (unsigned)ceil_div(n_items * kGroup, kThreads);
   KGC_DISPATCH_NF(nf, (agg_bwd_rel_kernel<NF><<<grid, kThreads, 0, as_stream(stream)>>>(
-                          (const float4*)x, (const float4*)ee, (const float4*)g3, rec_type, items, n_items, n_nodes,
-                          (int32_t)(n_edges2 / 2), (float4*)drel_final, (float4*)drel_part, D4)));
+                          (const float4*)x, (const float4*)ee, (const float4*)g3, rec_type, items, n_items, n_dst_rows,
+                          (int32_t)n_edges_in, (float4*)drel_final, (float4*)drel_part, D4)));
   KGC_LAUNCH_CHECK();
   return 0;
 }

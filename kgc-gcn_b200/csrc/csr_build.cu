@@ -56,13 +56,14 @@ cudaError_t cub_temp_bytes(int64_t n2, int64_t n_rows_max, size_t* out) {
 }
 
 __global__ void narrow_and_check(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                                 const int64_t* __restrict__ type, int64_t n2, int64_t n_nodes, int64_t n_types,
+                                 const int64_t* __restrict__ type, int64_t n2, int64_t n_src_rows, int64_t n_dst_rows,
+                                 int64_t n_types,
                                  int32_t* __restrict__ src32, int32_t* __restrict__ dst32,
                                  int32_t* __restrict__ type32, int32_t* __restrict__ iota, int32_t* flag) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n2) return;
   int64_t s = src[i], d = dst[i], t = type[i];
-  if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes || t < 0 || t >= n_types) atomicOr(flag, 1);
+  if (s < 0 || s >= n_src_rows || d < 0 || d >= n_dst_rows || t < 0 || t >= n_types) atomicOr(flag, 1);
   src32[i] = (int32_t)s;
   dst32[i] = (int32_t)d;
   type32[i] = (int32_t)t;
@@ -70,10 +71,10 @@ __global__ void narrow_and_check(const int64_t* __restrict__ src, const int64_t*
 }
 
 // deg[h*N + v] = #{e in half h : src_e == v}   (model.py:73-75: row = edge_index[0])
-__global__ void half_degree(const int32_t* __restrict__ src32, int64_t n2, int64_t n_nodes, int32_t* deg) {
+__global__ void half_degree(const int32_t* __restrict__ src32, int64_t n2, int64_t n_in, int64_t n_nodes, int32_t* deg) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n2) return;
-  int64_t h = (i >= n2 / 2) ? 1 : 0;
+  int64_t h = (i >= n_in) ? 1 : 0;
   atomicAdd(&deg[h * n_nodes + src32[i]], 1);   // integer atomics: order-independent, exact
 }
 
@@ -83,11 +84,12 @@ __device__ __forceinline__ float deg_inv_sqrt(int32_t d) {
 }
 
 __global__ void edge_norm(const int32_t* __restrict__ src32, const int32_t* __restrict__ dst32,
-                          const int32_t* __restrict__ deg, int64_t n2, int64_t n_nodes, float* __restrict__ norm) {
+                          const int32_t* __restrict__ deg, int64_t n2, int64_t n_in, int64_t n_nodes, int64_t dst_offset,
+                          float* __restrict__ norm) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n2) return;
-  const int32_t* dh = deg + ((i >= n2 / 2) ? n_nodes : 0);
-  norm[i] = deg_inv_sqrt(dh[src32[i]]) * deg_inv_sqrt(dh[dst32[i]]);   // model.py:78
+  const int32_t* dh = deg + ((i >= n_in) ? n_nodes : 0);
+  norm[i] = deg_inv_sqrt(dh[src32[i]]) * deg_inv_sqrt(dh[dst32[i] + dst_offset]);   // model.py:78
 }
 
 __global__ void histogram(const int32_t* __restrict__ key, int64_t n, int32_t* cnt) {
@@ -146,13 +148,15 @@ extern "C" size_t kgc_csr_workspace_bytes(int64_t n_edges2, int64_t n_nodes, int
   return make_layout(n_edges2, n_nodes, n_types, cub_bytes).total;
 }
 
-extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type, int64_t n2,
-                             int64_t n_nodes, int64_t n_types, int32_t* deg, float* norm, int32_t* perm_dst,
-                             int32_t* rowptr_dst, int32_t* rowmid_dst, kgc_edge_rec_t* rec_dst, int32_t* perm_src,
-                             int32_t* rowptr_src, kgc_edge_rec_t* rec_src, int32_t* perm_type, int32_t* rowptr_type,
-                             kgc_edge_rec_t* rec_type, void* workspace, size_t workspace_bytes, void* stream) {
-  KGC_REQUIRE(n2 >= 0 && n2 % 2 == 0, "n_edges2 must be even (in half + out half, model.py:84)");
-  KGC_REQUIRE(n_nodes > 0 && n_types > 0, "empty node or type set");
+extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type, int64_t n2, int64_t n_in,
+                             int64_t n_nodes, int64_t n_dst_rows, int64_t dst_offset, int64_t n_types,
+                             int32_t deg_given, int32_t* deg, float* norm, int32_t* perm_dst, int32_t* rowptr_dst,
+                             int32_t* rowmid_dst, kgc_edge_rec_t* rec_dst, int32_t* perm_src, int32_t* rowptr_src,
+                             kgc_edge_rec_t* rec_src, int32_t* perm_type, int32_t* rowptr_type, kgc_edge_rec_t* rec_type,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  KGC_REQUIRE(n2 >= 0 && n_in >= 0 && n_in <= n2, "n_edges_in must lie in [0, n_edges2] (in half first, model.py:84-90)");
+  KGC_REQUIRE(n_nodes > 0 && n_types > 0 && n_dst_rows > 0, "empty node or type set");
+  KGC_REQUIRE(dst_offset >= 0 && dst_offset + n_dst_rows <= n_nodes, "destination range must lie inside the node set");
   KGC_REQUIRE(n2 < (int64_t(1) << 31) && n_nodes < (int64_t(1) << 31) && n_types < (int64_t(1) << 31),
               "ids must fit int32");
   size_t cub_bytes = 0;
@@ -171,13 +175,13 @@ extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64
   int32_t* flag = (int32_t*)(ws + L.flag);
   void* cub_ws = ws + L.cub;
   const int grid = (int)ceil_div(n2 > 0 ? n2 : 1, kThreads);
-  const int grid_n = (int)ceil_div(n_nodes, kThreads);
+  const int grid_n = (int)ceil_div(n_dst_rows, kThreads);
 
   KGC_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, st));
-  KGC_CUDA_TRY(cudaMemsetAsync(deg, 0, size_t(2 * n_nodes) * 4, st));
+  if (!deg_given) KGC_CUDA_TRY(cudaMemsetAsync(deg, 0, size_t(2 * n_nodes) * 4, st));
   if (n2 > 0) {
-    narrow_and_check<<<grid, kThreads, 0, st>>>(src, dst, type, n2, n_nodes, n_types, src32, dst32, type32, iota,
-                                                flag);
+    narrow_and_check<<<grid, kThreads, 0, st>>>(src, dst, type, n2, n_nodes, n_dst_rows, n_types, src32, dst32, type32,
+                                                iota, flag);
     KGC_LAUNCH_CHECK();
   }
   int32_t bad = 0;
@@ -186,19 +190,21 @@ extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64
   KGC_REQUIRE(bad == 0, "edge list holds a node or type id out of range");
 
   if (n2 > 0) {
-    half_degree<<<grid, kThreads, 0, st>>>(src32, n2, n_nodes, deg);
-    KGC_LAUNCH_CHECK();
-    edge_norm<<<grid, kThreads, 0, st>>>(src32, dst32, deg, n2, n_nodes, norm);
+    if (!deg_given) {
+      half_degree<<<grid, kThreads, 0, st>>>(src32, n2, n_in, n_nodes, deg);
+      KGC_LAUNCH_CHECK();
+    }
+    edge_norm<<<grid, kThreads, 0, st>>>(src32, dst32, deg, n2, n_in, n_nodes, dst_offset, norm);
     KGC_LAUNCH_CHECK();
   }
   // dst-sorted (forward)
-  if (sorted_csr(dst32, n2, n_nodes, iota, key_sorted, perm_dst, rowptr_dst, cnt, cub_ws, cub_bytes, st)) return 1;
-  KGC_CUDA_TRY(cudaMemsetAsync(cnt2, 0, size_t(n_nodes) * 4, st));
-  if (n2 > 0) {
-    histogram<<<(int)ceil_div(n2 / 2, kThreads), kThreads, 0, st>>>(dst32, n2 / 2, cnt2);   // in-half edges per dst
+  if (sorted_csr(dst32, n2, n_dst_rows, iota, key_sorted, perm_dst, rowptr_dst, cnt, cub_ws, cub_bytes, st)) return 1;
+  KGC_CUDA_TRY(cudaMemsetAsync(cnt2, 0, size_t(n_dst_rows) * 4, st));
+  if (n_in > 0) {
+    histogram<<<(int)ceil_div(n_in, kThreads), kThreads, 0, st>>>(dst32, n_in, cnt2);   // in-half edges per dst
     KGC_LAUNCH_CHECK();
   }
-  add_rows<<<grid_n, kThreads, 0, st>>>(rowptr_dst, cnt2, n_nodes, rowmid_dst);
+  add_rows<<<grid_n, kThreads, 0, st>>>(rowptr_dst, cnt2, n_dst_rows, rowmid_dst);
   KGC_LAUNCH_CHECK();
   if (n2 > 0) {
     gather_records<<<grid, kThreads, 0, st>>>(perm_dst, src32, type32, norm, n2, rec_dst);

@@ -112,20 +112,28 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
   *q_out = q;
 }
 
-// stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
+// sums[0][c] = sum over blocks of partial 0, sums[1][c] = of partial 1 (fp64, fixed order)
 __global__ void __launch_bounds__(kFinCols * kFinLanes)
-colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int64_t n_rows, int Dout, float eps,
-                         int training, const float* __restrict__ rmean, const float* __restrict__ rvar,
-                         float* __restrict__ stats) {
+colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout, double* __restrict__ sums) {
   __shared__ double sm[2][kFinLanes][kFinCols];
   const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
   double s = 0, q = 0;
-  if (training) reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
+  reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
   if (lane != 0 || c >= Dout) return;
+  sums[c] = s;
+  sums[Dout + c] = q;
+}
+
+// stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
+__global__ void colstats_from_sums_kernel(const double* __restrict__ sums, int64_t n_rows, int Dout, float eps,
+                                          int training, const float* __restrict__ rmean,
+                                          const float* __restrict__ rvar, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Dout) return;
   double mean, var;
   if (training) {
-    mean = s / (double)n_rows;
-    var = q / (double)n_rows - mean * mean;
+    mean = sums[c] / (double)n_rows;
+    var = sums[Dout + c] / (double)n_rows - mean * mean;
     if (var < 0) var = 0;
   } else {
     mean = rmean[c];
@@ -134,17 +142,6 @@ colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, 
   stats[c] = (float)mean;
   stats[Dout + c] = (float)var;
   stats[2 * Dout + c] = (float)(1.0 / sqrt(var + (double)eps));
-}
-
-__global__ void __launch_bounds__(kFinCols * kFinLanes)
-colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout, float* __restrict__ sums) {
-  __shared__ double sm[2][kFinLanes][kFinCols];
-  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
-  double s = 0, q = 0;
-  reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
-  if (lane != 0 || c >= Dout) return;
-  sums[c] = (float)s;
-  sums[Dout + c] = (float)q;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -192,9 +189,9 @@ tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restric
 __global__ void __launch_bounds__(kThreads)
 tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
                       const float4* __restrict__ pre, const float4* __restrict__ stats,
-                      const float4* __restrict__ gamma, const float4* __restrict__ sums,
+                      const float4* __restrict__ gamma, const double* __restrict__ sums,
                       const uint8_t* __restrict__ mask_in, const uint8_t* __restrict__ mask_out, float keep_scale,
-                      int training, int64_t n_rows, int Do4, float4* __restrict__ d_res3) {
+                      int training, int64_t n_rows, int64_t n_rows_global, int Do4, float4* __restrict__ d_res3) {
   const int64_t n4 = n_rows * (int64_t)Do4;
   const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (i >= n4) return;
@@ -205,8 +202,11 @@ tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict
                           g.w * (1.f - t.w * t.w));
   float4 dp;
   if (training) {   // BatchNorm backward with batch statistics
-    const float inv_n = 1.0f / (float)n_rows;
-    const float4 s1 = __ldg(sums + c), s2 = __ldg(sums + Do4 + c);
+    const float inv_n = 1.0f / (float)n_rows_global;
+    const double* sp = sums + 4 * c;
+    const double* sq = sums + 4 * (Do4 + c);
+    const float4 s1 = make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]);
+    const float4 s2 = make_float4((float)sq[0], (float)sq[1], (float)sq[2], (float)sq[3]);
     dp.x = ga.x * rs.x * (dz.x - s1.x * inv_n - (v.x - m.x) * rs.x * s2.x * inv_n);
     dp.y = ga.y * rs.y * (dz.y - s1.y * inv_n - (v.y - m.y) * rs.y * s2.y * inv_n);
     dp.z = ga.z * rs.z * (dz.z - s1.z * inv_n - (v.z - m.z) * rs.z * s2.z * inv_n);
@@ -249,13 +249,21 @@ extern "C" int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uin
   return 0;
 }
 
-extern "C" int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
-                                     int32_t training, const float* running_mean, const float* running_var,
-                                     float* stats, void* stream) {
+extern "C" int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
+      partials, n_blocks, Dout, sums);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_t Dout, float eps, int32_t training,
+                                      const float* running_mean, const float* running_var, float* stats, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   KGC_REQUIRE(training || (running_mean && running_var), "eval mode needs running statistics");
-  colstats_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
-      partials, n_blocks, n_rows, Dout, eps, training, running_mean, running_var, stats);
+  KGC_REQUIRE(!training || sums, "training mode needs the column sums");
+  colstats_from_sums_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, as_stream(stream)>>>(
+      sums, n_rows, Dout, eps, training, running_mean, running_var, stats);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -282,23 +290,16 @@ extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, con
   return 0;
 }
 
-extern "C" int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, float* sums, void* stream) {
-  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
-  colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(partials, n_blocks, Dout, sums);
-  KGC_LAUNCH_CHECK();
-  return 0;
-}
-
 extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
-                                  const float* gamma, const float* sums, const uint8_t* mask_in,
+                                  const float* gamma, const double* sums, const uint8_t* mask_in,
                                   const uint8_t* mask_out, float keep_scale, int32_t training, int64_t n_rows,
-                                  int32_t Dout, float* d_res3, void* stream) {
+                                  int64_t n_rows_global, int32_t Dout, float* d_res3, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const int64_t n4 = n_rows * Do4;
   tail_bwd_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
       (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma,
-      (const float4*)sums, mask_in, mask_out, keep_scale, training, n_rows, Do4, (float4*)d_res3);
+      sums, mask_in, mask_out, keep_scale, training, n_rows, n_rows_global, Do4, (float4*)d_res3);
   KGC_LAUNCH_CHECK();
   return 0;
 }

@@ -67,24 +67,37 @@ class GraphPlan(object):
     rowptr_{dst,src}[N+1], rowptr_type[T+1], rowmid_dst[N], rec_{dst,src,type}[2E,4] int32 (bit view).
     """
 
-    def __init__(self, edge_index, edge_type, num_nodes, num_types):
+    def __init__(self, edge_index, edge_type, num_nodes, num_types, n_edges_in=None, n_dst_rows=None, dst_offset=0,
+                 deg=None):
+        """Single GPU: edge_index [2, 2E] with the in half first (defaults).  Partitioned: only the
+        edges this rank owns, ``n_edges_in`` in-half edges first, src = global ids, dst = LOCAL row ids in
+        [0, n_dst_rows) (global id = dst + dst_offset) and ``deg`` = the GLOBAL per-half degrees [2, num_nodes] int32."""
         edge_index = _lib.require_cuda(edge_index, torch.int64, 'edge_index')
         edge_type = _lib.require_cuda(edge_type, torch.int64, 'edge_type')
         if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.size(1) != edge_type.numel():
             raise ValueError('edge_index must be [2, 2E] and edge_type [2E]')
         n2 = int(edge_type.numel())
-        if n2 % 2 != 0:
-            raise ValueError('the edge list must hold an in half and an out half of equal size (model.py:84-90)')
+        if n_edges_in is None:
+            if n2 % 2 != 0:
+                raise ValueError('the edge list must hold an in half and an out half of equal size (model.py:84-90)')
+            n_edges_in = n2 // 2
         dev = edge_index.device
         N, T = int(num_nodes), int(num_types)
+        Nd = N if n_dst_rows is None else int(n_dst_rows)
         self.device, self.num_nodes, self.num_types, self.num_edges2 = dev, N, T, n2
+        self.num_dst_rows, self.dst_offset, self.num_edges_in = Nd, int(dst_offset), int(n_edges_in)
         i32 = dict(dtype=torch.int32, device=dev)
-        self.deg = torch.empty((2, N), **i32)
+        if deg is None:
+            self.deg = torch.empty((2, N), **i32)
+        else:
+            self.deg = _lib.require_cuda(deg, torch.int32, 'deg')
+            if tuple(self.deg.shape) != (2, N):
+                raise ValueError('deg must be [2, num_nodes]')
         self.norm = torch.empty((n2,), dtype=torch.float32, device=dev)
         self.perm_dst, self.perm_src, self.perm_type = (torch.empty((n2,), **i32) for _ in range(3))
-        self.rowptr_dst, self.rowptr_src = torch.empty((N + 1,), **i32), torch.empty((N + 1,), **i32)
+        self.rowptr_dst, self.rowptr_src = torch.empty((Nd + 1,), **i32), torch.empty((N + 1,), **i32)
         self.rowptr_type = torch.empty((T + 1,), **i32)
-        self.rowmid_dst = torch.empty((N,), **i32)
+        self.rowmid_dst = torch.empty((Nd,), **i32)
         self.rec_dst, self.rec_src, self.rec_type = (torch.empty((n2, 4), **i32) for _ in range(3))
         h = _lib.lib()
         ws_bytes = int(h.kgc_csr_workspace_bytes(n2, N, T))
@@ -93,7 +106,8 @@ class GraphPlan(object):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
         p = _lib.ptr
-        _lib.call('kgc_csr_build', p(src), p(dst), p(edge_type), n2, N, T, p(self.deg), p(self.norm),
+        _lib.call('kgc_csr_build', p(src), p(dst), p(edge_type), n2, self.num_edges_in, N, Nd, self.dst_offset, T,
+                  0 if deg is None else 1, p(self.deg), p(self.norm),
                   p(self.perm_dst), p(self.rowptr_dst), p(self.rowmid_dst), p(self.rec_dst),
                   p(self.perm_src), p(self.rowptr_src), p(self.rec_src),
                   p(self.perm_type), p(self.rowptr_type), p(self.rec_type), p(ws), ws_bytes, _lib.stream())
@@ -104,9 +118,10 @@ class GraphPlan(object):
         rp_src = self.rowptr_src.cpu().numpy().astype(np.int64)
         rp_typ = self.rowptr_type.cpu().numpy().astype(np.int64)
         rows = np.arange(N, dtype=np.int64)
-        # forward: row i of plane 0 (in half) = [rowptr, rowmid), row N+i of plane 1 (out half) = [rowmid, rowptr+1)
+        drows = np.arange(Nd, dtype=np.int64)
+        # forward: row i of plane 0 (in half) = [rowptr, rowmid), row Nd+i of plane 1 (out half) = [rowmid, rowptr+1)
         self.fwd = ReducePlan(build_levels(np.concatenate([rp_dst[:-1], rm_dst]), np.concatenate([rm_dst, rp_dst[1:]]),
-                                           np.concatenate([rows, rows + N])), dev)
+                                           np.concatenate([drows, drows + Nd])), dev)
         self.bwd_src = ReducePlan(build_levels(rp_src[:-1], rp_src[1:], rows), dev)
         self.bwd_rel = ReducePlan(build_levels(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64)), dev)
         self._scratch = {}

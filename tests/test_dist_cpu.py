@@ -1,0 +1,119 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: the dst-range partition, the halo all-gather /
+reduce-scatter plumbing of the partitioned layer and the entity-sharded rank reduction.  The per-rank
+arithmetic is stood in for by the oracle (numpy) - no kernel runs here; the CUDA kernels behind the same
+plumbing are checked on 2 GPUs by tests/test_gpu_dist.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mgcn_oracle as orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _agg_numpy(x_full, rel, ee_rows, src, dst, typ, norm, n_rows):
+    out = np.zeros((n_rows, x_full.shape[1]))
+    np.add.at(out, dst, norm[:, None] * x_full[src] * rel[typ] * ee_rows)
+    return out
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from kgc_gcn_b200.partition import partition_edges
+        from kgc_gcn_b200.conv import _Collectives
+        N, R, E, D = 64, 3, 300, 8
+        tri = orc.synthetic_triples(N, R, E, 5)
+        g = orc.build_graph(tri, N, R)
+        ei, et = g['edge_index'], g['edge_attr'][0]
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal((N, D))
+        ee = rng.standard_normal((2 * E, D))
+        rel = rng.standard_normal((2 * R + 1, D))
+        info = partition_edges(ei, et, N, world, rank)
+        lo, hi = info['lo'], info['hi']
+        coll = _Collectives(None, world, N)
+        # ---- halo all-gather puts the row blocks back in rank order
+        x_full = coll.all_gather_rows(torch.from_numpy(x[lo:hi].copy())).numpy()
+        np.testing.assert_array_equal(x_full, x)
+        # ---- ownership: every edge owned exactly once, in-half edges first, global degrees
+        owned = info['owned_eids']
+        assert (np.diff(owned) > 0).all() and (owned[:info['n_edges_in']] < E).all() and (owned[info['n_edges_in']:] >= E).all()
+        counts = torch.zeros(2 * E, dtype=torch.int64)
+        counts[torch.from_numpy(owned)] = 1
+        dist.all_reduce(counts)
+        assert int(counts.min()) == 1 and int(counts.max()) == 1
+        np.testing.assert_array_equal(info['deg'][0], orc.half_degree(ei[:, :E], N))
+        np.testing.assert_array_equal(info['deg'][1], orc.half_degree(ei[:, E:], N))
+        # ---- forward: local aggregation over owned edges == the rank's rows of the global aggregation
+        norm = np.concatenate([orc.compute_norm(ei[:, :E], N).numpy(), orc.compute_norm(ei[:, E:], N).numpy()]).astype(np.float64)
+        for h, sl in ((0, slice(0, info['n_edges_in'])), (1, slice(info['n_edges_in'], None))):
+            eids = owned[sl]
+            loc = _agg_numpy(x_full, rel, ee[eids], info['src'][sl], info['dst'][sl], info['type'][sl], norm[eids], hi - lo)
+            half = slice(0, E) if h == 0 else slice(E, 2 * E)
+            glob = _agg_numpy(x, rel, ee[half], ei[0, half], ei[1, half], et[half], norm[half], N)
+            np.testing.assert_allclose(loc, glob[lo:hi], rtol=1e-12, atol=1e-12)
+        # ---- backward: source-row gradients of the owned edges, reduce-scattered to the row owners
+        gsel = rng.standard_normal((N, D))                       # d agg (both halves share it here)
+        part = np.zeros((N, D))
+        np.add.at(part, info['src'], norm[owned][:, None] * gsel[info['dst'] + lo] * rel[info['type']] * ee[owned])
+        mine = coll.reduce_scatter_rows(torch.from_numpy(part)).numpy()
+        full = np.zeros((N, D))
+        np.add.at(full, ei[0], norm[:, None] * gsel[ei[1]] * rel[et] * ee)
+        np.testing.assert_allclose(mine, full[lo:hi], rtol=1e-10, atol=1e-12)
+        # ---- entity-sharded filtered rank: integer counts all-reduce to the unsharded answer, target logits sum exactly
+        B, NE = 16, 64
+        scores = rng.integers(-5, 6, (B, NE)).astype(np.float64)
+        obj = rng.integers(0, NE, B)
+        fptr = np.arange(0, 2 * B + 1, 2)
+        fidx = rng.integers(0, NE, 2 * B)
+        gt, eq = orc.rank_counts(scores, fptr, fidx, obj)
+        per = NE // world
+        s_lo, s_hi = rank * per, (rank + 1) * per
+        thr_local = np.where((obj >= s_lo) & (obj < s_hi), scores[np.arange(B), obj], 0.0)
+        thr = torch.from_numpy(thr_local)
+        dist.all_reduce(thr)                                      # each entry non-zero on exactly one rank
+        np.testing.assert_array_equal(thr.numpy(), scores[np.arange(B), obj])
+        keep = np.ones((B, NE), dtype=bool)
+        for q in range(B):
+            keep[q, fidx[fptr[q]:fptr[q + 1]]] = False
+            keep[q, obj[q]] = False
+        loc_gt = torch.from_numpy(((scores[:, s_lo:s_hi] > thr.numpy()[:, None]) & keep[:, s_lo:s_hi]).sum(1))
+        dist.all_reduce(loc_gt)
+        np.testing.assert_array_equal(loc_gt.numpy(), gt)
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_and_collectives_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    ctx = mp.get_context('spawn')
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert dict(ret) == {0: 'ok', 1: 'ok'}
+
+
+def test_partition_edges_rejects_uneven():
+    from kgc_gcn_b200.partition import partition_edges
+    with pytest.raises(ValueError):
+        partition_edges(np.zeros((2, 4), dtype=np.int64), np.zeros(4, dtype=np.int64), 7, 2, 0)
