@@ -225,30 +225,44 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    N, R, E, seed = WORKLOADS[args.workload]
-    # N > 1: every rank owns an independent, equally shaped graph partition (weak scaling; seeds differ per rank)
-    tri = orc.synthetic_triples(N, R, E, seed + 1000 * rank)
+    N1, R, E1, seed = WORKLOADS[args.workload]
+    # N GPUs: weak scaling of the dst-partitioned layer - the global graph has world x the nodes and
+    # triples of the named shape, nodes are range-partitioned by destination, every step all-gathers x (halo), reduce-
+    # scatters d_x and all-reduces the BatchNorm sums and the replicated-parameter gradients over NCCL.
+    N, E = N1 * world, E1 * world
+    tri = orc.synthetic_triples(N, R, E, seed)
     g = orc.build_graph(tri, N, R)
     p = orc.conv_params(N, R, E, D_IN, D_OUT, seed=0)
-    ei, et = torch.from_numpy(g['edge_index']).to(dev), torch.from_numpy(g['edge_attr'][0]).to(dev)
     torch.manual_seed(0)
-
     conv = k.MGCNConv(D_IN, D_OUT, 2 * R).to(dev)          # dropout p = 0.1, the reference default (model.py:49)
     with torch.no_grad():
         for name in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge'):
             getattr(conv, name).copy_(p['w'][name])
     conv.train()
-    x = p['x'].to(dev).requires_grad_(True)
-    ee = p['edge_embs'].to(dev).requires_grad_(True)
-    rl = p['rels'].to(dev).requires_grad_(True)
     gen = torch.Generator().manual_seed(1)
-    g_ent, g_rel = torch.randn(N, D_OUT, generator=gen).to(dev), torch.randn(2 * R, D_OUT, generator=gen).to(dev)
+    g_ent_all, g_rel = torch.randn(N, D_OUT, generator=gen), torch.randn(2 * R, D_OUT, generator=gen).to(dev)
+    rl = p['rels'].to(dev).requires_grad_(True)
+    if world == 1:
+        part = None
+        ei, et = torch.from_numpy(g['edge_index']).to(dev), torch.from_numpy(g['edge_attr'][0]).to(dev)
+        x = p['x'].to(dev).requires_grad_(True)
+        ee = p['edge_embs'].to(dev).requires_grad_(True)
+        g_ent = g_ent_all.to(dev)
+    else:
+        part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev)
+        x = p['x'][part.lo:part.hi].to(dev).requires_grad_(True)
+        ee = p['edge_embs'][part.owned_eids.cpu()].to(dev).requires_grad_(True)
+        g_ent = g_ent_all[part.lo:part.hi].to(dev)
+    del g_ent_all
     leaves = [x, ee, rl] + list(conv.parameters())
 
     def step():
         for t in leaves:
             t.grad = None
-        ent, rel = conv(x, ei, et, None, ee, rl)
+        if part is None:
+            ent, rel = conv(x, ei, et, None, ee, rl)
+        else:
+            ent, rel = conv.forward_partitioned(x, part, ee, rl)
         torch.autograd.backward([ent, rel], [g_ent, g_rel])
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -301,36 +315,40 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
         # ---- e2e: the whole training step through the reference-facing API, host ids in, loss out
-        e2e = {'ms_total': float('nan'), 'steps': 0, 'h2d': 0, 'd2h': 0} if args.no_e2e else \
-            e2e_train_step(k, orc, tri, g, N, R, E, dev, args)
+        if args.no_e2e:
+            e2e = {'ms_total': float('nan'), 'steps': 0, 'h2d': 0, 'd2h': 0, 'scope': 'skipped'}
+        elif world == 1:
+            e2e = e2e_train_step(k, orc, tri, g, N, R, E, dev, args)
+        else:
+            e2e = e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist)
     if dist is not None:
         t = torch.tensor([total_ms, e2e['ms_total']], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e['ms_total'] = float(t[0]), float(t[1])
-    value = world * 2 * E * args.steps / (total_ms * 1e-3)
-    e2e_value = world * 2 * E * e2e['steps'] / (e2e['ms_total'] * 1e-3) if e2e['steps'] else None
+    value = 2 * E * args.steps / (total_ms * 1e-3)          # E already counts every rank's triples
+    e2e_value = 2 * E * e2e['steps'] / (e2e['ms_total'] * 1e-3) if e2e['steps'] else None
 
     # ---- roofline of the dominant kernel, timed alone through the C ABI (rank 0)
     roof, kernels = None, None
-    if rank == 0:
+    if rank == 0 and world == 1:
         roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    fwd_b, bwd_b = algorithmic_bytes(N, R, E)
+    fwd_b, bwd_b = algorithmic_bytes(N1, R, E1)          # per GPU
     peak, peak_src = measured_peaks()
     line = {
         'metric': 'edges/sec GCN fwd+bwd', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload + '_shape', 'N': N, 'R': R, 'E': E, 'directed_edges': 2 * E, 'd_in': D_IN,
+        'config': {'workload': args.workload + '_shape' + ('' if world == 1 else ' x{} (one shape-sized partition per GPU)'.format(world)), 'N': N, 'R': R, 'E': E, 'directed_edges': 2 * E, 'd_in': D_IN,
                    'd_out': D_OUT, 'dropout': 'p=0.1 keep masks drawn inside the timed region (training mode)',
                    'l2': 'flushed between steps (256 MiB memset outside the timed events)', 'launch': launch_mode,
-                   'parallelism': 'single GPU' if world == 1 else 'one equally shaped graph partition per GPU, no exchange'},
+                   'parallelism': 'single GPU' if world == 1 else 'dst-range partition over {} GPUs: all-gather x / reduce-scatter d_x / all-reduce BN sums + replicated grads (NCCL)'.format(world)},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
                 'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1),
-                'scope': 'full training step: loader batch (K5) + MGCN forward + BCE + backward + clip + Adam + loss.item()'},
+                'scope': e2e['scope']},
         'gpu_launches': launches_per_step * args.steps,
         'clocks': clocks.summary(),
         'roofline': roof,
@@ -340,8 +358,8 @@ def run_ours(args, rank, world, local_rank):
                      'peak_source': peak_src, 'note': 'whole layer incl. the dense GEMMs and the BN/tanh tail, SURVEY.md 8(d) bytes'},
     }
     if not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_conv_baseline(orc, N, R, E, seed)
-    if not args.no_aux:
+        line['cpu_baseline'] = cpu_conv_baseline(orc, N1, R, E1, seed)
+    if not args.no_aux and world == 1:
         try:
             line['aux'] = aux_filtered_rank(k, dev, args)
         except Exception as exc:                       # pragma: no cover
@@ -384,7 +402,41 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
             ms += a.elapsed_time(b)
             n += 1
     del model, opt
-    return {'ms_total': ms, 'steps': n, 'h2d': BATCH * 8, 'd2h': 4}
+    return {'ms_total': ms, 'steps': n, 'h2d': BATCH * 8, 'd2h': 4,
+            'scope': 'full training step: loader batch (K5) + MGCN forward + BCE + backward + clip + Adam + loss.item()'}
+
+
+def e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist):
+    """N > 1: the partitioned encoder step through forward_partitioned with the batch coming from pinned host memory
+    every step (H2D) and the scalar loss read back (D2H).  The loss is a stand-in decoder: mean of the batch's entity and
+    relation rows, summed over ranks."""
+    steps, warm = args.steps, max(3, args.warmup)
+    rng = np.random.default_rng(0)
+    host = torch.empty((BATCH, 2), dtype=torch.int64).pin_memory()
+    ms, n = 0.0, 0
+    for i in range(warm + steps):
+        host[:, 0] = torch.from_numpy(rng.integers(0, N, BATCH))
+        host[:, 1] = torch.from_numpy(rng.integers(0, 2 * R, BATCH))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        batch = host.to(dev, non_blocking=True)
+        for t in leaves:
+            t.grad = None
+        ent, rel = conv.forward_partitioned(x, part, ee, rl)
+        mine = (batch[:, 0] >= part.lo) & (batch[:, 0] < part.hi)
+        rows = (batch[:, 0] - part.lo).clamp(0, part.hi - part.lo - 1)
+        loss = (ent[rows].mean(1) * mine).sum() + rel[batch[:, 1]].mean() / part.world
+        loss.backward()
+        tot = loss.detach().clone()
+        dist.all_reduce(tot)
+        tot.item()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ms += a.elapsed_time(b)
+            n += 1
+    return {'ms_total': ms, 'steps': n, 'h2d': BATCH * 16, 'd2h': 4,
+            'scope': 'partitioned encoder step: batch ids from pinned host memory -> forward_partitioned -> scalar loss -> backward -> loss.item()'}
 
 
 def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
