@@ -461,8 +461,8 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
     fns = {
         'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), p(eed), p(plan.rec_dst), p(it_f), n_f, p(agg), p(pf), D, st()),
         'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), p(eed), p(g3), p(plan.rec_src), p(it_s), n_s, N,
-                                      2 * E, p(d_ee), p(d_x), p(ps), D, st()),
-        'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(it_r), n_r, N, 2 * E,
+                                      E, p(g3[2]), p(d_ee), p(d_x), p(ps), D, st()),
+        'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(it_r), n_r, N, E,
                                       p(d_rel), p(pr), D, st()),
     }
     row = 4 * D
