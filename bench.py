@@ -272,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- launch mode: CUDA graph of the whole fwd+bwd (falls back to eager launches if capture fails)
     launch_mode = 'eager'
+    graph = None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -332,9 +333,14 @@ def run_ours(args, rank, world, local_rank):
     roof, kernels = None, None
     if rank == 0 and world == 1:
         roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush)
+    if dist is not None:
+        # release the CUDA graph (it holds the captured NCCL kernels) before the communicator goes away
+        run_step = None
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        shutdown(dist)
         return
     fwd_b, bwd_b = algorithmic_bytes(N1, R, E1)          # per GPU
     peak, peak_src = measured_peaks()
@@ -364,9 +370,22 @@ def run_ours(args, rank, world, local_rank):
             line['aux'] = aux_filtered_rank(k, dev, args)
         except Exception as exc:                       # pragma: no cover
             line['aux'] = {'error': repr(exc)}
-    print(json.dumps(line))
-    if dist is not None:
+    print(json.dumps(line), flush=True)
+    shutdown(dist)
+
+
+def shutdown(dist):
+    """Tear the process group down; a watchdog ends the process if NCCL teardown stalls (the JSON line is already out)."""
+    if dist is None:
+        return
+    sys.stdout.flush()
+    timer = threading.Timer(20.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
         dist.destroy_process_group()
+    finally:
+        timer.cancel()
 
 
 def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
