@@ -470,25 +470,24 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
     g3 = torch.randn((3, N, D), device=x.device)
     d_ee, d_x, d_rel = torch.empty_like(eed), torch.empty((N, D), device=x.device), torch.empty((T, D), device=x.device)
 
-    def part(rp):
-        n = rp.levels[0][2]
-        return torch.empty((max(n, 1), D), device=x.device)
-    pf, ps, pr = part(plan.fwd), part(plan.bwd_src), part(plan.bwd_rel)
-    it_f, n_f, _ = plan.fwd.levels[0]
-    it_s, n_s, _ = plan.bwd_src.levels[0]
-    it_r, n_r, _ = plan.bwd_rel.levels[0]
+    def carry(sp):
+        return torch.empty((max(sp.n_carry, 1), D), device=x.device)
+    pf, ps, pr = carry(plan.fwd), carry(plan.bwd_src), carry(plan.bwd_rel)
+    sf, ss, sr = plan.fwd, plan.bwd_src, plan.bwd_rel
+    n_f = n_s = n_r = (2 * E + 31) // 32                   # chunks (one warp each)
     fns = {
-        'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), p(eed), p(plan.rec_dst), p(it_f), n_f, p(agg), p(pf), D, st()),
-        'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), p(eed), p(g3), p(plan.rec_src), p(it_s), n_s, N,
-                                      E, p(g3[2]), p(d_ee), p(d_x), p(ps), D, st()),
-        'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(it_r), n_r, N, E,
-                                      p(d_rel), p(pr), D, st()),
+        'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), p(eed), p(plan.rec_dst), p(sf.rowflags), p(sf.chunks),
+                                  sf.n_rec, p(agg), p(pf), D, st()),
+        'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), p(eed), p(g3), p(plan.rec_src), p(ss.rowflags),
+                                      p(ss.chunks), ss.n_rec, N, E, p(g3[2]), p(d_ee), p(d_x), p(ps), D, st()),
+        'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(sr.rowflags),
+                                      p(sr.chunks), sr.n_rec, N, E, p(d_rel), p(pr), D, st()),
     }
     row = 4 * D
-    bytes_ = {   # per launch: edge-embedding stream + 16-byte records + each dense operand once + outputs once
-        'agg_fwd': 2 * E * (row + 16) + N * row + T * row + 2 * N * row + 16 * n_f,
-        'agg_bwd_src': 2 * E * (2 * row + 16) + N * row + 3 * N * row + T * row + N * row + 16 * n_s,
-        'agg_bwd_rel': 2 * E * (row + 16) + N * row + 2 * N * row + T * row + 16 * n_r,
+    bytes_ = {   # per launch: edge-embedding stream + 20 bytes of record per edge + each dense operand once + outputs once
+        'agg_fwd': 2 * E * (row + 20) + N * row + T * row + 2 * N * row + 8 * n_f,
+        'agg_bwd_src': 2 * E * (2 * row + 20) + N * row + 3 * N * row + T * row + N * row + 8 * n_s,
+        'agg_bwd_rel': 2 * E * (row + 20) + N * row + 2 * N * row + T * row + 8 * n_r,
     }
     peak, peak_src = measured_peaks()
     out = {}

@@ -33,10 +33,17 @@ extern "C" {
 
 #define KGC_ABI_VERSION 1
 
-/* Work item of a segmented reduction: rows [beg, end) of the input record / partial array are
- * summed; the result goes to row `out` of the final output (flags & 1) or of the partial
- * buffer of this level (flags & 1 == 0).  Built by the host plan (kgc_gcn_b200/plan.py). */
+/* Work item of a fix-up reduction level: rows [beg, end) of the carry / partial array are summed;
+ * the result goes to row `out` of the final output (flags & 1) or of the partial buffer of this
+ * level (flags & 1 == 0); flags >> 1 = the final row.  Built by the host plan (kgc_gcn_b200/plan.py). */
 typedef struct { int32_t beg, end, out, flags; } kgc_item_t;
+
+/* Streaming aggregation (K2/K3): the sorted records are cut into chunks of KGC_CHUNK_EDGES; a chunk's
+ * leading row that began in an earlier chunk goes to carry row head_slot when it ends inside the chunk, the
+ * row still open at the end of the chunk goes to carry row tail_slot (-1 = not needed).  rowflags[p] of a
+ * sorted record = output row | first-record-of-its-row << 30 | last-record-of-its-row << 31. */
+#define KGC_CHUNK_EDGES 32
+typedef struct { int32_t head_slot, tail_slot; } kgc_chunk_t;
 
 /* Edge record of a sorted CSR: 16 bytes, one 128-bit load per edge.
  *   dst-sorted : a = src,  b = type      src-sorted : a = dst, b = type
@@ -75,15 +82,20 @@ int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type,
 /* ---- K2: aggregation forward -----------------------------------------------------------------
  * Replaces the gather + MGCNConv.message product + norm + scatter-add of the "in" and "out"
  * propagations (model.py:99-100,111-118) in the aggregate-then-transform order:
- *   out[row] = sum over the item's records of  norm_e * x[a_e] (.) rel[b_e] (.) ee[eid_e]
- * over dst-sorted records; deterministic (fixed order, no float atomics).
- * x [n_nodes,D], rel [n_types,D], ee [n_edges2,D], out_final [*,D], out_part [*,D]. */
+ *   out[row] = sum over the row's records of  norm_e * x[a_e] (.) rel[b_e] (.) ee[eid_e]
+ * over dst-sorted records (row = plane * n_dst_rows + dst; plane 0 = in half, 1 = out half);
+ * deterministic (fixed order, no float atomics).  Rows that lie inside one chunk are written to
+ * out_final, chunk-boundary rows to carry (reduced by kgc_rows_reduce), rows without records by
+ * kgc_rows_fill.  x [n_nodes,D], rel [n_types,D], ee [n_edges2,D], out_final [*,D], carry [*,D]. */
 int kgc_agg_fwd(const float* x, const float* rel, const float* ee,
-                const kgc_edge_rec_t* rec_dst, const kgc_item_t* items, int64_t n_items,
-                float* out_final, float* out_part, int32_t D, void* stream);
+                const kgc_edge_rec_t* rec_dst, const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec,
+                float* out_final, float* carry, int32_t D, void* stream);
 
-/* Higher reduction levels shared by K2/K3: out[row] = sum of rows [beg,end) of `part_in`
- * (+ addend[row] on final rows when addend != NULL), in a fixed order. */
+/* out[rows[i]] = addend ? addend[rows[i]] : 0 for the rows no record maps to. */
+int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, float* out, int32_t D, void* stream);
+
+/* Fix-up levels shared by K2/K3: out[row] = sum of rows [beg,end) of `part_in` (carry rows, then partial
+ * rows of the previous level) (+ addend[row] on final rows when addend != NULL), in a fixed order. */
 int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items,
                     float* out_final, float* out_part, const float* addend, int32_t D, void* stream);
 
@@ -96,16 +108,16 @@ int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_ite
  *   d_x[j]   = sum_e p_e (.) ee[e]   (+ loop_addend[j], the self-loop term, on final rows when not NULL)
  * half_e = (eid_e >= n_edges_in). */
 int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
-                    const kgc_edge_rec_t* rec_src, const kgc_item_t* items, int64_t n_items,
+                    const kgc_edge_rec_t* rec_src, const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec,
                     int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend,
-                    float* d_ee, float* dx_final, float* dx_part, int32_t D, void* stream);
+                    float* d_ee, float* dx_final, float* carry, int32_t D, void* stream);
 
 /* Over type-sorted records (row t = relation type):
  *   d_rel[t] = sum_e norm_e * g3[half_e][b_e] (.) x[a_e] (.) ee[e] */
 int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
-                    const kgc_edge_rec_t* rec_type, const kgc_item_t* items, int64_t n_items,
+                    const kgc_edge_rec_t* rec_type, const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec,
                     int64_t n_dst_rows, int64_t n_edges_in,
-                    float* drel_final, float* drel_part, int32_t D, void* stream);
+                    float* drel_final, float* carry, int32_t D, void* stream);
 
 /* ---- K4: layer tail ------------------------------------------------------------------------------
  * Replaces model.py:103-106: out = (drop(in_res) + drop(out_res) + loop_res) / 3 [+ bias];

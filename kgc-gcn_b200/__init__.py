@@ -8,12 +8,12 @@ there is no CPU fallback.
 from .conv import MGCNConv, get_param            # noqa: F401
 from .model import MGCN, ConvE                   # noqa: F401
 from .data_loader import DataLoader, KBDataset, GraphData, BatchIterator, epoch_permutation   # noqa: F401
-from .plan import GraphPlan, get_plan, build_levels   # noqa: F401
+from .plan import GraphPlan, get_plan, build_levels, build_stream_plan   # noqa: F401
 from .scoring import (EntityTable, filtered_rank, pack_queries, pair_scores, predict, evaluate,   # noqa: F401
                       score_kpad)
 from .partition import GraphPartition, partition_edges   # noqa: F401
 from . import _lib                               # noqa: F401
 
 __all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
-           'get_plan', 'build_levels', 'get_param', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
+           'get_plan', 'build_levels', 'build_stream_plan', 'get_param', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
            'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges']

@@ -81,9 +81,9 @@ class _ConvFn(torch.autograd.Function):
 
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
-        def level0(items, n_items, out_final, part):
-            _lib.call('kgc_agg_fwd', p(x_full), p(relp), p(ee), p(plan.rec_dst), p(items), n_items, p(out_final),
-                      p(part), D, st())
+        def level0(sp, out_final, carry):
+            _lib.call('kgc_agg_fwd', p(x_full), p(relp), p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
+                      p(out_final), p(carry), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
 
         v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
@@ -166,14 +166,15 @@ class _ConvFn(torch.autograd.Function):
         d_ee = torch.empty_like(ee)
         loop_addend = g3[2] if coll is None else None
 
-        def level0_src(items, n_items, out_final, part):
-            _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), p(ee), p(g3), p(plan.rec_src), p(items), n_items,
-                      plan.num_dst_rows, plan.num_edges_in, p(loop_addend), p(d_ee), p(out_final), p(part), D, st())
+        def level0_src(sp, out_final, carry):
+            _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), p(ee), p(g3), p(plan.rec_src), p(sp.rowflags), p(sp.chunks),
+                      sp.n_rec, plan.num_dst_rows, plan.num_edges_in, p(loop_addend), p(d_ee), p(out_final), p(carry),
+                      D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
 
-        def level0_rel(items, n_items, out_final, part):
-            _lib.call('kgc_agg_bwd_rel', p(x_full), p(ee), p(g3), p(plan.rec_type), p(items), n_items,
-                      plan.num_dst_rows, plan.num_edges_in, p(out_final), p(part), D, st())
+        def level0_rel(sp, out_final, carry):
+            _lib.call('kgc_agg_bwd_rel', p(x_full), p(ee), p(g3), p(plan.rec_type), p(sp.rowflags), p(sp.chunks), sp.n_rec,
+                      plan.num_dst_rows, plan.num_edges_in, p(out_final), p(carry), D, st())
         plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
 
         if coll is None:

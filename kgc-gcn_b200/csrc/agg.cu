@@ -6,21 +6,27 @@
 //   agg[dst] = sum_e norm_e * x[src_e] (.) rel[type_e] (.) ee[e]      (this file)
 //   res      = agg @ W                                                   (dense GEMM, host side)
 //
-// Layout: every row is D floats = D4 float4.  A GROUP of 8 lanes owns one work item (a run of
-// <= 32 sorted edge records of one output row); lane g of the group owns float4 columns
-// g, g+8, g+16, ... (NF of them), so the 8 lanes read 128 contiguous bytes per step.  A warp
-// therefore works on 4 items at once, which keeps enough independent 128-bit loads in flight
-// on the low-degree rows that dominate knowledge graphs.  Rows longer than one item are reduced
-// through partial rows by kgc_rows_reduce in a fixed order: no float atomics anywhere, results
-// are bit-reproducible run to run.
+// Streaming design (round 1, second version - the first one gave one 8-lane group a whole output row and
+// was latency-bound at 25-40% of HBM peak, profiles/r01_ncu_agg_kernels.md):
+//   * the sorted edge records are cut into CHUNKS of 32 consecutive records, one warp per chunk, whatever
+//     the row boundaries: every warp has the same amount of work and there is no per-row launch overhead;
+//   * lane l owns float4 columns l and l + 32 of a row (D <= 256), so a 400-byte row is one fully
+//     coalesced 25-lane request; 4 edges are in flight per warp (records prefetched one trip ahead);
+//   * a row that lies inside one chunk is written straight to the output; the (at most two) rows a chunk
+//     shares with its neighbours go to CARRY rows, which kgc_rows_reduce adds in a fixed order.
+// No float atomics anywhere: results are bit-reproducible run to run.
 #include "common.cuh"
 
 namespace kgc {
 namespace {
 
-constexpr int kGroup = 8;
+constexpr int kGroup = 8;          // kgc_rows_reduce: lanes per partial-row group
 constexpr int kThreads = 256;
-constexpr int kMaxNF = 8;   // D <= 8 * 8 * 4 = 256
+constexpr int kMaxNF = 8;          // kgc_rows_reduce: D <= 8 * 8 * 4 = 256
+constexpr int kChunk = KGC_CHUNK_EDGES;
+constexpr int kUnroll = 4;         // edges in flight per warp
+constexpr int kWarpsPerBlock = kThreads / 32;
+constexpr uint32_t kRowMask = 0x3FFFFFFFu, kFirst = 0x40000000u, kLast = 0x80000000u;
 
 __device__ __forceinline__ float4 mul3s(float s, const float4& a, const float4& b, const float4& c) {
   // s * ((a*b)*c), the reference's product order (model.py:115) followed by the norm (model.py:118)
@@ -37,206 +43,155 @@ __device__ __forceinline__ float4 scale4(float s, const float4& a) {
   return make_float4(s * a.x, s * a.y, s * a.z, s * a.w);
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-template <int NF>
-__global__ void __launch_bounds__(kThreads)
-agg_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ rel, const float4* __restrict__ ee,
-               const kgc_edge_rec_t* __restrict__ rec, const kgc_item_t* __restrict__ items, int64_t n_items,
-               float4* __restrict__ out_final, float4* __restrict__ out_part, int D4) {
-  const int64_t item = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / kGroup;
-  const int g = threadIdx.x % kGroup;
-  if (item >= n_items) return;
-  const int4 it = __ldg(reinterpret_cast<const int4*>(items + item));
+enum Mode { kFwd = 0, kBwdSrc = 1, kBwdRel = 2 };
+
+struct StreamArgs {
+  const float4* x;            // node rows (global ids)
+  const float4* rel;          // relation rows (fwd, bwd_src)
+  const float4* ee;           // edge-embedding rows (global edge ids of this rank)
+  const float4* g3;           // bwd: [2, n_dst_rows, D] upstream planes
+  const float4* addend;       // bwd_src: self-loop term added on rows finished inside a chunk (or null)
+  const kgc_edge_rec_t* rec;
+  const uint32_t* rowflags;   // row | first << 30 | last << 31 per sorted record
+  const kgc_chunk_t* chunks;
+  float4* out_final;
+  float4* carry;
+  float4* d_ee;               // bwd_src: per-edge output
+  int64_t n_rec;
+  int64_t plane;              // n_dst_rows * D4 (bwd)
+  int32_t n_edges_in;         // records with eid >= n_edges_in belong to the out half (bwd)
+  int32_t D4;
+};
+
+// One warp walks one chunk of kChunk sorted records.
+template <int MODE, int NF>
+__global__ void __launch_bounds__(kThreads, 2)
+agg_stream_kernel(const StreamArgs A) {
+  const int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int64_t cb = chunk * kChunk;
+  if (cb >= A.n_rec) return;
+  const int64_t ce = cb + kChunk < A.n_rec ? cb + kChunk : A.n_rec;
+  const int D4 = A.D4;
+  const int2 slots = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
+
+  int4 rc[kUnroll];
+  uint32_t rf[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const int64_t p = cb + u < ce ? cb + u : ce - 1;
+    rc[u] = ld_rec(A.rec + p);
+    rf[u] = __ldg(A.rowflags + p);
+  }
   float4 acc[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool started_here = (rf[0] & kFirst) != 0;
+  bool open_row = false;
 
-  int e = it.x;
-  for (; e + 1 < it.y; e += 2) {   // two edges per trip: 4*NF independent 128-bit loads in flight per lane
-    const int4 r0 = ld_rec(rec + e), r1 = ld_rec(rec + e + 1);
-    float4 a0[NF], b0[NF], a1[NF], b1[NF];
+  for (int64_t p = cb; p < ce; p += kUnroll) {
+    // records of the next trip (their addresses do not depend on data: a pure prefetch)
+    int4 rn[kUnroll];
+    uint32_t fn[kUnroll];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        a0[f] = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        b0[f] = __ldg(x + (int64_t)r0.y * D4 + c);
-        a1[f] = ld_stream(ee + (int64_t)r1.x * D4 + c);
-        b1[f] = __ldg(x + (int64_t)r1.y * D4 + c);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t q = p + kUnroll + u < ce ? p + kUnroll + u : ce - 1;
+      rn[u] = ld_rec(A.rec + q);
+      fn[u] = __ldg(A.rowflags + q);
+    }
+    // all row loads of this trip first, then the arithmetic
+    float4 va[kUnroll][NF], vb[kUnroll][NF], vc[kUnroll][NF], vx[kUnroll][MODE == kBwdSrc ? NF : 1];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int4 r = rc[u];
+      const int64_t row = rf[u] & kRowMask;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const int c = lane + f * 32;
+        if (c < D4) {
+          va[u][f] = ld_stream(A.ee + (int64_t)r.x * D4 + c);
+          if (MODE == kFwd) {
+            vb[u][f] = __ldg(A.x + (int64_t)r.y * D4 + c);
+            vc[u][f] = __ldg(A.rel + (int64_t)r.z * D4 + c);
+          } else if (MODE == kBwdSrc) {
+            vb[u][f] = __ldg(A.g3 + (r.x >= A.n_edges_in ? A.plane : 0) + (int64_t)r.y * D4 + c);
+            vc[u][f] = __ldg(A.rel + (int64_t)r.z * D4 + c);
+            vx[u][f] = __ldg(A.x + row * D4 + c);              // x[src]: L1-resident across a row
+          } else {
+            vb[u][f] = __ldg(A.g3 + (r.x >= A.n_edges_in ? A.plane : 0) + (int64_t)r.z * D4 + c);
+            vc[u][f] = __ldg(A.x + (int64_t)r.y * D4 + c);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        add4(acc[f], mul3s(__int_as_float(r0.w), b0[f], __ldg(rel + (int64_t)r0.z * D4 + c), a0[f]));
-        add4(acc[f], mul3s(__int_as_float(r1.w), b1[f], __ldg(rel + (int64_t)r1.z * D4 + c), a1[f]));
-      }
-    }
-  }
-  if (e < it.y) {
-    const int4 r0 = ld_rec(rec + e);
+    for (int u = 0; u < kUnroll; ++u) {
+      if (p + u < ce) {                                       // warp-uniform
+        const int4 r = rc[u];
+        const uint32_t flags = rf[u];
+        const int64_t row = flags & kRowMask;
+        const float nrm = __int_as_float(r.w);
+        if (flags & kFirst) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        const float4 a = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        const float4 b = __ldg(x + (int64_t)r0.y * D4 + c);
-        add4(acc[f], mul3s(__int_as_float(r0.w), b, __ldg(rel + (int64_t)r0.z * D4 + c), a));
-      }
-    }
-  }
-  float4* out = ((it.w & 1) ? out_final : out_part) + (int64_t)it.z * D4;
+          for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+          started_here = true;
+        }
+        open_row = true;
 #pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const int c = g + f * kGroup;
-    if (c < D4) out[c] = acc[f];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ backward (src rows)
-template <int NF>
-__global__ void __launch_bounds__(kThreads)
-agg_bwd_src_kernel(const float4* __restrict__ x, const float4* __restrict__ rel, const float4* __restrict__ ee,
-                   const float4* __restrict__ g3, const kgc_edge_rec_t* __restrict__ rec,
-                   const kgc_item_t* __restrict__ items, int64_t n_items, int64_t n_nodes, int32_t half_edges,
-                   const float4* __restrict__ loop_addend, float4* __restrict__ d_ee, float4* __restrict__ dx_final,
-                   float4* __restrict__ dx_part, int D4) {
-  const int64_t item = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / kGroup;
-  const int g = threadIdx.x % kGroup;
-  if (item >= n_items) return;
-  const int4 it = __ldg(reinterpret_cast<const int4*>(items + item));
-  const bool final_row = (it.w & 1) != 0;
-  // flags >> 1 carries the source row j when the item writes a partial (out is then a slot id)
-  const int64_t j = final_row ? it.z : (it.w >> 1);
-  const int64_t plane = n_nodes * (int64_t)D4;
-  float4 acc[NF], xj[NF];
+        for (int f = 0; f < NF; ++f) {
+          const int c = lane + f * 32;
+          if (c < D4) {
+            if (MODE == kFwd) {
+              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));
+            } else if (MODE == kBwdSrc) {
+              const float4 pe = scale4(nrm, mul4(vb[u][f], vc[u][f]));          // norm * g[dst] * rel[type]
+              st_stream(A.d_ee + (int64_t)r.x * D4 + c, mul4(pe, vx[u][f]));
+              add4(acc[f], mul4(pe, va[u][f]));
+            } else {
+              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));           // norm * g[dst] * x[src] * ee
+            }
+          }
+        }
+        if (flags & kLast) {                                    // the row ends here
+          float4* out = started_here ? A.out_final + row * D4 : A.carry + (int64_t)slots.x * D4;
 #pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const int c = g + f * kGroup;
-    acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < D4) xj[f] = __ldg(x + j * D4 + c);
-  }
-  int e = it.x;
-  for (; e + 1 < it.y; e += 2) {
-    const int4 r0 = ld_rec(rec + e), r1 = ld_rec(rec + e + 1);
-    const float4* gp0 = g3 + (r0.x >= half_edges ? plane : 0) + (int64_t)r0.y * D4;
-    const float4* gp1 = g3 + (r1.x >= half_edges ? plane : 0) + (int64_t)r1.y * D4;
-    float4 a0[NF], b0[NF], a1[NF], b1[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        a0[f] = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        b0[f] = __ldg(gp0 + c);
-        a1[f] = ld_stream(ee + (int64_t)r1.x * D4 + c);
-        b1[f] = __ldg(gp1 + c);
+          for (int f = 0; f < NF; ++f) {
+            const int c = lane + f * 32;
+            if (c < D4) {
+              float4 v = acc[f];
+              if (MODE == kBwdSrc && started_here && A.addend != nullptr) add4(v, __ldg(A.addend + row * D4 + c));
+              out[c] = v;
+            }
+          }
+          open_row = false;
+        }
       }
     }
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        const float4 p0 = scale4(__int_as_float(r0.w), mul4(b0[f], __ldg(rel + (int64_t)r0.z * D4 + c)));
-        const float4 p1 = scale4(__int_as_float(r1.w), mul4(b1[f], __ldg(rel + (int64_t)r1.z * D4 + c)));
-        st_stream(d_ee + (int64_t)r0.x * D4 + c, mul4(p0, xj[f]));
-        st_stream(d_ee + (int64_t)r1.x * D4 + c, mul4(p1, xj[f]));
-        add4(acc[f], mul4(p0, a0[f]));
-        add4(acc[f], mul4(p1, a1[f]));
-      }
+    for (int u = 0; u < kUnroll; ++u) {
+      rc[u] = rn[u];
+      rf[u] = fn[u];
     }
   }
-  if (e < it.y) {
-    const int4 r0 = ld_rec(rec + e);
-    const float4* gp0 = g3 + (r0.x >= half_edges ? plane : 0) + (int64_t)r0.y * D4;
+  if (open_row) {                                               // the row continues in the next chunk
+    float4* out = A.carry + (int64_t)slots.y * D4;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        const float4 a = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        const float4 p0 = scale4(__int_as_float(r0.w), mul4(__ldg(gp0 + c), __ldg(rel + (int64_t)r0.z * D4 + c)));
-        st_stream(d_ee + (int64_t)r0.x * D4 + c, mul4(p0, xj[f]));
-        add4(acc[f], mul4(p0, a));
-      }
-    }
-  }
-  if (final_row) {
-    float4* out = dx_final + j * D4;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        float4 v = acc[f];
-        if (loop_addend != nullptr) add4(v, __ldg(loop_addend + j * D4 + c));     // self-loop term of d_x
-        out[c] = v;
-      }
-    }
-  } else {
-    float4* out = dx_part + (int64_t)it.z * D4;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
+      const int c = lane + f * 32;
       if (c < D4) out[c] = acc[f];
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ backward (type rows)
-template <int NF>
-__global__ void __launch_bounds__(kThreads)
-agg_bwd_rel_kernel(const float4* __restrict__ x, const float4* __restrict__ ee, const float4* __restrict__ g3,
-                   const kgc_edge_rec_t* __restrict__ rec, const kgc_item_t* __restrict__ items, int64_t n_items,
-                   int64_t n_nodes, int32_t half_edges, float4* __restrict__ out_final,
-                   float4* __restrict__ out_part, int D4) {
-  const int64_t item = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / kGroup;
-  const int g = threadIdx.x % kGroup;
-  if (item >= n_items) return;
-  const int4 it = __ldg(reinterpret_cast<const int4*>(items + item));
-  const int64_t plane = n_nodes * (int64_t)D4;
-  float4 acc[NF];
-#pragma unroll
-  for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e = it.x;
-  for (; e + 1 < it.y; e += 2) {
-    const int4 r0 = ld_rec(rec + e), r1 = ld_rec(rec + e + 1);
-    const float4* gp0 = g3 + (r0.x >= half_edges ? plane : 0) + (int64_t)r0.z * D4;
-    const float4* gp1 = g3 + (r1.x >= half_edges ? plane : 0) + (int64_t)r1.z * D4;
-    float4 a0[NF], a1[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        a0[f] = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        a1[f] = ld_stream(ee + (int64_t)r1.x * D4 + c);
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        add4(acc[f], mul3s(__int_as_float(r0.w), __ldg(gp0 + c), __ldg(x + (int64_t)r0.y * D4 + c), a0[f]));
-        add4(acc[f], mul3s(__int_as_float(r1.w), __ldg(gp1 + c), __ldg(x + (int64_t)r1.y * D4 + c), a1[f]));
-      }
-    }
-  }
-  if (e < it.y) {
-    const int4 r0 = ld_rec(rec + e);
-    const float4* gp0 = g3 + (r0.x >= half_edges ? plane : 0) + (int64_t)r0.z * D4;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const int c = g + f * kGroup;
-      if (c < D4) {
-        const float4 a = ld_stream(ee + (int64_t)r0.x * D4 + c);
-        add4(acc[f], mul3s(__int_as_float(r0.w), __ldg(gp0 + c), __ldg(x + (int64_t)r0.y * D4 + c), a));
-      }
-    }
-  }
-  float4* out = ((it.w & 1) ? out_final : out_part) + (int64_t)it.z * D4;
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const int c = g + f * kGroup;
-    if (c < D4) out[c] = acc[f];
-  }
+// out[rows[i]] = addend ? addend[rows[i]] : 0   (rows without any edge record)
+__global__ void rows_fill_kernel(const int32_t* __restrict__ rows, int64_t n_rows, const float4* __restrict__ addend,
+                                 float4* __restrict__ out, int D4) {
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (i >= n_rows) return;
+  const int64_t r = rows[i];
+  for (int c = lane; c < D4; c += 32)
+    out[r * D4 + c] = addend ? __ldg(addend + r * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------ higher levels
@@ -318,21 +273,73 @@ inline int check_dim(int32_t D, int* D4, int* NF) {
     default: { constexpr int NF = 8; __VA_ARGS__; } break; \
   }
 
+template <int MODE>
+int launch_stream(const StreamArgs& A, cudaStream_t st) {
+  if (A.n_rec == 0) return 0;
+  const int64_t n_chunks = ceil_div(A.n_rec, kChunk);
+  const unsigned grid = (unsigned)ceil_div(n_chunks, kWarpsPerBlock);
+  if (A.D4 <= 32) {
+    agg_stream_kernel<MODE, 1><<<grid, kThreads, 0, st>>>(A);
+  } else {
+    agg_stream_kernel<MODE, 2><<<grid, kThreads, 0, st>>>(A);
+  }
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 }  // namespace kgc
 
 using namespace kgc;
 
 extern "C" int kgc_agg_fwd(const float* x, const float* rel, const float* ee, const kgc_edge_rec_t* rec_dst,
-                           const kgc_item_t* items, int64_t n_items, float* out_final, float* out_part, int32_t D,
-                           void* stream) {
+                           const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec, float* out_final,
+                           float* carry, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
-  if (n_items == 0) return 0;
-  const unsigned grid = (unsigned)ceil_div(n_items * kGroup, kThreads);
-  KGC_DISPATCH_NF(nf, (agg_fwd_kernel<NF><<<grid, kThreads, 0, as_stream(stream)>>>(
-                          (const float4*)x, (const float4*)rel, (const float4*)ee, rec_dst, items, n_items,
-                          (float4*)out_final, (float4*)out_part, D4)));
+  StreamArgs A = {};
+  A.x = (const float4*)x; A.rel = (const float4*)rel; A.ee = (const float4*)ee;
+  A.rec = rec_dst; A.rowflags = rowflags; A.chunks = chunks;
+  A.out_final = (float4*)out_final; A.carry = (float4*)carry;
+  A.n_rec = n_rec; A.D4 = D4;
+  return launch_stream<kFwd>(A, as_stream(stream));
+}
+
+extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
+                               const kgc_edge_rec_t* rec_src, const uint32_t* rowflags, const kgc_chunk_t* chunks,
+                               int64_t n_rec, int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend,
+                               float* d_ee, float* dx_final, float* carry, int32_t D, void* stream) {
+  int D4, nf;
+  KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
+  StreamArgs A = {};
+  A.x = (const float4*)x; A.rel = (const float4*)rel; A.ee = (const float4*)ee; A.g3 = (const float4*)g3;
+  A.addend = (const float4*)loop_addend;
+  A.rec = rec_src; A.rowflags = rowflags; A.chunks = chunks;
+  A.out_final = (float4*)dx_final; A.carry = (float4*)carry; A.d_ee = (float4*)d_ee;
+  A.n_rec = n_rec; A.plane = n_dst_rows * (int64_t)D4; A.n_edges_in = (int32_t)n_edges_in; A.D4 = D4;
+  return launch_stream<kBwdSrc>(A, as_stream(stream));
+}
+
+extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3, const kgc_edge_rec_t* rec_type,
+                               const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec, int64_t n_dst_rows,
+                               int64_t n_edges_in, float* drel_final, float* carry, int32_t D, void* stream) {
+  int D4, nf;
+  KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
+  StreamArgs A = {};
+  A.x = (const float4*)x; A.ee = (const float4*)ee; A.g3 = (const float4*)g3;
+  A.rec = rec_type; A.rowflags = rowflags; A.chunks = chunks;
+  A.out_final = (float4*)drel_final; A.carry = (float4*)carry;
+  A.n_rec = n_rec; A.plane = n_dst_rows * (int64_t)D4; A.n_edges_in = (int32_t)n_edges_in; A.D4 = D4;
+  return launch_stream<kBwdRel>(A, as_stream(stream));
+}
+
+extern "C" int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, float* out, int32_t D,
+                             void* stream) {
+  int D4, nf;
+  KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
+  if (n_rows == 0) return 0;
+  rows_fill_kernel<<<(unsigned)ceil_div(n_rows * 32, 256), 256, 0, as_stream(stream)>>>(rows, n_rows, (const float4*)addend,
+                                                                                   (float4*)out, D4);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -345,36 +352,6 @@ extern "C" int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, in
   KGC_DISPATCH_NF(nf, (rows_reduce_kernel<NF><<<(unsigned)n_items, kThreads, 0, as_stream(stream)>>>(
                           (const float4*)part_in, items, (float4*)out_final, (float4*)out_part,
                           (const float4*)addend, D4)));
-  KGC_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
-                               const kgc_edge_rec_t* rec_src, const kgc_item_t* items, int64_t n_items,
-                               int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend, float* d_ee,
-                               float* dx_final, float* dx_part, int32_t D, void* stream) {
-  int D4, nf;
-  KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
-  if (n_items == 0) return 0;
-  const unsigned grid = (unsigned)ceil_div(n_items * kGroup, kThreads);
-  KGC_DISPATCH_NF(nf, (agg_bwd_src_kernel<NF><<<grid, kThreads, 0, as_stream(stream)>>>(
-                          (const float4*)x, (const float4*)rel, (const float4*)ee, (const float4*)g3, rec_src, items,
-                          n_items, n_dst_rows, (int32_t)n_edges_in, (const float4*)loop_addend, (float4*)d_ee,
-                          (float4*)dx_final, (float4*)dx_part, D4)));
-  KGC_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3, const kgc_edge_rec_t* rec_type,
-                               const kgc_item_t* items, int64_t n_items, int64_t n_dst_rows, int64_t n_edges_in,
-                               float* drel_final, float* drel_part, int32_t D, void* stream) {
-  int D4, nf;
-  KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
-  if (n_items == 0) return 0;
-  const unsigned grid = (unsigned)ceil_div(n_items * kGroup, kThreads);
-  KGC_DISPATCH_NF(nf, (agg_bwd_rel_kernel<NF><<<grid, kThreads, 0, as_stream(stream)>>>(
-                          (const float4*)x, (const float4*)ee, (const float4*)g3, rec_type, items, n_items, n_dst_rows,
-                          (int32_t)n_edges_in, (float4*)drel_final, (float4*)drel_part, D4)));
   KGC_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-CHUNK0 = 32      # edge records per level-0 item (one 8-lane group walks them)
+CHUNK0 = 32      # build_levels default fan-in of the first level
 CHUNK1 = 1024    # partial rows per item on the higher levels (one 256-thread block)
 
 
@@ -49,15 +49,69 @@ def build_levels(seg_beg, seg_end, seg_row, chunk0=CHUNK0, chunk1=CHUNK1):
         chunk = chunk1
 
 
-class ReducePlan(object):
-    """Device copy of the level tables of one segmented reduction."""
+CHUNK_EDGES = 32  # KGC_CHUNK_EDGES: sorted records per streaming chunk (one warp)
 
-    def __init__(self, levels, device):
-        self.levels = [(torch.from_numpy(it).to(device), int(it.shape[0]), n_part) for it, n_part in levels]
-        self.max_part = max(n_part for _, _, n_part in self.levels)
 
-    def num_items(self):
-        return [n for _, n, _ in self.levels]
+def build_stream_plan(seg_beg, seg_end, seg_row, n_rec, chunk=CHUNK_EDGES, fan_in=CHUNK1):
+    """Host-side scheduling of one streaming aggregation (pure integer numpy).
+
+    The segments [seg_beg, seg_end) tile the sorted record array in order (empty segments allowed); segment s
+    reduces into output row seg_row[s].  Returns dict with
+      rowflags [n_rec] uint32   row | first-record-of-segment << 30 | last-record-of-segment << 31
+      chunks   [n_chunks, 2] int32  (head_slot, tail_slot) carry rows of every chunk of ``chunk`` records, -1 if unused
+      n_carry                   number of carry rows
+      fill_rows [k] int32       output rows of the empty segments (written by kgc_rows_fill)
+      levels                    build_levels() tables that reduce the carry rows of the rows spanning several chunks
+    A row's carry rows get consecutive slot numbers in chunk order, so each spanning row is one contiguous
+    segment of the carry array."""
+    beg = np.asarray(seg_beg, dtype=np.int64)
+    end = np.asarray(seg_end, dtype=np.int64)
+    row = np.asarray(seg_row, dtype=np.int64)
+    assert row.size == 0 or int(row.max()) < (1 << 30)
+    length = end - beg
+    nz = length > 0
+    rec_seg = np.repeat(np.arange(beg.shape[0], dtype=np.int64), length)
+    assert rec_seg.shape[0] == n_rec
+    flags = row[rec_seg].astype(np.uint32)
+    flags[beg[nz]] |= np.uint32(1 << 30)
+    flags[end[nz] - 1] |= np.uint32(1 << 31)
+    n_chunks = -(-n_rec // chunk) if n_rec else 0
+    cb = np.arange(n_chunks, dtype=np.int64) * chunk
+    ce = np.minimum(cb + chunk, n_rec)
+    if n_chunks:
+        lead = rec_seg[cb]                               # segment of the chunk's first record
+        trail = rec_seg[ce - 1]                          # ... and of its last record
+        needs_head = (beg[lead] < cb) & (end[lead] <= ce)    # began earlier and ends inside this chunk
+        needs_tail = end[trail] > ce                         # still open at the end of the chunk
+    else:
+        needs_head = needs_tail = np.zeros(0, dtype=bool)
+    inter = np.stack([needs_head, needs_tail], 1).reshape(-1)
+    slot = np.cumsum(inter) - 1
+    slots = np.where(inter, slot, -1).reshape(-1, 2).astype(np.int32)
+    n_carry = int(inter.sum())
+    # rows spanning several chunks: carry rows tail(c_first) .. head(c_last), consecutive by construction
+    c_first = beg // chunk
+    c_last = (end - 1) // chunk
+    span = nz & (c_last > c_first)
+    s_beg = slots[c_first[span], 1].astype(np.int64)
+    s_end = slots[c_last[span], 0].astype(np.int64) + 1
+    assert (s_end - s_beg == (c_last - c_first)[span] + 1).all()
+    levels = build_levels(s_beg, s_end, row[span], fan_in, fan_in) if span.any() else []
+    return {'rowflags': flags, 'chunks': slots, 'n_carry': n_carry, 'fill_rows': row[~nz].astype(np.int32),
+            'levels': levels}
+
+
+class StreamPlan(object):
+    """Device copy of one streaming-aggregation schedule (see build_stream_plan)."""
+
+    def __init__(self, sp, n_rec, device):
+        self.n_rec = int(n_rec)
+        self.rowflags = torch.from_numpy(sp['rowflags'].view(np.int32)).to(device)
+        self.chunks = torch.from_numpy(np.ascontiguousarray(sp['chunks'])).to(device)
+        self.n_carry = sp['n_carry']
+        self.fill_rows = torch.from_numpy(sp['fill_rows']).to(device)
+        self.n_fill = int(sp['fill_rows'].shape[0])
+        self.levels = [(torch.from_numpy(it).to(device), int(it.shape[0]), n_part) for it, n_part in sp['levels']]
 
 
 class GraphPlan(object):
@@ -117,13 +171,15 @@ class GraphPlan(object):
         rm_dst = self.rowmid_dst.cpu().numpy().astype(np.int64)
         rp_src = self.rowptr_src.cpu().numpy().astype(np.int64)
         rp_typ = self.rowptr_type.cpu().numpy().astype(np.int64)
-        rows = np.arange(N, dtype=np.int64)
+        # forward: records of dst row i = [rowptr[i], rowmid[i]) (in half, output row i) then [rowmid[i], rowptr[i+1])
+        # (out half, output row Nd + i): 2 * Nd segments in record order
+        fb = np.stack([rp_dst[:-1], rm_dst], 1).reshape(-1)
+        fe = np.stack([rm_dst, rp_dst[1:]], 1).reshape(-1)
         drows = np.arange(Nd, dtype=np.int64)
-        # forward: row i of plane 0 (in half) = [rowptr, rowmid), row Nd+i of plane 1 (out half) = [rowmid, rowptr+1)
-        self.fwd = ReducePlan(build_levels(np.concatenate([rp_dst[:-1], rm_dst]), np.concatenate([rm_dst, rp_dst[1:]]),
-                                           np.concatenate([drows, drows + Nd])), dev)
-        self.bwd_src = ReducePlan(build_levels(rp_src[:-1], rp_src[1:], rows), dev)
-        self.bwd_rel = ReducePlan(build_levels(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64)), dev)
+        fr = np.stack([drows, drows + Nd], 1).reshape(-1)
+        self.fwd = StreamPlan(build_stream_plan(fb, fe, fr, n2), n2, dev)
+        self.bwd_src = StreamPlan(build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2), n2, dev)
+        self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64), n2), n2, dev)
         self._scratch = {}
 
     def scratch(self, name, shape, dtype=torch.float32):
@@ -135,17 +191,19 @@ class GraphPlan(object):
             self._scratch[key] = t
         return t
 
-    def run_reduction(self, rp, level0, out_final, D, addend=None, tag=''):
-        """Launch level 0 through ``level0(items, n_items, out_final, out_part)`` and the higher levels
-        through kgc_rows_reduce, chaining the partial-row buffers."""
-        prev = None
-        for li, (items, n_items, n_part) in enumerate(rp.levels):
+    def run_reduction(self, sp, level0, out_final, D, addend=None, tag=''):
+        """Launch the streaming kernel through ``level0(sp, out_final, carry)``, fill the rows without records and
+        reduce the carry rows of chunk-spanning rows through kgc_rows_reduce (fixed order, deterministic)."""
+        carry = self.scratch(tag + 'carry', (max(sp.n_carry, 1), D))
+        level0(sp, out_final, carry)
+        if sp.n_fill:
+            _lib.call('kgc_rows_fill', _lib.ptr(sp.fill_rows), sp.n_fill, _lib.ptr(addend), _lib.ptr(out_final), D,
+                      _lib.stream())
+        prev = carry
+        for li, (items, n_items, n_part) in enumerate(sp.levels):
             part = self.scratch('{}part{}'.format(tag, li), (n_part, D)) if n_part else None
-            if li == 0:
-                level0(items, n_items, out_final, part)
-            else:
-                _lib.call('kgc_rows_reduce', _lib.ptr(prev), _lib.ptr(items), n_items, _lib.ptr(out_final),
-                          _lib.ptr(part), _lib.ptr(addend), D, _lib.stream())
+            _lib.call('kgc_rows_reduce', _lib.ptr(prev), _lib.ptr(items), n_items, _lib.ptr(out_final),
+                      _lib.ptr(part), _lib.ptr(addend), D, _lib.stream())
             prev = part
 
 

@@ -59,6 +59,95 @@ def test_build_levels_empty_rows_write_zero():
     assert levels[0][0].tolist() == [[0, 0, 0, 1], [0, 2, 1, 3], [2, 2, 2, 5]]
 
 
+def simulate_stream(sp, values, n_out, chunk=32):
+    """What kgc_agg_* (one warp per chunk) + kgc_rows_fill + kgc_rows_reduce do, in numpy."""
+    out = np.full(n_out, np.nan)
+    carry = np.full(max(sp['n_carry'], 1), np.nan)
+    flags = sp['rowflags']
+    n_rec = flags.shape[0]
+    for c in range(sp['chunks'].shape[0]):
+        head, tail = sp['chunks'][c]
+        cb, ce = c * chunk, min((c + 1) * chunk, n_rec)
+        started = bool(flags[cb] & (1 << 30))
+        acc, open_row = 0.0, False
+        for p in range(cb, ce):
+            row = int(flags[p] & 0x3FFFFFFF)
+            if flags[p] & (1 << 30):
+                acc, started = 0.0, True
+            open_row = True
+            acc += values[p]
+            if flags[p] & (1 << 31):
+                if started:
+                    assert np.isnan(out[row])
+                    out[row] = acc
+                else:
+                    assert head >= 0 and np.isnan(carry[head])
+                    carry[head] = acc
+                open_row = False
+        if open_row:
+            assert tail >= 0 and np.isnan(carry[tail])
+            carry[tail] = acc
+    for r in sp['fill_rows']:
+        assert np.isnan(out[r])
+        out[r] = 0.0
+    cur = carry
+    for items, n_part in sp['levels']:
+        part = np.full(n_part, np.nan)
+        for beg, end, o, fl in items.tolist():
+            s = cur[beg:end].sum()
+            assert not np.isnan(s)
+            if fl & 1:
+                assert np.isnan(out[o])
+                out[o] = s
+            else:
+                part[o] = s
+        cur = part
+    return out
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3])
+def test_stream_plan_exact(seed):
+    """Every output row is produced exactly once and equals the segment sum, whatever the chunk alignment."""
+    from kgc_gcn_b200 import build_stream_plan
+    rng = np.random.default_rng(seed)
+    S = 300
+    lens = rng.integers(0, 6, S)
+    lens[5], lens[100], lens[S - 1] = 40000, 33, 1024 * 32 + 7      # hubs: several fix-up levels
+    if seed == 3:
+        lens[:] = 0
+        lens[17] = 5                                                   # almost everything empty
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    rows = rng.permutation(S)
+    n_rec = int(ptr[-1])
+    sp = build_stream_plan(ptr[:-1], ptr[1:], rows, n_rec)
+    vals = rng.integers(-5, 6, n_rec).astype(np.float64)
+    out = simulate_stream(sp, vals, S)
+    exp = np.array([vals[ptr[i]:ptr[i + 1]].sum() for i in range(S)])
+    np.testing.assert_array_equal(out[rows], exp)
+    assert sp['chunks'].shape == (-(-n_rec // 32), 2)
+    for items, _ in sp['levels']:
+        assert (items[:, 1] - items[:, 0]).max() <= 1024
+
+
+def test_stream_plan_forward_layout():
+    """Two planes interleaved in record order (in half then out half of every dst row), as GraphPlan builds it."""
+    from kgc_gcn_b200 import build_stream_plan
+    rowptr = np.array([0, 3, 3, 70, 71])
+    rowmid = np.array([1, 3, 40, 70])
+    fb = np.stack([rowptr[:-1], rowmid], 1).reshape(-1)
+    fe = np.stack([rowmid, rowptr[1:]], 1).reshape(-1)
+    fr = np.stack([np.arange(4), np.arange(4) + 4], 1).reshape(-1)
+    sp = build_stream_plan(fb, fe, fr, 71)
+    vals = np.arange(71, dtype=np.float64)
+    out = simulate_stream(sp, vals, 8)
+    exp = np.zeros(8)
+    for i in range(4):
+        exp[i] = vals[rowptr[i]:rowmid[i]].sum()
+        exp[4 + i] = vals[rowmid[i]:rowptr[i + 1]].sum()
+    np.testing.assert_array_equal(out, exp)
+    assert sorted(sp['fill_rows'].tolist()) == [1, 3, 5]
+
+
 def params(**kw):
     base = dict(gcn_in_dim=20, gcn_out_dim=200, gcn_drop=0.0, hidden_drop=0.0, feat_drop=0.0, k_w=10, k_h=20,
                 num_filter=2, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=128)
