@@ -24,7 +24,6 @@ constexpr int kGroup = 8;          // kgc_rows_reduce: lanes per partial-row gro
 constexpr int kThreads = 256;
 constexpr int kMaxNF = 8;          // kgc_rows_reduce: D <= 8 * 8 * 4 = 256
 constexpr int kChunk = KGC_CHUNK_EDGES;
-constexpr int kUnroll = 4;         // edges in flight per warp
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr uint32_t kRowMask = 0x3FFFFFFFu, kFirst = 0x40000000u, kLast = 0x80000000u;
 
@@ -63,74 +62,71 @@ struct StreamArgs {
   int32_t D4;
 };
 
-// One warp walks one chunk of kChunk sorted records.
+// One warp walks one chunk of kChunk (= 32) sorted records.  Lane l first loads record cb + l (one coalesced
+// 512-byte + 128-byte request for the whole chunk); every edge's record is then broadcast with warp shuffles,
+// so all gather addresses of the chunk are known after a single memory round trip.  kU edges are in flight per
+// trip: phase 1 issues their DRAM / L2 row loads (edge embedding + the gathered operand), phase 2 consumes them
+// in record order with the L1-resident operands (relation row, and the source row in the backward pass).
+template <int MODE> struct Unroll { static constexpr int value = 8; };
+template <> struct Unroll<kBwdRel> { static constexpr int value = 4; };      // three DRAM/L2 operands per edge
+
 template <int MODE, int NF>
 __global__ void __launch_bounds__(kThreads, 2)
 agg_stream_kernel(const StreamArgs A) {
+  constexpr int kU = Unroll<MODE>::value;
+  static_assert(kChunk == 32, "one record per lane");
   const int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int64_t cb = chunk * kChunk;
   if (cb >= A.n_rec) return;
-  const int64_t ce = cb + kChunk < A.n_rec ? cb + kChunk : A.n_rec;
+  const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
   const int D4 = A.D4;
   const int2 slots = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
-
-  int4 rc[kUnroll];
-  uint32_t rf[kUnroll];
+  const int4 myrec = ld_rec(A.rec + cb + (lane < cnt ? lane : cnt - 1));
+  const uint32_t myflag = __ldg(A.rowflags + cb + (lane < cnt ? lane : cnt - 1));
+  bool active[NF];
 #pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const int64_t p = cb + u < ce ? cb + u : ce - 1;
-    rc[u] = ld_rec(A.rec + p);
-    rf[u] = __ldg(A.rowflags + p);
-  }
+  for (int f = 0; f < NF; ++f) active[f] = lane + f * 32 < D4;
+
   float4 acc[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool started_here = (rf[0] & kFirst) != 0;
+  bool started_here = (__shfl_sync(0xffffffffu, myflag, 0) & kFirst) != 0;
   bool open_row = false;
 
-  for (int64_t p = cb; p < ce; p += kUnroll) {
-    // records of the next trip (their addresses do not depend on data: a pure prefetch)
-    int4 rn[kUnroll];
-    uint32_t fn[kUnroll];
+  for (int base = 0; base < cnt; base += kU) {
+    float4 va[kU][NF], vb[kU][NF], vc[kU][MODE == kBwdRel ? NF : 1];
+    // ---- phase 1: the long-latency row loads of kU edges
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t q = p + kUnroll + u < ce ? p + kUnroll + u : ce - 1;
-      rn[u] = ld_rec(A.rec + q);
-      fn[u] = __ldg(A.rowflags + q);
-    }
-    // all row loads of this trip first, then the arithmetic
-    float4 va[kUnroll][NF], vb[kUnroll][NF], vc[kUnroll][NF], vx[kUnroll][MODE == kBwdSrc ? NF : 1];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int4 r = rc[u];
-      const int64_t row = rf[u] & kRowMask;
+    for (int u = 0; u < kU; ++u) {
+      const int e = base + u < cnt ? base + u : cnt - 1;          // clamped: a duplicate load, never consumed
+      const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
+      const uint32_t ra = (uint32_t)__shfl_sync(0xffffffffu, myrec.y, e);
+      const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         const int c = lane + f * 32;
-        if (c < D4) {
-          va[u][f] = ld_stream(A.ee + (int64_t)r.x * D4 + c);
+        if (active[f]) {
+          va[u][f] = ld_stream(A.ee + (uint64_t)eid * D4 + c);
           if (MODE == kFwd) {
-            vb[u][f] = __ldg(A.x + (int64_t)r.y * D4 + c);
-            vc[u][f] = __ldg(A.rel + (int64_t)r.z * D4 + c);
+            vb[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
           } else if (MODE == kBwdSrc) {
-            vb[u][f] = __ldg(A.g3 + (r.x >= A.n_edges_in ? A.plane : 0) + (int64_t)r.y * D4 + c);
-            vc[u][f] = __ldg(A.rel + (int64_t)r.z * D4 + c);
-            vx[u][f] = __ldg(A.x + row * D4 + c);              // x[src]: L1-resident across a row
+            vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)ra * D4 + c);
           } else {
-            vb[u][f] = __ldg(A.g3 + (r.x >= A.n_edges_in ? A.plane : 0) + (int64_t)r.z * D4 + c);
-            vc[u][f] = __ldg(A.x + (int64_t)r.y * D4 + c);
+            vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)rb * D4 + c);
+            vc[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
           }
         }
       }
     }
+    // ---- phase 2: consume in record order
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (p + u < ce) {                                       // warp-uniform
-        const int4 r = rc[u];
-        const uint32_t flags = rf[u];
+    for (int u = 0; u < kU; ++u) {
+      if (base + u < cnt) {                                      // warp-uniform
+        const int e = base + u;
+        const uint32_t flags = __shfl_sync(0xffffffffu, myflag, e);
+        const float nrm = __int_as_float(__shfl_sync(0xffffffffu, myrec.w, e));
         const int64_t row = flags & kRowMask;
-        const float nrm = __int_as_float(r.w);
         if (flags & kFirst) {
 #pragma unroll
           for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -140,24 +136,27 @@ agg_stream_kernel(const StreamArgs A) {
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const int c = lane + f * 32;
-          if (c < D4) {
+          if (active[f]) {
             if (MODE == kFwd) {
-              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));
+              const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+              add4(acc[f], mul3s(nrm, vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c), va[u][f]));
             } else if (MODE == kBwdSrc) {
-              const float4 pe = scale4(nrm, mul4(vb[u][f], vc[u][f]));          // norm * g[dst] * rel[type]
-              st_stream(A.d_ee + (int64_t)r.x * D4 + c, mul4(pe, vx[u][f]));
+              const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+              const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
+              const float4 pe = scale4(nrm, mul4(vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c)));   // norm * g[dst] * rel
+              st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, __ldg(A.x + row * D4 + c)));        // * x[src] (L1)
               add4(acc[f], mul4(pe, va[u][f]));
             } else {
-              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));           // norm * g[dst] * x[src] * ee
+              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));                                   // norm * g * x * ee
             }
           }
         }
-        if (flags & kLast) {                                    // the row ends here
+        if (flags & kLast) {                                     // the row ends here
           float4* out = started_here ? A.out_final + row * D4 : A.carry + (int64_t)slots.x * D4;
 #pragma unroll
           for (int f = 0; f < NF; ++f) {
             const int c = lane + f * 32;
-            if (c < D4) {
+            if (active[f]) {
               float4 v = acc[f];
               if (MODE == kBwdSrc && started_here && A.addend != nullptr) add4(v, __ldg(A.addend + row * D4 + c));
               out[c] = v;
@@ -167,18 +166,13 @@ agg_stream_kernel(const StreamArgs A) {
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      rc[u] = rn[u];
-      rf[u] = fn[u];
-    }
   }
-  if (open_row) {                                               // the row continues in the next chunk
+  if (open_row) {                                                // the row continues in the next chunk
     float4* out = A.carry + (int64_t)slots.y * D4;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int c = lane + f * 32;
-      if (c < D4) out[c] = acc[f];
+      if (active[f]) out[c] = acc[f];
     }
   }
 }
