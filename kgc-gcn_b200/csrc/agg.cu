@@ -127,6 +127,10 @@ agg_stream_kernel(const StreamArgs A) {
         const uint32_t flags = __shfl_sync(0xffffffffu, myflag, e);
         const float nrm = __int_as_float(__shfl_sync(0xffffffffu, myrec.w, e));
         const int64_t row = flags & kRowMask;
+        // shuffles stay outside the lane predicate: every lane of the warp must take part
+        const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+        const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
+        (void)rb; (void)eid;
         if (flags & kFirst) {
 #pragma unroll
           for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -138,11 +142,8 @@ agg_stream_kernel(const StreamArgs A) {
           const int c = lane + f * 32;
           if (active[f]) {
             if (MODE == kFwd) {
-              const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
               add4(acc[f], mul3s(nrm, vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c), va[u][f]));
             } else if (MODE == kBwdSrc) {
-              const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
-              const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
               const float4 pe = scale4(nrm, mul4(vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c)));   // norm * g[dst] * rel
               st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, __ldg(A.x + row * D4 + c)));        // * x[src] (L1)
               add4(acc[f], mul4(pe, va[u][f]));
