@@ -69,6 +69,7 @@ struct StreamArgs {
 // in record order with the L1-resident operands (relation row, and the source row in the backward pass).
 template <int MODE> struct Unroll { static constexpr int value = 8; };
 template <> struct Unroll<kBwdRel> { static constexpr int value = 4; };      // three DRAM/L2 operands per edge
+template <> struct Unroll<kBwdSrc> { static constexpr int value = 6; };      // ee, g[dst] and x[src] per edge
 
 template <int MODE, int NF>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -95,7 +96,7 @@ agg_stream_kernel(const StreamArgs A) {
   bool open_row = false;
 
   for (int base = 0; base < cnt; base += kU) {
-    float4 va[kU][NF], vb[kU][NF], vc[kU][MODE == kBwdRel ? NF : 1];
+    float4 va[kU][NF], vb[kU][NF], vc[kU][MODE == kFwd ? 1 : NF];
     // ---- phase 1: the long-latency row loads of kU edges
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -103,6 +104,7 @@ agg_stream_kernel(const StreamArgs A) {
       const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
       const uint32_t ra = (uint32_t)__shfl_sync(0xffffffffu, myrec.y, e);
       const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+      const uint32_t erow = __shfl_sync(0xffffffffu, myflag, e) & kRowMask;
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         const int c = lane + f * 32;
@@ -112,6 +114,7 @@ agg_stream_kernel(const StreamArgs A) {
             vb[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
           } else if (MODE == kBwdSrc) {
             vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)ra * D4 + c);
+            vc[u][f] = __ldg(A.x + (uint64_t)erow * D4 + c);                 // x[src]: one miss per row, then L1
           } else {
             vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)rb * D4 + c);
             vc[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
@@ -145,7 +148,7 @@ agg_stream_kernel(const StreamArgs A) {
               add4(acc[f], mul3s(nrm, vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c), va[u][f]));
             } else if (MODE == kBwdSrc) {
               const float4 pe = scale4(nrm, mul4(vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c)));   // norm * g[dst] * rel
-              st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, __ldg(A.x + row * D4 + c)));        // * x[src] (L1)
+              st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, vc[u][f]));                           // * x[src]
               add4(acc[f], mul4(pe, va[u][f]));
             } else {
               add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));                                   // norm * g * x * ee
