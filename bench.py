@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (N entities, R relations, E train triples, synthetic seed)        SURVEY.md 8(d)
     'wn18rr': (40943, 11, 86835, 0),
     'fb15k237': (14541, 237, 272115, 1),
+    'wikidata5m': (4594485, 822, 20614279, 2),
 }
 D_IN, D_OUT, BATCH = 100, 200, 128
 
@@ -495,11 +496,19 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
     }
     peak, peak_src = measured_peaks()
     out = {}
+    cp_dst = torch.empty_like(eed)
+    ms_cp = time_kernel(lambda: cp_dst.copy_(eed), flush)
+    cp_bytes = 2 * eed.numel() * 4
+    out['copy_same_size_reference'] = {'ms': ms_cp, 'algorithmic_bytes': cp_bytes, 'achieved_gbs': cp_bytes / (ms_cp * 1e-3) / 1e9,
+                                       'frac': cp_bytes / (ms_cp * 1e-3) / 1e9 / peak,
+                                       'note': 'torch copy of the edge-embedding table, timed the same way: what a plain '
+                                               'streaming kernel of this size reaches (launch latency + tail included)'}
+    del cp_dst
     for name, fn in fns.items():
         ms = time_kernel(fn, flush)
         gbs = bytes_[name] / (ms * 1e-3) / 1e9
         out[name] = {'ms': ms, 'algorithmic_bytes': bytes_[name], 'achieved_gbs': gbs, 'frac': gbs / peak}
-    top = max(out, key=lambda n: out[n]['ms'])
+    top = max((n for n in out if n.startswith('agg_')), key=lambda n: out[n]['ms'])
     roof = {'kernel': top, 'bound': 'hbm', 'achieved': out[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
             'frac': out[top]['frac'], 'traffic': None, 'peak_source': peak_src,
             'how': 'kernel launched alone through the C ABI, CUDA events on the launch stream, L2 flushed before each launch'}
