@@ -481,9 +481,9 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
     sf, ss, sr = plan.fwd, plan.bwd_src, plan.bwd_rel
     n_f = n_s = n_r = (2 * E + 31) // 32                   # chunks (one warp each)
     fns = {
-        'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), p(eed), p(plan.rec_dst), p(sf.rowflags), p(sf.chunks),
+        'agg_fwd': lambda: L.call('kgc_agg_fwd', p(xd), p(relp), T, p(eed), p(plan.rec_dst), p(sf.rowflags), p(sf.chunks),
                                   sf.n_rec, p(agg), p(pf), D, st()),
-        'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), p(eed), p(g3), p(plan.rec_src), p(ss.rowflags),
+        'agg_bwd_src': lambda: L.call('kgc_agg_bwd_src', p(xd), p(relp), T, p(eed), p(g3), p(plan.rec_src), p(ss.rowflags),
                                       p(ss.chunks), ss.n_rec, N, E, p(g3[2]), p(d_ee), p(d_x), p(ps), D, st()),
         'agg_bwd_rel': lambda: L.call('kgc_agg_bwd_rel', p(xd), p(eed), p(g3), p(plan.rec_type), p(sr.rowflags),
                                       p(sr.chunks), sr.n_rec, N, E, p(d_rel), p(pr), D, st()),

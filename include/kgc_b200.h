@@ -87,7 +87,7 @@ int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64_t* type,
  * deterministic (fixed order, no float atomics).  Rows that lie inside one chunk are written to
  * out_final, chunk-boundary rows to carry (reduced by kgc_rows_reduce), rows without records by
  * kgc_rows_fill.  x [n_nodes,D], rel [n_types,D], ee [n_edges2,D], out_final [*,D], carry [*,D]. */
-int kgc_agg_fwd(const float* x, const float* rel, const float* ee,
+int kgc_agg_fwd(const float* x, const float* rel, int64_t n_types, const float* ee,
                 const kgc_edge_rec_t* rec_dst, const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec,
                 float* out_final, float* carry, int32_t D, void* stream);
 
@@ -107,7 +107,7 @@ int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_ite
  *   d_ee[e]  = p_e (.) x[j]                                  (one row per edge, no reduction)
  *   d_x[j]   = sum_e p_e (.) ee[e]   (+ loop_addend[j], the self-loop term, on final rows when not NULL)
  * half_e = (eid_e >= n_edges_in). */
-int kgc_agg_bwd_src(const float* x, const float* rel, const float* ee, const float* g3,
+int kgc_agg_bwd_src(const float* x, const float* rel, int64_t n_types, const float* ee, const float* g3,
                     const kgc_edge_rec_t* rec_src, const uint32_t* rowflags, const kgc_chunk_t* chunks, int64_t n_rec,
                     int64_t n_dst_rows, int64_t n_edges_in, const float* loop_addend,
                     float* d_ee, float* dx_final, float* carry, int32_t D, void* stream);

@@ -82,7 +82,7 @@ class _ConvFn(torch.autograd.Function):
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
-            _lib.call('kgc_agg_fwd', p(x_full), p(relp), p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
+            _lib.call('kgc_agg_fwd', p(x_full), p(relp), relp.shape[0], p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
                       p(out_final), p(carry), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
 
@@ -167,7 +167,7 @@ class _ConvFn(torch.autograd.Function):
         loop_addend = g3[2] if coll is None else None
 
         def level0_src(sp, out_final, carry):
-            _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), p(ee), p(g3), p(plan.rec_src), p(sp.rowflags), p(sp.chunks),
+            _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), relp.shape[0], p(ee), p(g3), p(plan.rec_src), p(sp.rowflags), p(sp.chunks),
                       sp.n_rec, plan.num_dst_rows, plan.num_edges_in, p(loop_addend), p(d_ee), p(out_final), p(carry),
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
