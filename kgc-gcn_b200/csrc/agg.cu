@@ -15,6 +15,9 @@
 //   * a row that lies inside one chunk is written straight to the output; the (at most two) rows a chunk
 //     shares with its neighbours go to CARRY rows, which kgc_rows_reduce adds in a fixed order.
 // No float atomics anywhere: results are bit-reproducible run to run.
+// Tried and rejected in round 1: staging every operand row with one bulk async copy (cp.async.bulk, UBLKCP) into
+// per-warp shared-memory stages - correct but 0.2-0.3 of the HBM peak: the copy engine retires roughly one 400-byte
+// request per 30 cycles per SM, far below what 128-bit LDGs sustain.
 #include "common.cuh"
 
 namespace kgc {
@@ -24,6 +27,7 @@ constexpr int kGroup = 8;          // kgc_rows_reduce: lanes per partial-row gro
 constexpr int kThreads = 256;
 constexpr int kMaxNF = 8;          // kgc_rows_reduce: D <= 8 * 8 * 4 = 256
 constexpr int kChunk = KGC_CHUNK_EDGES;
+constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr uint32_t kRowMask = 0x3FFFFFFFu, kFirst = 0x40000000u, kLast = 0x80000000u;
 
 __device__ __forceinline__ float4 mul3s(float s, const float4& a, const float4& b, const float4& c) {
@@ -61,163 +65,122 @@ struct StreamArgs {
   int32_t D4;
 };
 
-// ---- PTX: mbarrier + bulk async copy (global -> shared, completes on an mbarrier; SASS: UBLKCP) ----------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+// One warp walks one chunk of kChunk (= 32) sorted records.  Lane l first loads record cb + l (one coalesced
+// 512-byte + 128-byte request for the whole chunk); every edge's record is then broadcast with warp shuffles,
+// so all gather addresses of the chunk are known after a single memory round trip.  kU edges are in flight per
+// trip: phase 1 issues their DRAM / L2 row loads (edge embedding + the gathered operand), phase 2 consumes them
+// in record order with the L1-resident operands (relation row, and the source row in the backward pass).
+template <int MODE> struct Unroll { static constexpr int value = 8; };
+template <> struct Unroll<kBwdRel> { static constexpr int value = 4; };      // three DRAM/L2 operands per edge
+template <> struct Unroll<kBwdSrc> { static constexpr int value = 6; };      // ee, g[dst] and x[src] per edge
 
-// One warp walks one chunk of kChunk (= 32) sorted records (third version; the register-staged second version
-// was co-limited by instruction issue and by 16 warps x 8 edges of loads in flight, ~0.5 of the HBM peak).
-//   1. lane l loads record cb + l (one coalesced request for the whole chunk);
-//   2. lane l issues one bulk async copy per operand ROW of its edge (edge-embedding row, gathered x / g row and,
-//      for large relation tables, the relation row) from global memory straight into the warp's shared-memory
-//      stage: 2-3 x 32 rows (25-38 KB for D = 100) in flight per warp without a single staging register; the copies
-//      complete on the warp's mbarrier (expect_tx = the chunk's bytes);
-//   3. the warp consumes the 32 edges from shared memory in record order (lane c owns float4 column c; a row is
-//      one conflict-free 400-byte LDS wave), writes rows that lie inside the chunk straight to the output and the
-//      <= 2 boundary rows to carry rows.
-// One CTA per SM owns as many such warps as shared memory allows (8 for D = 100); the grid is persistent.
-constexpr int kSmemBudget = 216 * 1024;
-
-template <int MODE, bool kRelBulk, int NF>
-__global__ void __launch_bounds__(512, 1)
-agg_bulk_kernel(const StreamArgs A, const int n_arr, const int64_t n_chunks) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+template <int MODE, int NF>
+__global__ void __launch_bounds__(kThreads, 2)
+agg_stream_kernel(const StreamArgs A) {
+  constexpr int kU = Unroll<MODE>::value;
   static_assert(kChunk == 32, "one record per lane");
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, n_warps = blockDim.x / 32;
+  const int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int64_t cb = chunk * kChunk;
+  if (cb >= A.n_rec) return;
+  const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
   const int D4 = A.D4;
-  const uint32_t row_bytes = (uint32_t)D4 * 16u;
-  const uint32_t arr_bytes = row_bytes * kChunk;
-  uint8_t* stage = smem_raw + (size_t)warp * n_arr * arr_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_warps * n_arr * arr_bytes) + warp;
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncwarp();
-  const float4* s_ee = reinterpret_cast<const float4*>(stage);
-  const float4* s_b = reinterpret_cast<const float4*>(stage + arr_bytes);
-  const float4* s_c = reinterpret_cast<const float4*>(stage + 2 * arr_bytes);     // rel (fwd/bwd_src bulk) or x (bwd_rel)
+  const int2 slots = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
+  const int4 myrec = ld_rec(A.rec + cb + (lane < cnt ? lane : cnt - 1));
+  const uint32_t myflag = __ldg(A.rowflags + cb + (lane < cnt ? lane : cnt - 1));
   bool active[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) active[f] = lane + f * 32 < D4;
-  uint32_t phase = 0;
 
-  for (int64_t chunk = blockIdx.x * (int64_t)n_warps + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * n_warps) {
-    const int64_t cb = chunk * kChunk;
-    const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
-    const int2 slots = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
-    const int4 myrec = ld_rec(A.rec + cb + (lane < cnt ? lane : cnt - 1));
-    const uint32_t myflag = __ldg(A.rowflags + cb + (lane < cnt ? lane : cnt - 1));
-    // ---- issue the chunk's row copies
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * (uint32_t)n_arr * row_bytes);
-    __syncwarp();
-    if (lane < cnt) {
-      const uint32_t eid = (uint32_t)myrec.x, ra = (uint32_t)myrec.y, rb = (uint32_t)myrec.z;
-      bulk_g2s(stage + lane * row_bytes, A.ee + (uint64_t)eid * D4, row_bytes, bar);
-      if (MODE == kFwd) {
-        bulk_g2s(stage + arr_bytes + lane * row_bytes, A.x + (uint64_t)ra * D4, row_bytes, bar);
-        if (kRelBulk) bulk_g2s(stage + 2 * arr_bytes + lane * row_bytes, A.rel + (uint64_t)rb * D4, row_bytes, bar);
-      } else if (MODE == kBwdSrc) {
-        bulk_g2s(stage + arr_bytes + lane * row_bytes, A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)ra * D4,
-                 row_bytes, bar);
-        if (kRelBulk) bulk_g2s(stage + 2 * arr_bytes + lane * row_bytes, A.rel + (uint64_t)rb * D4, row_bytes, bar);
-      } else {
-        bulk_g2s(stage + arr_bytes + lane * row_bytes, A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)rb * D4,
-                 row_bytes, bar);
-        bulk_g2s(stage + 2 * arr_bytes + lane * row_bytes, A.x + (uint64_t)ra * D4, row_bytes, bar);
-      }
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-
-    // ---- consume in record order
-    float4 acc[NF];
+  float4 acc[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool started_here = (__shfl_sync(0xffffffffu, myflag, 0) & kFirst) != 0;
-    bool open_row = false;
-#pragma unroll 4
-    for (int e = 0; e < cnt; ++e) {
-      // shuffles stay outside every lane predicate: all 32 lanes take part
-      const uint32_t flags = __shfl_sync(0xffffffffu, myflag, e);
-      const float nrm = __int_as_float(__shfl_sync(0xffffffffu, myrec.w, e));
-      const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+  for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool started_here = (__shfl_sync(0xffffffffu, myflag, 0) & kFirst) != 0;
+  bool open_row = false;
+
+  for (int base = 0; base < cnt; base += kU) {
+    float4 va[kU][NF], vb[kU][NF], vc[kU][MODE == kFwd ? 1 : NF];
+    // ---- phase 1: the long-latency row loads of kU edges
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int e = base + u < cnt ? base + u : cnt - 1;          // clamped: a duplicate load, never consumed
       const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
-      (void)rb; (void)eid;
-      const int64_t row = flags & kRowMask;
-      if (flags & kFirst) {
-#pragma unroll
-        for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-        started_here = true;
-      }
-      open_row = true;
+      const uint32_t ra = (uint32_t)__shfl_sync(0xffffffffu, myrec.y, e);
+      const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+      const uint32_t erow = __shfl_sync(0xffffffffu, myflag, e) & kRowMask;
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         const int c = lane + f * 32;
         if (active[f]) {
-          const float4 va = s_ee[e * D4 + c];
-          const float4 vb = s_b[e * D4 + c];
+          va[u][f] = ld_stream(A.ee + (uint64_t)eid * D4 + c);
           if (MODE == kFwd) {
-            const float4 vr = kRelBulk ? s_c[e * D4 + c] : __ldg(A.rel + (uint64_t)rb * D4 + c);
-            add4(acc[f], mul3s(nrm, vb, vr, va));                                    // norm * ((x * rel) * ee)
+            vb[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
           } else if (MODE == kBwdSrc) {
-            const float4 vr = kRelBulk ? s_c[e * D4 + c] : __ldg(A.rel + (uint64_t)rb * D4 + c);
-            const float4 pe = scale4(nrm, mul4(vb, vr));                              // norm * g[dst] * rel
-            st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, __ldg(A.x + row * D4 + c)));   // * x[src]
-            add4(acc[f], mul4(pe, va));
+            vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)ra * D4 + c);
+            vc[u][f] = __ldg(A.x + (uint64_t)erow * D4 + c);                 // x[src]: one miss per row, then L1
           } else {
-            add4(acc[f], mul3s(nrm, vb, s_c[e * D4 + c], va));                       // norm * ((g * x) * ee)
+            vb[u][f] = __ldg(A.g3 + ((int)eid >= A.n_edges_in ? A.plane : 0) + (uint64_t)rb * D4 + c);
+            vc[u][f] = __ldg(A.x + (uint64_t)ra * D4 + c);
           }
         }
       }
-      if (flags & kLast) {                                       // the row ends here
-        float4* out = started_here ? A.out_final + row * D4 : A.carry + (int64_t)slots.x * D4;
+    }
+    // ---- phase 2: consume in record order
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (base + u < cnt) {                                      // warp-uniform
+        const int e = base + u;
+        const uint32_t flags = __shfl_sync(0xffffffffu, myflag, e);
+        const float nrm = __int_as_float(__shfl_sync(0xffffffffu, myrec.w, e));
+        const int64_t row = flags & kRowMask;
+        // shuffles stay outside the lane predicate: every lane of the warp must take part
+        const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, myrec.z, e);
+        const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, myrec.x, e);
+        (void)rb; (void)eid;
+        if (flags & kFirst) {
+#pragma unroll
+          for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+          started_here = true;
+        }
+        open_row = true;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const int c = lane + f * 32;
           if (active[f]) {
-            float4 v = acc[f];
-            if (MODE == kBwdSrc && started_here && A.addend != nullptr) add4(v, __ldg(A.addend + row * D4 + c));
-            out[c] = v;
+            if (MODE == kFwd) {
+              add4(acc[f], mul3s(nrm, vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c), va[u][f]));
+            } else if (MODE == kBwdSrc) {
+              const float4 pe = scale4(nrm, mul4(vb[u][f], __ldg(A.rel + (uint64_t)rb * D4 + c)));   // norm * g[dst] * rel
+              st_stream(A.d_ee + (uint64_t)eid * D4 + c, mul4(pe, vc[u][f]));                           // * x[src]
+              add4(acc[f], mul4(pe, va[u][f]));
+            } else {
+              add4(acc[f], mul3s(nrm, vb[u][f], vc[u][f], va[u][f]));                                   // norm * g * x * ee
+            }
           }
         }
-        open_row = false;
-      }
-    }
-    if (open_row) {                                              // the row continues in the next chunk
-      float4* out = A.carry + (int64_t)slots.y * D4;
+        if (flags & kLast) {                                     // the row ends here
+          float4* out = started_here ? A.out_final + row * D4 : A.carry + (int64_t)slots.x * D4;
 #pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const int c = lane + f * 32;
-        if (active[f]) out[c] = acc[f];
+          for (int f = 0; f < NF; ++f) {
+            const int c = lane + f * 32;
+            if (active[f]) {
+              float4 v = acc[f];
+              if (MODE == kBwdSrc && started_here && A.addend != nullptr) add4(v, __ldg(A.addend + row * D4 + c));
+              out[c] = v;
+            }
+          }
+          open_row = false;
+        }
       }
     }
-    __syncwarp();                                                // every lane is done with the stage before it is refilled
+  }
+  if (open_row) {                                                // the row continues in the next chunk
+    float4* out = A.carry + (int64_t)slots.y * D4;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int c = lane + f * 32;
+      if (active[f]) out[c] = acc[f];
+    }
   }
 }
 
@@ -311,37 +274,18 @@ inline int check_dim(int32_t D, int* D4, int* NF) {
     default: { constexpr int NF = 8; __VA_ARGS__; } break; \
   }
 
-template <int MODE, bool kRelBulk, int NF>
-int launch_bulk(const StreamArgs& A, int n_arr, cudaStream_t st) {
+template <int MODE>
+int launch_stream(const StreamArgs& A, cudaStream_t st) {
+  if (A.n_rec == 0) return 0;
   const int64_t n_chunks = ceil_div(A.n_rec, kChunk);
-  const size_t stage = (size_t)n_arr * kChunk * A.D4 * 16;
-  int warps = (int)(kSmemBudget / stage);
-  if (warps > 16) warps = 16;
-  if (warps < 1) return fail("launch_bulk", "row too wide for one shared-memory stage");
-  const size_t smem = warps * stage + 16 * sizeof(uint64_t);
-  auto kern = agg_bulk_kernel<MODE, kRelBulk, NF>;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    KGC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  const unsigned grid = (unsigned)ceil_div(n_chunks, kWarpsPerBlock);
+  if (A.D4 <= 32) {
+    agg_stream_kernel<MODE, 1><<<grid, kThreads, 0, st>>>(A);
+  } else {
+    agg_stream_kernel<MODE, 2><<<grid, kThreads, 0, st>>>(A);
   }
-  int64_t grid = ceil_div(n_chunks, warps);
-  if (grid > kNumSMs) grid = kNumSMs;
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(A, n_arr, n_chunks);
   KGC_LAUNCH_CHECK();
   return 0;
-}
-
-template <int MODE>
-int launch_stream(const StreamArgs& A, int64_t n_types, cudaStream_t st) {
-  if (A.n_rec == 0) return 0;
-  // relation rows ride the bulk copies when the table would not stay in the (small) L1 left beside the stages
-  const bool rel_bulk = MODE != kBwdRel && n_types * (int64_t)A.D4 * 16 > 12 * 1024;
-  const int n_arr = (MODE == kBwdRel || rel_bulk) ? 3 : 2;
-  if (A.D4 <= 32) {
-    return rel_bulk ? launch_bulk<MODE, true, 1>(A, n_arr, st) : launch_bulk<MODE, false, 1>(A, n_arr, st);
-  }
-  return rel_bulk ? launch_bulk<MODE, true, 2>(A, n_arr, st) : launch_bulk<MODE, false, 2>(A, n_arr, st);
 }
 
 }  // namespace
@@ -352,6 +296,7 @@ using namespace kgc;
 extern "C" int kgc_agg_fwd(const float* x, const float* rel, int64_t n_types, const float* ee,
                            const kgc_edge_rec_t* rec_dst, const uint32_t* rowflags, const kgc_chunk_t* chunks,
                            int64_t n_rec, float* out_final, float* carry, int32_t D, void* stream) {
+  (void)n_types;
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   StreamArgs A = {};
@@ -359,7 +304,7 @@ extern "C" int kgc_agg_fwd(const float* x, const float* rel, int64_t n_types, co
   A.rec = rec_dst; A.rowflags = rowflags; A.chunks = chunks;
   A.out_final = (float4*)out_final; A.carry = (float4*)carry;
   A.n_rec = n_rec; A.D4 = D4;
-  return launch_stream<kFwd>(A, n_types, as_stream(stream));
+  return launch_stream<kFwd>(A, as_stream(stream));
 }
 
 extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, int64_t n_types, const float* ee, const float* g3,
@@ -368,13 +313,14 @@ extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, int64_t n_types
                                float* d_ee, float* dx_final, float* carry, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
+  (void)n_types;
   StreamArgs A = {};
   A.x = (const float4*)x; A.rel = (const float4*)rel; A.ee = (const float4*)ee; A.g3 = (const float4*)g3;
   A.addend = (const float4*)loop_addend;
   A.rec = rec_src; A.rowflags = rowflags; A.chunks = chunks;
   A.out_final = (float4*)dx_final; A.carry = (float4*)carry; A.d_ee = (float4*)d_ee;
   A.n_rec = n_rec; A.plane = n_dst_rows * (int64_t)D4; A.n_edges_in = (int32_t)n_edges_in; A.D4 = D4;
-  return launch_stream<kBwdSrc>(A, n_types, as_stream(stream));
+  return launch_stream<kBwdSrc>(A, as_stream(stream));
 }
 
 extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3, const kgc_edge_rec_t* rec_type,
@@ -387,7 +333,7 @@ extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
   A.rec = rec_type; A.rowflags = rowflags; A.chunks = chunks;
   A.out_final = (float4*)drel_final; A.carry = (float4*)carry;
   A.n_rec = n_rec; A.plane = n_dst_rows * (int64_t)D4; A.n_edges_in = (int32_t)n_edges_in; A.D4 = D4;
-  return launch_stream<kBwdRel>(A, 0, as_stream(stream));
+  return launch_stream<kBwdRel>(A, as_stream(stream));
 }
 
 extern "C" int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, float* out, int32_t D,
