@@ -148,6 +148,20 @@ int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pr
                        float keep_scale, int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout,
                        float* d_res3, void* stream);
 
+/* ---- K4b: dense transforms on the tensor cores with fp32-grade accuracy (3xTF32) --------------------------
+ * Replaces the fp32 matmuls of model.py:116 (x_j_rel @ W, after the aggregate-then-transform reordering
+ * agg_h @ W_h) and of its autograd (d_res_h @ W_h^T):   C[M,N] = A[M,K] @ Bt[N,K]^T
+ * A: fp32 row-major, leading dimension lda (a multiple of 4), streamed through TMA; Bt: the small operand,
+ * packed once per call by kgc_gemm_pack_b from B viewed as element (k, n) = B[k*stride_k + n*stride_n]
+ * (hi / lo TF32 split, zero padded; size kgc_gemm_packed_b_bytes).  K <= 256, N <= 1024.
+ * Every fp32 value v is split v = hi + lo (hi = top 19 bits); C = A_hi Bt_hi + A_lo Bt_hi + A_hi Bt_lo is
+ * accumulated in fp32 by tcgen05.mma kind::tf32 - error ~2^-22 relative per product, i.e. fp32-level. */
+size_t kgc_gemm_packed_b_bytes(int32_t N, int32_t K);
+int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t N, int32_t K, float* packed,
+                    void* stream);
+int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
+                int64_t ldc, void* stream);
+
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's
  * query ids qid[B] (int64) and the query->objects CSR (ptr int64 [Q+1], idx int32 [nnz]):

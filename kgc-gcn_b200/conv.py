@@ -29,6 +29,25 @@ def _mm(a, b, out):
     return torch.mm(a, b, out=out)
 
 
+def gemm_nt(a, b_kn, out, plan=None, tag='b'):
+    """out[M, N] = a[M, K] @ b_kn[K, N] on the tensor cores with fp32-grade accuracy (K4b, 3xTF32).
+    ``a`` and ``out`` are row-major (possibly row-strided views); ``b_kn`` is any strided [K, N] view of the small
+    operand (a weight or its transpose): it is split and packed per call (a few KB)."""
+    M, K = a.shape
+    N = b_kn.shape[1]
+    if a.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError('gemm_nt needs unit inner strides')
+    nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(N, K))
+    if nbytes == 0:
+        raise ValueError('gemm_nt: unsupported shape K={} N={}'.format(K, N))
+    packed = plan.scratch('gemm_pack_' + tag, (nbytes // 4,)) if plan is not None else \
+        torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+    p = _lib.ptr
+    _lib.call('kgc_gemm_pack_b', p(b_kn), b_kn.stride(0), b_kn.stride(1), N, K, p(packed), _lib.stream())
+    _lib.call('kgc_gemm_nt', p(a), M, K, a.stride(0), p(packed), N, p(out), out.stride(0), _lib.stream())
+    return out
+
+
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
@@ -89,9 +108,9 @@ class _ConvFn(torch.autograd.Function):
         v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
         w_loop_s = v * w_loop
         res3 = plan.scratch('res3', (3, Nl, Dout))
-        _mm(agg[0], w_in, res3[0])
-        _mm(agg[1], w_out, res3[1])
-        _mm(x, w_loop_s, res3[2])
+        gemm_nt(agg[0], w_in, res3[0], plan, 'f0')
+        gemm_nt(agg[1], w_out, res3[1], plan, 'f1')
+        gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
 
         nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
@@ -148,9 +167,9 @@ class _ConvFn(torch.autograd.Function):
 
         # ---- dense transforms (fp32 GEMMs)
         g3 = plan.scratch('g3', (3, Nl, D))
-        _mm(d_res3[0], w_in.t(), g3[0])
-        _mm(d_res3[1], w_out.t(), g3[1])
-        _mm(d_res3[2], w_loop_s.t(), g3[2])
+        gemm_nt(d_res3[0], w_in.t(), g3[0], plan, 'g0')
+        gemm_nt(d_res3[1], w_out.t(), g3[1], plan, 'g1')
+        gemm_nt(d_res3[2], w_loop_s.t(), g3[2], plan, 'g2')
         # replicated-parameter gradients: one flat buffer so that a partitioned run needs ONE all-reduce
         flat = torch.empty((3 * D * Dout + T * D + (Dout if ctx.has_bias else 0),), dtype=torch.float32, device=dev)
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))

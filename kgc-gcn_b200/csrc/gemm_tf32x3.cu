@@ -1,0 +1,389 @@
+// Dense transforms of the layer on the 5th-generation tensor cores with fp32-grade accuracy ("3xTF32").
+//
+// The reference multiplies in plain fp32 (torch default, TF32 off): res_h = agg_h @ W_h, g_h = d_res_h @ W_h^T
+// (model.py:116 and its autograd).  Nine such N x 100 x 200 GEMMs are half of a training step when left to the
+// fp32 SIMT path (profiles/r01_launches_conv_step.md).  Here every fp32 operand is split into two TF32 numbers,
+//   v = hi + lo,   hi = v with the low 13 mantissa bits cleared (exactly a TF32),  lo = v - hi (exact in fp32),
+// and C = A_hi B_hi + A_lo B_hi + A_hi B_lo is accumulated in fp32 in TMEM by tcgen05.mma kind::tf32: the dropped
+// term A_lo B_lo and the rounding of lo to TF32 are both ~2^-22 relative, i.e. fp32-level.
+//
+//   C[M, N] = A[M, K] @ Bt[N, K]^T        A row-major fp32 (streamed), Bt = the small operand, pre-split and packed
+//
+// Persistent CTAs; a CTA owns one column tile of C (NT <= 112 columns) and keeps the hi / lo tiles of Bt for it
+// resident in shared memory; warp roles:
+//   warp 0      TMA producer: Bt tiles once, then raw fp32 A tiles (128 rows x 32 K, 128-byte swizzle) into a 3-deep ring
+//   warps 2-5   splitter: raw tile -> hi (in place) + lo tile (element-wise on the swizzled bytes, layout-agnostic),
+//               fence.proxy.async, then hand the stage to the MMA warp
+//   warp 1      one thread issues 3 tcgen05.mma (M = 128, N = NT, K = 8) per 8-wide k-step
+//   warps 6-9   epilogue: tcgen05.ld -> fp32 rows of C (each thread owns a row, 128-byte segments)
+//   warp 10     TMEM allocator (2 accumulator stages)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace kgc {
+namespace {
+
+constexpr int kBM = 128;                  // rows of A / C per tile (UMMA M)
+constexpr int kBK = 32;                   // fp32 elements per K block = one 128-byte swizzle row
+constexpr int kUK = 8;                    // K per tf32 MMA
+constexpr int kMaxKB = 8;                 // K <= 256
+constexpr int kStages = 3;
+constexpr int kTileA = kBM * kBK * 4;     // 16 KB
+constexpr int kThreadsG = 352;            // 11 warps
+constexpr int kBBudget = 116 * 1024;      // resident hi + lo tiles of Bt
+constexpr int kTmemColsG = 256;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(s_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          s_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_g(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// K-major tile, 128-byte swizzle (rows of 32 fp32), 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct GemmParams {
+  int64_t M;
+  int32_t N, K;
+  int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles;
+  float* C;
+  int64_t ldc;
+};
+
+__global__ void __launch_bounds__(kThreadsG, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                   const __grid_constant__ CUtensorMap map_blo, const GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int tile_b = P.NT * kBK * 4;                               // bytes of one Bt K-block tile (NT rows x 128 B)
+  const int tile_b_al = (tile_b + 1023) & ~1023;                   // keep every tile 1024-byte aligned (swizzle atoms)
+  uint8_t* s_bhi = base;                                           // [n_kb][tile_b_al]
+  uint8_t* s_blo = s_bhi + P.n_kb * tile_b_al;
+  uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [kStages][hi 16 KB | lo 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + kStages * 2 * kTileA);
+  uint64_t* b_full = bars;
+  uint64_t* raw_full = bars + 1;                                   // [kStages] TMA landed
+  uint64_t* split_full = raw_full + kStages;                       // [kStages] hi/lo ready
+  uint64_t* empty = split_full + kStages;                          // [kStages] MMAs done with the stage
+  uint64_t* acc_full = empty + kStages;                            // [2]
+  uint64_t* acc_empty = acc_full + 2;                              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  if (warp == 0 && lane == 0) {
+    mb_init(b_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mb_init(raw_full + i, 1);
+      mb_init(split_full + i, 4);
+      mb_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mb_init(acc_full + i, 1);
+      mb_init(acc_empty + i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(kTmemColsG)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work: this CTA owns column tile nt and the row tiles mt = first, first + step, ...
+  const int nt = blockIdx.x % P.n_ntiles;
+  const int first = blockIdx.x / P.n_ntiles;
+  const int step = gridDim.x / P.n_ntiles;                         // host launches a multiple of n_ntiles CTAs
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mb_expect_tx(b_full, 2u * P.n_kb * tile_b);
+      for (int kb = 0; kb < P.n_kb; ++kb) {
+        tma_2d(s_bhi + kb * tile_b_al, &map_bhi, b_full, kb * kBK, nt * P.NT);
+        tma_2d(s_blo + kb * tile_b_al, &map_blo, b_full, kb * kBK, nt * P.NT);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = first; mt < P.n_mtiles; mt += step) {
+        for (int kb = 0; kb < P.n_kb; ++kb) {
+          mb_wait(empty + stage, phase ^ 1);
+          mb_expect_tx(raw_full + stage, kTileA);
+          tma_2d(s_a + stage * 2 * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    // ================================================================== splitter: v -> (hi, lo)
+    const int t = threadIdx.x - 64;                                // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = first; mt < P.n_mtiles; mt += step) {
+      for (int kb = 0; kb < P.n_kb; ++kb) {
+        mb_wait(raw_full + stage, phase);
+        uint4* hi = reinterpret_cast<uint4*>(s_a + stage * 2 * kTileA);
+        uint4* lo = hi + kTileA / 16;
+#pragma unroll
+        for (int i = 0; i < kTileA / 16 / 128; ++i) {              // 8 x 16-byte vectors per thread, conflict-free
+          uint4 v = hi[t + i * 128];
+          uint4 h, l;
+          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[t + i * 128] = h;
+          lo[t + i * 128] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mb_arrive(split_full + stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      mb_wait(b_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int mt = first; mt < P.n_mtiles; mt += step) {
+        mb_wait(acc_empty + acc, acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_addr = tmem_base + acc * 128;
+        for (int kb = 0; kb < P.n_kb; ++kb) {
+          mb_wait(split_full + stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int nk = min(kBK / kUK, P.ksteps - kb * (kBK / kUK));
+          const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * 2 * kTileA));
+          const uint64_t a_lo = sw128_desc(s_u32(s_a + stage * 2 * kTileA + kTileA));
+          const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
+          const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
+          for (int k = 0; k < nk; ++k) {                           // + k * 32 bytes along K (16-byte units in the descriptor)
+            umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            umma_tf32(d_addr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          }
+          umma_commit_g(empty + stage);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_g(acc_full + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6 && warp <= 9) {
+    // ================================================================== epilogue: TMEM -> C rows
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int mt = first; mt < P.n_mtiles; mt += step) {
+      mb_wait(acc_full + acc, acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t m = (int64_t)mt * kBM + row;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
+      float* crow = P.C + m * P.ldc + nt * P.NT;
+      const int n_valid = min(P.NT, P.N - nt * P.NT);
+      for (int c0 = 0; c0 < P.NT; c0 += 16) {                     // NT is a multiple of 16
+        uint32_t v[16];
+        tmem_ld16_g(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < P.M) {
+          if (c0 + 16 <= n_valid && ((reinterpret_cast<uintptr_t>(crow + c0) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(crow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_valid) crow[c0 + j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mb_arrive(acc_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 10) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsG) : "memory");
+  }
+}
+
+// Bt_hi / Bt_lo [n_pad, k_pad] from B viewed as element (k, n) = B[k * sk + n * sn]; zero padded
+__global__ void pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t sn, int N, int K, int n_pad, int k_pad,
+                              float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad * k_pad) return;
+  const int n = i / k_pad, k = i % k_pad;
+  float v = 0.f;
+  if (n < N && k < K) v = B[(int64_t)k * sk + (int64_t)n * sn];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    KGC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    KGC_REQUIRE(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return 0;
+}
+// fp32 [rows, cols] with row pitch `pitch` floats -> boxes of 32 (K) x box_rows, 128-byte swizzle, zero fill
+int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+  EncodeTiledFn enc;
+  if (encode_fn(&enc)) return 1;
+  KGC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (pitch * 4) % 16 == 0, "operand must be 16-byte aligned with a 16-byte pitch");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+struct Tiling {
+  int n_kb, k_pad, ksteps, NT, n_ntiles, n_pad;
+};
+int make_tiling(int N, int K, Tiling* t) {
+  if (N <= 0 || K <= 0 || K > kMaxKB * kBK || N > 1024) return 1;
+  t->n_kb = (K + kBK - 1) / kBK;
+  t->k_pad = t->n_kb * kBK;
+  t->ksteps = (K + kUK - 1) / kUK;
+  int nt_max = kBBudget / (2 * t->n_kb * kBK * 4);
+  nt_max = nt_max / 16 * 16;
+  if (nt_max > 128) nt_max = 128;
+  if (nt_max < 16) return 1;
+  t->n_ntiles = (N + nt_max - 1) / nt_max;
+  t->NT = ((N + t->n_ntiles - 1) / t->n_ntiles + 15) / 16 * 16;
+  t->n_pad = t->NT * t->n_ntiles;
+  return 0;
+}
+
+}  // namespace
+}  // namespace kgc
+
+using namespace kgc;
+
+extern "C" size_t kgc_gemm_packed_b_bytes(int32_t N, int32_t K) {
+  Tiling t;
+  if (make_tiling(N, K, &t)) return 0;
+  return (size_t)2 * t.n_pad * t.k_pad * sizeof(float);
+}
+
+extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t N, int32_t K, float* packed,
+                               void* stream) {
+  Tiling t;
+  KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
+  const int total = t.n_pad * t.k_pad;
+  pack_b_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(B, stride_k, stride_n, N, K, t.n_pad, t.k_pad, packed,
+                                                                    packed + total);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
+                           int64_t ldc, void* stream) {
+  Tiling t;
+  KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
+  KGC_REQUIRE(M > 0 && lda >= K && ldc >= N, "bad leading dimensions");
+  CUtensorMap ma, mbh, mbl;
+  const int total = t.n_pad * t.k_pad;
+  if (make_map_f32(&ma, A, M, K, lda, kBM)) return 1;
+  if (make_map_f32(&mbh, packed_b, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
+  if (make_map_f32(&mbl, packed_b + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
+  GemmParams P;
+  P.M = M; P.N = N; P.K = K;
+  P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
+  P.n_mtiles = (int32_t)ceil_div(M, kBM);
+  P.C = C; P.ldc = ldc;
+  const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
+  const size_t smem = (size_t)2 * t.n_kb * tile_b_al + (size_t)kStages * 2 * kTileA + 256 + 1024;
+  KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
+  static size_t attr = 0;
+  if (smem > attr) {
+    KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  // a multiple of n_ntiles CTAs, at most one per SM, never more row-tile owners than row tiles
+  int per = kNumSMs / t.n_ntiles;
+  if (per > P.n_mtiles) per = P.n_mtiles;
+  if (per < 1) per = 1;
+  gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, P);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}

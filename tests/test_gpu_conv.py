@@ -251,3 +251,27 @@ def test_state_dict_names(k):
     for bn in ('conv1.ent_bn', 'conv2.bn0', 'conv2.bn1', 'conv2.bn2'):
         expect |= {bn + s for s in ('.weight', '.bias', '.running_mean', '.running_var', '.num_batches_tracked')}
     assert keys == expect
+
+
+@pytest.mark.parametrize('M,K,N', [(1000, 100, 200), (40943, 200, 100), (5, 12, 20), (129, 36, 24), (300, 256, 17)])
+def test_gemm_tf32x3_fp32_grade(k, M, K, N):
+    """K4b: the 3xTF32 tensor-core GEMM is as close to the exact product as a plain fp32 GEMM is."""
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(K, N, generator=g) * 0.1
+    truth = (a.double() @ b.double())
+    scale = float(truth.abs().max())
+    out = torch.full((M, N), float('nan'), device='cuda')
+    k.gemm_nt(a.cuda(), b.cuda(), out)
+    err = float((out.cpu().double() - truth).abs().max()) / scale
+    err_fp32 = float(((a @ b).double() - truth).abs().max()) / scale
+    assert err <= max(4 * err_fp32, 2e-6), (err, err_fp32)
+    # transposed small operand (strided view) and a row-strided A / C, as the layer uses them
+    bt = (torch.randn(N, K, generator=g) * 0.1)
+    big = torch.randn(M, K + 4, generator=g).cuda()
+    a2 = big[:, :K]
+    out2 = torch.full((M, N + 4), float('nan'), device='cuda')
+    k.gemm_nt(a2, bt.cuda().t(), out2[:, :N])
+    truth2 = a2.cpu().double() @ bt.double().t()
+    assert float((out2[:, :N].cpu().double() - truth2).abs().max()) / float(truth2.abs().max()) <= 2e-6
+    assert torch.isnan(out2[:, N:]).all()                        # nothing written outside the N valid columns
