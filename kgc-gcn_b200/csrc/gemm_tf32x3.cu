@@ -3,9 +3,9 @@
 // The reference multiplies in plain fp32 (torch default, TF32 off): res_h = agg_h @ W_h, g_h = d_res_h @ W_h^T
 // (model.py:116 and its autograd).  Nine such N x 100 x 200 GEMMs are half of a training step when left to the
 // fp32 SIMT path (profiles/r01_launches_conv_step.md).  Here every fp32 operand is split into two TF32 numbers,
-//   v = hi + lo,   hi = v with the low 13 mantissa bits cleared (exactly a TF32),  lo = v - hi (exact in fp32),
-// and C = A_hi B_hi + A_lo B_hi + A_hi B_lo is accumulated in fp32 in TMEM by tcgen05.mma kind::tf32: the dropped
-// term A_lo B_lo and the rounding of lo to TF32 are both ~2^-22 relative, i.e. fp32-level.
+//   v = hi + lo,   hi = v rounded to the nearest TF32 (cvt.rna.tf32.f32),  lo = v - hi (exact in fp32, |lo| <= 2^-11 |v|)
+// rounded to TF32 in turn, and C = A_lo B_hi + A_hi B_lo + A_hi B_hi is accumulated in fp32 in TMEM by tcgen05.mma
+// kind::tf32: the dropped term A_lo B_lo and the rounding of lo are both <= 2^-22 relative, i.e. fp32-level.
 //
 //   C[M, N] = A[M, K] @ Bt[N, K]^T        A row-major fp32 (streamed), Bt = the small operand, pre-split and packed
 //
@@ -73,6 +73,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+__device__ __forceinline__ uint32_t tf32_rn(float v) {      // round to nearest TF32 (10-bit mantissa), result in fp32 bits
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_rn(__uint_as_float(v));
+  lo = tf32_rn(__uint_as_float(v) - __uint_as_float(hi));
 }
 __device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
@@ -184,11 +193,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int i = 0; i < kTileA / 16 / 128; ++i) {              // 8 x 16-byte vectors per thread, conflict-free
           uint4 v = hi[t + i * 128];
           uint4 h, l;
-          h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
           hi[t + i * 128] = h;
           lo[t + i * 128] = l;
         }
@@ -219,9 +227,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
           const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
           for (int k = 0; k < nk; ++k) {                           // + k * 32 bytes along K (16-byte units in the descriptor)
-            umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
             umma_tf32(d_addr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
           }
           umma_commit_g(empty + stage);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -280,9 +288,10 @@ __global__ void pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t s
   const int n = i / k_pad, k = i % k_pad;
   float v = 0.f;
   if (n < N && k < K) v = B[(int64_t)k * sk + (int64_t)n * sn];
-  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  hi[i] = h;
-  lo[i] = v - h;
+  uint32_t h, l;
+  split_tf32(__float_as_uint(v), h, l);
+  hi[i] = __uint_as_float(h);
+  lo[i] = __uint_as_float(l);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -265,6 +265,7 @@ def test_gemm_tf32x3_fp32_grade(k, M, K, N):
     k.gemm_nt(a.cuda(), b.cuda(), out)
     err = float((out.cpu().double() - truth).abs().max()) / scale
     err_fp32 = float(((a @ b).double() - truth).abs().max()) / scale
+    print('gemm_tf32x3 M={} K={} N={}: err {:.2e} (fp32 GEMM {:.2e})'.format(M, K, N, err, err_fp32))
     assert err <= max(4 * err_fp32, 2e-6), (err, err_fp32)
     # transposed small operand (strided view) and a row-strided A / C, as the layer uses them
     bt = (torch.randn(N, K, generator=g) * 0.1)
