@@ -28,10 +28,12 @@ constexpr int kBM = 128;                  // rows of A / C per tile (UMMA M)
 constexpr int kBK = 32;                   // fp32 elements per K block = one 128-byte swizzle row
 constexpr int kUK = 8;                    // K per tf32 MMA
 constexpr int kMaxKB = 8;                 // K <= 256
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;             // raw A ring (TMA targets, split in place into hi)
+constexpr int kLoStages = 2;              // lo tiles live only between the splitter and the MMA
 constexpr int kTileA = kBM * kBK * 4;     // 16 KB
 constexpr int kThreadsG = 352;            // 11 warps
-constexpr int kBBudget = 116 * 1024;      // resident hi + lo tiles of Bt
+constexpr int kBBudget = 88 * 1024;       // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
+                                          // the ring must cover TMA latency + split + MMA, ~6 K-blocks in flight)
 constexpr int kTmemColsG = 256;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,7 +109,7 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
 struct GemmParams {
   int64_t M;
   int32_t N, K;
-  int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles;
+  int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles, stages;
   float* C;
   int64_t ldc;
 };
@@ -122,13 +124,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int tile_b_al = (tile_b + 1023) & ~1023;                   // keep every tile 1024-byte aligned (swizzle atoms)
   uint8_t* s_bhi = base;                                           // [n_kb][tile_b_al]
   uint8_t* s_blo = s_bhi + P.n_kb * tile_b_al;
-  uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [kStages][hi 16 KB | lo 16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + kStages * 2 * kTileA);
+  const int kStages = P.stages;
+  uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [stages][16 KB] raw fp32 tile, split in place into hi
+  uint8_t* s_lo = s_a + kStages * kTileA;                          // [kLoStages][16 KB] lo tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kLoStages * kTileA);
   uint64_t* b_full = bars;
-  uint64_t* raw_full = bars + 1;                                   // [kStages] TMA landed
-  uint64_t* split_full = raw_full + kStages;                       // [kStages] hi/lo ready
-  uint64_t* empty = split_full + kStages;                          // [kStages] MMAs done with the stage
-  uint64_t* acc_full = empty + kStages;                            // [2]
+  uint64_t* raw_full = bars + 1;                                   // [kMaxStages] TMA landed
+  uint64_t* split_full = raw_full + kMaxStages;                    // [kMaxStages] hi/lo ready
+  uint64_t* empty = split_full + kMaxStages;                       // [kMaxStages] MMAs done with the raw/hi stage
+  uint64_t* lo_empty = empty + kMaxStages;                         // [kLoStages] MMAs done with the lo stage
+  uint64_t* acc_full = lo_empty + kLoStages;                       // [2]
   uint64_t* acc_empty = acc_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -139,6 +144,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mb_init(split_full + i, 4);
       mb_init(empty + i, 1);
     }
+    for (int i = 0; i < kLoStages; ++i) mb_init(lo_empty + i, 1);
     for (int i = 0; i < 2; ++i) {
       mb_init(acc_full + i, 1);
       mb_init(acc_empty + i, 4);
@@ -174,7 +180,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kb = 0; kb < P.n_kb; ++kb) {
           mb_wait(empty + stage, phase ^ 1);
           mb_expect_tx(raw_full + stage, kTileA);
-          tma_2d(s_a + stage * 2 * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
+          tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -182,13 +188,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp >= 2 && warp <= 5) {
     // ================================================================== splitter: v -> (hi, lo)
     const int t = threadIdx.x - 64;                                // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, ls = 0;
+    uint32_t phase = 0, lphase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       for (int kb = 0; kb < P.n_kb; ++kb) {
         mb_wait(raw_full + stage, phase);
-        uint4* hi = reinterpret_cast<uint4*>(s_a + stage * 2 * kTileA);
-        uint4* lo = hi + kTileA / 16;
+        mb_wait(lo_empty + ls, lphase ^ 1);                        // the MMAs that read this lo stage have retired
+        uint4* hi = reinterpret_cast<uint4*>(s_a + stage * kTileA);
+        uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * kTileA);
 #pragma unroll
         for (int i = 0; i < kTileA / 16 / 128; ++i) {              // 8 x 16-byte vectors per thread, conflict-free
           uint4 v = hi[t + i * 128];
@@ -204,13 +211,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         __syncwarp();
         if (lane == 0) mb_arrive(split_full + stage);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++ls == kLoStages) { ls = 0; lphase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, ls = 0;
       uint32_t phase = 0, acc_phase = 0;
       mb_wait(b_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -222,8 +230,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mb_wait(split_full + stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int nk = min(kBK / kUK, P.ksteps - kb * (kBK / kUK));
-          const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * 2 * kTileA));
-          const uint64_t a_lo = sw128_desc(s_u32(s_a + stage * 2 * kTileA + kTileA));
+          const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * kTileA));
+          const uint64_t a_lo = sw128_desc(s_u32(s_lo + ls * kTileA));
           const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
           const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
           for (int k = 0; k < nk; ++k) {                           // + k * 32 bytes along K (16-byte units in the descriptor)
@@ -232,7 +240,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
           }
           umma_commit_g(empty + stage);
+          umma_commit_g(lo_empty + ls);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++ls == kLoStages) ls = 0;
         }
         umma_commit_g(acc_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -381,8 +391,12 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
   P.C = C; P.ldc = ldc;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
-  const size_t smem = (size_t)2 * t.n_kb * tile_b_al + (size_t)kStages * 2 * kTileA + 256 + 1024;
-  KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
+  const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + (size_t)kLoStages * kTileA + 512 + 1024;
+  int stages = (int)((226 * 1024 - fixed) / kTileA);
+  if (stages > kMaxStages) stages = kMaxStages;
+  KGC_REQUIRE(stages >= 2, "shared-memory plan does not fit");
+  P.stages = stages;
+  const size_t smem = fixed + (size_t)stages * kTileA;
   static size_t attr = 0;
   if (smem > attr) {
     KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
