@@ -11,11 +11,11 @@
 //
 // Persistent CTAs; a CTA owns one column tile of C (NT <= 112 columns) and keeps the hi / lo tiles of Bt for it
 // resident in shared memory; warp roles:
-//   warp 0      TMA producer: Bt tiles once, then raw fp32 A tiles (128 rows x 32 K, 128-byte swizzle) into a 3-deep ring
+//   warp 0      TMA producer: Bt tiles once, then raw fp32 A tiles (128 rows x 32 K, 128-byte swizzle) into a 4-6 deep ring
 //   warps 2-5   splitter: raw tile -> hi (in place) + lo tile (element-wise on the swizzled bytes, layout-agnostic),
 //               fence.proxy.async, then hand the stage to the MMA warp
 //   warp 1      one thread issues 3 tcgen05.mma (M = 128, N = NT, K = 8) per 8-wide k-step
-//   warps 6-9   epilogue: tcgen05.ld -> fp32 rows of C (each thread owns a row, 128-byte segments)
+//   warps 6-9   epilogue: tcgen05.ld -> 32x32 transpose through shared memory -> coalesced 128-byte row segments of C
 //   warp 10     TMEM allocator (2 accumulator stages)
 #include <cuda.h>
 
@@ -35,6 +35,7 @@ constexpr int kThreadsG = 352;            // 11 warps
 constexpr int kBBudget = 88 * 1024;       // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
                                           // the ring must cover TMA latency + split + MMA, ~6 K-blocks in flight)
 constexpr int kTmemColsG = 256;
+constexpr int kEpiStage = 4 * 32 * 33 * 4 + 128;  // epilogue transpose tiles (16,896 B) + pad to keep the barriers 8-byte aligned
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
@@ -88,12 +89,15 @@ __device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& l
 __device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_g(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld32_g(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
 // K-major tile, 128-byte swizzle (rows of 32 fp32), 8-row atoms 1024 B apart
@@ -127,7 +131,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int kStages = P.stages;
   uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [stages][16 KB] raw fp32 tile, split in place into hi
   uint8_t* s_lo = s_a + kStages * kTileA;                          // [kLoStages][16 KB] lo tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kLoStages * kTileA);
+  uint8_t* s_stage = s_lo + kLoStages * kTileA;                    // [4 epilogue warps][32 x 33 floats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kEpiStage);
   uint64_t* b_full = bars;
   uint64_t* raw_full = bars + 1;                                   // [kMaxStages] TMA landed
   uint64_t* split_full = raw_full + kMaxStages;                    // [kMaxStages] hi/lo ready
@@ -249,33 +254,34 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp >= 6 && warp <= 9) {
-    // ================================================================== epilogue: TMEM -> C rows
+    // ================================================================== epilogue: TMEM -> smem transpose -> coalesced C rows
+    // A thread owns a TMEM lane (= a row of C), so storing straight from registers would issue 32 scattered
+    // 16-byte stores per instruction (measured: the LSU then bounds the whole kernel).  Each warp transposes its
+    // 32 x 32 block through a padded shared-memory tile and writes whole 128-byte row segments.
     const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
+    float* stg = reinterpret_cast<float*>(s_stage) + (warp - 6) * (32 * 33);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       mb_wait(acc_full + acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t m = (int64_t)mt * kBM + row;
+      const int64_t m0 = (int64_t)mt * kBM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
-      float* crow = P.C + m * P.ldc + nt * P.NT;
       const int n_valid = min(P.NT, P.N - nt * P.NT);
-      for (int c0 = 0; c0 < P.NT; c0 += 16) {                     // NT is a multiple of 16
-        uint32_t v[16];
-        tmem_ld16_g(taddr + c0, v);
+      const int rows_valid = (int)min((int64_t)32, P.M - m0);
+      for (int c0 = 0; c0 < P.NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32_g(taddr + c0, v);                                // columns past NT belong to the allocation: ignored below
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < P.M) {
-          if (c0 + 16 <= n_valid && ((reinterpret_cast<uintptr_t>(crow + c0) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<uint4*>(crow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < n_valid) crow[c0 + j] = __uint_as_float(v[j]);
-          }
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);     // bank (lane + j) % 32: conflict-free
+        __syncwarp();
+        const int c = c0 + lane;
+        if (c < n_valid) {
+          float* cp = P.C + m0 * P.ldc + nt * P.NT + c;
+          for (int r = 0; r < rows_valid; ++r) cp[r * P.ldc] = stg[r * 33 + lane];  // 128 contiguous bytes per row
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -391,7 +397,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
   P.C = C; P.ldc = ldc;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
-  const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + (size_t)kLoStages * kTileA + 512 + 1024;
+  const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + (size_t)kLoStages * kTileA + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
   if (stages > kMaxStages) stages = kMaxStages;
   KGC_REQUIRE(stages >= 2, "shared-memory plan does not fit");
