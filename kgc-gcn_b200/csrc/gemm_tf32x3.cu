@@ -3,8 +3,8 @@
 // The reference multiplies in plain fp32 (torch default, TF32 off): res_h = agg_h @ W_h, g_h = d_res_h @ W_h^T
 // (model.py:116 and its autograd).  Nine such N x 100 x 200 GEMMs are half of a training step when left to the
 // fp32 SIMT path (profiles/r01_launches_conv_step.md).  Here every fp32 operand is split into two TF32 numbers,
-//   v = hi + lo,   hi = v rounded to the nearest TF32 (cvt.rna.tf32.f32),  lo = v - hi (exact in fp32, |lo| <= 2^-11 |v|)
-// rounded to TF32 in turn, and C = A_lo B_hi + A_hi B_lo + A_hi B_hi is accumulated in fp32 in TMEM by tcgen05.mma
+//   v = hi + lo,   hi = the top 19 bits of v (exactly a TF32; round-to-nearest for the small packed operand),
+//   lo = v - hi (exact in fp32, read as TF32 by the tensor core), and C = A_lo B_hi + A_hi B_lo + A_hi B_hi is accumulated in fp32 in TMEM by tcgen05.mma
 // kind::tf32: the dropped term A_lo B_lo and the rounding of lo are both <= 2^-22 relative, i.e. fp32-level.
 //
 //   C[M, N] = A[M, K] @ Bt[N, K]^T        A row-major fp32 (streamed), Bt = the small operand, pre-split and packed
@@ -12,11 +12,11 @@
 // Persistent CTAs; a CTA owns one column tile of C (NT <= 112 columns) and keeps the hi / lo tiles of Bt for it
 // resident in shared memory; warp roles:
 //   warp 0      TMA producer: Bt tiles once, then raw fp32 A tiles (128 rows x 32 K, 128-byte swizzle) into a 4-6 deep ring
-//   warps 2-5   splitter: raw tile -> hi (in place) + lo tile (element-wise on the swizzled bytes, layout-agnostic),
+//   warps 2-9   splitter: raw tile -> hi (in place) + lo tile (element-wise on the swizzled bytes, layout-agnostic),
 //               fence.proxy.async, then hand the stage to the MMA warp
 //   warp 1      one thread issues 3 tcgen05.mma (M = 128, N = NT, K = 8) per 8-wide k-step
-//   warps 6-9   epilogue: tcgen05.ld -> 32x32 transpose through shared memory -> coalesced 128-byte row segments of C
-//   warp 10     TMEM allocator (2 accumulator stages)
+//   warps 10-13 epilogue: tcgen05.ld -> 32x32 transpose through shared memory -> coalesced 128-byte row segments of C
+//   warp 14     TMEM allocator (2 accumulator stages)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,7 +31,8 @@ constexpr int kMaxKB = 8;                 // K <= 256
 constexpr int kMaxStages = 8;             // raw A ring (TMA targets, split in place into hi)
 constexpr int kLoStages = 2;              // lo tiles live only between the splitter and the MMA
 constexpr int kTileA = kBM * kBK * 4;     // 16 KB
-constexpr int kThreadsG = 352;            // 11 warps
+constexpr int kThreadsG = 480;            // 15 warps: TMA, MMA, 8 splitters, 4 epilogue, TMEM allocator
+constexpr int kSplitWarps = 8;
 constexpr int kBBudget = 88 * 1024;       // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
                                           // the ring must cover TMA latency + split + MMA, ~6 K-blocks in flight)
 constexpr int kTmemColsG = 256;
@@ -146,7 +147,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     mb_init(b_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mb_init(raw_full + i, 1);
-      mb_init(split_full + i, 4);
+      mb_init(split_full + i, kSplitWarps);
       mb_init(empty + i, 1);
     }
     for (int i = 0; i < kLoStages; ++i) mb_init(lo_empty + i, 1);
@@ -157,7 +158,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 10) {
+  if (warp == 14) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(kTmemColsG)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -190,9 +191,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
+  } else if (warp >= 2 && warp < 2 + kSplitWarps) {
     // ================================================================== splitter: v -> (hi, lo)
-    const int t = threadIdx.x - 64;                                // 0..127
+    const int t = threadIdx.x - 64;                                // 0..255
     int stage = 0, ls = 0;
     uint32_t phase = 0, lphase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
@@ -201,16 +202,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mb_wait(lo_empty + ls, lphase ^ 1);                        // the MMAs that read this lo stage have retired
         uint4* hi = reinterpret_cast<uint4*>(s_a + stage * kTileA);
         uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * kTileA);
+        constexpr int kSplitThreads = kSplitWarps * 32;
+        uint4 v[kTileA / 16 / kSplitThreads];
 #pragma unroll
-        for (int i = 0; i < kTileA / 16 / 128; ++i) {              // 8 x 16-byte vectors per thread, conflict-free
-          uint4 v = hi[t + i * 128];
+        for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) v[i] = hi[t + i * kSplitThreads];   // conflict-free 16-byte vectors
+#pragma unroll
+        for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) {
+          // streamed operand: hi = top 19 bits (exactly a TF32), lo = v - hi exactly; the tensor core reads lo as TF32.
+          // (2 instructions per element; the small operand Bt is split with round-to-nearest by kgc_gemm_pack_b.)
           uint4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          hi[t + i * 128] = h;
-          lo[t + i * 128] = l;
+          h.x = v[i].x & 0xFFFFE000u; h.y = v[i].y & 0xFFFFE000u; h.z = v[i].z & 0xFFFFE000u; h.w = v[i].w & 0xFFFFE000u;
+          l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
+          hi[t + i * kSplitThreads] = h;
+          lo[t + i * kSplitThreads] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
@@ -253,13 +260,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 6 && warp <= 9) {
+  } else if (warp >= 10 && warp <= 13) {
     // ================================================================== epilogue: TMEM -> smem transpose -> coalesced C rows
     // A thread owns a TMEM lane (= a row of C), so storing straight from registers would issue 32 scattered
     // 16-byte stores per instruction (measured: the LSU then bounds the whole kernel).  Each warp transposes its
     // 32 x 32 block through a padded shared-memory tile and writes whole 128-byte row segments.
     const int quarter = warp % 4;
-    float* stg = reinterpret_cast<float*>(s_stage) + (warp - 6) * (32 * 33);
+    float* stg = reinterpret_cast<float*>(s_stage) + (warp - 10) * (32 * 33);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
@@ -291,7 +298,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 10) {
+  if (warp == 14) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsG) : "memory");
   }
 }
