@@ -161,6 +161,9 @@ int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t 
                     void* stream);
 int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                 int64_t ldc, void* stream);
+/* Debug aid: device buffer of 8 x 64 int64 that CTA 0 of the next kgc_gemm_nt launches fills with clock64() stamps
+ * per warp role (NULL switches it off; off by default). */
+void kgc_gemm_set_debug(long long* buf);
 
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's

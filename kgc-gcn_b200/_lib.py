@@ -37,6 +37,7 @@ SIGNATURES = {
     'kgc_gemm_packed_b_bytes': (_sz, [_i32, _i32]),
     'kgc_gemm_pack_b': (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'kgc_gemm_nt': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
+    'kgc_gemm_set_debug': (None, [_vp]),
     'kgc_label_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
     'kgc_neg_sample': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

@@ -3,8 +3,8 @@
 // The reference multiplies in plain fp32 (torch default, TF32 off): res_h = agg_h @ W_h, g_h = d_res_h @ W_h^T
 // (model.py:116 and its autograd).  Nine such N x 100 x 200 GEMMs are half of a training step when left to the
 // fp32 SIMT path (profiles/r01_launches_conv_step.md).  Here every fp32 operand is split into two TF32 numbers,
-//   v = hi + lo,   hi = the top 19 bits of v (exactly a TF32; round-to-nearest for the small packed operand),
-//   lo = v - hi (exact in fp32, read as TF32 by the tensor core), and C = A_lo B_hi + A_hi B_lo + A_hi B_hi is accumulated in fp32 in TMEM by tcgen05.mma
+//   v = hi + lo,   hi = v rounded to the nearest TF32 (cvt.rna.tf32.f32),  lo = v - hi (exact in fp32, |lo| <= 2^-11 |v|)
+// rounded to TF32 in turn, and C = A_lo B_hi + A_hi B_lo + A_hi B_hi is accumulated in fp32 in TMEM by tcgen05.mma
 // kind::tf32: the dropped term A_lo B_lo and the rounding of lo are both <= 2^-22 relative, i.e. fp32-level.
 //
 //   C[M, N] = A[M, K] @ Bt[N, K]^T        A row-major fp32 (streamed), Bt = the small operand, pre-split and packed
@@ -117,6 +117,7 @@ struct GemmParams {
   int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles, stages;
   float* C;
   int64_t ldc;
+  long long* dbg;     // optional timeline of CTA 0: [role][event] clock64 stamps (debug aid)
 };
 
 __global__ void __launch_bounds__(kThreadsG, 1)
@@ -167,6 +168,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0;
+  int dbg_n = 0;
+#define KGC_DBG(role) do { if (dbg_on && dbg_n < 64) P.dbg[(role) * 64 + dbg_n++] = clock64(); } while (0)
 
   // work: this CTA owns column tile nt and the row tiles mt = first, first + step, ...
   const int nt = blockIdx.x % P.n_ntiles;
@@ -185,6 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int mt = first; mt < P.n_mtiles; mt += step) {
         for (int kb = 0; kb < P.n_kb; ++kb) {
           mb_wait(empty + stage, phase ^ 1);
+          KGC_DBG(0);
           mb_expect_tx(raw_full + stage, kTileA);
           tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -199,7 +204,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       for (int kb = 0; kb < P.n_kb; ++kb) {
         mb_wait(raw_full + stage, phase);
-        mb_wait(lo_empty + ls, lphase ^ 1);                        // the MMAs that read this lo stage have retired
+        if (t == 0) KGC_DBG(1);
+        mb_wait(lo_empty + ls, lphase ^ 1);
+        if (t == 0) KGC_DBG(2);                        // the MMAs that read this lo stage have retired
         uint4* hi = reinterpret_cast<uint4*>(s_a + stage * kTileA);
         uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * kTileA);
         constexpr int kSplitThreads = kSplitWarps * 32;
@@ -208,20 +215,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) v[i] = hi[t + i * kSplitThreads];   // conflict-free 16-byte vectors
 #pragma unroll
         for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) {
-          // streamed operand: hi = top 19 bits (exactly a TF32), lo = v - hi exactly; the tensor core reads lo as TF32.
-          // (2 instructions per element; the small operand Bt is split with round-to-nearest by kgc_gemm_pack_b.)
+          // hi = nearest TF32, lo = nearest TF32 of (v - hi): measurably tighter than truncation at K = 200
           uint4 h, l;
-          h.x = v[i].x & 0xFFFFE000u; h.y = v[i].y & 0xFFFFE000u; h.z = v[i].z & 0xFFFFE000u; h.w = v[i].w & 0xFFFFE000u;
-          l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
+          split_tf32(v[i].x, h.x, l.x);
+          split_tf32(v[i].y, h.y, l.y);
+          split_tf32(v[i].z, h.z, l.z);
+          split_tf32(v[i].w, h.w, l.w);
           hi[t + i * kSplitThreads] = h;
           lo[t + i * kSplitThreads] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) mb_arrive(split_full + stage);
+        if (t == 0) KGC_DBG(3);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
         if (++ls == kLoStages) { ls = 0; lphase ^= 1; }
       }
@@ -240,6 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t d_addr = tmem_base + acc * 128;
         for (int kb = 0; kb < P.n_kb; ++kb) {
           mb_wait(split_full + stage, phase);
+          KGC_DBG(4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int nk = min(kBK / kUK, P.ksteps - kb * (kBK / kUK));
           const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * kTileA));
@@ -253,6 +260,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
           umma_commit_g(empty + stage);
           umma_commit_g(lo_empty + ls);
+          KGC_DBG(5);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++ls == kLoStages) ls = 0;
         }
@@ -271,6 +279,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint32_t acc_phase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       mb_wait(acc_full + acc, acc_phase);
+      if (warp == 10 && lane == 0) KGC_DBG(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t m0 = (int64_t)mt * kBM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
@@ -293,6 +302,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mb_arrive(acc_empty + acc);
+      if (warp == 10 && lane == 0) KGC_DBG(7);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -388,6 +398,9 @@ extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_
   return 0;
 }
 
+static long long* g_gemm_dbg = nullptr;
+extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 8 * 64 int64, or NULL
+
 extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                            int64_t ldc, void* stream) {
   Tiling t;
@@ -402,7 +415,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   P.M = M; P.N = N; P.K = K;
   P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
-  P.C = C; P.ldc = ldc;
+  P.C = C; P.ldc = ldc; P.dbg = g_gemm_dbg;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
   const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + (size_t)kLoStages * kTileA + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
