@@ -78,6 +78,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a fully converged warp (PTX elect.sync).  The surrounding code stays warp-uniform, so ptxas keeps the
+// shared-memory / instruction descriptors in UNIFORM registers; running the whole role under `if (lane == 0)` makes
+// them per-thread values and every tcgen05.mma then pays a chain of R2UR moves (~120 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t tf32_rn(float v) {      // round to nearest TF32 (10-bit mantissa), result in fp32 bits
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -233,8 +248,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+    // ================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       int stage = 0, acc = 0, ls = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -246,25 +261,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t d_addr = tmem_base + acc * 128;
         for (int kb = 0; kb < P.n_kb; ++kb) {
           mb_wait(split_full + stage, phase);
-          KGC_DBG(4);
+          if (lane == 0) KGC_DBG(4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int nk = min(kBK / kUK, P.ksteps - kb * (kBK / kUK));
           const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * kTileA));
           const uint64_t a_lo = sw128_desc(s_u32(s_lo + ls * kTileA));
           const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
           const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
-          for (int k = 0; k < nk; ++k) {                           // + k * 32 bytes along K (16-byte units in the descriptor)
-            umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
-            umma_tf32(d_addr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-            umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          if (elect_one()) {
+            for (int k = 0; k < nk; ++k) {                         // + k * 32 bytes along K (16-byte units in the descriptor)
+              umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
+              umma_tf32(d_addr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+            }
+            umma_commit_g(empty + stage);
+            umma_commit_g(lo_empty + ls);
+            if (kb == P.n_kb - 1) umma_commit_g(acc_full + acc);
           }
-          umma_commit_g(empty + stage);
-          umma_commit_g(lo_empty + ls);
-          KGC_DBG(5);
+          __syncwarp();
+          if (lane == 0) KGC_DBG(5);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++ls == kLoStages) ls = 0;
         }
-        umma_commit_g(acc_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -78,6 +78,21 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp (PTX elect.sync).  The surrounding code stays warp-uniform, so ptxas keeps the
+// shared-memory / instruction descriptors in UNIFORM registers; running the whole role under `if (lane == 0)` makes
+// them per-thread values and every tcgen05.mma then pays a chain of R2UR moves (~120 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -240,8 +255,8 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+    // ================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, a_phase = 0;
       const uint32_t a_base = smem_u32(S.a), b_base = smem_u32(S.b);
@@ -260,22 +275,27 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             tc_fence_after();
             const int nk = min(kBlockK / kUmmaK, P.ksteps - kb * (kBlockK / kUmmaK));
             const uint64_t bdesc = make_sw128_desc(b_base + stage * kTileBytes);
-            for (int k = 0; k < nk; ++k) {
-#pragma unroll
-              for (int m = 0; m < kNumM; ++m) {
-                const uint64_t adesc = make_sw128_desc(a_base + (m * kMaxKBlocks + kb) * kTileBytes);
+            const uint64_t adesc0 = make_sw128_desc(a_base + kb * kTileBytes);
+            const uint64_t adesc1 = make_sw128_desc(a_base + (kMaxKBlocks + kb) * kTileBytes);
+            const uint32_t d0 = tmem_base + acc * (kMTiles * kBlockN);
+            if (elect_one()) {
+              for (int k = 0; k < nk; ++k) {
                 // + k * 32 bytes along K inside the swizzle row: descriptor start address is in 16-byte units
-                umma_bf16(tmem_base + acc * (kMTiles * kBlockN) + m * kBlockN, adesc + 2 * k, bdesc + 2 * k, kInstrDesc,
-                          (kb | k) != 0 ? 1u : 0u);
+                const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                umma_bf16(d0, adesc0 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
+                if (kNumM == 2) umma_bf16(d0 + kBlockN, adesc1 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
+              }
+              umma_commit(S.empty + stage);                    // B stage is free once these MMAs retire
+              if (kb == P.n_kblocks - 1) {
+                umma_commit(S.acc_full + acc);                 // accumulators of this entity tile are complete
+                if (t == t1 - 1) umma_commit(S.a_empty);       // A tiles may be overwritten
               }
             }
-            umma_commit(S.empty + stage);                      // B stage is free once these MMAs retire
+            __syncwarp();
             if (++stage == kStagesB) { stage = 0; phase ^= 1; }
           }
-          umma_commit(S.acc_full + acc);                       // accumulators of this entity tile are complete
           if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(S.a_empty);                                // A tiles may be overwritten
       }
     }
   } else if (warp >= kEpiWarp0 && (warp - kEpiWarp0) / 4 < kNumM) {
