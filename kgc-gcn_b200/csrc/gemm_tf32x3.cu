@@ -311,9 +311,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);     // bank (lane + j) % 32: conflict-free
         __syncwarp();
         const int c = c0 + lane;
-        if (c < n_valid) {
-          float* cp = P.C + m0 * P.ldc + nt * P.NT + c;
-          for (int r = 0; r < rows_valid; ++r) cp[r * P.ldc] = stg[r * 33 + lane];  // 128 contiguous bytes per row
+        float* cp = P.C + m0 * P.ldc + nt * P.NT + c;
+        const bool col_ok = c < n_valid;
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 8) {                       // 8 independent LDS, then 8 coalesced 128-byte row stores
+          float tmp[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tmp[j] = stg[(r0 + j) * 33 + lane];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col_ok && r0 + j < rows_valid) cp[(int64_t)(r0 + j) * P.ldc] = tmp[j];
         }
         __syncwarp();
       }
