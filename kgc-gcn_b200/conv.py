@@ -98,6 +98,16 @@ class _ConvFn(torch.autograd.Function):
         # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition)
         x_full = x if coll is None else coll.all_gather_rows(x)
 
+        v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
+        w_loop_s = v * w_loop
+        res3 = plan.scratch('res3', (3, Nl, Dout))
+        # the self-loop transform only needs x: it runs on the plan's side stream next to the aggregation (the GEMM is
+        # shared-memory / tensor bound, the aggregation HBM-latency bound, so the two overlap on the same SMs)
+        main = torch.cuda.current_stream()
+        side = plan.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
@@ -105,12 +115,9 @@ class _ConvFn(torch.autograd.Function):
                       p(out_final), p(carry), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
 
-        v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
-        w_loop_s = v * w_loop
-        res3 = plan.scratch('res3', (3, Nl, Dout))
         gemm_nt(agg[0], w_in, res3[0], plan, 'f0')
         gemm_nt(agg[1], w_out, res3[1], plan, 'f1')
-        gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
+        main.wait_stream(side)
 
         nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
@@ -165,21 +172,27 @@ class _ConvFn(torch.autograd.Function):
         sums32 = sums.float()
         d_beta, d_gamma = sums32[0], sums32[1]
 
-        # ---- dense transforms (fp32 GEMMs)
-        g3 = plan.scratch('g3', (3, Nl, D))
-        gemm_nt(d_res3[0], w_in.t(), g3[0], plan, 'g0')
-        gemm_nt(d_res3[1], w_out.t(), g3[1], plan, 'g1')
-        gemm_nt(d_res3[2], w_loop_s.t(), g3[2], plan, 'g2')
         # replicated-parameter gradients: one flat buffer so that a partitioned run needs ONE all-reduce
         flat = torch.empty((3 * D * Dout + T * D + (Dout if ctx.has_bias else 0),), dtype=torch.float32, device=dev)
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
         d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
-        _mm(agg[0].t(), d_res3[0], d_w_in)
-        _mm(agg[1].t(), d_res3[1], d_w_out)
-        _mm(x.t(), d_res3[2], m_loop)                                  # [D, Dout]
-        if ctx.has_bias:
-            torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
+        # the weight-gradient reductions (fp32 cuBLAS, K = the node rows) only need agg, x and d_res3: they run on the
+        # side stream while the main stream does the g3 transforms and the K3 aggregation passes
+        main = torch.cuda.current_stream()
+        side = plan.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _mm(agg[0].t(), d_res3[0], d_w_in)
+            _mm(agg[1].t(), d_res3[1], d_w_out)
+            _mm(x.t(), d_res3[2], m_loop)                              # [D, Dout]
+            if ctx.has_bias:
+                torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 
+        # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
+        g3 = plan.scratch('g3', (3, Nl, D))
+        gemm_nt(d_res3[0], w_in.t(), g3[0], plan, 'g0')
+        gemm_nt(d_res3[1], w_out.t(), g3[1], plan, 'g1')
+        gemm_nt(d_res3[2], w_loop_s.t(), g3[2], plan, 'g2')
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
         d_x_full = torch.empty((n_global, D), dtype=torch.float32, device=dev)
         d_ee = torch.empty_like(ee)
@@ -196,6 +209,7 @@ class _ConvFn(torch.autograd.Function):
                       plan.num_dst_rows, plan.num_edges_in, p(out_final), p(carry), D, st())
         plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
 
+        main.wait_stream(side)
         if coll is None:
             d_x = d_x_full
         else:

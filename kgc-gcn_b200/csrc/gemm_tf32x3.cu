@@ -9,6 +9,11 @@
 //
 //   C[M, N] = A[M, K] @ Bt[N, K]^T        A row-major fp32 (streamed), Bt = the small operand, pre-split and packed
 //
+// Measured limits (round 1, tests/gemm_timeline.py + ncu): the kernel is bound by the SHARED-MEMORY port, not by the
+// tensor pipe: SS-mode MMAs re-read the A tile three times per k-step, the splitter moves 3x the tile bytes and the
+// epilogue transposes through shared memory - about 600 KB of shared-memory traffic per 128 x 80 output tile
+// (~4,700 cycles at 128 B/cycle).  Next step: A_hi / A_lo in TMEM (tcgen05.st by the splitter, TS-mode MMA).
+//
 // Persistent CTAs; a CTA owns one column tile of C (NT <= 112 columns) and keeps the hi / lo tiles of Bt for it
 // resident in shared memory; warp roles:
 //   warp 0      TMA producer: Bt tiles once, then raw fp32 A tiles (128 rows x 32 K, 128-byte swizzle) into a 4-6 deep ring
@@ -33,7 +38,7 @@ constexpr int kLoStages = 2;              // lo tiles live only between the spli
 constexpr int kTileA = kBM * kBK * 4;     // 16 KB
 constexpr int kThreadsG = 480;            // 15 warps: TMA, MMA, 8 splitters, 4 epilogue, TMEM allocator
 constexpr int kSplitWarps = 8;
-constexpr int kBBudget = 88 * 1024;       // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
+constexpr int kBBudget = 116 * 1024;      // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
                                           // the ring must cover TMA latency + split + MMA, ~6 K-blocks in flight)
 constexpr int kTmemColsG = 256;
 constexpr int kEpiStage = 4 * 32 * 33 * 4 + 128;  // epilogue transpose tiles (16,896 B) + pad to keep the barriers 8-byte aligned
