@@ -165,6 +165,13 @@ int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* 
  * per warp role (NULL switches it off; off by default). */
 void kgc_gemm_set_debug(long long* buf);
 
+/* ---- K4c: weight-gradient reductions  C[Ka,Nb] = A[M,Ka]^T @ B[M,Nb]  (autograd of model.py:116 w.r.t. W) ----
+ * Plain fp32 FMAs; every CTA reduces a slab of rows into a register-resident Ka x Nb partial, partials are added
+ * in CTA order (deterministic).  Ka <= 128, Nb <= 256, all dimensions / leading dimensions multiples of 4. */
+size_t kgc_gemm_tn_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb);
+int kgc_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
+                float* C, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's
  * query ids qid[B] (int64) and the query->objects CSR (ptr int64 [Q+1], idx int32 [nnz]):

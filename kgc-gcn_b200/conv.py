@@ -48,6 +48,21 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b'):
     return out
 
 
+def gemm_tn(a, b, out, plan=None):
+    """out[Ka, Nb] = a[M, Ka]^T @ b[M, Nb] (K4c): the weight-gradient reduction over the node rows, plain fp32 FMAs,
+    per-CTA partials added in a fixed order."""
+    M, Ka = a.shape
+    Nb = b.shape[1]
+    if a.stride(1) != 1 or b.stride(1) != 1 or not out.is_contiguous():
+        raise ValueError('gemm_tn needs unit inner strides and a contiguous output')
+    nbytes = int(_lib.lib().kgc_gemm_tn_workspace_bytes(M, Ka, Nb))
+    ws = plan.scratch('gemm_tn_ws', (nbytes // 4,)) if plan is not None else \
+        torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+    p = _lib.ptr
+    _lib.call('kgc_gemm_tn', p(a), a.stride(0), p(b), b.stride(0), M, Ka, Nb, p(out), p(ws), nbytes, _lib.stream())
+    return out
+
+
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
@@ -101,13 +116,7 @@ class _ConvFn(torch.autograd.Function):
         v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
         w_loop_s = v * w_loop
         res3 = plan.scratch('res3', (3, Nl, Dout))
-        # the self-loop transform only needs x: it runs on the plan's side stream next to the aggregation (the GEMM is
-        # shared-memory / tensor bound, the aggregation HBM-latency bound, so the two overlap on the same SMs)
-        main = torch.cuda.current_stream()
-        side = plan.side_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
+        gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
@@ -117,7 +126,6 @@ class _ConvFn(torch.autograd.Function):
 
         gemm_nt(agg[0], w_in, res3[0], plan, 'f0')
         gemm_nt(agg[1], w_out, res3[1], plan, 'f1')
-        main.wait_stream(side)
 
         nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
@@ -176,17 +184,12 @@ class _ConvFn(torch.autograd.Function):
         flat = torch.empty((3 * D * Dout + T * D + (Dout if ctx.has_bias else 0),), dtype=torch.float32, device=dev)
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
         d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
-        # the weight-gradient reductions (fp32 cuBLAS, K = the node rows) only need agg, x and d_res3: they run on the
-        # side stream while the main stream does the g3 transforms and the K3 aggregation passes
-        main = torch.cuda.current_stream()
-        side = plan.side_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            _mm(agg[0].t(), d_res3[0], d_w_in)
-            _mm(agg[1].t(), d_res3[1], d_w_out)
-            _mm(x.t(), d_res3[2], m_loop)                              # [D, Dout]
-            if ctx.has_bias:
-                torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
+        # weight-gradient reductions over the node rows (K4c: register-tiled fp32, deterministic)
+        gemm_tn(agg[0], d_res3[0], d_w_in, plan)
+        gemm_tn(agg[1], d_res3[1], d_w_out, plan)
+        gemm_tn(x, d_res3[2], m_loop, plan)                            # [D, Dout]
+        if ctx.has_bias:
+            torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
         g3 = plan.scratch('g3', (3, Nl, D))
@@ -209,7 +212,6 @@ class _ConvFn(torch.autograd.Function):
                       plan.num_dst_rows, plan.num_edges_in, p(out_final), p(carry), D, st())
         plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
 
-        main.wait_stream(side)
         if coll is None:
             d_x = d_x_full
         else:

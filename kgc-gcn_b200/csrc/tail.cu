@@ -84,7 +84,7 @@ tail_fwd_kernel(const float4* __restrict__ res3, const uint8_t* __restrict__ mas
 // Column finalisers: one block per 8 columns; 32 row-lanes stride over the per-block partials, then the
 // 32 lane sums are added in lane order - fixed order, deterministic, and ~100x less serial than one
 // thread per column.
-constexpr int kFinCols = 8, kFinLanes = 32;
+constexpr int kFinCols = 2, kFinLanes = 128;     // 100 blocks of 256 threads for Dout = 200
 
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int64_t n_blocks, int Dout,
                                                 int c, int lane, double (*sm)[kFinLanes][kFinCols], double* s_out,

@@ -10,7 +10,8 @@ import torch
 from . import _lib
 
 CHUNK0 = 32      # build_levels default fan-in of the first level
-CHUNK1 = 1024    # partial rows per item on the higher levels (one 256-thread block)
+CHUNK1 = 128     # partial rows per item on the fix-up levels (one 256-thread block = 32 groups x 4 rows each):
+                 # a 38k-edge hub row (1,187 carry rows) becomes 10 parallel items + 1, not 2 long serial ones
 
 
 def build_levels(seg_beg, seg_end, seg_row, chunk0=CHUNK0, chunk1=CHUNK1):
@@ -181,12 +182,6 @@ class GraphPlan(object):
         self.bwd_src = StreamPlan(build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2), n2, dev)
         self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64), n2), n2, dev)
         self._scratch = {}
-
-    def side_stream(self):
-        """Second CUDA stream of the plan (independent transforms run next to the aggregation kernels)."""
-        if getattr(self, '_side', None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
 
     def scratch(self, name, shape, dtype=torch.float32):
         """Reusable device workspace (caller-allocated, as the C ABI requires)."""

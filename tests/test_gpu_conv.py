@@ -276,3 +276,22 @@ def test_gemm_tf32x3_fp32_grade(k, M, K, N):
     truth2 = a2.cpu().double() @ bt.double().t()
     assert float((out2[:, :N].cpu().double() - truth2).abs().max()) / float(truth2.abs().max()) <= 2e-6
     assert torch.isnan(out2[:, N:]).all()                        # nothing written outside the N valid columns
+
+
+@pytest.mark.parametrize('M,Ka,Nb', [(40943, 100, 200), (1000, 12, 20), (77, 128, 256), (3, 4, 8)])
+def test_gemm_tn_weight_gradient(k, M, Ka, Nb):
+    """K4c: C = A^T @ B over the node rows, fp32, deterministic."""
+    g = torch.Generator().manual_seed(M + Ka)
+    a = torch.randn(M, Ka, generator=g)
+    b = torch.randn(M, Nb, generator=g)
+    truth = a.double().t() @ b.double()
+    scale = float(truth.abs().max())
+    out = torch.empty(Ka, Nb, device='cuda')
+    k.gemm_tn(a.cuda(), b.cuda(), out)
+    err = float((out.cpu().double() - truth).abs().max()) / scale
+    err_fp32 = float(((a.t() @ b).double() - truth).abs().max()) / scale
+    print('gemm_tn M={} Ka={} Nb={}: err {:.2e} (fp32 GEMM {:.2e})'.format(M, Ka, Nb, err, err_fp32))
+    assert err <= max(4 * err_fp32, 2e-6)
+    out2 = torch.empty(Ka, Nb, device='cuda')
+    k.gemm_tn(a.cuda(), b.cuda(), out2)
+    assert torch.equal(out, out2)

@@ -112,7 +112,7 @@ def test_stream_plan_exact(seed):
     rng = np.random.default_rng(seed)
     S = 300
     lens = rng.integers(0, 6, S)
-    lens[5], lens[100], lens[S - 1] = 40000, 33, 1024 * 32 + 7      # hubs: several fix-up levels
+    lens[5], lens[100], lens[S - 1] = 40000, 33, 128 * 128 * 32 + 7  # hubs: several fix-up levels
     if seed == 3:
         lens[:] = 0
         lens[17] = 5                                                   # almost everything empty
@@ -126,7 +126,7 @@ def test_stream_plan_exact(seed):
     np.testing.assert_array_equal(out[rows], exp)
     assert sp['chunks'].shape == (-(-n_rec // 32), 2)
     for items, _ in sp['levels']:
-        assert (items[:, 1] - items[:, 0]).max() <= 1024
+        assert (items[:, 1] - items[:, 0]).max() <= 128
 
 
 def test_stream_plan_forward_layout():
