@@ -122,7 +122,11 @@ int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
 /* ---- K4: layer tail ------------------------------------------------------------------------------
  * Replaces model.py:103-106: out = (drop(in_res) + drop(out_res) + loop_res) / 3 [+ bias];
  * BatchNorm1d over the node rows; tanh.  res3 is [3,n_rows,Dout] (in, out, loop planes).
- * mask_in / mask_out: uint8 keep masks [n_rows,Dout] or NULL (no dropout); keep_scale = 1/(1-p).
+ * Dropout (nn.Dropout on in_res and out_res, model.py:103): either injected uint8 keep masks mask_in / mask_out
+ * [n_rows,Dout] (tests replay the reference's own draws this way), or - masks NULL, seed != NULL, drop_p > 0 - a
+ * counter-based Philox4x32-10 stream keyed by *seed (device int64), counter = (float4 index, plane): the forward
+ * and the backward regenerate the same mask, nothing is stored.  keep_scale = 1/(1-p).  kgc_dropout_mask writes
+ * the mask of one plane (0 = in, 1 = out) for inspection.
  *   kgc_tail_fwd           writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares; fp64)
  *   kgc_colsum_finalize    reduces the partials in a fixed order into sums[2,Dout] (fp64).  A partitioned
  *                          graph all-reduces these 2*Dout doubles across ranks here.
@@ -130,8 +134,10 @@ int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
  *                          when training, or from the running statistics (training == 0)
  *   kgc_tail_apply         all_ent = tanh((pre - mean) * rstd * gamma + beta) */
 int64_t kgc_tail_num_blocks(int64_t n_rows);
-int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, float keep_scale,
-                 const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials, void* stream);
+int kgc_dropout_mask(const int64_t* seed, int32_t plane, float drop_p, int64_t n_elem, uint8_t* mask, void* stream);
+int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, const int64_t* seed, float drop_p,
+                 float keep_scale, const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials,
+                 void* stream);
 int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, void* stream);
 int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_t Dout, float eps, int32_t training,
                            const float* running_mean, const float* running_var, float* stats, void* stream);
@@ -145,8 +151,8 @@ int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* p
                         int64_t n_rows, int32_t Dout, double* partials, void* stream);
 int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
                        const float* gamma, const double* sums, const uint8_t* mask_in, const uint8_t* mask_out,
-                       float keep_scale, int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout,
-                       float* d_res3, void* stream);
+                       const int64_t* seed, float drop_p, float keep_scale, int32_t training, int64_t n_rows,
+                       int64_t n_rows_global, int32_t Dout, float* d_res3, void* stream);
 
 /* ---- K4b: dense transforms on the tensor cores with fp32-grade accuracy (3xTF32) --------------------------
  * Replaces the fp32 matmuls of model.py:116 (x_j_rel @ W, after the aggregate-then-transform reordering

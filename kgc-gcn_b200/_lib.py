@@ -28,12 +28,13 @@ SIGNATURES = {
     'kgc_agg_bwd_src': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     'kgc_agg_bwd_rel': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     'kgc_tail_num_blocks': (_i64, [_i64]),
-    'kgc_tail_fwd': (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    'kgc_dropout_mask': (ctypes.c_int, [_vp, _i32, _f32, _i64, _vp, _vp]),
+    'kgc_tail_fwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _i32, _vp, _vp, _vp]),
     'kgc_colsum_finalize': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     'kgc_colstats_from_sums': (ctypes.c_int, [_vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
     'kgc_tail_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     'kgc_tail_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
-    'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i64, _i32, _vp, _vp]),
+    'kgc_tail_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _i64, _i64, _i32, _vp, _vp]),
     'kgc_gemm_packed_b_bytes': (_sz, [_i32, _i32]),
     'kgc_gemm_pack_b': (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'kgc_gemm_nt': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),

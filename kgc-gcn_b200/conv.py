@@ -97,7 +97,7 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, rels, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, bias,
-                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll):
+                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll, seed, drop_p):
         # x: this rank's node rows [Nl, D] (all rows on one GPU); ee: the rows of the edges this rank owns
         Nl, D = x.shape
         Dout = w_in.shape[1]
@@ -133,8 +133,8 @@ class _ConvFn(torch.autograd.Function):
         pre = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
         stats = torch.empty((3, Dout), dtype=torch.float32, device=x.device)
         all_ent = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
-        _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), float(keep_scale), p(bias), Nl, Dout, p(pre),
-                  p(partials), st())
+        _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), p(seed), float(drop_p), float(keep_scale), p(bias),
+                  Nl, Dout, p(pre), p(partials), st())
         if training:
             _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
             if coll is not None:
@@ -146,15 +146,16 @@ class _ConvFn(torch.autograd.Function):
 
         ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias, ctx.coll = plan, bool(training), float(keep_scale), \
             bias is not None, coll
+        ctx.drop_p = float(drop_p)
         ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre,
-                              all_ent, stats, mask_in, mask_out, w_loop_s)
+                              all_ent, stats, mask_in, mask_out, w_loop_s, seed)
         ctx.mark_non_differentiable(stats)
         return all_ent, all_rel, stats
 
     @staticmethod
     def backward(ctx, g_ent, g_rel, _g_stats):
         (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent, stats, mask_in,
-         mask_out, w_loop_s) = ctx.saved_tensors
+         mask_out, w_loop_s, seed) = ctx.saved_tensors
         plan, coll = ctx.plan, ctx.coll
         Nl, D = x.shape
         n_global = plan.num_nodes
@@ -176,7 +177,7 @@ class _ConvFn(torch.autograd.Function):
         if coll is not None:
             coll.all_reduce(sums)
         _lib.call('kgc_tail_bwd_apply', p(g_ent), p(all_ent), p(pre), p(stats), p(gamma), p(sums), p(mask_in),
-                  p(mask_out), ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
+                  p(mask_out), p(seed), ctx.drop_p, ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
         sums32 = sums.float()
         d_beta, d_gamma = sums32[0], sums32[1]
 
@@ -235,7 +236,7 @@ class _ConvFn(torch.autograd.Function):
         d_rels = d_relp[:-1]
         d_loop_rel = d_loop_rel + d_relp[-1:]
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 class MGCNConv(nn.Module):
@@ -264,6 +265,10 @@ class MGCNConv(nn.Module):
         else:
             self.register_parameter('bias', None)
         self._forced_masks = None
+        # dropout stream of the CUDA path: a device-resident counter (not part of the state dict); every training
+        # forward advances it and the tail kernels key a Philox4x32-10 generator with it (K4, no mask tensors)
+        self.register_buffer('_drop_seed', torch.zeros(1, dtype=torch.int64), persistent=False)
+        self._drop_seeded = False
 
     def set_dropout_masks(self, mask_in, mask_out):
         """Inject the two keep masks ([N, Dout], 0/1) the next training forward uses instead of drawing
@@ -277,29 +282,43 @@ class MGCNConv(nn.Module):
         return get_plan(ei, et, num_ent, 1).norm[:edge_index.size(1)].clone()
 
     def _masks(self, n_rows, device):
+        """-> (mask_in, mask_out, keep_scale, seed, drop_p).  Training with p > 0: injected masks if set, otherwise a
+        fresh seed for the in-kernel counter-based generator (first seed drawn from torch's generator, so
+        torch.manual_seed makes runs reproducible)."""
         p = self.drop.p
         if not self.training or p == 0.0:
-            return None, None, 1.0
+            return None, None, 1.0, None, 0.0
         if self._forced_masks is not None:
             m_in, m_out = self._forced_masks
             return (m_in.to(device=device, dtype=torch.uint8).contiguous(),
-                    m_out.to(device=device, dtype=torch.uint8).contiguous(), 1.0 / (1.0 - p))
-        shape = (n_rows, self.out_channels)
-        m_in = torch.empty(shape, dtype=torch.uint8, device=device).bernoulli_(1.0 - p)
-        m_out = torch.empty(shape, dtype=torch.uint8, device=device).bernoulli_(1.0 - p)
-        return m_in, m_out, 1.0 / (1.0 - p)
+                    m_out.to(device=device, dtype=torch.uint8).contiguous(), 1.0 / (1.0 - p), None, p)
+        if not self._drop_seeded:
+            self._drop_seed.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+            self._drop_seeded = True
+        self._drop_seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)     # new stream every step (device op: graph-capturable)
+        return None, None, 1.0 / (1.0 - p), self._drop_seed.clone(), p
+
+    def dropout_masks(self, seed, n_rows):
+        """The two keep masks [n_rows, Dout] the tail kernels derive from ``seed`` (int64 device tensor): for tests."""
+        out = []
+        for plane in (0, 1):
+            m = torch.empty((n_rows, self.out_channels), dtype=torch.uint8, device=seed.device)
+            _lib.call('kgc_dropout_mask', _lib.ptr(seed), plane, float(self.drop.p), m.numel(), _lib.ptr(m), _lib.stream())
+            out.append(m)
+        return out
 
     def forward(self, x, edge_index, edge_type, edge_norm, edge_embs, rels_embs, size=None):
         # edge_norm and size are accepted and ignored, exactly as the reference does (model.py:82, SURVEY fact 6)
         num_ent = x.size(0)
         plan = get_plan(edge_index, edge_type, num_ent, rels_embs.size(0) + 1)
-        m_in, m_out, keep_scale = self._masks(num_ent, x.device)
+        m_in, m_out, keep_scale, seed, drop_p = self._masks(num_ent, x.device)
+        self._last_seed = seed
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
         all_ent, all_rel, stats = _ConvFn.apply(
             x, rels_embs, edge_embs, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, plan, m_in, m_out, keep_scale,
-            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None)
+            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None, seed, drop_p)
         self._update_running_stats(stats, num_ent)
         return all_ent, all_rel
 
@@ -318,14 +337,17 @@ class MGCNConv(nn.Module):
         ``edge_embs_local`` = the rows of the edges it owns (``part.owned_eids`` order), ``part`` = a
         GraphPartition.  Exchanges: all-gather of x (forward), reduce-scatter of d_x (backward), all-reduce of the
         BatchNorm column sums (2 x Dout doubles, both ways) and of the replicated-parameter gradients."""
-        m_in, m_out, keep_scale = self._masks(x_local.size(0), x_local.device)
+        m_in, m_out, keep_scale, seed, drop_p = self._masks(x_local.size(0), x_local.device)
+        if seed is not None:
+            seed = seed + part.rank          # decorrelate the row blocks of different ranks
+        self._last_seed = seed
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
         coll = _Collectives(part.group, part.world, part.num_nodes)
         all_ent, all_rel, stats = _ConvFn.apply(
             x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,
-            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, coll)
+            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, coll, seed, drop_p)
         self._update_running_stats(stats, part.num_nodes)
         return all_ent, all_rel
 

@@ -100,13 +100,23 @@ gemm_tn_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __
   }
 }
 
-// C[e] = sum over CTAs, in CTA order (fixed -> deterministic)
-__global__ void gemm_tn_reduce_kernel(const float* __restrict__ partial, int n_parts, int n_elem, float* __restrict__ C) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_elem) return;
+// C[e] = sum over the CTA partials in a FIXED order (deterministic): 8 part-lanes per element stride over the
+// partials, then their 8 sums are added in lane order.  blockDim = (32 elements, 8 part-lanes).
+__global__ void __launch_bounds__(256)
+gemm_tn_reduce_kernel(const float* __restrict__ partial, int n_parts, int n_elem, float* __restrict__ C) {
+  __shared__ float sm[8][33];
+  const int e = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int g = 0; g < n_parts; ++g) s += partial[(int64_t)g * n_elem + e];
-  C[e] = s;
+  if (e < n_elem)
+    for (int g = threadIdx.y; g < n_parts; g += 8) s += partial[(int64_t)g * n_elem + e];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < n_elem) {
+    float t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][threadIdx.x];
+    C[e] = t;
+  }
 }
 
 inline int n_ctas(int64_t M) {
@@ -129,7 +139,7 @@ int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t 
   }
   kern<<<g, kThreadsTN, smem, st>>>(A, lda, B, ldb, M, Ka, Nb, rows_per_cta, ws);
   KGC_LAUNCH_CHECK();
-  gemm_tn_reduce_kernel<<<(Ka * Nb + 255) / 256, 256, 0, st>>>(ws, g, Ka * Nb, C);
+  gemm_tn_reduce_kernel<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(ws, g, Ka * Nb, C);
   KGC_LAUNCH_CHECK();
   return 0;
 }

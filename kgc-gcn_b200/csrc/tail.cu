@@ -26,6 +26,40 @@ __device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t idx4, float s)
   return make_float4(v.x ? s : 0.f, v.y ? s : 0.f, v.z ? s : 0.f, v.w ? s : 0.f);
 }
 
+// Counter-based dropout: Philox4x32-10 keyed by the step's seed, counter = (float4 index, plane).  The forward and
+// the backward regenerate the same keep mask from (seed, index), so no mask tensor is written or read.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// keep-scale per lane of one float4: s where the 32-bit draw >= drop_thr (= p * 2^32), else 0
+__device__ __forceinline__ float4 philox_mask4(int64_t idx4, uint32_t plane, uint64_t seed, uint32_t drop_thr, float s) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), plane, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return make_float4(r.x >= drop_thr ? s : 0.f, r.y >= drop_thr ? s : 0.f, r.z >= drop_thr ? s : 0.f,
+                     r.w >= drop_thr ? s : 0.f);
+}
+struct DropCfg {
+  const uint8_t* mask_in;     // injected keep masks (tests / replay of recorded draws) ...
+  const uint8_t* mask_out;
+  const int64_t* seed;        // ... or a device-resident seed for the counter-based generator (NULL = no dropout)
+  uint32_t drop_thr;
+  float keep_scale;
+};
+__device__ __forceinline__ float4 drop_scale4(const DropCfg& d, int plane, int64_t i) {
+  const uint8_t* m = plane == 0 ? d.mask_in : d.mask_out;
+  if (m != nullptr) return mask4(m, i, d.keep_scale);
+  if (d.seed != nullptr) return philox_mask4(i, (uint32_t)plane, (uint64_t)__ldg(d.seed), d.drop_thr, d.keep_scale);
+  return make_float4(1.f, 1.f, 1.f, 1.f);
+}
+
 // Sum the per-thread double4 accumulators of the RL row-lanes of a block, in lane order, and store
 // them as partials[block][which][col].
 __device__ __forceinline__ void block_store_partials(double4 a, double4 b, int rl, int c, int RL, int Do4,
@@ -51,8 +85,7 @@ __device__ __forceinline__ void block_store_partials(double4 a, double4 b, int r
 }
 
 __global__ void __launch_bounds__(kThreads)
-tail_fwd_kernel(const float4* __restrict__ res3, const uint8_t* __restrict__ mask_in,
-                const uint8_t* __restrict__ mask_out, float keep_scale, const float4* __restrict__ bias,
+tail_fwd_kernel(const float4* __restrict__ res3, const DropCfg drop, const float4* __restrict__ bias,
                 int64_t n_rows, int Do4, float4* __restrict__ pre, double* __restrict__ partials) {
   extern __shared__ double4 sm[];
   const int RL = kThreads / Do4;
@@ -66,8 +99,8 @@ tail_fwd_kernel(const float4* __restrict__ res3, const uint8_t* __restrict__ mas
       const int64_t i = r * Do4 + c;
       float4 a = __ldg(res3 + i), b = __ldg(res3 + plane + i);
       const float4 l = __ldg(res3 + 2 * plane + i);
-      if (mask_in) { const float4 m = mask4(mask_in, i, keep_scale); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; }
-      if (mask_out) { const float4 m = mask4(mask_out, i, keep_scale); b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w; }
+      { const float4 m = drop_scale4(drop, 0, i); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; }
+      { const float4 m = drop_scale4(drop, 1, i); b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w; }
       float4 o;   // (drop(in) + drop(out) + loop) / 3 [+ bias]   (model.py:103-105)
       o.x = (a.x + b.x + l.x) / 3.0f + bv.x;
       o.y = (a.y + b.y + l.y) / 3.0f + bv.y;
@@ -189,8 +222,7 @@ tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restric
 __global__ void __launch_bounds__(kThreads)
 tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
                       const float4* __restrict__ pre, const float4* __restrict__ stats,
-                      const float4* __restrict__ gamma, const double* __restrict__ sums,
-                      const uint8_t* __restrict__ mask_in, const uint8_t* __restrict__ mask_out, float keep_scale,
+                      const float4* __restrict__ gamma, const double* __restrict__ sums, const DropCfg drop,
                       int training, int64_t n_rows, int64_t n_rows_global, int Do4, float4* __restrict__ d_res3) {
   const int64_t n4 = n_rows * (int64_t)Do4;
   const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
@@ -216,8 +248,8 @@ tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict
   }
   const float4 third = make_float4(dp.x / 3.0f, dp.y / 3.0f, dp.z / 3.0f, dp.w / 3.0f);
   float4 a = third, b = third;
-  if (mask_in) { const float4 k = mask4(mask_in, i, keep_scale); a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w; }
-  if (mask_out) { const float4 k = mask4(mask_out, i, keep_scale); b.x *= k.x; b.y *= k.y; b.z *= k.z; b.w *= k.w; }
+  { const float4 k = drop_scale4(drop, 0, i); a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w; }
+  { const float4 k = drop_scale4(drop, 1, i); b.x *= k.x; b.y *= k.y; b.z *= k.z; b.w *= k.w; }
   d_res3[i] = a;
   d_res3[n4 + i] = b;
   d_res3[2 * n4 + i] = third;
@@ -236,15 +268,47 @@ extern "C" int64_t kgc_tail_num_blocks(int64_t n_rows) {
   return nb < kMaxBlocks ? nb : kMaxBlocks;
 }
 
-extern "C" int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, float keep_scale,
-                            const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials,
-                            void* stream) {
+static DropCfg make_drop(const uint8_t* mask_in, const uint8_t* mask_out, const int64_t* seed, float drop_p, float keep_scale) {
+  DropCfg d;
+  d.mask_in = mask_in;
+  d.mask_out = mask_out;
+  d.seed = (seed != nullptr && drop_p > 0.f) ? seed : nullptr;
+  const double thr = (double)drop_p * 4294967296.0;
+  d.drop_thr = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
+  d.keep_scale = keep_scale;
+  return d;
+}
+
+// one float4 of keep flags per thread: exactly the mask the tail kernels regenerate from (seed, plane)
+__global__ void dropout_mask_kernel(const int64_t* __restrict__ seed, uint32_t plane, uint32_t drop_thr, int64_t n4,
+                                    uchar4* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 m = philox_mask4(i, plane, (uint64_t)__ldg(seed), drop_thr, 1.0f);
+  out[i] = make_uchar4(m.x != 0.f, m.y != 0.f, m.z != 0.f, m.w != 0.f);
+}
+
+extern "C" int kgc_dropout_mask(const int64_t* seed, int32_t plane, float drop_p, int64_t n_elem, uint8_t* mask, void* stream) {
+  KGC_REQUIRE(seed != nullptr && n_elem % 4 == 0 && plane >= 0, "bad arguments");
+  const DropCfg d = make_drop(nullptr, nullptr, seed, drop_p, 1.0f);
+  const int64_t n4 = n_elem / 4;
+  if (n4 == 0) return 0;
+  dropout_mask_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(seed, (uint32_t)plane, d.drop_thr,
+                                                                                     n4, (uchar4*)mask);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, const int64_t* seed,
+                            float drop_p, float keep_scale, const float* bias, int64_t n_rows, int32_t Dout, float* pre,
+                            double* partials, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   KGC_REQUIRE(n_rows > 0, "n_rows must be positive");
   const int Do4 = Dout / 4;
   const size_t smem = partial_smem(Do4);   // <= 16 KB
   tail_fwd_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
-      (const float4*)res3, mask_in, mask_out, keep_scale, (const float4*)bias, n_rows, Do4, (float4*)pre, partials);
+      (const float4*)res3, make_drop(mask_in, mask_out, seed, drop_p, keep_scale), (const float4*)bias, n_rows, Do4,
+      (float4*)pre, partials);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -292,14 +356,15 @@ extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, con
 
 extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
                                   const float* gamma, const double* sums, const uint8_t* mask_in,
-                                  const uint8_t* mask_out, float keep_scale, int32_t training, int64_t n_rows,
-                                  int64_t n_rows_global, int32_t Dout, float* d_res3, void* stream) {
+                                  const uint8_t* mask_out, const int64_t* seed, float drop_p, float keep_scale,
+                                  int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout, float* d_res3,
+                                  void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const int64_t n4 = n_rows * Do4;
   tail_bwd_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
       (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma,
-      sums, mask_in, mask_out, keep_scale, training, n_rows, n_rows_global, Do4, (float4*)d_res3);
+      sums, make_drop(mask_in, mask_out, seed, drop_p, keep_scale), training, n_rows, n_rows_global, Do4, (float4*)d_res3);
   KGC_LAUNCH_CHECK();
   return 0;
 }

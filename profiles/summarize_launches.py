@@ -1,0 +1,36 @@
+"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: one MGCNConv fwd+bwd step (eager launches)."""
+import collections
+import csv
+import re
+import sys
+
+
+def main(path, which=5):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+    hdr, data = rows[hi], rows[hi + 1:]
+    kn, mv, idc = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('ID')
+
+    def short(n):
+        n = n.replace('kgc::<unnamed>::', '').replace('void ', '')
+        return re.sub(r'\(.*', '', n)[:84]
+    seq = [(int(r[idc]), short(r[kn]), float(r[mv].replace(',', ''))) for r in data]
+    idx = [i for i, s in enumerate(seq) if s[1].startswith('agg_stream_kernel<0') or s[1].startswith('agg_fwd_kernel')]
+    first_of_step = [i for i, s in enumerate(seq) if 'distribution_elementwise' in s[1]]
+    starts = [i for j, i in enumerate(first_of_step) if j % 2 == 0]
+    a, b = starts[which], starts[which + 1]
+    step = seq[a:b]
+    tot = sum(s[2] for s in step)
+    agg = collections.OrderedDict()
+    for _, n, t in step:
+        agg.setdefault(n, [0, 0.0])
+        agg[n][0] += 1
+        agg[n][1] += t
+    print('| kernel | launches | total us | share |\n|---|---:|---:|---:|')
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print('| `{}` | {} | {:.1f} | {:.1%} |'.format(n, c, t / 1e3, t / tot))
+    print('| **total** | {} | {:.1f} | 100% |'.format(len(step), tot / 1e3))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 5)

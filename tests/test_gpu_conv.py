@@ -295,3 +295,34 @@ def test_gemm_tn_weight_gradient(k, M, Ka, Nb):
     out2 = torch.empty(Ka, Nb, device='cuda')
     k.gemm_tn(a.cuda(), b.cuda(), out2)
     assert torch.equal(out, out2)
+
+
+def test_in_kernel_dropout_matches_its_own_masks(k):
+    """K4 Philox dropout: a training step with the in-kernel generator equals, bit for bit, the same step with the
+    masks that generator produces injected explicitly; the keep rate is 1 - p; seeds change every step."""
+    z, _ = synth_case(1500, 4, 6000, 100, 200, 61)
+    d_in, d_out, R = 100, 200, 4
+    conv = make_conv(k, z, d_in, d_out, R, 0.1).train()
+    torch.manual_seed(7)
+    dev = 'cuda'
+
+    def run(masks):
+        x = torch.from_numpy(z['x']).to(dev).requires_grad_(True)
+        ee = torch.from_numpy(z['edge_embs']).to(dev).requires_grad_(True)
+        rl = torch.from_numpy(z['rels']).to(dev).requires_grad_(True)
+        conv.set_dropout_masks(*masks) if masks else conv.set_dropout_masks(None, None)
+        conv.zero_grad()
+        ent, rel = conv(x, torch.from_numpy(z['edge_index']).to(dev), torch.from_numpy(z['edge_type']).to(dev), None, ee, rl)
+        torch.autograd.backward([ent, rel], [torch.from_numpy(z['g_ent']).to(dev), torch.from_numpy(z['g_rel']).to(dev)])
+        return [ent, rel, x.grad, ee.grad, rl.grad, conv.in_weight.grad.clone(), conv.out_weight.grad.clone()]
+    a = run(None)
+    seed1 = conv._last_seed.clone()
+    m_in, m_out = conv.dropout_masks(seed1, 1500)
+    keep = float(m_in.float().mean())
+    assert abs(keep - 0.9) < 0.005 and not torch.equal(m_in, m_out)
+    b = run((m_in, m_out))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    run(None)
+    assert int(conv._last_seed) != int(seed1)
+    assert '_drop_seed' not in conv.state_dict()
