@@ -198,7 +198,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': val, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -375,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
             line['aux'] = aux_filtered_rank(k, dev, args)
         except Exception as exc:                       # pragma: no cover
             line['aux'] = {'error': repr(exc)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     shutdown(dist)
 
 
@@ -571,6 +571,25 @@ def aux_filtered_rank(k, dev, args):
                          'note': 'un-padded flops 2*B*N*200 / sweep-kernel CUDA-event time vs measured sustained cuBLAS bf16'}}
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Everything libraries print on fd 1 (NCCL prints its version there) goes to stderr; the ONE JSON line is written
+    to the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -584,6 +603,7 @@ def main():
     ap.add_argument('--aux-full', action='store_true', help='scoring sweep at N = 1M, 2M and 4,594,485')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
     args = ap.parse_args()
+    guard_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
