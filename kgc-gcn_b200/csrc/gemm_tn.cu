@@ -12,8 +12,7 @@
 namespace kgc {
 namespace {
 
-constexpr int kWarpsTN = 16;               // 16 warps x (TI x TO) register tiles: 4 warps per scheduler hide the LDS latency
-constexpr int kThreadsTN = kWarpsTN * 32;
+constexpr int kThreadsTN = 256;
 constexpr int kRowsPerStage = 16;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -29,7 +28,7 @@ template <int TI, int TO>
 __global__ void __launch_bounds__(kThreadsTN)
 gemm_tn_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t M,
                        int Ka, int Nb, int64_t rows_per_cta, float* __restrict__ partial) {
-  constexpr int KaP = kWarpsTN * TI, NbP = 32 * TO;
+  constexpr int KaP = 8 * TI, NbP = 32 * TO;
   extern __shared__ __align__(16) float sm[];
   float* sa = sm;                                         // [2][kRowsPerStage][KaP]
   float* sb = sm + 2 * kRowsPerStage * KaP;               // [2][kRowsPerStage][NbP]
@@ -131,7 +130,7 @@ int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t 
               cudaStream_t st) {
   const int g = n_ctas(M);
   const int64_t rows_per_cta = ceil_div(M, g);
-  const size_t smem = (size_t)2 * kRowsPerStage * (kWarpsTN * TI + 32 * TO) * sizeof(float);
+  const size_t smem = (size_t)2 * kRowsPerStage * (8 * TI + 32 * TO) * sizeof(float);
   auto kern = gemm_tn_partial_kernel<TI, TO>;
   static bool attr = false;
   if (!attr) {
@@ -162,6 +161,6 @@ extern "C" int kgc_gemm_tn(const float* A, int64_t lda, const float* B, int64_t 
   KGC_REQUIRE(workspace && workspace_bytes >= kgc_gemm_tn_workspace_bytes(M, Ka, Nb), "workspace too small");
   cudaStream_t st = as_stream(stream);
   float* ws = static_cast<float*>(workspace);
-  if (Ka <= kWarpsTN * 7 && Nb <= 32 * 7) return launch_tn<7, 7>(A, lda, B, ldb, M, Ka, Nb, C, ws, st);
-  return launch_tn<8, 8>(A, lda, B, ldb, M, Ka, Nb, C, ws, st);
+  if (Ka <= 8 * 13 && Nb <= 32 * 7) return launch_tn<13, 7>(A, lda, B, ldb, M, Ka, Nb, C, ws, st);
+  return launch_tn<16, 8>(A, lda, B, ldb, M, Ka, Nb, C, ws, st);
 }

@@ -16,9 +16,10 @@ def main(path, which=5):
         return re.sub(r'\(.*', '', n)[:84]
     seq = [(int(r[idc]), short(r[kn]), float(r[mv].replace(',', ''))) for r in data]
     idx = [i for i, s in enumerate(seq) if s[1].startswith('agg_stream_kernel<0') or s[1].startswith('agg_fwd_kernel')]
-    first_of_step = [i for i, s in enumerate(seq) if 'distribution_elementwise' in s[1]]
-    starts = [i for j, i in enumerate(first_of_step) if j % 2 == 0]
-    a, b = starts[which], starts[which + 1]
+    # a step = the launches between two consecutive forward aggregation kernels (shifted to the step's first launch)
+    first = next(i for i, s in enumerate(seq) if s[1].startswith('pack_b_kernel') or 'distribution_elementwise' in s[1])
+    shift = idx[0] - first if first < idx[0] else 0
+    a, b = idx[which] - shift, idx[which + 1] - shift
     step = seq[a:b]
     tot = sum(s[2] for s in step)
     agg = collections.OrderedDict()
