@@ -178,6 +178,13 @@ size_t kgc_gemm_tn_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb);
 int kgc_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
                 float* C, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same product on the tensor cores (3xTF32, fp32-grade): both operands are MN-major for the MMA (TMA boxes of
+ * 32 columns x 32 rows, 128-byte swizzle), both are split hi / lo in shared memory, D[128 x Nb] stays in TMEM for the
+ * CTA's row slab; per-CTA partials are added in CTA order.  Ka <= 128, Nb <= 224, multiples of 4. */
+size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb);
+int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
+                   float* C, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's
  * query ids qid[B] (int64) and the query->objects CSR (ptr int64 [Q+1], idx int32 [nnz]):

@@ -40,6 +40,8 @@ SIGNATURES = {
     'kgc_gemm_nt': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_gemm_set_debug': (None, [_vp]),
     'kgc_gemm_tn_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'kgc_gemm_tn_tc_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'kgc_gemm_tn_tc': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     'kgc_gemm_tn': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     'kgc_label_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
     'kgc_neg_sample': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
@@ -71,7 +73,7 @@ def lib():
 
 
 LAUNCHES = 0     # kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {'kgc_csr_build': 16, 'kgc_score_pairs': 3, 'kgc_rank_finalize': 2, 'kgc_gemm_tn': 2}
+_KERNELS_PER_CALL = {'kgc_csr_build': 16, 'kgc_score_pairs': 3, 'kgc_rank_finalize': 2, 'kgc_gemm_tn': 2, 'kgc_gemm_tn_tc': 2}
 
 
 def call(name, *args):

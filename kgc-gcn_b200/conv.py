@@ -48,18 +48,20 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b'):
     return out
 
 
-def gemm_tn(a, b, out, plan=None):
-    """out[Ka, Nb] = a[M, Ka]^T @ b[M, Nb] (K4c): the weight-gradient reduction over the node rows, plain fp32 FMAs,
-    per-CTA partials added in a fixed order."""
+def gemm_tn(a, b, out, plan=None, tensor_cores=True):
+    """out[Ka, Nb] = a[M, Ka]^T @ b[M, Nb] (K4c): the weight-gradient reduction over the node rows.  Tensor-core path
+    (3xTF32, MN-major operands) for Ka <= 128, Nb <= 224; register-tiled fp32 FMA kernel for wider outputs.  Both add
+    their per-CTA partials in a fixed order (deterministic)."""
     M, Ka = a.shape
     Nb = b.shape[1]
     if a.stride(1) != 1 or b.stride(1) != 1 or not out.is_contiguous():
         raise ValueError('gemm_tn needs unit inner strides and a contiguous output')
-    nbytes = int(_lib.lib().kgc_gemm_tn_workspace_bytes(M, Ka, Nb))
-    ws = plan.scratch('gemm_tn_ws', (nbytes // 4,)) if plan is not None else \
+    name = 'kgc_gemm_tn_tc' if (tensor_cores and Ka <= 128 and Nb <= 224) else 'kgc_gemm_tn'
+    nbytes = int(getattr(_lib.lib(), name + '_workspace_bytes')(M, Ka, Nb))
+    ws = plan.scratch(name + '_ws', (nbytes // 4,)) if plan is not None else \
         torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
     p = _lib.ptr
-    _lib.call('kgc_gemm_tn', p(a), a.stride(0), p(b), b.stride(0), M, Ka, Nb, p(out), p(ws), nbytes, _lib.stream())
+    _lib.call(name, p(a), a.stride(0), p(b), b.stride(0), M, Ka, Nb, p(out), p(ws), nbytes, _lib.stream())
     return out
 
 

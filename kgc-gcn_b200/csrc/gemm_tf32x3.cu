@@ -406,6 +406,205 @@ int make_tiling(int N, int K, Tiling* t) {
   return 0;
 }
 
+
+// ================================================================================================================
+// Weight-gradient reduction on the tensor cores:  C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb]  (contraction over the node rows)
+//
+// Both operands are MN-major for the MMA (the contraction index m is the SLOW index of both row-major arrays): a TMA
+// box of 32 columns x 32 rows lands as 32 swizzled 128-byte rows = four 8-row K-atoms of an MN-major SWIZZLE_128B
+// operand; the boxes of consecutive 32-column groups sit kTnBox bytes apart (leading byte offset), 8-row groups 1024
+// bytes apart.  One tcgen05.mma kind::tf32 consumes 8 rows (K = 8).  Both operands are streamed, so both are split
+// (hi in place, lo into a second ring) by the splitter warps; D[128 x 208] stays in TMEM for the CTA's whole row slab
+// and is written once as a partial; partials are added in CTA order by gemm_tn_partials_reduce (deterministic).
+constexpr int kTnRows = 32;                      // node rows per K block
+constexpr int kTnBox = kTnRows * 128;            // one 32-column x 32-row box: 4 KB
+constexpr int kTnStages = 3;
+constexpr int kTnLoStages = 2;
+
+struct GemmTnParams {
+  int64_t M;
+  int32_t Ka, Nb, ga, gb, n_pad;                 // ga / gb = 32-column groups of A / B; n_pad = MMA N (multiple of 16)
+  int64_t rows_per_cta;
+  float* partial;                                // [grid][Ka][Nb]
+};
+
+__device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address
+  d |= (uint64_t)(kTnBox >> 4) << 16;                     // leading byte offset: next 32-element MN group
+  d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: next 8-row K group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreadsG, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int stage_bytes = (P.ga + P.gb) * kTnBox;          // A boxes then B boxes
+  uint8_t* s_raw = base;                                   // [kTnStages][stage_bytes]  raw -> hi (in place)
+  uint8_t* s_lo = s_raw + kTnStages * stage_bytes;         // [kTnLoStages][stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kTnLoStages * stage_bytes);
+  uint64_t* raw_full = bars;                               // [kTnStages]
+  uint64_t* split_full = raw_full + kTnStages;             // [kTnStages]
+  uint64_t* empty = split_full + kTnStages;                // [kTnStages]
+  uint64_t* lo_empty = empty + kTnStages;                  // [kTnLoStages]
+  uint64_t* acc_full = lo_empty + kTnLoStages;             // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kTnStages; ++i) {
+      mb_init(raw_full + i, 1);
+      mb_init(split_full + i, kSplitWarps);
+      mb_init(empty + i, 1);
+    }
+    for (int i = 0; i < kTnLoStages; ++i) mb_init(lo_empty + i, 1);
+    mb_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 14) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(kTmemColsG)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t m0 = blockIdx.x * P.rows_per_cta;
+  const int64_t m1 = m0 + P.rows_per_cta < P.M ? m0 + P.rows_per_cta : P.M;
+  const int n_kb = m1 > m0 ? (int)((m1 - m0 + kTnRows - 1) / kTnRows) : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mb_wait(empty + stage, phase ^ 1);
+        mb_expect_tx(raw_full + stage, (uint32_t)stage_bytes);
+        uint8_t* dst = s_raw + stage * stage_bytes;
+        const int row = (int)(m0 + (int64_t)kb * kTnRows);
+        // rows past m1 belong to the next CTA's slab: they are masked out by the splitter (zeroed), rows past M are
+        // zero-filled by TMA
+        for (int g = 0; g < P.ga; ++g) tma_2d(dst + g * kTnBox, &map_a, raw_full + stage, g * 32, row);
+        for (int g = 0; g < P.gb; ++g) tma_2d(dst + (P.ga + g) * kTnBox, &map_b, raw_full + stage, g * 32, row);
+        if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + kSplitWarps) {
+    const int t = threadIdx.x - 64;
+    constexpr int kSplitThreads = kSplitWarps * 32;
+    int stage = 0, ls = 0;
+    uint32_t phase = 0, lphase = 0;
+    const int n_vec = stage_bytes / 16;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mb_wait(raw_full + stage, phase);
+      mb_wait(lo_empty + ls, lphase ^ 1);
+      uint4* hi = reinterpret_cast<uint4*>(s_raw + stage * stage_bytes);
+      uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * stage_bytes);
+      // rows of this K block that lie past the CTA's slab must not contribute: a 16-byte vector v of a box belongs to
+      // box row (v % 256) / 8  (32 rows x 8 vectors per box; the swizzle permutes vectors only inside a row)
+      const int rows_valid = (int)min((int64_t)kTnRows, m1 - (m0 + (int64_t)kb * kTnRows));
+      for (int v = t; v < n_vec; v += kSplitThreads) {
+        uint4 x = hi[v];
+        if (((v & 255) >> 3) >= rows_valid) x = make_uint4(0u, 0u, 0u, 0u);
+        uint4 h, l;
+        split_tf32(x.x, h.x, l.x);
+        split_tf32(x.y, h.y, l.y);
+        split_tf32(x.z, h.z, l.z);
+        split_tf32(x.w, h.w, l.w);
+        hi[v] = h;
+        lo[v] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mb_arrive(split_full + stage);
+      if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+      if (++ls == kTnLoStages) { ls = 0; lphase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // MN-major A and B (bits 15, 16), TF32 operands, fp32 accumulate, M = 128, N = n_pad
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.n_pad >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);
+    int stage = 0, ls = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mb_wait(split_full + stage, phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t hi_a = s_u32(s_raw + stage * stage_bytes), hi_b = hi_a + P.ga * kTnBox;
+      const uint32_t lo_a = s_u32(s_lo + ls * stage_bytes), lo_b = lo_a + P.ga * kTnBox;
+      if (elect_one()) {
+        for (int k = 0; k < kTnRows / kUK; ++k) {                  // 8 node rows per MMA: the next 8-row K group is 1024 B on
+          const uint32_t off = k * 1024;
+          umma_tf32(tmem_base, sw128_mn_desc(lo_a + off), sw128_mn_desc(hi_b + off), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, sw128_mn_desc(hi_a + off), sw128_mn_desc(lo_b + off), idesc, 1u);
+          umma_tf32(tmem_base, sw128_mn_desc(hi_a + off), sw128_mn_desc(hi_b + off), idesc, 1u);
+        }
+        umma_commit_g(empty + stage);
+        umma_commit_g(lo_empty + ls);
+        if (kb == n_kb - 1) umma_commit_g(acc_full);
+      }
+      __syncwarp();
+      if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+      if (++ls == kTnLoStages) ls = 0;
+    }
+  } else if (warp >= 10 && warp <= 13) {
+    // epilogue: D row i (TMEM lane) -> partial[cta][i][0..Nb)
+    const int quarter = warp % 4;
+    const int i = quarter * 32 + lane;
+    float* out = P.partial + ((int64_t)blockIdx.x * P.Ka + i) * P.Nb;
+    if (n_kb > 0) {
+      mb_wait(acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < P.n_pad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32_g(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (i < P.Ka) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < P.Nb) out[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+    } else if (i < P.Ka) {
+      for (int j = 0; j < P.Nb; ++j) out[j] = 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 14) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsG) : "memory");
+  }
+}
+
+// C[e] = sum over the CTA partials in a FIXED order: 8 part-lanes per element, then their sums in lane order
+__global__ void __launch_bounds__(256)
+gemm_tn_partials_reduce(const float* __restrict__ partial, int n_parts, int n_elem, float* __restrict__ C) {
+  __shared__ float sm[8][33];
+  const int e = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (e < n_elem)
+    for (int g = threadIdx.y; g < n_parts; g += 8) s += partial[(int64_t)g * n_elem + e];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < n_elem) {
+    float t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][threadIdx.x];
+    C[e] = t;
+  }
+}
+
+// fp32 [rows, cols] -> boxes of 32 columns x 32 rows (MN-major operand tiles), 128-byte swizzle, zero fill
+int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch) {
+  return make_map_f32(map, ptr, rows, cols, pitch, kTnRows);
+}
+
 }  // namespace
 }  // namespace kgc
 
@@ -463,6 +662,46 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   if (per > P.n_mtiles) per = P.n_mtiles;
   if (per < 1) per = 1;
   gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, P);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {
+  (void)M;
+  return (size_t)kNumSMs * Ka * Nb * sizeof(float);
+}
+
+// C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb] on the tensor cores (3xTF32).  Ka <= 128, Nb <= 224, multiples of 4.
+extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
+                              float* C, void* workspace, size_t workspace_bytes, void* stream) {
+  KGC_REQUIRE(M > 0 && Ka > 0 && Nb > 0 && Ka <= 128 && Nb <= 224, "supported: Ka <= 128, Nb <= 224");
+  KGC_REQUIRE(Ka % 4 == 0 && Nb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "dimensions and leading dimensions must be multiples of 4");
+  KGC_REQUIRE(workspace && workspace_bytes >= kgc_gemm_tn_tc_workspace_bytes(M, Ka, Nb), "workspace too small");
+  CUtensorMap ma, mb;
+  if (make_map_f32_mn(&ma, A, M, Ka, lda) || make_map_f32_mn(&mb, B, M, Nb, ldb)) return 1;
+  GemmTnParams P;
+  P.M = M; P.Ka = Ka; P.Nb = Nb;
+  P.ga = 4;                                   // the MMA always reads M = 128 rows of D: 4 groups (columns past Ka are zero-filled)
+  P.n_pad = (Nb + 15) / 16 * 16;
+  P.gb = (P.n_pad + 31) / 32;
+  int grid = (int)ceil_div(M, 2 * kTnRows);   // at least two K blocks per CTA
+  if (grid > kNumSMs) grid = kNumSMs;
+  if (grid < 1) grid = 1;
+  P.rows_per_cta = ceil_div(ceil_div(M, grid), kTnRows) * kTnRows;     // slabs start on K-block boundaries
+  grid = (int)ceil_div(M, P.rows_per_cta);
+  P.partial = static_cast<float*>(workspace);
+  const size_t stage = (size_t)(P.ga + P.gb) * kTnBox;
+  const size_t smem = (kTnStages + kTnLoStages) * stage + 512 + 1024;
+  KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
+  static size_t attr = 0;
+  if (smem > attr) {
+    KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  cudaStream_t st = as_stream(stream);
+  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, P);
+  KGC_LAUNCH_CHECK();
+  gemm_tn_partials_reduce<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(P.partial, grid, Ka * Nb, C);
   KGC_LAUNCH_CHECK();
   return 0;
 }
