@@ -373,7 +373,8 @@ int encode_fn(EncodeTiledFn* out) {
   return 0;
 }
 // fp32 [rows, cols] with row pitch `pitch` floats -> boxes of 32 (K) x box_rows, 128-byte swizzle, zero fill
-int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc;
   if (encode_fn(&enc)) return 1;
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (pitch * 4) % 16 == 0, "operand must be 16-byte aligned with a 16-byte pitch");
@@ -382,7 +383,7 @@ int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, 
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return 0;
@@ -411,9 +412,9 @@ int make_tiling(int N, int K, Tiling* t) {
 // Weight-gradient reduction on the tensor cores:  C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb]  (contraction over the node rows)
 //
 // Both operands are MN-major for the MMA (the contraction index m is the SLOW index of both row-major arrays): a TMA
-// box of 32 columns x 32 rows lands as 32 swizzled 128-byte rows = four 8-row K-atoms of an MN-major SWIZZLE_128B
-// operand; the boxes of consecutive 32-column groups sit kTnBox bytes apart (leading byte offset), 8-row groups 1024
-// bytes apart.  One tcgen05.mma kind::tf32 consumes 8 rows (K = 8).  Both operands are streamed, so both are split
+// box of 32 columns x 32 rows lands as 32 swizzled 128-byte rows = eight 4-row K atoms of an MN-major
+// SWIZZLE_128B_BASE32B operand; the boxes of consecutive 32-column groups sit kTnBox bytes apart (leading byte offset),
+// 4-row atoms 512 bytes apart (stride byte offset).  One tcgen05.mma kind::tf32 consumes 8 rows (K = 8 = two atoms).  Both operands are streamed, so both are split
 // (hi in place, lo into a second ring) by the splitter warps; D[128 x 208] stays in TMEM for the CTA's whole row slab
 // and is written once as a partial; partials are added in CTA order by gemm_tn_partials_reduce (deterministic).
 constexpr int kTnRows = 32;                      // node rows per K block
@@ -428,13 +429,16 @@ struct GemmTnParams {
   float* partial;                                // [grid][Ka][Nb]
 };
 
+// MN-major TF32 operands have ONE legal shared-memory layout on sm_100: 128-byte swizzle with 32-byte atoms
+// (UMMA layout type SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 MN elements),
+// 4-row K atoms (32-byte chunks XOR-ed with row % 4), atoms 512 B apart along K, MN groups kTnBox apart.
 __device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address
   d |= (uint64_t)(kTnBox >> 4) << 16;                     // leading byte offset: next 32-element MN group
-  d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: next 8-row K group
+  d |= (uint64_t)(512 >> 4) << 32;                        // stride byte offset: next 4-row K atom
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -602,7 +606,7 @@ gemm_tn_partials_reduce(const float* __restrict__ partial, int n_parts, int n_el
 
 // fp32 [rows, cols] -> boxes of 32 columns x 32 rows (MN-major operand tiles), 128-byte swizzle, zero fill
 int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch) {
-  return make_map_f32(map, ptr, rows, cols, pitch, kTnRows);
+  return make_map_f32(map, ptr, rows, cols, pitch, kTnRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 }  // namespace
