@@ -71,23 +71,24 @@ class _Collectives(object):
     def __init__(self, group, world, n_global):
         self.group, self.world, self.n_global = group, int(world), int(n_global)
 
-    def all_gather_rows(self, x_local):
+    def all_gather_rows(self, x_local, async_op=False):
         import torch.distributed as dist
         out = torch.empty((self.world * x_local.shape[0],) + tuple(x_local.shape[1:]), dtype=x_local.dtype,
                           device=x_local.device)
-        dist.all_gather_into_tensor(out, x_local.contiguous(), group=self.group)
-        return out
+        work = dist.all_gather_into_tensor(out, x_local.contiguous(), group=self.group, async_op=async_op)
+        return (out, work) if async_op else out
 
-    def reduce_scatter_rows(self, full):
+    def reduce_scatter_rows(self, full, async_op=False):
         import torch.distributed as dist
         rows = full.shape[0] // self.world
         if dist.get_backend(self.group) == 'gloo':       # gloo (CPU tests of the host logic) has no reduce-scatter
             dist.all_reduce(full, group=self.group)
             r = dist.get_rank(self.group)
-            return full[r * rows:(r + 1) * rows].clone()
+            out = full[r * rows:(r + 1) * rows].clone()
+            return (out, None) if async_op else out
         out = torch.empty((rows,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-        dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group)
-        return out
+        work = dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group, async_op=async_op)
+        return (out, work) if async_op else out
 
     def all_reduce(self, t):
         import torch.distributed as dist
@@ -112,13 +113,20 @@ class _ConvFn(torch.autograd.Function):
         relp = torch.cat([rels, loop_rel], 0).contiguous()          # model.py:86
         if relp.shape[0] != plan.num_types:
             raise ValueError('rels_embs rows + 1 must equal the number of edge types of the plan')
-        # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition)
-        x_full = x if coll is None else coll.all_gather_rows(x)
+        # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition); it runs on
+        # NCCL's stream while this rank's self-loop transform (which only needs its own rows) runs here
+        gather = None
+        if coll is None:
+            x_full = x
+        else:
+            x_full, gather = coll.all_gather_rows(x, async_op=True)
 
         v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
         w_loop_s = v * w_loop
         res3 = plan.scratch('res3', (3, Nl, Dout))
         gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
+        if gather is not None:
+            gather.wait()
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
@@ -209,6 +217,9 @@ class _ConvFn(torch.autograd.Function):
                       sp.n_rec, plan.num_dst_rows, plan.num_edges_in, p(loop_addend), p(d_ee), p(out_final), p(carry),
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
+        scatter = None
+        if coll is not None:       # source-row gradients go back to their owners while the d_rel pass runs here
+            d_x, scatter = coll.reduce_scatter_rows(d_x_full, async_op=True)
 
         def level0_rel(sp, out_final, carry):
             _lib.call('kgc_agg_bwd_rel', p(x_full), p(ee), p(g3), p(plan.rec_type), p(sp.rowflags), p(sp.chunks), sp.n_rec,
@@ -218,9 +229,10 @@ class _ConvFn(torch.autograd.Function):
         if coll is None:
             d_x = d_x_full
         else:
-            d_x = coll.reduce_scatter_rows(d_x_full)                 # every rank contributed to every source row
-            d_x += g3[2]
             coll.all_reduce(flat)
+            if scatter is not None:
+                scatter.wait()
+            d_x += g3[2]                                              # self-loop term of this rank's rows
         v = (loop_rel * loop_edge).reshape(D, 1)
         d_w_loop = v * m_loop
         d_v = (m_loop * w_loop).sum(1).reshape(1, D)
