@@ -195,31 +195,34 @@ __global__ void rows_fill_kernel(const int32_t* __restrict__ rows, int64_t n_row
     out[r * D4 + c] = addend ? __ldg(addend + r * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// ------------------------------------------------------------------------------------------------ higher levels
-// One block per item; 32 groups stride over the item's partial rows, then group 0 adds the 32
-// group sums in index order.  Fan-in up to 1024 rows per item keeps the level count at <= 3 even
-// for a 9M-edge hub row.
+// ------------------------------------------------------------------------------------------------ fix-up levels
+// One 1024-thread block per item: 128 groups of 8 lanes stride over the item's carry / partial rows (4 rows in flight
+// per group), the 4 groups of a warp are combined with shuffles, the 32 warp sums through shared memory - always in the
+// same order, so the result is deterministic.  Fan-in up to 2048 rows per item: a 38k-edge hub row (1,187 carry rows)
+// is ONE item and one launch; a 9M-edge hub needs two levels.
+constexpr int kRedThreads = 1024;
+constexpr int kRedGroups = kRedThreads / kGroup;     // 128
+
 template <int NF>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kRedThreads)
 rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restrict__ items,
                    float4* __restrict__ out_final, float4* __restrict__ out_part,
                    const float4* __restrict__ addend, int D4) {
-  __shared__ float4 sm[kThreads / kGroup][kMaxNF * kGroup];
+  __shared__ float4 sm[kRedThreads / 32][NF * kGroup];
   const int4 it = __ldg(reinterpret_cast<const int4*>(items + blockIdx.x));
-  const int grp = threadIdx.x / kGroup, g = threadIdx.x % kGroup;
+  const int grp = threadIdx.x / kGroup, g = threadIdx.x % kGroup, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   float4 acc[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  constexpr int kStride = kThreads / kGroup;
   int r = it.x + grp;
-  for (; r + 3 * kStride < it.y; r += 4 * kStride) {      // 4 independent rows in flight, added in row order
+  for (; r + 3 * kRedGroups < it.y; r += 4 * kRedGroups) {      // 4 independent rows in flight, added in row order
     float4 v[4][NF];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         const int c = g + f * kGroup;
-        if (c < D4) v[u][f] = __ldg(part_in + (int64_t)(r + u * kStride) * D4 + c);
+        if (c < D4) v[u][f] = __ldg(part_in + (int64_t)(r + u * kRedGroups) * D4 + c);
       }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -229,17 +232,27 @@ rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restr
         if (c < D4) add4(acc[f], v[u][f]);
       }
   }
-  for (; r < it.y; r += kStride) {
+  for (; r < it.y; r += kRedGroups) {
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int c = g + f * kGroup;
       if (c < D4) add4(acc[f], __ldg(part_in + (int64_t)r * D4 + c));
     }
   }
+  // the 4 groups of a warp hold the same columns: (g0 + g1) + (g2 + g3), fixed order
 #pragma unroll
-  for (int f = 0; f < NF; ++f) sm[grp][g + f * kGroup] = acc[f];
+  for (int f = 0; f < NF; ++f) {
+    float4 t;
+    t.x = __shfl_xor_sync(0xffffffffu, acc[f].x, 8); t.y = __shfl_xor_sync(0xffffffffu, acc[f].y, 8);
+    t.z = __shfl_xor_sync(0xffffffffu, acc[f].z, 8); t.w = __shfl_xor_sync(0xffffffffu, acc[f].w, 8);
+    add4(acc[f], t);
+    t.x = __shfl_xor_sync(0xffffffffu, acc[f].x, 16); t.y = __shfl_xor_sync(0xffffffffu, acc[f].y, 16);
+    t.z = __shfl_xor_sync(0xffffffffu, acc[f].z, 16); t.w = __shfl_xor_sync(0xffffffffu, acc[f].w, 16);
+    add4(acc[f], t);
+    if (lane < kGroup) sm[warp][g + f * kGroup] = acc[f];
+  }
   __syncthreads();
-  if (grp == 0) {
+  if (warp == 0 && lane < kGroup) {
     const bool final_row = (it.w & 1) != 0;
     float4* out = (final_row ? out_final : out_part) + (int64_t)it.z * D4;
 #pragma unroll
@@ -247,7 +260,7 @@ rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restr
       const int c = g + f * kGroup;
       if (c < D4) {
         float4 v = sm[0][c];
-        for (int k = 1; k < kThreads / kGroup; ++k) add4(v, sm[k][c]);
+        for (int k = 1; k < kRedThreads / 32; ++k) add4(v, sm[k][c]);
         if (final_row && addend != nullptr) add4(v, __ldg(addend + (int64_t)it.z * D4 + c));
         out[c] = v;
       }
@@ -352,7 +365,7 @@ extern "C" int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, in
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   if (n_items == 0) return 0;
-  KGC_DISPATCH_NF(nf, (rows_reduce_kernel<NF><<<(unsigned)n_items, kThreads, 0, as_stream(stream)>>>(
+  KGC_DISPATCH_NF(nf, (rows_reduce_kernel<NF><<<(unsigned)n_items, kRedThreads, 0, as_stream(stream)>>>(
                           (const float4*)part_in, items, (float4*)out_final, (float4*)out_part,
                           (const float4*)addend, D4)));
   KGC_LAUNCH_CHECK();

@@ -10,8 +10,8 @@ import torch
 from . import _lib
 
 CHUNK0 = 32      # build_levels default fan-in of the first level
-CHUNK1 = 128     # partial rows per item on the fix-up levels (one 256-thread block = 32 groups x 4 rows each):
-                 # a 38k-edge hub row (1,187 carry rows) becomes 10 parallel items + 1, not 2 long serial ones
+CHUNK1 = 2048    # carry / partial rows per item on the fix-up levels (one 1024-thread block): a 38k-edge hub row
+                 # (1,187 carry rows) is one item and ONE launch; a 9M-edge hub needs two levels
 
 
 def build_levels(seg_beg, seg_end, seg_row, chunk0=CHUNK0, chunk1=CHUNK1):

@@ -41,7 +41,7 @@ def test_build_levels_exact(seed):
     ptr = np.concatenate([[0], np.cumsum(lens)])
     rows = rng.permutation(400)
     levels = build_levels(ptr[:-1], ptr[1:], rows, 32, 1024)
-    assert len(levels) == 3 and levels[-1][1] == 0
+    assert len(levels) >= 2 and levels[-1][1] == 0
     vals = rng.integers(-5, 6, ptr[-1]).astype(np.float64)
     out = simulate(levels, vals, 400)
     exp = np.array([vals[ptr[i]:ptr[i + 1]].sum() for i in range(400)])
@@ -112,7 +112,7 @@ def test_stream_plan_exact(seed):
     rng = np.random.default_rng(seed)
     S = 300
     lens = rng.integers(0, 6, S)
-    lens[5], lens[100], lens[S - 1] = 40000, 33, 128 * 128 * 32 + 7  # hubs: several fix-up levels
+    lens[5], lens[100], lens[S - 1] = 40000, 33, 2048 * 32 * 3 + 7   # hubs: one and two fix-up levels
     if seed == 3:
         lens[:] = 0
         lens[17] = 5                                                   # almost everything empty
@@ -126,7 +126,7 @@ def test_stream_plan_exact(seed):
     np.testing.assert_array_equal(out[rows], exp)
     assert sp['chunks'].shape == (-(-n_rec // 32), 2)
     for items, _ in sp['levels']:
-        assert (items[:, 1] - items[:, 0]).max() <= 128
+        assert (items[:, 1] - items[:, 0]).max() <= 2048
 
 
 def test_stream_plan_forward_layout():
