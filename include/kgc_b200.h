@@ -95,8 +95,9 @@ int kgc_agg_fwd(const float* x, const float* rel, int64_t n_types, const float* 
 int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, float* out, int32_t D, void* stream);
 
 /* Fix-up levels shared by K2/K3: out[row] = sum of rows [beg,end) of `part_in` (carry rows, then partial
- * rows of the previous level) (+ addend[row] on final rows when addend != NULL), in a fixed order. */
-int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items,
+ * rows of the previous level) (+ addend[row] on final rows when addend != NULL), in a fixed order.  The first
+ * n_large items get a 1024-thread block each (hub rows), the others one 8-lane group each. */
+int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items, int64_t n_large,
                     float* out_final, float* out_part, const float* addend, int32_t D, void* stream);
 
 /* ---- K3: aggregation backward ------------------------------------------------------------------

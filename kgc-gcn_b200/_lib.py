@@ -24,7 +24,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'kgc_agg_fwd': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_fill': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
-    'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
     'kgc_agg_bwd_src': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     'kgc_agg_bwd_rel': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     'kgc_tail_num_blocks': (_i64, [_i64]),

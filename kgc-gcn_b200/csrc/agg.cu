@@ -199,18 +199,47 @@ __global__ void rows_fill_kernel(const int32_t* __restrict__ rows, int64_t n_row
 // One 1024-thread block per item: 128 groups of 8 lanes stride over the item's carry / partial rows (4 rows in flight
 // per group), the 4 groups of a warp are combined with shuffles, the 32 warp sums through shared memory - always in the
 // same order, so the result is deterministic.  Fan-in up to 2048 rows per item: a 38k-edge hub row (1,187 carry rows)
-// is ONE item and one launch; a 9M-edge hub needs two levels.
+// is ONE item and one launch; a 9M-edge hub needs two levels.  The first n_large items of a level get a block each;
+// the (thousands of) small items - rows that merely straddle a chunk boundary - get one 8-lane group each.
 constexpr int kRedThreads = 1024;
 constexpr int kRedGroups = kRedThreads / kGroup;     // 128
 
 template <int NF>
 __global__ void __launch_bounds__(kRedThreads)
-rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restrict__ items,
-                   float4* __restrict__ out_final, float4* __restrict__ out_part,
+rows_reduce_kernel(const float4* __restrict__ part_in, const kgc_item_t* __restrict__ items, int64_t n_items,
+                   int64_t n_large, float4* __restrict__ out_final, float4* __restrict__ out_part,
                    const float4* __restrict__ addend, int D4) {
   __shared__ float4 sm[kRedThreads / 32][NF * kGroup];
-  const int4 it = __ldg(reinterpret_cast<const int4*>(items + blockIdx.x));
   const int grp = threadIdx.x / kGroup, g = threadIdx.x % kGroup, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if ((int64_t)blockIdx.x >= n_large) {
+    // small items (a row that merely straddles one or two chunk boundaries: 2-16 carry rows): one 8-lane group each
+    const int64_t item = n_large + ((int64_t)blockIdx.x - n_large) * kRedGroups + grp;
+    if (item >= n_items) return;
+    const int4 it = __ldg(reinterpret_cast<const int4*>(items + item));
+    float4 acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = it.x; r < it.y; ++r) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const int c = g + f * kGroup;
+        if (c < D4) add4(acc[f], __ldg(part_in + (int64_t)r * D4 + c));
+      }
+    }
+    const bool final_row = (it.w & 1) != 0;
+    float4* out = (final_row ? out_final : out_part) + (int64_t)it.z * D4;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int c = g + f * kGroup;
+      if (c < D4) {
+        float4 v = acc[f];
+        if (final_row && addend != nullptr) add4(v, __ldg(addend + (int64_t)it.z * D4 + c));
+        out[c] = v;
+      }
+    }
+    return;
+  }
+  const int4 it = __ldg(reinterpret_cast<const int4*>(items + blockIdx.x));
   float4 acc[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -360,13 +389,15 @@ extern "C" int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* a
   return 0;
 }
 
-extern "C" int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items, float* out_final,
-                               float* out_part, const float* addend, int32_t D, void* stream) {
+extern "C" int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items, int64_t n_large,
+                               float* out_final, float* out_part, const float* addend, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
+  KGC_REQUIRE(n_large >= 0 && n_large <= n_items, "n_large must lie in [0, n_items]");
   if (n_items == 0) return 0;
-  KGC_DISPATCH_NF(nf, (rows_reduce_kernel<NF><<<(unsigned)n_items, kRedThreads, 0, as_stream(stream)>>>(
-                          (const float4*)part_in, items, (float4*)out_final, (float4*)out_part,
+  const unsigned grid = (unsigned)(n_large + ceil_div(n_items - n_large, kRedGroups));
+  KGC_DISPATCH_NF(nf, (rows_reduce_kernel<NF><<<grid, kRedThreads, 0, as_stream(stream)>>>(
+                          (const float4*)part_in, items, n_items, n_large, (float4*)out_final, (float4*)out_part,
                           (const float4*)addend, D4)));
   KGC_LAUNCH_CHECK();
   return 0;

@@ -50,6 +50,7 @@ def build_levels(seg_beg, seg_end, seg_row, chunk0=CHUNK0, chunk1=CHUNK1):
         chunk = chunk1
 
 
+SMALL_ITEM = 16   # fix-up items with at most this many rows are summed by one 8-lane group instead of a whole block
 CHUNK_EDGES = 32  # KGC_CHUNK_EDGES: sorted records per streaming chunk (one warp)
 
 
@@ -112,7 +113,13 @@ class StreamPlan(object):
         self.n_carry = sp['n_carry']
         self.fill_rows = torch.from_numpy(sp['fill_rows']).to(device)
         self.n_fill = int(sp['fill_rows'].shape[0])
-        self.levels = [(torch.from_numpy(it).to(device), int(it.shape[0]), n_part) for it, n_part in sp['levels']]
+        self.levels = []
+        for it, n_part in sp['levels']:
+            # hub rows first (a block each), then the many rows that merely straddle a chunk boundary (a lane group each)
+            large = (it[:, 1] - it[:, 0]) > SMALL_ITEM
+            order = np.concatenate([np.nonzero(large)[0], np.nonzero(~large)[0]])
+            self.levels.append((torch.from_numpy(np.ascontiguousarray(it[order])).to(device), int(it.shape[0]), n_part,
+                                int(large.sum())))
 
 
 class GraphPlan(object):
@@ -201,9 +208,9 @@ class GraphPlan(object):
             _lib.call('kgc_rows_fill', _lib.ptr(sp.fill_rows), sp.n_fill, _lib.ptr(addend), _lib.ptr(out_final), D,
                       _lib.stream())
         prev = carry
-        for li, (items, n_items, n_part) in enumerate(sp.levels):
+        for li, (items, n_items, n_part, n_large) in enumerate(sp.levels):
             part = self.scratch('{}part{}'.format(tag, li), (n_part, D)) if n_part else None
-            _lib.call('kgc_rows_reduce', _lib.ptr(prev), _lib.ptr(items), n_items, _lib.ptr(out_final),
+            _lib.call('kgc_rows_reduce', _lib.ptr(prev), _lib.ptr(items), n_items, n_large, _lib.ptr(out_final),
                       _lib.ptr(part), _lib.ptr(addend), D, _lib.stream())
             prev = part
 
