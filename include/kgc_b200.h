@@ -96,7 +96,7 @@ int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, floa
 
 /* Fix-up levels shared by K2/K3: out[row] = sum of rows [beg,end) of `part_in` (carry rows, then partial
  * rows of the previous level) (+ addend[row] on final rows when addend != NULL), in a fixed order.  The first
- * n_large items get a 1024-thread block each (hub rows), the others one 8-lane group each. */
+ * n_large items get a 512-thread block each (hub rows), the others one 8-lane group each. */
 int kgc_rows_reduce(const float* part_in, const kgc_item_t* items, int64_t n_items, int64_t n_large,
                     float* out_final, float* out_part, const float* addend, int32_t D, void* stream);
 

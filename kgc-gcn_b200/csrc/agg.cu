@@ -196,13 +196,13 @@ __global__ void rows_fill_kernel(const int32_t* __restrict__ rows, int64_t n_row
 }
 
 // ------------------------------------------------------------------------------------------------ fix-up levels
-// One 1024-thread block per item: 128 groups of 8 lanes stride over the item's carry / partial rows (4 rows in flight
+// One 512-thread block per item: 64 groups of 8 lanes stride over the item's carry / partial rows (4 rows in flight
 // per group), the 4 groups of a warp are combined with shuffles, the 32 warp sums through shared memory - always in the
 // same order, so the result is deterministic.  Fan-in up to 2048 rows per item: a 38k-edge hub row (1,187 carry rows)
 // is ONE item and one launch; a 9M-edge hub needs two levels.  The first n_large items of a level get a block each;
 // the (thousands of) small items - rows that merely straddle a chunk boundary - get one 8-lane group each.
-constexpr int kRedThreads = 1024;
-constexpr int kRedGroups = kRedThreads / kGroup;     // 128
+constexpr int kRedThreads = 512;
+constexpr int kRedGroups = kRedThreads / kGroup;     // 64
 
 template <int NF>
 __global__ void __launch_bounds__(kRedThreads)
