@@ -36,6 +36,9 @@ WORKLOADS = {
     'wikidata5m': (4594485, 822, 20614279, 2),
 }
 D_IN, D_OUT, BATCH = 100, 200, 128
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this bench command
+# (profiles/r01_ncu_conv_kernels_final.md); below the algorithmic bytes because x / g / rel rows hit L2
+NCU_TRAFFIC = {'wn18rr': {'agg_fwd': 96.55e6, 'agg_bwd_src': 165.89e6, 'agg_bwd_rel': 110.87e6}}
 
 
 def params_ns():
@@ -337,7 +340,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel, timed alone through the C ABI (rank 0)
     roof, kernels = None, None
     if rank == 0 and world == 1:
-        roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush)
+        roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush, args.workload)
     if dist is not None:
         # release the CUDA graph (it holds the captured NCCL kernels) before the communicator goes away
         run_step = None
@@ -463,7 +466,7 @@ def e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist):
             'scope': 'partitioned encoder step: batch ids from pinned host memory -> forward_partitioned -> scalar loss -> backward -> loss.item()'}
 
 
-def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
+def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush, workload='wn18rr'):
     """Each level-0 aggregation kernel alone through the C ABI, CUDA events, L2 flushed before every launch."""
     L = k._lib
     p, st = L.ptr, L.stream
@@ -510,7 +513,7 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush):
         out[name] = {'ms': ms, 'algorithmic_bytes': bytes_[name], 'achieved_gbs': gbs, 'frac': gbs / peak}
     top = max((n for n in out if n.startswith('agg_')), key=lambda n: out[n]['ms'])
     roof = {'kernel': top, 'bound': 'hbm', 'achieved': out[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-            'frac': out[top]['frac'], 'traffic': None, 'peak_source': peak_src,
+            'frac': out[top]['frac'], 'traffic': NCU_TRAFFIC.get(workload, {}).get(top), 'peak_source': peak_src,
             'how': 'kernel launched alone through the C ABI, CUDA events on the launch stream, L2 flushed before each launch'}
     return roof, out
 
