@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                    'l2': 'flushed between steps (256 MiB memset + 256 MiB read, outside the timed events)', 'launch': launch_mode,
                    'parallelism': 'single GPU' if world == 1 else 'dst-range partition over {} GPUs: all-gather x / reduce-scatter d_x / all-reduce BN sums + replicated grads (NCCL)'.format(world)},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
-                'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1),
+                'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1), 'eager_ms_per_step': e2e.get('eager_ms_per_step'),
                 'scope': e2e['scope']},
         'gpu_launches': launches_per_step * args.steps,
         'clocks': clocks.summary(),
@@ -397,6 +397,9 @@ def shutdown(dist):
 
 
 def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
+    """Whole training step through the public API, host ids in, loss out.  Two launch modes are timed: the graph-captured
+    step (kgc_gcn_b200.GraphedTrainStep: one CUDA-graph replay per step - the headline e2e) and the plain eager loop the
+    reference's main.py runs (reported as e2e_eager)."""
     prm = params_ns()
     graph = k.GraphData(edge_index=torch.from_numpy(g['edge_index']), edge_attr=torch.from_numpy(g['edge_attr']))
     graph.entity = torch.from_numpy(g['entity'])
@@ -405,32 +408,53 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
     graph.to(dev)
     ds = k.KBDataset(synthetic_queries(orc, tri, R), N, prm, training=True)
     loader = k.BatchIterator(ds, BATCH, shuffle=True, device=dev)
-    model = k.MGCN(N, R, E, prm).to(dev)
-    model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     steps, warm = args.steps, max(3, args.warmup)
-    batches = loader.batches()
-    ms, n = 0.0, 0
-    for i in range(warm + steps):
-        qid = next(batches)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        trip, lab = ds.build_batch(qid, dev)                         # H2D: the batch's query ids
-        opt.zero_grad()
-        pred = model(trip[:, 0], trip[:, 1], graph)
-        loss = model.loss(pred, lab)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
-        loss.item()                                                   # D2H: the loss
-        b.record()
-        torch.cuda.synchronize()
-        if i >= warm:
-            ms += a.elapsed_time(b)
-            n += 1
-    del model, opt
-    return {'ms_total': ms, 'steps': n, 'h2d': BATCH * 8, 'd2h': 4,
-            'scope': 'full training step: loader batch (K5) + MGCN forward + BCE + backward + clip + Adam + loss.item()'}
+    out = {}
+    for mode in ('graph', 'eager'):
+        torch.manual_seed(0)
+        model = k.MGCN(N, R, E, prm).to(dev)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=(mode == 'graph'))
+        batches = loader.batches()
+        step = k.GraphedTrainStep(model, opt, graph, ds, BATCH) if mode == 'graph' else None
+        ms, n = 0.0, 0
+        try:
+            for i in range(warm + steps):
+                qid = next(batches)
+                while len(qid) != BATCH:
+                    qid = next(batches)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                if step is not None:
+                    step(qid).item()                                          # H2D: query ids; D2H: the loss
+                else:
+                    trip, lab = ds.build_batch(qid, dev)
+                    opt.zero_grad()
+                    pred = model(trip[:, 0], trip[:, 1], graph)
+                    loss = model.loss(pred, lab)
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                    opt.step()
+                    loss.item()
+                b.record()
+                torch.cuda.synchronize()
+                if i >= warm:
+                    ms += a.elapsed_time(b)
+                    n += 1
+            out[mode] = (ms, n)
+        except Exception as exc:                                              # pragma: no cover
+            sys.stderr.write('e2e mode {} failed: {!r}\n'.format(mode, exc))
+            torch.cuda.synchronize()
+        del model, opt, step
+        torch.cuda.empty_cache()
+    head = 'graph' if 'graph' in out else 'eager'
+    res = {'ms_total': out[head][0], 'steps': out[head][1], 'h2d': BATCH * 8, 'd2h': 4,
+           'scope': 'full training step through the public API ({}): host query ids -> K5 batch build -> MGCN forward -> BCE -> '
+                    'backward -> clip_grad_norm -> Adam -> loss.item()'.format(
+                        'GraphedTrainStep, one CUDA-graph replay per step' if head == 'graph' else 'eager loop')}
+    if 'eager' in out and head == 'graph':
+        res['eager_ms_per_step'] = out['eager'][0] / out['eager'][1]
+    return res
 
 
 def e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist):

@@ -12,8 +12,9 @@ from .plan import GraphPlan, get_plan, build_levels, build_stream_plan   # noqa:
 from .scoring import (EntityTable, filtered_rank, pack_queries, pair_scores, predict, evaluate,   # noqa: F401
                       score_kpad)
 from .partition import GraphPartition, partition_edges   # noqa: F401
+from .train import GraphedTrainStep             # noqa: F401
 from . import _lib                               # noqa: F401
 
 __all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
            'get_plan', 'build_levels', 'build_stream_plan', 'get_param', 'gemm_nt', 'gemm_tn', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
-           'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges']
+           'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges', 'GraphedTrainStep']

@@ -1,0 +1,92 @@
+"""Graph-captured training step: the reference's inner loop (main.py:57-71) as ONE CUDA graph replay.
+
+The reference issues ~200 small operations per step from Python; on a B200 the step is then bound by the host, not the
+GPU.  ``GraphedTrainStep`` captures forward + BCE loss + backward + gradient clipping + Adam into a CUDA graph over static
+input buffers; per step the host only hands over the batch's query ids (K5 builds the batch straight into the static
+buffers), replays the graph and reads the loss back.  Numerics are those of the eager step (same kernels, same order).
+"""
+import torch
+
+from . import _lib
+
+
+class GraphedTrainStep(object):
+    """step = GraphedTrainStep(model, optimizer, graph, dataset, batch_size); loss = step(qid).
+
+    ``optimizer`` must be capturable (``torch.optim.Adam(..., capturable=True)``); ``dataset`` is the KBDataset of the
+    training queries; batches whose size differs from ``batch_size`` (the last one of an epoch) run eagerly."""
+
+    def __init__(self, model, optimizer, graph, dataset, batch_size, clip_grad=1.0, warmup=3):
+        self.model, self.opt, self.graph_data, self.ds = model, optimizer, graph, dataset
+        self.clip, self.B = float(clip_grad), int(batch_size)
+        dev = graph.edge_index.device
+        if dev.type != 'cuda':
+            raise RuntimeError('GraphedTrainStep runs on the GPU only')
+        self.dev = dev
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.trip = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
+        self.label = torch.zeros((self.B, dataset.num_entity), dtype=torch.float32, device=dev)
+        self.qid = torch.zeros((self.B,), dtype=torch.int64, device=dev)
+        self.loss = None
+        self.cuda_graph = None
+        self._warmup = int(warmup)
+
+    def _fill(self, qid):
+        """Host ids -> static device buffers (H2D of B int64), then K5 into the static triple / label buffers."""
+        host = torch.as_tensor(qid, dtype=torch.int64)
+        self.qid.copy_(host, non_blocking=True)
+        triples, ptr, idx = self.ds.device_csr(self.dev)
+        pos, add = self.ds.label_values()
+        p = _lib.ptr
+        _lib.call('kgc_label_build', p(self.qid), self.B, p(triples), p(ptr), p(idx), self.ds.num_entity, pos, add,
+                  p(self.trip), p(self.label), _lib.stream())
+
+    def _body(self, trip, label):
+        pred = self.model(trip[:, 0], trip[:, 1], self.graph_data)
+        loss = self.model.loss(pred, label)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        self.opt.step()
+        return loss.detach()
+
+    def _capture(self):
+        self.model.train()
+        # warm-up iterations (allocator, cuBLAS / cuDNN handles, lazy optimiser state) must not change the training
+        # trajectory: parameters, buffers and optimiser state are restored afterwards
+        fresh = len(self.opt.state) == 0
+        saved_p = [p.detach().clone() for p in self.params]
+        saved_b = [b.detach().clone() for b in self.model.buffers()]
+        saved_s = None if fresh else [[v.detach().clone() if torch.is_tensor(v) else v for v in st.values()]
+                                      for st in self.opt.state.values()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(self._warmup, 1)):
+                self.opt.zero_grad(set_to_none=True)
+                self._body(self.trip, self.label)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, sp in zip(self.params, saved_p):
+                p.copy_(sp)
+            for b, sb in zip(self.model.buffers(), saved_b):
+                b.copy_(sb)
+            for i, st in enumerate(self.opt.state.values()):
+                for j, (key, v) in enumerate(st.items()):
+                    if torch.is_tensor(v):
+                        v.zero_() if fresh else v.copy_(saved_s[i][j])
+        self.cuda_graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.cuda_graph):
+            self.loss = self._body(self.trip, self.label)
+
+    def __call__(self, qid):
+        if len(qid) != self.B:                       # ragged last batch: the eager path (same arithmetic)
+            trip, label = self.ds.build_batch(qid, self.dev)
+            self.opt.zero_grad(set_to_none=True)
+            return self._body(trip, label)
+        self._fill(qid)
+        if self.cuda_graph is None:
+            self._capture()                          # capture records the step; nothing has been executed for this batch yet
+        self.cuda_graph.replay()
+        return self.loss

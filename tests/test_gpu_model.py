@@ -97,3 +97,38 @@ def test_iterators(toy):
         assert lab.shape == (trip.shape[0], 7)
         seen += trip.shape[0]
     assert seen == 17
+
+
+def test_graphed_train_step_matches_eager(toy):
+    """GraphedTrainStep (one CUDA-graph replay per step) follows the eager loop of main.py:57-71 step for step."""
+    import copy
+    k, dl, m0, z = toy
+    prm = params(lbl_smooth=0.0)
+    ds = dl._get_dataset('train', prm)
+    qids = [list(range(0, 16)), list(range(1, 17)), list(range(0, 16))]
+    losses = {}
+    finals = {}
+    for mode in ('eager', 'graph'):
+        torch.manual_seed(3)
+        m = copy.deepcopy(m0).train()
+        m.conv1.drop.p = 0.0
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2, capturable=(mode == 'graph'))
+        step = k.GraphedTrainStep(m, opt, dl.graph, ds, 16, warmup=0) if mode == 'graph' else None
+        ls = []
+        for q in qids:
+            if step is not None:
+                ls.append(float(step(q).item()))
+            else:
+                trip, lab = ds.build_batch(q, 'cuda')
+                opt.zero_grad()
+                loss = m.loss(m(trip[:, 0], trip[:, 1], dl.graph), lab)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+                opt.step()
+                ls.append(float(loss.item()))
+        losses[mode] = ls
+        finals[mode] = {n: p.detach().clone() for n, p in m.named_parameters()}
+    for a, b in zip(losses['eager'], losses['graph']):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (losses)
+    for n in finals['eager']:
+        assert torch.allclose(finals['eager'][n], finals['graph'][n], rtol=1e-4, atol=1e-6), n
