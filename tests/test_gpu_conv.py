@@ -327,3 +327,95 @@ def test_in_kernel_dropout_matches_its_own_masks(k):
     run(None)
     assert int(conv._last_seed) != int(seed1)
     assert '_drop_seed' not in conv.state_dict()
+
+
+def test_conv_full_wn18rr_shape_vs_oracle_f64(k):
+    """BASELINE.json configs[1] at FULL size (40,943 entities, 11 relations, 86,835 triples, Zipf objects): outputs and
+    every gradient against the oracle's float64 run on the same inputs."""
+    z, p = synth_case(40943, 11, 86835, 100, 200, 0)
+    dt = torch.float64
+    w64 = {kk: v.to(dt) for kk, v in p['w'].items()}
+    ent64, rel64, g64, _ = orc.conv_fwd_bwd(p['x'].to(dt), torch.from_numpy(z['edge_index']),
+                                            torch.from_numpy(z['edge_type']), p['edge_embs'].to(dt), p['rels'].to(dt),
+                                            w64, torch.from_numpy(z['g_ent']), torch.from_numpy(z['g_rel']))
+    _, ent, rel, grads = run_case(k, z)
+    close(ent, ent64.numpy(), 'all_ent')
+    close(rel, rel64.numpy(), 'all_rel')
+    names = {'x': 'entity_embedding', 'edge_embs': 'edge_embeddings', 'rels': 'relation_embedding'}
+    for key, g in grads.items():
+        # gradients w.r.t. the BatchNorm shift are ~0 by construction in training mode (pure round-off): absolute floor
+        if key == 'w.ent_bn.bias':
+            assert float(g.abs().max()) < 1e-2
+            continue
+        close(g, g64[names.get(key, 'conv1.' + key[2:])].numpy(), 'grad ' + key, rtol=2e-5)
+
+
+def test_conv_edge_cases(k):
+    """Edgeless graph, wide rows (D > 128: the two-float4-per-lane instantiation), a single node."""
+    # (a) no edges at all: the layer reduces to the self-loop branch
+    N, R, d_in, d_out = 50, 2, 100, 200
+    p = orc.conv_params(N, R, 0, d_in, d_out, seed=5)
+    conv = k.MGCNConv(d_in, d_out, 2 * R, dropout=0.0).cuda().train()
+    with torch.no_grad():
+        for name in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge'):
+            getattr(conv, name).copy_(p['w'][name])
+    ei = torch.zeros((2, 0), dtype=torch.int64, device='cuda')
+    et = torch.zeros((0,), dtype=torch.int64, device='cuda')
+    x = p['x'].cuda().requires_grad_(True)
+    ee = torch.zeros((0, d_in), device='cuda', requires_grad=True)
+    ent, rel = conv(x, ei, et, None, ee, p['rels'].cuda())
+    w64 = {kk: v.double() for kk, v in p['w'].items()}
+    ent64, rel64, _ = orc.conv_forward(p['x'].double(), ei.cpu(), et.cpu(), torch.zeros(0, d_in).double(), p['rels'].double(),
+                                       w64, training=True)
+    close(ent, ent64.numpy(), 'edgeless all_ent')
+    ent.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()
+    # (b) D = 160 (> 128) and Dout = 72 with hubs
+    z, p2 = synth_case(300, 3, 2500, 160, 72, 77)
+    dt = torch.float64
+    w64 = {kk: v.to(dt) for kk, v in p2['w'].items()}
+    e64, r64, g64, _ = orc.conv_fwd_bwd(p2['x'].to(dt), torch.from_numpy(z['edge_index']), torch.from_numpy(z['edge_type']),
+                                        p2['edge_embs'].to(dt), p2['rels'].to(dt), w64, torch.from_numpy(z['g_ent']),
+                                        torch.from_numpy(z['g_rel']))
+    _, ent, rel, grads = run_case(k, z)
+    close(ent, e64.numpy(), 'wide all_ent')
+    close(grads['x'], g64['entity_embedding'].numpy(), 'wide d_x')
+    close(grads['edge_embs'], g64['edge_embeddings'].numpy(), 'wide d_ee')
+    close(grads['rels'], g64['relation_embedding'].numpy(), 'wide d_rel')
+
+
+def test_conv_linearity_and_determinism_at_fb15k237_shape(k):
+    """Size-independent properties at BASELINE.json configs[2] size (14,541 entities, 237 relations, 272,115 triples):
+    the aggregation is linear in the edge embeddings (agg(2 ee) = 2 agg(ee) exactly: scaling by 2 is exact in fp32) and two
+    runs are bit-identical."""
+    N, R, E, D = 14541, 237, 272115, 100
+    tri = orc.synthetic_triples(N, R, E, 1)
+    g = orc.build_graph(tri, N, R)
+    ei, et = torch.from_numpy(g['edge_index']).cuda(), torch.from_numpy(g['edge_attr'][0]).cuda()
+    plan = k.get_plan(ei, et, N, 2 * R + 1)
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(N, D, generator=gen).cuda()
+    rel = torch.randn(2 * R + 1, D, generator=gen).cuda()
+    ee = torch.randn(2 * E, D, generator=gen).cuda()
+    L = k._lib
+    p, st = L.ptr, L.stream
+
+    def agg(eet):
+        out = torch.empty((2, N, D), device='cuda')
+
+        def level0(sp, out_final, carry):
+            L.call('kgc_agg_fwd', p(x), p(rel), rel.shape[0], p(eet), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
+                   p(out_final), p(carry), D, st())
+        plan.run_reduction(plan.fwd, level0, out, D, tag='t')
+        return out
+    a1, a2, a3 = agg(ee), agg(ee), agg(ee * 2)
+    assert torch.equal(a1, a2)
+    assert torch.equal(a3, a1 * 2)
+    # row sums against a float64 scatter of the same per-edge messages (checksum of the whole output)
+    src, dst, typ = g['edge_index'][0], g['edge_index'][1], g['edge_attr'][0]
+    norm = plan.norm.double()
+    msg = norm[:, None] * x.double()[torch.from_numpy(src).cuda()] * rel.double()[torch.from_numpy(typ).cuda()] * ee.double()
+    ref = torch.zeros((2 * N, D), dtype=torch.float64, device='cuda')
+    rows = torch.from_numpy(dst).cuda() + (torch.arange(2 * E, device='cuda') >= E) * N
+    ref.index_add_(0, rows, msg)
+    close(a1.reshape(2 * N, D), ref.cpu().numpy(), 'fb15k237 agg', rtol=2e-5)
