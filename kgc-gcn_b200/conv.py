@@ -56,12 +56,17 @@ def gemm_tn(a, b, out, plan=None, tensor_cores=True):
     Nb = b.shape[1]
     if a.stride(1) != 1 or b.stride(1) != 1 or not out.is_contiguous():
         raise ValueError('gemm_tn needs unit inner strides and a contiguous output')
-    name = 'kgc_gemm_tn_tc' if (tensor_cores and Ka <= 128 and Nb <= 224) else 'kgc_gemm_tn'
-    nbytes = int(getattr(_lib.lib(), name + '_workspace_bytes')(M, Ka, Nb))
-    ws = plan.scratch(name + '_ws', (nbytes // 4,)) if plan is not None else \
-        torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
-    p = _lib.ptr
-    _lib.call(name, p(a), a.stride(0), p(b), b.stride(0), M, Ka, Nb, p(out), p(ws), nbytes, _lib.stream())
+    if Nb > 256:
+        raise ValueError('gemm_tn supports Nb <= 256')
+    name = 'kgc_gemm_tn_tc' if (tensor_cores and Nb <= 224) else 'kgc_gemm_tn'
+    for i0 in range(0, Ka, 128):                       # wider A: one call per block of 128 columns (= 128 contiguous rows of out)
+        kb = min(128, Ka - i0)
+        a_blk, out_blk = a[:, i0:i0 + kb], out[i0:i0 + kb]
+        nbytes = int(getattr(_lib.lib(), name + '_workspace_bytes')(M, kb, Nb))
+        ws = plan.scratch(name + '_ws', (nbytes // 4,)) if plan is not None else \
+            torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+        p = _lib.ptr
+        _lib.call(name, p(a_blk), a.stride(0), p(b), b.stride(0), M, kb, Nb, p(out_blk), p(ws), nbytes, _lib.stream())
     return out
 
 
