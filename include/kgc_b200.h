@@ -158,7 +158,8 @@ int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pr
 /* ---- K4b: dense transforms on the tensor cores with fp32-grade accuracy (3xTF32) --------------------------
  * Replaces the fp32 matmuls of model.py:116 (x_j_rel @ W, after the aggregate-then-transform reordering
  * agg_h @ W_h) and of its autograd (d_res_h @ W_h^T):   C[M,N] = A[M,K] @ Bt[N,K]^T
- * A: fp32 row-major, leading dimension lda (a multiple of 4), streamed through TMA; Bt: the small operand,
+ * A: fp32 row-major, leading dimension lda (a multiple of 4), streamed through TMA; C: fp32 row-major, 16-byte
+ * aligned, leading dimension ldc (a multiple of 4), written by TMA stores; Bt: the small operand,
  * packed once per call by kgc_gemm_pack_b from B viewed as element (k, n) = B[k*stride_k + n*stride_n]
  * (hi / lo TF32 split, zero padded; size kgc_gemm_packed_b_bytes).  K <= 256, N <= 1024.
  * Every fp32 value v is split v = hi + lo (hi = top 19 bits); C = A_hi Bt_hi + A_lo Bt_hi + A_hi Bt_lo is

@@ -44,7 +44,12 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b'):
         torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
     p = _lib.ptr
     _lib.call('kgc_gemm_pack_b', p(b_kn), b_kn.stride(0), b_kn.stride(1), N, K, p(packed), _lib.stream())
-    _lib.call('kgc_gemm_nt', p(a), M, K, a.stride(0), p(packed), N, p(out), out.stride(0), _lib.stream())
+    # C is written by TMA stores: 16-byte aligned rows; an odd pitch goes through a padded buffer
+    dst = out if (out.data_ptr() % 16 == 0 and out.stride(0) % 4 == 0) else \
+        torch.empty((M, (N + 3) // 4 * 4), dtype=torch.float32, device=a.device)[:, :N]
+    _lib.call('kgc_gemm_nt', p(a), M, K, a.stride(0), p(packed), N, p(dst), dst.stride(0), _lib.stream())
+    if dst is not out:
+        out.copy_(dst)
     return out
 
 

@@ -33,15 +33,18 @@ constexpr int kBM = 128;                  // rows of A / C per tile (UMMA M)
 constexpr int kBK = 32;                   // fp32 elements per K block = one 128-byte swizzle row
 constexpr int kUK = 8;                    // K per tf32 MMA
 constexpr int kMaxKB = 8;                 // K <= 256
-constexpr int kMaxStages = 8;             // raw A ring (TMA targets, split in place into hi)
-constexpr int kLoStages = 2;              // lo tiles live only between the splitter and the MMA
+constexpr int kMaxStages = 8;             // raw A ring (TMA targets)
+constexpr int kAStages = 4;               // TMEM stages of the split A operand: 32 hi + 32 lo columns each
+constexpr int kAccCols = 256;             // two fp32 accumulator stages of 128 columns
+constexpr int kTmemColsTS = kAccCols + kAStages * 64;   // 512: the whole tensor memory of the SM
 constexpr int kTileA = kBM * kBK * 4;     // 16 KB
 constexpr int kThreadsG = 480;            // 15 warps: TMA, MMA, 8 splitters, 4 epilogue, TMEM allocator
 constexpr int kSplitWarps = 8;
 constexpr int kBBudget = 116 * 1024;      // resident hi + lo tiles of Bt (the rest of shared memory is the A ring:
                                           // the ring must cover TMA latency + split + MMA, ~6 K-blocks in flight)
 constexpr int kTmemColsG = 256;
-constexpr int kEpiStage = 4 * 32 * 33 * 4 + 128;  // epilogue transpose tiles (16,896 B) + pad to keep the barriers 8-byte aligned
+constexpr int kEpiBuf = 32 * 128;          // one epilogue buffer: a TMA-store box of 32 rows x 32 fp32 columns
+constexpr int kEpiStage = 4 * 2 * kEpiBuf; // 4 epilogue warps, double buffered (32 KB)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
@@ -73,6 +76,18 @@ __device__ __forceinline__ void tma_2d(void* smem_dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(s_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(s_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -81,6 +96,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// TS form: the A operand (128 rows x 8 TF32) is read from tensor memory, [lane 0.., column a_tmem..a_tmem+7]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16_g(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 // One lane of a fully converged warp (PTX elect.sync).  The surrounding code stays warp-uniform, so ptxas keeps the
@@ -142,8 +176,15 @@ struct GemmParams {
 
 __global__ void __launch_bounds__(kThreadsG, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, const GemmParams P) {
+                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+                   const __grid_constant__ CUtensorMap map_c16, const GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
+  if (P.dbg != nullptr && threadIdx.x == 0) {                      // debug aid: launch-to-exit envelope over all CTAs (ns)
+    long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    atomicMin(reinterpret_cast<long long*>(P.dbg) + 8 * 64 + 0, g);
+    if (blockIdx.x == 0) { P.dbg[8 * 64 + 2] = g; P.dbg[8 * 64 + 3] = clock64(); }
+  }
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int tile_b = P.NT * kBK * 4;                               // bytes of one Bt K-block tile (NT rows x 128 B)
@@ -151,16 +192,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* s_bhi = base;                                           // [n_kb][tile_b_al]
   uint8_t* s_blo = s_bhi + P.n_kb * tile_b_al;
   const int kStages = P.stages;
-  uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [stages][16 KB] raw fp32 tile, split in place into hi
-  uint8_t* s_lo = s_a + kStages * kTileA;                          // [kLoStages][16 KB] lo tiles
-  uint8_t* s_stage = s_lo + kLoStages * kTileA;                    // [4 epilogue warps][32 x 33 floats]
+  uint8_t* s_a = s_blo + P.n_kb * tile_b_al;                       // [stages][16 KB] raw fp32 tiles (TMA targets)
+  uint8_t* s_stage = s_a + kStages * kTileA;                       // [4 epilogue warps][2 buffers][32 x 32 floats]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kEpiStage);
   uint64_t* b_full = bars;
   uint64_t* raw_full = bars + 1;                                   // [kMaxStages] TMA landed
-  uint64_t* split_full = raw_full + kMaxStages;                    // [kMaxStages] hi/lo ready
-  uint64_t* empty = split_full + kMaxStages;                       // [kMaxStages] MMAs done with the raw/hi stage
-  uint64_t* lo_empty = empty + kMaxStages;                         // [kLoStages] MMAs done with the lo stage
-  uint64_t* acc_full = lo_empty + kLoStages;                       // [2]
+  uint64_t* raw_empty = raw_full + kMaxStages;                     // [kMaxStages] splitters have read the raw stage
+  uint64_t* split_full = raw_empty + kMaxStages;                   // [kAStages] hi / lo of a K block are in TMEM
+  uint64_t* split_empty = split_full + kAStages;                   // [kAStages] MMAs done with the TMEM A stage
+  uint64_t* acc_full = split_empty + kAStages;                     // [2]
   uint64_t* acc_empty = acc_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -168,10 +208,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     mb_init(b_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mb_init(raw_full + i, 1);
-      mb_init(split_full + i, kSplitWarps);
-      mb_init(empty + i, 1);
+      mb_init(raw_empty + i, kSplitWarps);
     }
-    for (int i = 0; i < kLoStages; ++i) mb_init(lo_empty + i, 1);
+    for (int i = 0; i < kAStages; ++i) {
+      mb_init(split_full + i, kSplitWarps);
+      mb_init(split_empty + i, 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mb_init(acc_full + i, 1);
       mb_init(acc_empty + i, 4);
@@ -180,7 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 14) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(kTmemColsG)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(kTmemColsTS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -188,6 +230,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + kAccCols;                    // A stages: [kAStages][hi 32 columns | lo 32 columns]
   const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0;
   int dbg_n = 0;
 #define KGC_DBG(role) do { if (dbg_on && dbg_n < 64) P.dbg[(role) * 64 + dbg_n++] = clock64(); } while (0)
@@ -208,7 +251,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t phase = 0;
       for (int mt = first; mt < P.n_mtiles; mt += step) {
         for (int kb = 0; kb < P.n_kb; ++kb) {
-          mb_wait(empty + stage, phase ^ 1);
+          mb_wait(raw_empty + stage, phase ^ 1);
           KGC_DBG(0);
           mb_expect_tx(raw_full + stage, kTileA);
           tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
@@ -217,129 +260,153 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp >= 2 && warp < 2 + kSplitWarps) {
-    // ================================================================== splitter: v -> (hi, lo)
-    const int t = threadIdx.x - 64;                                // 0..255
-    int stage = 0, ls = 0;
-    uint32_t phase = 0, lphase = 0;
+    // ================================================================== splitter: raw row -> (hi, lo) in TENSOR MEMORY
+    // A warp can only touch the TMEM lanes of its quarter (warp % 4); two warps share a quarter and take 16 of the 32
+    // K columns each.  Thread = row r of the tile: its 128-byte row sits at r * 128 with the 16-byte chunks XOR-ed by
+    // r % 8 (TMA 128-byte swizzle) - 8 consecutive rows hit 8 different chunks, so the LDS.128 are conflict-free.
+    const int quarter = warp % 4, half = (warp - 2) / 4;
+    const int r = quarter * 32 + lane;
+    int stage = 0, ts = 0;
+    uint32_t phase = 0, tphase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       for (int kb = 0; kb < P.n_kb; ++kb) {
         mb_wait(raw_full + stage, phase);
-        if (t == 0) KGC_DBG(1);
-        mb_wait(lo_empty + ls, lphase ^ 1);
-        if (t == 0) KGC_DBG(2);                        // the MMAs that read this lo stage have retired
-        uint4* hi = reinterpret_cast<uint4*>(s_a + stage * kTileA);
-        uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * kTileA);
-        constexpr int kSplitThreads = kSplitWarps * 32;
-        uint4 v[kTileA / 16 / kSplitThreads];
+        if (warp == 2 && lane == 0) KGC_DBG(1);
+        const uint8_t* row = s_a + stage * kTileA + r * 128;
+        uint4 v[4];
 #pragma unroll
-        for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) v[i] = hi[t + i * kSplitThreads];   // conflict-free 16-byte vectors
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(row + (((half * 4 + i) ^ (r & 7)) << 4));
+        uint32_t h[16], l[16];
 #pragma unroll
-        for (int i = 0; i < kTileA / 16 / kSplitThreads; ++i) {
+        for (int i = 0; i < 4; ++i) {
           // hi = nearest TF32, lo = nearest TF32 of (v - hi): measurably tighter than truncation at K = 200
-          uint4 h, l;
-          split_tf32(v[i].x, h.x, l.x);
-          split_tf32(v[i].y, h.y, l.y);
-          split_tf32(v[i].z, h.z, l.z);
-          split_tf32(v[i].w, h.w, l.w);
-          hi[t + i * kSplitThreads] = h;
-          lo[t + i * kSplitThreads] = l;
+          split_tf32(v[i].x, h[4 * i + 0], l[4 * i + 0]);
+          split_tf32(v[i].y, h[4 * i + 1], l[4 * i + 1]);
+          split_tf32(v[i].z, h[4 * i + 2], l[4 * i + 2]);
+          split_tf32(v[i].w, h[4 * i + 3], l[4 * i + 3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
-        if (lane == 0) mb_arrive(split_full + stage);
-        if (t == 0) KGC_DBG(3);
+        if (lane == 0) mb_arrive(raw_empty + stage);               // the raw tile is in registers: hand the stage back to TMA
+        mb_wait(split_empty + ts, tphase ^ 1);                     // the MMAs that read this TMEM stage have retired
+        if (warp == 2 && lane == 0) KGC_DBG(2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_a + ((uint32_t)(quarter * 32) << 16) + ts * 64 + half * 16;
+        tmem_st16_g(taddr, h);
+        tmem_st16_g(taddr + 32, l);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mb_arrive(split_full + ts);
+        if (warp == 2 && lane == 0) KGC_DBG(3);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
-        if (++ls == kLoStages) { ls = 0; lphase ^= 1; }
+        if (++ts == kAStages) { ts = 0; tphase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
     {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      int stage = 0, acc = 0, ls = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int ts = 0, acc = 0;
+      uint32_t tphase = 0, acc_phase = 0;
       mb_wait(b_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int mt = first; mt < P.n_mtiles; mt += step) {
         mb_wait(acc_empty + acc, acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_addr = tmem_base + acc * 128;
+        const uint32_t d_addr = tmem_base + acc * (kAccCols / 2);
         for (int kb = 0; kb < P.n_kb; ++kb) {
-          mb_wait(split_full + stage, phase);
+          mb_wait(split_full + ts, tphase);
           if (lane == 0) KGC_DBG(4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int nk = min(kBK / kUK, P.ksteps - kb * (kBK / kUK));
-          const uint64_t a_hi = sw128_desc(s_u32(s_a + stage * kTileA));
-          const uint64_t a_lo = sw128_desc(s_u32(s_lo + ls * kTileA));
+          const uint32_t a_hi = tmem_a + ts * 64, a_lo = a_hi + 32;            // TS mode: the A operand is read from TMEM
           const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
           const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
           if (elect_one()) {
-            for (int k = 0; k < nk; ++k) {                         // + k * 32 bytes along K (16-byte units in the descriptor)
-              umma_tf32(d_addr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
-              umma_tf32(d_addr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-              umma_tf32(d_addr, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < nk; ++k) {                         // + 8 TMEM columns / + 32 bytes (2 descriptor units) along K
+              umma_tf32_ts(d_addr, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
+              umma_tf32_ts(d_addr, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+              umma_tf32_ts(d_addr, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
             }
-            umma_commit_g(empty + stage);
-            umma_commit_g(lo_empty + ls);
+            umma_commit_g(split_empty + ts);
             if (kb == P.n_kb - 1) umma_commit_g(acc_full + acc);
           }
           __syncwarp();
           if (lane == 0) KGC_DBG(5);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (++ls == kLoStages) ls = 0;
+          if (++ts == kAStages) { ts = 0; tphase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 10 && warp <= 13) {
-    // ================================================================== epilogue: TMEM -> smem transpose -> coalesced C rows
-    // A thread owns a TMEM lane (= a row of C), so storing straight from registers would issue 32 scattered
-    // 16-byte stores per instruction (measured: the LSU then bounds the whole kernel).  Each warp transposes its
-    // 32 x 32 block through a padded shared-memory tile and writes whole 128-byte row segments.
+    // ================================================================== epilogue: TMEM -> swizzled smem boxes -> TMA store
+    // A thread owns a TMEM lane (= a row of C).  Storing rows straight from registers (or 128-byte row segments after
+    // a shared-memory transpose) keeps the LSU busy for ~1,400 cycles per 32 x 32 block (measured); instead each warp
+    // lays its 32 x 32 block out as a TMA box (128-byte rows, 128-byte swizzle: conflict-free 16-byte stores; a
+    // 16-column tail of the tile uses a 64-byte-swizzled box) and one lane hands it to the TMA engine, which also
+    // clips rows >= M and columns >= N.  Wide rows matter: the engine retires one row request at a time.
     const int quarter = warp % 4;
-    float* stg = reinterpret_cast<float*>(s_stage) + (warp - 10) * (32 * 33);
-    int acc = 0;
+    uint8_t* stg = s_stage + (warp - 10) * (2 * kEpiBuf);          // two buffers of one box
+    const int64_t row_q = quarter * 32;
+    int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
     for (int mt = first; mt < P.n_mtiles; mt += step) {
       mb_wait(acc_full + acc, acc_phase);
       if (warp == 10 && lane == 0) KGC_DBG(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t m0 = (int64_t)mt * kBM + quarter * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
-      const int n_valid = min(P.NT, P.N - nt * P.NT);
-      const int rows_valid = (int)min((int64_t)32, P.M - m0);
+      const int64_t m0 = (int64_t)mt * kBM + row_q;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (kAccCols / 2);
       for (int c0 = 0; c0 < P.NT; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32_g(taddr + c0, v);                                // columns past NT belong to the allocation: ignored below
+        tmem_ld32_g(taddr + c0, v);                                // columns past NT belong to the allocation: never stored
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);     // bank (lane + j) % 32: conflict-free
-        __syncwarp();
-        const int c = c0 + lane;
-        float* cp = P.C + m0 * P.ldc + nt * P.NT + c;
-        const bool col_ok = c < n_valid;
-#pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 8) {                       // 8 independent LDS, then 8 coalesced 128-byte row stores
-          float tmp[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) tmp[j] = stg[(r0 + j) * 33 + lane];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (col_ok && r0 + j < rows_valid) cp[(int64_t)(r0 + j) * P.ldc] = tmp[j];
+        if (c0 + 32 >= P.NT) {                                     // last read of this accumulator: give it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mb_arrive(acc_empty + acc);
         }
+        // the TMA store that read this buffer two blocks ago must have drained it (bulk groups are per thread: lane 0)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
+        uint8_t* bb = stg + buf * kEpiBuf;
+        const bool wide = c0 + 32 <= P.NT;                         // 32-column box (128-byte rows), else the 16-column tail box
+        if (wide) {
+          uint8_t* bx = bb + lane * 128;
+          const int sw = lane & 7;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(bx + ((q ^ sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          uint8_t* bx = bb + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(bx + ((q ^ sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const int col = nt * P.NT + c0;
+          if (m0 < P.M && col < P.N) tma_store_2d(wide ? &map_c : &map_c16, bb, col, (int)m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf ^= 1;
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mb_arrive(acc_empty + acc);
       if (warp == 10 && lane == 0) KGC_DBG(7);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (P.dbg != nullptr && threadIdx.x == 0) {
+    long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    atomicMax(reinterpret_cast<long long*>(P.dbg) + 8 * 64 + 1, g);
+    if (blockIdx.x == 0) { P.dbg[8 * 64 + 4] = g; P.dbg[8 * 64 + 5] = clock64(); }
+  }
   if (warp == 14) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsG) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsTS) : "memory");
   }
 }
 
@@ -374,16 +441,32 @@ int encode_fn(EncodeTiledFn* out) {
 }
 // fp32 [rows, cols] with row pitch `pitch` floats -> boxes of 32 (K) x box_rows, 128-byte swizzle, zero fill
 int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
-                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = kBK) {
   EncodeTiledFn enc;
   if (encode_fn(&enc)) return 1;
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (pitch * 4) % 16 == 0, "operand must be 16-byte aligned with a 16-byte pitch");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+// partial sums [parts][rows][cols] fp32 -> boxes of 32 columns x 32 rows of one part, 128-byte swizzle (TMA stores clip)
+int make_map_f32_parts(CUtensorMap* map, const void* ptr, int64_t parts, int64_t rows, int64_t cols) {
+  EncodeTiledFn enc;
+  if (encode_fn(&enc)) return 1;
+  KGC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cols % 4 == 0, "partials must be 16-byte aligned with a 16-byte pitch");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)parts};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)rows * cols * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return 0;
@@ -443,7 +526,8 @@ __device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(kThreadsG, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTnParams P) {
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_p, const GemmTnParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -557,24 +641,39 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (++ls == kTnLoStages) ls = 0;
     }
   } else if (warp >= 10 && warp <= 13) {
-    // epilogue: D row i (TMEM lane) -> partial[cta][i][0..Nb)
+    // epilogue: D row i (TMEM lane) -> partial[cta][i][0..Nb).  One 4-byte store per thread would touch 32 sectors
+    // per instruction (rows are Nb * 4 bytes apart); instead each warp lays a 32 x 32 block out as a 128-byte-swizzled
+    // box in the (now idle) pipeline stages and one lane issues a TMA store, clipped at Ka rows / Nb columns.
     const int quarter = warp % 4;
     const int i = quarter * 32 + lane;
     float* out = P.partial + ((int64_t)blockIdx.x * P.Ka + i) * P.Nb;
     if (n_kb > 0) {
-      mb_wait(acc_full, 0);
+      mb_wait(acc_full, 0);                                        // every MMA has retired: shared memory is free
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      uint8_t* stg = s_raw + (warp - 10) * (2 * kEpiBuf);
+      int buf = 0;
       for (int c0 = 0; c0 < P.n_pad; c0 += 32) {
         uint32_t v[32];
         tmem_ld32_g(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (i < P.Ka) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        uint8_t* bb = stg + buf * kEpiBuf;
+        uint8_t* bx = bb + lane * 128;
+        const int sw = lane & 7;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < P.Nb) out[c0 + j] = __uint_as_float(v[j]);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(bx + ((q ^ sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (c0 < P.Nb && quarter * 32 < P.Ka) tma_store_3d(&map_p, bb, c0, quarter * 32, (int)blockIdx.x);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        buf ^= 1;
       }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (i < P.Ka) {
       for (int j = 0; j < P.Nb; ++j) out[j] = 0.f;
     }
@@ -632,15 +731,18 @@ extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_
 }
 
 static long long* g_gemm_dbg = nullptr;
-extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 8 * 64 int64, or NULL
+extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 9 * 64 int64, or NULL
 
 extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                            int64_t ldc, void* stream) {
   Tiling t;
   KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
   KGC_REQUIRE(M > 0 && lda >= K && ldc >= N, "bad leading dimensions");
-  CUtensorMap ma, mbh, mbl;
+  KGC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0, "C must be 16-byte aligned with a 16-byte row pitch (TMA store)");
+  CUtensorMap ma, mbh, mbl, mc, mc16;
   const int total = t.n_pad * t.k_pad;
+  if (make_map_f32(&mc, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+  if (make_map_f32(&mc16, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
   if (make_map_f32(&ma, A, M, K, lda, kBM)) return 1;
   if (make_map_f32(&mbh, packed_b, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   if (make_map_f32(&mbl, packed_b + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
@@ -650,7 +752,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
   P.C = C; P.ldc = ldc; P.dbg = g_gemm_dbg;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
-  const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + (size_t)kLoStages * kTileA + kEpiStage + 512 + 1024;
+  const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
   if (stages > kMaxStages) stages = kMaxStages;
   KGC_REQUIRE(stages >= 2, "shared-memory plan does not fit");
@@ -665,7 +767,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   int per = kNumSMs / t.n_ntiles;
   if (per > P.n_mtiles) per = P.n_mtiles;
   if (per < 1) per = 1;
-  gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, P);
+  gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, mc, mc16, P);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -694,6 +796,8 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
   P.rows_per_cta = ceil_div(ceil_div(M, grid), kTnRows) * kTnRows;     // slabs start on K-block boundaries
   grid = (int)ceil_div(M, P.rows_per_cta);
   P.partial = static_cast<float*>(workspace);
+  CUtensorMap mp;
+  if (make_map_f32_parts(&mp, P.partial, grid, Ka, Nb)) return 1;
   const size_t stage = (size_t)(P.ga + P.gb) * kTnBox;
   const size_t smem = (kTnStages + kTnLoStages) * stage + 512 + 1024;
   KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
@@ -703,7 +807,7 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
     attr = smem;
   }
   cudaStream_t st = as_stream(stream);
-  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, P);
+  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, mp, P);
   KGC_LAUNCH_CHECK();
   gemm_tn_partials_reduce<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(P.partial, grid, Ka * Nb, C);
   KGC_LAUNCH_CHECK();

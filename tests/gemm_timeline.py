@@ -7,14 +7,19 @@ L = k._lib
 M, K, N = 40943, 100, 200
 a = torch.randn(M, K, device='cuda'); b = torch.randn(K, N, device='cuda'); out = torch.empty(M, N, device='cuda')
 for _ in range(3): k.gemm_nt(a, b, out)
-dbg = torch.zeros(8 * 64, dtype=torch.int64, device='cuda')
+dbg = torch.zeros(9 * 64, dtype=torch.int64, device='cuda')
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda'); flush.zero_(); flush.sum()
+dbg[8 * 64] = 1 << 62
 L.lib().kgc_gemm_set_debug(L.ptr(dbg))
-k.gemm_nt(a, b, out)
+e0.record(); k.gemm_nt(a, b, out); e1.record()
 torch.cuda.synchronize()
 L.lib().kgc_gemm_set_debug(None)
-d = dbg.cpu().view(8, 64)
+env = dbg.cpu().view(9, 64)[8]
+d = dbg.cpu().view(9, 64)[:8]
+print('events (pack_b + gemm): %.1f us; all-CTA envelope %.1f us; CTA0 entry->exit %.1f us = %d clk (%.2f GHz); CTA0 entry->first TMA %d clk' % (e0.elapsed_time(e1) * 1e3, (int(env[1]) - int(env[0])) / 1e3, (int(env[4]) - int(env[2])) / 1e3, int(env[5]) - int(env[3]), (int(env[5]) - int(env[3])) / max(1, int(env[4]) - int(env[2])), int(d[d > 0].min()) - int(env[3])))
 t0 = int(d[d > 0].min())
 names = ['tma_issue', 'split_raw_ready', 'split_lo_free', 'split_done', 'mma_split_ready', 'mma_issued', 'epi_acc_ready', 'epi_done']
 for r, n in enumerate(names):
     v = [int(x) - t0 for x in d[r] if int(x) > 0]
-    print('%-16s' % n, v[:24])
+    print('%-16s' % n, v[:64])
