@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_2d(void* smem_dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          s_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -132,11 +139,10 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ uint32_t tf32_rn(float v) {      // round to nearest TF32 (10-bit mantissa), result in fp32 bits
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
+// Round to the nearest TF32 (10-bit mantissa, ties away from zero = cvt.rna.tf32.f32), result in fp32 bits.  Done with
+// two integer instructions: cvt.rna runs on the quarter-rate conversion pipe (16 lanes / clock / SM), which made the
+// splitter warps the bottleneck of both GEMM kernels (measured: ~512 cycles per 128 x 32 tile for the cvt alone).
+__device__ __forceinline__ uint32_t tf32_rn(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
   hi = tf32_rn(__uint_as_float(v));
   lo = tf32_rn(__uint_as_float(v) - __uint_as_float(hi));
@@ -456,6 +462,21 @@ int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, 
   return 0;
 }
 
+// the complete 32-column groups of fp32 [rows, cols] as ONE box: dims (32 columns, rows, groups), group stride 128 B
+int make_map_f32_mn_groups(CUtensorMap* map, const void* ptr, int64_t rows, int groups, int64_t pitch) {
+  EncodeTiledFn enc;
+  if (encode_fn(&enc)) return 1;
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, 128};
+  cuuint32_t box[3] = {32, 32, (cuuint32_t)groups};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (grouped operand) failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
 // partial sums [parts][rows][cols] fp32 -> boxes of 32 columns x 32 rows of one part, 128-byte swizzle (TMA stores clip)
 int make_map_f32_parts(CUtensorMap* map, const void* ptr, int64_t parts, int64_t rows, int64_t cols) {
   EncodeTiledFn enc;
@@ -508,8 +529,10 @@ constexpr int kTnLoStages = 2;
 struct GemmTnParams {
   int64_t M;
   int32_t Ka, Nb, ga, gb, n_pad;                 // ga / gb = 32-column groups of A / B; n_pad = MMA N (multiple of 16)
+  int32_t ga_full, gb_full;                      // groups that lie completely inside the operand (fetched by one 3-D TMA)
   int64_t rows_per_cta;
   float* partial;                                // [grid][Ka][Nb]
+  long long* dbg;                                // optional timeline of CTA 0 (debug aid, see kgc_gemm_set_debug)
 };
 
 // MN-major TF32 operands have ONE legal shared-memory layout on sm_100: 128-byte swizzle with 32-byte atoms
@@ -527,8 +550,15 @@ __device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr) {
 
 __global__ void __launch_bounds__(kThreadsG, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_a3, const __grid_constant__ CUtensorMap map_b3,
                   const __grid_constant__ CUtensorMap map_p, const GemmTnParams P) {
   extern __shared__ uint8_t smem_raw[];
+  if (P.dbg != nullptr && threadIdx.x == 0) {                      // debug aid: launch-to-exit envelope over all CTAs (ns)
+    long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    atomicMin(reinterpret_cast<long long*>(P.dbg) + 8 * 64 + 0, g);
+    if (blockIdx.x == 0) { P.dbg[8 * 64 + 2] = g; P.dbg[8 * 64 + 3] = clock64(); }
+  }
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int stage_bytes = (P.ga + P.gb) * kTnBox;          // A boxes then B boxes
@@ -562,6 +592,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0;
+  int dbg_n = 0;
 
   const int64_t m0 = blockIdx.x * P.rows_per_cta;
   const int64_t m1 = m0 + P.rows_per_cta < P.M ? m0 + P.rows_per_cta : P.M;
@@ -573,13 +605,18 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
         mb_wait(empty + stage, phase ^ 1);
+        KGC_DBG(0);
         mb_expect_tx(raw_full + stage, (uint32_t)stage_bytes);
         uint8_t* dst = s_raw + stage * stage_bytes;
         const int row = (int)(m0 + (int64_t)kb * kTnRows);
         // rows past m1 belong to the next CTA's slab: they are masked out by the splitter (zeroed), rows past M are
         // zero-filled by TMA
-        for (int g = 0; g < P.ga; ++g) tma_2d(dst + g * kTnBox, &map_a, raw_full + stage, g * 32, row);
-        for (int g = 0; g < P.gb; ++g) tma_2d(dst + (P.ga + g) * kTnBox, &map_b, raw_full + stage, g * 32, row);
+        // one instruction fetches all the complete 32-column groups of an operand (a TMA issue costs ~170 cycles of the
+        // producer thread); the ragged last group and the all-padding groups go through the zero-filling 2-D map
+        if (P.ga_full > 0) tma_3d(dst, &map_a3, raw_full + stage, 0, row, 0);
+        for (int g = P.ga_full; g < P.ga; ++g) tma_2d(dst + g * kTnBox, &map_a, raw_full + stage, g * 32, row);
+        if (P.gb_full > 0) tma_3d(dst + P.ga * kTnBox, &map_b3, raw_full + stage, 0, row, 0);
+        for (int g = P.gb_full; g < P.gb; ++g) tma_2d(dst + (P.ga + g) * kTnBox, &map_b, raw_full + stage, g * 32, row);
         if (++stage == kTnStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -591,7 +628,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int n_vec = stage_bytes / 16;
     for (int kb = 0; kb < n_kb; ++kb) {
       mb_wait(raw_full + stage, phase);
+      if (t == 0) KGC_DBG(1);
       mb_wait(lo_empty + ls, lphase ^ 1);
+      if (t == 0) KGC_DBG(2);
       uint4* hi = reinterpret_cast<uint4*>(s_raw + stage * stage_bytes);
       uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * stage_bytes);
       // rows of this K block that lie past the CTA's slab must not contribute: a 16-byte vector v of a box belongs to
@@ -611,6 +650,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mb_arrive(split_full + stage);
+      if (t == 0) KGC_DBG(3);
       if (++stage == kTnStages) { stage = 0; phase ^= 1; }
       if (++ls == kTnLoStages) { ls = 0; lphase ^= 1; }
     }
@@ -622,6 +662,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t phase = 0;
     for (int kb = 0; kb < n_kb; ++kb) {
       mb_wait(split_full + stage, phase);
+      if (lane == 0) KGC_DBG(4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t hi_a = s_u32(s_raw + stage * stage_bytes), hi_b = hi_a + P.ga * kTnBox;
       const uint32_t lo_a = s_u32(s_lo + ls * stage_bytes), lo_b = lo_a + P.ga * kTnBox;
@@ -637,6 +678,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (kb == n_kb - 1) umma_commit_g(acc_full);
       }
       __syncwarp();
+      if (lane == 0) KGC_DBG(5);
       if (++stage == kTnStages) { stage = 0; phase ^= 1; }
       if (++ls == kTnLoStages) ls = 0;
     }
@@ -649,6 +691,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float* out = P.partial + ((int64_t)blockIdx.x * P.Ka + i) * P.Nb;
     if (n_kb > 0) {
       mb_wait(acc_full, 0);                                        // every MMA has retired: shared memory is free
+      if (warp == 10 && lane == 0) KGC_DBG(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       uint8_t* stg = s_raw + (warp - 10) * (2 * kEpiBuf);
@@ -674,12 +717,19 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         buf ^= 1;
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (warp == 10 && lane == 0) KGC_DBG(7);
     } else if (i < P.Ka) {
       for (int j = 0; j < P.Nb; ++j) out[j] = 0.f;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (P.dbg != nullptr && threadIdx.x == 0) {
+    long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    atomicMax(reinterpret_cast<long long*>(P.dbg) + 8 * 64 + 1, g);
+    if (blockIdx.x == 0) { P.dbg[8 * 64 + 4] = g; P.dbg[8 * 64 + 5] = clock64(); }
+  }
   if (warp == 14) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsG) : "memory");
   }
@@ -713,6 +763,8 @@ int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 
 using namespace kgc;
 
+static long long* g_gemm_dbg = nullptr;
+
 extern "C" size_t kgc_gemm_packed_b_bytes(int32_t N, int32_t K) {
   Tiling t;
   if (make_tiling(N, K, &t)) return 0;
@@ -730,7 +782,6 @@ extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_
   return 0;
 }
 
-static long long* g_gemm_dbg = nullptr;
 extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 9 * 64 int64, or NULL
 
 extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
@@ -796,8 +847,14 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
   P.rows_per_cta = ceil_div(ceil_div(M, grid), kTnRows) * kTnRows;     // slabs start on K-block boundaries
   grid = (int)ceil_div(M, P.rows_per_cta);
   P.partial = static_cast<float*>(workspace);
-  CUtensorMap mp;
+  P.dbg = g_gemm_dbg;
+  CUtensorMap mp, ma3, mb3;
   if (make_map_f32_parts(&mp, P.partial, grid, Ka, Nb)) return 1;
+  P.ga_full = Ka / 32;
+  P.gb_full = Nb / 32;
+  ma3 = ma; mb3 = mb;                         // placeholders when an operand has no complete group
+  if (P.ga_full > 0 && make_map_f32_mn_groups(&ma3, A, M, P.ga_full, lda)) return 1;
+  if (P.gb_full > 0 && make_map_f32_mn_groups(&mb3, B, M, P.gb_full, ldb)) return 1;
   const size_t stage = (size_t)(P.ga + P.gb) * kTnBox;
   const size_t smem = (kTnStages + kTnLoStages) * stage + 512 + 1024;
   KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
@@ -807,7 +864,7 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
     attr = smem;
   }
   cudaStream_t st = as_stream(stream);
-  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, mp, P);
+  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, ma3, mb3, mp, P);
   KGC_LAUNCH_CHECK();
   gemm_tn_partials_reduce<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(P.partial, grid, Ka * Nb, C);
   KGC_LAUNCH_CHECK();
