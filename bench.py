@@ -414,7 +414,7 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
         torch.manual_seed(0)
         model = k.MGCN(N, R, E, prm).to(dev)
         model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=(mode == 'graph'))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=(mode == 'graph'))
         batches = loader.batches()
         step = k.GraphedTrainStep(model, opt, graph, ds, BATCH) if mode == 'graph' else None
         ms, n = 0.0, 0

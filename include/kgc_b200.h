@@ -169,8 +169,8 @@ int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t 
                     void* stream);
 int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                 int64_t ldc, void* stream);
-/* Debug aid: device buffer of 8 x 64 int64 that CTA 0 of the next kgc_gemm_nt launches fills with clock64() stamps
- * per warp role (NULL switches it off; off by default). */
+/* Debug aid: device buffer of 9 x 64 int64 that CTA 0 of the next kgc_gemm_nt / kgc_gemm_tn_tc launches fills with
+ * clock64() stamps per warp role, row 8 = global-timer envelope (NULL switches it off; off by default). */
 void kgc_gemm_set_debug(long long* buf);
 
 /* ---- K4c: weight-gradient reductions  C[Ka,Nb] = A[M,Ka]^T @ B[M,Nb]  (autograd of model.py:116 w.r.t. W) ----
@@ -203,6 +203,21 @@ int kgc_label_build(const int64_t* qid, int64_t B, const int64_t* triples, const
  * not a positive of query qid[b]; -1 if every try collides. */
 int kgc_neg_sample(const int64_t* qid, int64_t B, const int64_t* ptr, const int32_t* idx, int64_t n_entity,
                    const uint32_t* draws, int32_t k, int32_t tries, int32_t* neg, void* stream);
+
+/* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------
+ * Replaces model.py:177-179 (x = mm(x, all_ent^T); x += bias; sigmoid) where the caller needs the dense matrix
+ * (BCE against the multi-hot label, main.py:63-66).  Forward: the K4b tensor-core kernel (3xTF32, fp32-grade) with
+ * the entity table E[n_ent, D] as the streamed operand and the queries X[B, D] as the packed small one
+ * (kgc_gemm_pack_b with stride_k = 1, stride_n = ld_x); the epilogue adds bias[n], applies the logistic sigmoid and
+ * TMA-stores the block transposed:  pred[b, n] = sigmoid(X[b,:] . E[n,:] + bias[n]),  pred row pitch ld_pred
+ * (a multiple of 4, >= n_ent; 16-byte aligned).  D <= 256, D % 4 == 0, B <= 1024.
+ * Backward through the sigmoid: d_logitT[n, b] = d_pred[b, n] * pred[b, n] * (1 - pred[b, n]) written TRANSPOSED
+ * ([n_ent, ldt], ldt >= B, columns [B, ldt) zeroed) so that d_X = kgc_gemm_tn_tc(d_logitT, E) and
+ * d_E = kgc_gemm_nt(d_logitT, X) stream it row-major; d_bias[n] = sum_b d_logitT[n, b] in a fixed order. */
+int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                     const float* bias, float* pred, int64_t ld_pred, void* stream);
+int kgc_score_1n_bwd_logit(const float* d_pred, int64_t ld_dp, const float* pred, int64_t ld_p, int64_t n_ent,
+                           int32_t B, int32_t ldt, float* d_logitT, float* d_bias, void* stream);
 
 /* ---- K6: fused 1-N scoring + filter + rank (tcgen05 / TMA) --------------------------------------------
  * Replaces model.py:177-178 (X @ all_ent^T + bias) and main.py:122-126 (filter, rank) without

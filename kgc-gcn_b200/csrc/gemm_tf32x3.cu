@@ -177,6 +177,9 @@ struct GemmParams {
   int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles, stages;
   float* C;
   int64_t ldc;
+  const float* row_bias;   // optional: C[m, n] = f(acc + row_bias[m])
+  int32_t act;             // 0: identity, 1: logistic sigmoid
+  int32_t trans_c;         // store C transposed: Ct[n, m] (the tensor maps then describe Ct)
   long long* dbg;     // optional timeline of CTA 0: [role][event] clock64 stamps (debug aid)
 };
 
@@ -376,7 +379,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         __syncwarp();
         uint8_t* bb = stg + buf * kEpiBuf;
         const bool wide = c0 + 32 <= P.NT;                         // 32-column box (128-byte rows), else the 16-column tail box
-        if (wide) {
+        if (P.row_bias != nullptr) {                               // 1-N scoring: + bias[entity], logistic sigmoid (model.py:178-179)
+          const float bv = m0 + lane < P.M ? P.row_bias[m0 + lane] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float z = __uint_as_float(v[j]) + bv;
+            v[j] = __float_as_uint(P.act == 1 ? 1.f / (1.f + expf(-z)) : z);
+          }
+        }
+        if (P.trans_c) {
+          // transposed block: element (row = lane, column j) -> box row j, 4-byte slot lane (bank = a permutation of lane)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<uint32_t*>(bb + j * 128 + ((((lane >> 2) ^ (j & 7)) << 4) | ((lane & 3) << 2))) = v[j];
+        } else if (wide) {
           uint8_t* bx = bb + lane * 128;
           const int sw = lane & 7;
 #pragma unroll
@@ -393,7 +409,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         __syncwarp();
         if (lane == 0) {
           const int col = nt * P.NT + c0;
-          if (m0 < P.M && col < P.N) tma_store_2d(wide ? &map_c : &map_c16, bb, col, (int)m0);
+          if (m0 < P.M && col < P.N) {
+            if (P.trans_c) tma_store_2d(wide ? &map_c : &map_c16, bb, (int)m0, col);     // Ct: inner coordinate = row of C
+            else tma_store_2d(wide ? &map_c : &map_c16, bb, col, (int)m0);
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         buf ^= 1;
@@ -784,16 +803,22 @@ extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_
 
 extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 9 * 64 int64, or NULL
 
-extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
-                           int64_t ldc, void* stream) {
+// C[M, N] = f(A[M, K] @ Bt^T + row_bias) (trans_c = 0) or Ct[N, M] = the same, stored transposed (trans_c = 1)
+static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
+                          int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c, void* stream) {
   Tiling t;
   KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
-  KGC_REQUIRE(M > 0 && lda >= K && ldc >= N, "bad leading dimensions");
+  KGC_REQUIRE(M > 0 && lda >= K && ldc >= (trans_c ? M : (int64_t)N), "bad leading dimensions");
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0, "C must be 16-byte aligned with a 16-byte row pitch (TMA store)");
   CUtensorMap ma, mbh, mbl, mc, mc16;
   const int total = t.n_pad * t.k_pad;
-  if (make_map_f32(&mc, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
-  if (make_map_f32(&mc16, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
+  if (trans_c) {     // Ct[N, M]: boxes of 32 rows of C (inner) x 32 / 16 columns of C
+    if (make_map_f32(&mc, C, N, M, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+    if (make_map_f32(&mc16, C, N, M, ldc, 16, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+  } else {
+    if (make_map_f32(&mc, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+    if (make_map_f32(&mc16, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
+  }
   if (make_map_f32(&ma, A, M, K, lda, kBM)) return 1;
   if (make_map_f32(&mbh, packed_b, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   if (make_map_f32(&mbl, packed_b + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
@@ -801,7 +826,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   P.M = M; P.N = N; P.K = K;
   P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
-  P.C = C; P.ldc = ldc; P.dbg = g_gemm_dbg;
+  P.C = C; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.dbg = g_gemm_dbg;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
   const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
@@ -821,6 +846,19 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
   gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, mc, mc16, P);
   KGC_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
+                           int64_t ldc, void* stream) {
+  return launch_gemm_nt(A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, stream);
+}
+
+// pred[b, n] = sigmoid(X[b, :] . E[n, :] + bias[n]): the entity table is the streamed operand, the queries the packed
+// small one, the epilogue adds the entity bias, applies the sigmoid and stores the block transposed into pred[B, N]
+extern "C" int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                                const float* bias, float* pred, int64_t ld_pred, void* stream) {
+  KGC_REQUIRE(bias != nullptr, "bias is required");
+  return launch_gemm_nt(ent, n_ent, D, ld_ent, packed_x, B, pred, ld_pred, bias, 1, 1, stream);
 }
 
 extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {

@@ -3,8 +3,9 @@
 Same constructors, forward signatures, parameter / state-dict names, so a checkpoint
 written by the reference loads here and vice versa.  The encoder is the CUDA MGCNConv; the ConvE front
 end (bn0 -> 7x7 conv -> bn1 -> relu -> fc -> bn2 -> relu, model.py:161-175) is SURVEY.md "next" row N2 and
-stays on torch/cuDNN; the 1-N scoring tail is torch.addmm + sigmoid in ``forward`` (which must return
-the dense [B,N] matrix to stay call-compatible) and the fused tensor-core kernel in ``rank``.
+stays on torch/cuDNN; the 1-N scoring tail of ``forward`` (which must return the dense [B,N] matrix to stay
+call-compatible) and its autograd run on the 3xTF32 tensor-core kernels (K6t, scoring.score_1n); ``rank`` uses the
+fused tensor-core scoring + ranking kernel (K6).
 """
 import torch
 import torch.nn as nn
@@ -47,7 +48,10 @@ class ConvE(nn.Module):
 
     def forward(self, src_emb, rel_emb, all_ent):
         x = self.query(src_emb, rel_emb)
-        # model.py:177-179: mm, += bias, sigmoid
+        # model.py:177-179: mm, += bias, sigmoid - on the tensor-core scorer (K6t) for the shapes it takes
+        from .scoring import score_1n, score_1n_supported
+        if score_1n_supported(x, all_ent):
+            return score_1n(x, all_ent, self.bias)
         return torch.sigmoid(torch.addmm(self.bias, x, all_ent.transpose(1, 0)))
 
 

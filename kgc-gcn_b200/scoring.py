@@ -13,6 +13,63 @@ import torch
 from . import _lib
 
 
+class _Score1N(torch.autograd.Function):
+    """pred[B, N] = sigmoid(x @ all_ent^T + bias) with its autograd on the tensor-core kernels (K6t): the training-time
+    scoring tail of model.py:177-179."""
+
+    @staticmethod
+    def forward(ctx, x, all_ent, bias):
+        from .conv import gemm_nt  # noqa: F401  (same packing routine)
+        x = _lib.require_cuda(x.detach(), torch.float32, 'x')
+        ent = _lib.require_cuda(all_ent.detach(), torch.float32, 'all_ent')
+        bias_ = _lib.require_cuda(bias.detach(), torch.float32, 'bias')
+        B, D = int(x.shape[0]), int(x.shape[1])
+        N = int(ent.shape[0])
+        ldp = (N + 3) // 4 * 4
+        p = _lib.ptr
+        nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(B, D))
+        packed = torch.empty((nbytes // 4,), dtype=torch.float32, device=x.device)
+        buf = torch.empty((B, ldp), dtype=torch.float32, device=x.device)
+        _lib.call('kgc_gemm_pack_b', p(x), x.stride(1), x.stride(0), B, D, p(packed), _lib.stream())
+        _lib.call('kgc_score_1n_fwd', p(ent), N, D, ent.stride(0), p(packed), B, p(bias_), p(buf), ldp, _lib.stream())
+        pred = buf[:, :N]
+        ctx.save_for_backward(x, ent, pred)
+        return pred
+
+    @staticmethod
+    def backward(ctx, d_pred):
+        from .conv import gemm_nt, gemm_tn
+        x, ent, pred = ctx.saved_tensors
+        B, D = int(x.shape[0]), int(x.shape[1])
+        N = int(ent.shape[0])
+        if d_pred.stride(1) != 1:
+            d_pred = d_pred.contiguous()
+        ldt = (B + 3) // 4 * 4
+        d_logit_t = torch.empty((N, ldt), dtype=torch.float32, device=x.device)
+        d_bias = torch.empty((N,), dtype=torch.float32, device=x.device)
+        p = _lib.ptr
+        _lib.call('kgc_score_1n_bwd_logit', p(d_pred), d_pred.stride(0), p(pred), pred.stride(0), N, B, ldt,
+                  p(d_logit_t), p(d_bias), _lib.stream())
+        d_x = d_ent = None
+        if ctx.needs_input_grad[0]:
+            d_x = gemm_tn(d_logit_t, ent, torch.empty((ldt, D), dtype=torch.float32, device=x.device))[:B]
+        if ctx.needs_input_grad[1]:
+            d_ent = gemm_nt(d_logit_t[:, :B], x, torch.empty((N, D), dtype=torch.float32, device=x.device))
+        return d_x, d_ent, (d_bias if ctx.needs_input_grad[2] else None)
+
+
+def score_1n_supported(x, all_ent):
+    """Shapes the tensor-core training scorer takes (anything else stays on torch.addmm + sigmoid)."""
+    return (x.is_cuda and x.dtype == torch.float32 and all_ent.dtype == torch.float32 and x.dim() == 2
+            and 0 < x.shape[0] <= 256 and x.shape[1] <= 224 and x.shape[1] % 4 == 0
+            and all_ent.stride(1) == 1 and all_ent.stride(0) % 4 == 0 and all_ent.data_ptr() % 16 == 0)
+
+
+def score_1n(x, all_ent, bias):
+    """sigmoid(x @ all_ent^T + bias) [B, N] (model.py:177-179), differentiable."""
+    return _Score1N.apply(x, all_ent, bias)
+
+
 def score_kpad(d):
     kpad = int(_lib.lib().kgc_score_kpad(int(d)))
     if kpad < 0:

@@ -195,3 +195,36 @@ def test_toy_predict_identical_metrics(k, golden_dir):
     lab = torch.from_numpy(np.stack([orc.make_label(q['label'], 7) for q in dl.triplets['valid_tail']]))
     ref = orc.filtered_ranks_dense(torch.from_numpy(z['eval.tail.score.f32']), lab, trip[:, 2].cpu()).numpy()
     np.testing.assert_array_equal(out['ranks'].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize('B,N,D', [(128, 40943, 200), (77, 1001, 200), (5, 14, 32), (256, 3000, 100), (1, 130, 8)])
+def test_score_1n_training_path(k, B, N, D):
+    """K6t: dense sigmoid scores (model.py:177-179) and their autograd on the 3xTF32 tensor-core kernels agree with the
+    fp64 evaluation of the same expression to fp32 accuracy; nothing is written outside [B, N]."""
+    from kgc_gcn_b200.scoring import score_1n, score_1n_supported
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x = (torch.randn(B, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    ent = (torch.randn(N, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    bias = (torch.randn(N, generator=g) * 0.1).cuda().requires_grad_(True)
+    label = (torch.rand(B, N, generator=g) < 0.01).float().cuda()
+    assert score_1n_supported(x, ent)
+    pred = score_1n(x, ent, bias)
+    assert pred.shape == (B, N)
+    loss = torch.nn.functional.binary_cross_entropy(pred, label)
+    loss.backward()
+    xd, ed, bd = (t.detach().double().requires_grad_(True) for t in (x, ent, bias))
+    pred_ref = torch.sigmoid(xd @ ed.t() + bd)
+    loss_ref = torch.nn.functional.binary_cross_entropy(pred_ref, label.double())
+    loss_ref.backward()
+    # fp32 tolerance: sigmoid output <= 1 -> absolute 2e-6; gradients relative to their largest entry
+    assert float((pred.detach().double() - pred_ref.detach()).abs().max()) <= 2e-6
+    assert abs(float(loss) - float(loss_ref)) <= 2e-6 * max(1.0, abs(float(loss_ref)))
+    for got, ref, name in ((x.grad, xd.grad, 'x'), (ent.grad, ed.grad, 'ent'), (bias.grad, bd.grad, 'bias')):
+        scale = float(ref.abs().max())
+        err = float((got.double() - ref).abs().max())
+        print('score_1n B={} N={} D={} d_{}: err {:.2e} / scale {:.2e}'.format(B, N, D, name, err, scale))
+        assert err <= 2e-5 * scale + 1e-9, (name, err, scale)
+    # deterministic
+    x2, e2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, ent, bias))
+    torch.nn.functional.binary_cross_entropy(score_1n(x2, e2, b2), label).backward()
+    assert torch.equal(x2.grad, x.grad) and torch.equal(e2.grad, ent.grad) and torch.equal(b2.grad, bias.grad)
