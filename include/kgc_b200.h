@@ -169,6 +169,12 @@ int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t 
                     void* stream);
 int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                 int64_t ldc, void* stream);
+/* Same kernel with the streamed operand AND the result transposed in memory (the long dimension M contiguous):
+ *   Ct[n, m] = sum_k At[k, m] * Bt[n, k],  At: [K, M] row-major, pitch ldat;  Ct: [N, M] row-major, pitch ldct.
+ * M % 32 == 0.  Used for the autograd of ConvE's fc layer (model.py:173): d_W[out, flat] = d_y^T @ x_flat and
+ * d_x_flat[B, flat] = d_y @ W, where flat = 39,200 is the long dimension. */
+int kgc_gemm_nt_trans(const float* At, int64_t M, int32_t K, int64_t ldat, const float* packed_b, int32_t N,
+                      float* Ct, int64_t ldct, void* stream);
 /* Debug aid: device buffer of 9 x 64 int64 that CTA 0 of the next kgc_gemm_nt / kgc_gemm_tn_tc launches fills with
  * clock64() stamps per warp role, row 8 = global-timer envelope (NULL switches it off; off by default). */
 void kgc_gemm_set_debug(long long* buf);
@@ -186,6 +192,13 @@ int kgc_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_
 size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb);
 int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
                    float* C, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Split-K product of K-major operands with a LONG contraction (ConvE's fc forward, model.py:173: y[B, out] =
+ * x_flat[B, flat] @ W[out, flat]^T, flat = 39,200):  C[Ma, Nb] = A[Ma, K] @ Bt[Nb, K]^T.  The K range is cut into
+ * per-CTA slabs, both operands are streamed and split (3xTF32), partial products stay in TMEM and are added in CTA
+ * order.  Ma <= 128, Nb <= 224, Nb / lda / ldb multiples of 4; workspace = kgc_gemm_tn_tc_workspace_bytes(K, Ma, Nb). */
+int kgc_gemm_nt_splitk(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t K, int32_t Ma, int32_t Nb,
+                       float* C, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's

@@ -5,7 +5,8 @@
 Compute runs in libkgc_b200.so (hand-written sm_100a CUDA behind the C ABI of include/kgc_b200.h);
 there is no CPU fallback.
 """
-from .conv import MGCNConv, get_param, gemm_nt, gemm_tn   # noqa: F401
+from .conv import (MGCNConv, get_param, gemm_nt, gemm_tn, gemm_nt_trans, gemm_nt_splitk,   # noqa: F401
+                   linear_tc, linear_tc_supported)
 from .model import MGCN, ConvE                   # noqa: F401
 from .data_loader import DataLoader, KBDataset, GraphData, BatchIterator, epoch_permutation   # noqa: F401
 from .plan import GraphPlan, get_plan, build_levels, build_stream_plan   # noqa: F401
@@ -16,5 +17,5 @@ from .train import GraphedTrainStep             # noqa: F401
 from . import _lib                               # noqa: F401
 
 __all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
-           'get_plan', 'build_levels', 'build_stream_plan', 'get_param', 'gemm_nt', 'gemm_tn', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
+           'get_plan', 'build_levels', 'build_stream_plan', 'get_param', 'gemm_nt', 'gemm_tn', 'gemm_nt_trans', 'gemm_nt_splitk', 'linear_tc', 'linear_tc_supported', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
            'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges', 'GraphedTrainStep']

@@ -53,6 +53,82 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b'):
     return out
 
 
+def _pack_b(b_kn):
+    K, N = b_kn.shape
+    nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(N, K))
+    if nbytes == 0:
+        raise ValueError('unsupported small operand K={} N={} (K <= 256, N <= 1024)'.format(K, N))
+    packed = torch.empty((nbytes // 4,), dtype=torch.float32, device=b_kn.device)
+    _lib.call('kgc_gemm_pack_b', _lib.ptr(b_kn), b_kn.stride(0), b_kn.stride(1), N, K, _lib.ptr(packed), _lib.stream())
+    return packed
+
+
+def gemm_nt_trans(a_t, b_kn, out_t):
+    """out_t[N, M] = (a_t[K, M]^T @ b_kn[K, N])^T: K4b with the streamed operand and the result transposed in memory, so
+    that the long dimension M is contiguous in both (M % 32 == 0, K <= 256)."""
+    K, M = a_t.shape
+    N = b_kn.shape[1]
+    if a_t.stride(1) != 1 or out_t.stride(1) != 1 or out_t.shape != (N, M):
+        raise ValueError('gemm_nt_trans needs unit inner strides and out_t of shape [N, M]')
+    p = _lib.ptr
+    _lib.call('kgc_gemm_nt_trans', p(a_t), M, K, a_t.stride(0), p(_pack_b(b_kn)), N, p(out_t), out_t.stride(0), _lib.stream())
+    return out_t
+
+
+def gemm_nt_splitk(a, bt, out):
+    """out[Ma, Nb] = a[Ma, K] @ bt[Nb, K]^T for a long contraction K (split over the CTAs; Ma <= 128, Nb <= 224)."""
+    Ma, K = a.shape
+    Nb = bt.shape[0]
+    if a.stride(1) != 1 or bt.stride(1) != 1 or not out.is_contiguous():
+        raise ValueError('gemm_nt_splitk needs unit inner strides and a contiguous output')
+    nbytes = int(_lib.lib().kgc_gemm_tn_tc_workspace_bytes(K, Ma, Nb))
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+    p = _lib.ptr
+    _lib.call('kgc_gemm_nt_splitk', p(a), a.stride(0), p(bt), bt.stride(0), K, Ma, Nb, p(out), p(ws), nbytes, _lib.stream())
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b for a wide input (ConvE's fc, model.py:173: 39,200 -> 200) on the 3xTF32 tensor-core kernels:
+    split-K forward, transposed-operand kernels for d_W and d_x."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x_, w_ = x.detach(), weight.detach()
+        y = gemm_nt_splitk(x_, w_, torch.empty((x_.shape[0], w_.shape[0]), dtype=torch.float32, device=x.device))
+        if bias is not None:
+            y += bias.detach()
+        ctx.save_for_backward(x_, w_)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_nt_trans(w, dy.t(), torch.empty_like(x))          # d_x[B, F] = d_y @ W
+        if ctx.needs_input_grad[1]:
+            dw = gemm_nt_trans(x, dy, torch.empty_like(w))              # d_W[O, F] = d_y^T @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def linear_tc_supported(x, weight):
+    B, F = x.shape
+    O = weight.shape[0]
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.is_contiguous()
+            and weight.is_contiguous() and 0 < B <= 128 and O <= 224 and O % 4 == 0 and F % 32 == 0 and F >= 4096
+            and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
+
+
+def linear_tc(x, weight, bias=None):
+    """Differentiable y = x @ weight^T + bias on the tensor-core kernels (see linear_tc_supported for the shapes)."""
+    return _LinearFn.apply(x, weight, bias)
+
+
 def gemm_tn(a, b, out, plan=None, tensor_cores=True):
     """out[Ka, Nb] = a[M, Ka]^T @ b[M, Nb] (K4c): the weight-gradient reduction over the node rows.  Tensor-core path
     (3xTF32, MN-major operands) for Ka <= 128, Nb <= 224; register-tiled fp32 FMA kernel for wider outputs.  Both add

@@ -180,6 +180,7 @@ struct GemmParams {
   const float* row_bias;   // optional: C[m, n] = f(acc + row_bias[m])
   int32_t act;             // 0: identity, 1: logistic sigmoid
   int32_t trans_c;         // store C transposed: Ct[n, m] (the tensor maps then describe Ct)
+  int32_t trans_a;         // A is given transposed, At[K, M] row-major (M % 32 == 0): tiles land as [m group][k][32 m]
   long long* dbg;     // optional timeline of CTA 0: [role][event] clock64 stamps (debug aid)
 };
 
@@ -263,7 +264,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mb_wait(raw_empty + stage, phase ^ 1);
           KGC_DBG(0);
           mb_expect_tx(raw_full + stage, kTileA);
-          tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
+          if (P.trans_a) tma_3d(s_a + stage * kTileA, &map_a, raw_full + stage, 0, kb * kBK, mt * (kBM / 32));
+          else tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -281,18 +283,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int kb = 0; kb < P.n_kb; ++kb) {
         mb_wait(raw_full + stage, phase);
         if (warp == 2 && lane == 0) KGC_DBG(1);
-        const uint8_t* row = s_a + stage * kTileA + r * 128;
-        uint4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(row + (((half * 4 + i) ^ (r & 7)) << 4));
         uint32_t h[16], l[16];
+        if (P.trans_a) {
+          // At tile: box (32 m, 32 k) per m group = quarter; this thread's row m = lane is a COLUMN of the box: k-th
+          // value at row k, 16-byte chunk (lane / 4) ^ (k % 8) - the 32 lanes of a warp hit 32 different banks
+          const uint8_t* col = s_a + stage * kTileA + quarter * 4096 + ((lane & 3) << 2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          // hi = nearest TF32, lo = nearest TF32 of (v - hi): measurably tighter than truncation at K = 200
-          split_tf32(v[i].x, h[4 * i + 0], l[4 * i + 0]);
-          split_tf32(v[i].y, h[4 * i + 1], l[4 * i + 1]);
-          split_tf32(v[i].z, h[4 * i + 2], l[4 * i + 2]);
-          split_tf32(v[i].w, h[4 * i + 3], l[4 * i + 3]);
+          for (int i = 0; i < 16; ++i) {
+            const int kk = half * 16 + i;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(col + kk * 128 + (((lane >> 2) ^ (kk & 7)) << 4));
+            split_tf32(v, h[i], l[i]);
+          }
+        } else {
+          const uint8_t* row = s_a + stage * kTileA + r * 128;
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(row + (((half * 4 + i) ^ (r & 7)) << 4));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // hi = nearest TF32, lo = nearest TF32 of (v - hi): measurably tighter than truncation at K = 200
+            split_tf32(v[i].x, h[4 * i + 0], l[4 * i + 0]);
+            split_tf32(v[i].y, h[4 * i + 1], l[4 * i + 1]);
+            split_tf32(v[i].z, h[4 * i + 2], l[4 * i + 2]);
+            split_tf32(v[i].w, h[4 * i + 3], l[4 * i + 3]);
+          }
         }
         __syncwarp();
         if (lane == 0) mb_arrive(raw_empty + stage);               // the raw tile is in registers: hand the stage back to TMA
@@ -481,19 +495,25 @@ int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, 
   return 0;
 }
 
-// the complete 32-column groups of fp32 [rows, cols] as ONE box: dims (32 columns, rows, groups), group stride 128 B
-int make_map_f32_mn_groups(CUtensorMap* map, const void* ptr, int64_t rows, int groups, int64_t pitch) {
+// 32-column groups of fp32 [rows, cols] fetched by ONE box: dims (32 columns, rows, groups), group stride 128 B;
+// the box takes 32 rows x box_groups groups and lands as [group][row][32 columns]
+int make_map_f32_groups(CUtensorMap* map, const void* ptr, int64_t rows, int groups, int64_t pitch, int box_groups,
+                        CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc;
   if (encode_fn(&enc)) return 1;
+  KGC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (pitch * 4) % 16 == 0, "operand must be 16-byte aligned with a 16-byte pitch");
   cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)groups};
   cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, 128};
-  cuuint32_t box[3] = {32, 32, (cuuint32_t)groups};
+  cuuint32_t box[3] = {32, 32, (cuuint32_t)box_groups};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KGC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (grouped operand) failed (" + std::to_string((int)r) + ")");
   return 0;
+}
+int make_map_f32_mn_groups(CUtensorMap* map, const void* ptr, int64_t rows, int groups, int64_t pitch) {
+  return make_map_f32_groups(map, ptr, rows, groups, pitch, groups, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 // partial sums [parts][rows][cols] fp32 -> boxes of 32 columns x 32 rows of one part, 128-byte swizzle (TMA stores clip)
@@ -549,6 +569,7 @@ struct GemmTnParams {
   int64_t M;
   int32_t Ka, Nb, ga, gb, n_pad;                 // ga / gb = 32-column groups of A / B; n_pad = MMA N (multiple of 16)
   int32_t ga_full, gb_full;                      // groups that lie completely inside the operand (fetched by one 3-D TMA)
+  int32_t kmajor;                                // split-K product of K-major operands (see kgc_gemm_nt_splitk)
   int64_t rows_per_cta;
   float* partial;                                // [grid][Ka][Nb]
   long long* dbg;                                // optional timeline of CTA 0 (debug aid, see kgc_gemm_set_debug)
@@ -625,9 +646,18 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int kb = 0; kb < n_kb; ++kb) {
         mb_wait(empty + stage, phase ^ 1);
         KGC_DBG(0);
-        mb_expect_tx(raw_full + stage, (uint32_t)stage_bytes);
         uint8_t* dst = s_raw + stage * stage_bytes;
         const int row = (int)(m0 + (int64_t)kb * kTnRows);
+        if (P.kmajor) {
+          // K-major operands A[Ka, K], Bt[Nb, K]: a K block is 32 contraction COLUMNS; A lands as 128 rows x 128 B,
+          // Bt as n_pad rows x 128 B (128-byte swizzle), rows past Ka / Nb and columns past K zero-filled by TMA
+          mb_expect_tx(raw_full + stage, (uint32_t)(kTileA + P.n_pad * 128));
+          tma_2d(dst, &map_a, raw_full + stage, row, 0);
+          tma_2d(dst + kTileA, &map_b, raw_full + stage, row, 0);
+          if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
+        mb_expect_tx(raw_full + stage, (uint32_t)stage_bytes);
         // rows past m1 belong to the next CTA's slab: they are masked out by the splitter (zeroed), rows past M are
         // zero-filled by TMA
         // one instruction fetches all the complete 32-column groups of an operand (a TMA issue costs ~170 cycles of the
@@ -654,7 +684,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint4* lo = reinterpret_cast<uint4*>(s_lo + ls * stage_bytes);
       // rows of this K block that lie past the CTA's slab must not contribute: a 16-byte vector v of a box belongs to
       // box row (v % 256) / 8  (32 rows x 8 vectors per box; the swizzle permutes vectors only inside a row)
-      const int rows_valid = (int)min((int64_t)kTnRows, m1 - (m0 + (int64_t)kb * kTnRows));
+      const int rows_valid = P.kmajor ? kTnRows : (int)min((int64_t)kTnRows, m1 - (m0 + (int64_t)kb * kTnRows));
       for (int v = t; v < n_vec; v += kSplitThreads) {
         uint4 x = hi[v];
         if (((v & 255) >> 3) >= rows_valid) x = make_uint4(0u, 0u, 0u, 0u);
@@ -685,7 +715,21 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t hi_a = s_u32(s_raw + stage * stage_bytes), hi_b = hi_a + P.ga * kTnBox;
       const uint32_t lo_a = s_u32(s_lo + ls * stage_bytes), lo_b = lo_a + P.ga * kTnBox;
-      if (elect_one()) {
+      if (P.kmajor) {
+        const uint32_t idesc_k = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.n_pad >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint64_t a_hi = sw128_desc(hi_a), a_lo = sw128_desc(lo_a);
+        const uint64_t b_hi = sw128_desc(hi_a + kTileA), b_lo = sw128_desc(lo_a + kTileA);
+        if (elect_one()) {
+          for (int k = 0; k < kTnRows / kUK; ++k) {
+            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc_k, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc_k, 1u);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc_k, 1u);
+          }
+          umma_commit_g(empty + stage);
+          umma_commit_g(lo_empty + ls);
+          if (kb == n_kb - 1) umma_commit_g(acc_full);
+        }
+      } else if (elect_one()) {
         for (int k = 0; k < kTnRows / kUK; ++k) {                  // 8 node rows per MMA: the next 8-row K group is 1024 B on
           const uint32_t off = k * 1024;
           umma_tf32(tmem_base, sw128_mn_desc(lo_a + off), sw128_mn_desc(hi_b + off), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -805,10 +849,11 @@ extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // de
 
 // C[M, N] = f(A[M, K] @ Bt^T + row_bias) (trans_c = 0) or Ct[N, M] = the same, stored transposed (trans_c = 1)
 static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
-                          int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c, void* stream) {
+                          int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c, int32_t trans_a, void* stream) {
   Tiling t;
   KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
-  KGC_REQUIRE(M > 0 && lda >= K && ldc >= (trans_c ? M : (int64_t)N), "bad leading dimensions");
+  KGC_REQUIRE(M > 0 && lda >= (trans_a ? M : (int64_t)K) && ldc >= (trans_c ? M : (int64_t)N), "bad leading dimensions");
+  KGC_REQUIRE(!trans_a || M % 32 == 0, "a transposed A operand needs M % 32 == 0");
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0, "C must be 16-byte aligned with a 16-byte row pitch (TMA store)");
   CUtensorMap ma, mbh, mbl, mc, mc16;
   const int total = t.n_pad * t.k_pad;
@@ -819,14 +864,18 @@ static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, con
     if (make_map_f32(&mc, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
     if (make_map_f32(&mc16, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
   }
-  if (make_map_f32(&ma, A, M, K, lda, kBM)) return 1;
+  if (trans_a) {     // At[K, M]: dims (32 m, K, M / 32 groups), one box = 4 groups x 32 k
+    if (make_map_f32_groups(&ma, A, K, (int)(M / 32), lda, kBM / 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else if (make_map_f32(&ma, A, M, K, lda, kBM)) {
+    return 1;
+  }
   if (make_map_f32(&mbh, packed_b, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   if (make_map_f32(&mbl, packed_b + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   GemmParams P;
   P.M = M; P.N = N; P.K = K;
   P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
-  P.C = C; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.dbg = g_gemm_dbg;
+  P.C = C; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.trans_a = trans_a; P.dbg = g_gemm_dbg;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
   const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
@@ -850,7 +899,14 @@ static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, con
 
 extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                            int64_t ldc, void* stream) {
-  return launch_gemm_nt(A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, stream);
+  return launch_gemm_nt(A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, 0, stream);
+}
+
+// Ct[N, M] = (A @ Bt^T)^T with A given transposed, At[K, M] row-major: the long dimension M is contiguous in BOTH the
+// streamed operand and the result (a [K, M] weight or activation matrix and a gradient of the same shape)
+extern "C" int kgc_gemm_nt_trans(const float* At, int64_t M, int32_t K, int64_t ldat, const float* packed_b, int32_t N,
+                                 float* Ct, int64_t ldct, void* stream) {
+  return launch_gemm_nt(At, M, K, ldat, packed_b, N, Ct, ldct, nullptr, 0, 1, 1, stream);
 }
 
 // pred[b, n] = sigmoid(X[b, :] . E[n, :] + bias[n]): the entity table is the streamed operand, the queries the packed
@@ -858,7 +914,7 @@ extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, co
 extern "C" int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
                                 const float* bias, float* pred, int64_t ld_pred, void* stream) {
   KGC_REQUIRE(bias != nullptr, "bias is required");
-  return launch_gemm_nt(ent, n_ent, D, ld_ent, packed_x, B, pred, ld_pred, bias, 1, 1, stream);
+  return launch_gemm_nt(ent, n_ent, D, ld_ent, packed_x, B, pred, ld_pred, bias, 1, 1, 0, stream);
 }
 
 extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {
@@ -867,14 +923,20 @@ extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t 
 }
 
 // C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb] on the tensor cores (3xTF32).  Ka <= 128, Nb <= 224, multiples of 4.
-extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
-                              float* C, void* workspace, size_t workspace_bytes, void* stream) {
+static int launch_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
+                             float* C, void* workspace, size_t workspace_bytes, int32_t kmajor, void* stream) {
   KGC_REQUIRE(M > 0 && Ka > 0 && Nb > 0 && Ka <= 128 && Nb <= 224, "supported: Ka <= 128, Nb <= 224");
-  KGC_REQUIRE(Ka % 4 == 0 && Nb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "dimensions and leading dimensions must be multiples of 4");
+  KGC_REQUIRE(Nb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && (kmajor || Ka % 4 == 0), "dimensions and leading dimensions must be multiples of 4");
   KGC_REQUIRE(workspace && workspace_bytes >= kgc_gemm_tn_tc_workspace_bytes(M, Ka, Nb), "workspace too small");
   CUtensorMap ma, mb;
-  if (make_map_f32_mn(&ma, A, M, Ka, lda) || make_map_f32_mn(&mb, B, M, Nb, ldb)) return 1;
   GemmTnParams P;
+  P.n_pad = (Nb + 15) / 16 * 16;
+  if (kmajor) {      // A[Ka, M], Bt[Nb, M] with the contraction index M contiguous
+    if (make_map_f32(&ma, A, Ka, M, lda, kBM) || make_map_f32(&mb, B, Nb, M, ldb, P.n_pad)) return 1;
+  } else if (make_map_f32_mn(&ma, A, M, Ka, lda) || make_map_f32_mn(&mb, B, M, Nb, ldb)) {
+    return 1;
+  }
+  P.kmajor = kmajor;
   P.M = M; P.Ka = Ka; P.Nb = Nb;
   P.ga = 4;                                   // the MMA always reads M = 128 rows of D: 4 groups (columns past Ka are zero-filled)
   P.n_pad = (Nb + 15) / 16 * 16;
@@ -888,8 +950,8 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
   P.dbg = g_gemm_dbg;
   CUtensorMap mp, ma3, mb3;
   if (make_map_f32_parts(&mp, P.partial, grid, Ka, Nb)) return 1;
-  P.ga_full = Ka / 32;
-  P.gb_full = Nb / 32;
+  P.ga_full = kmajor ? 0 : Ka / 32;
+  P.gb_full = kmajor ? 0 : Nb / 32;
   ma3 = ma; mb3 = mb;                         // placeholders when an operand has no complete group
   if (P.ga_full > 0 && make_map_f32_mn_groups(&ma3, A, M, P.ga_full, lda)) return 1;
   if (P.gb_full > 0 && make_map_f32_mn_groups(&mb3, B, M, P.gb_full, ldb)) return 1;
@@ -907,4 +969,16 @@ extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64
   gemm_tn_partials_reduce<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(P.partial, grid, Ka * Nb, C);
   KGC_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
+                              float* C, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_gemm_tn_tc(A, lda, B, ldb, M, Ka, Nb, C, workspace, workspace_bytes, 0, stream);
+}
+
+// C[Ma, Nb] = A[Ma, K] @ Bt[Nb, K]^T with a LONG contraction (K >> Ma, Nb): the K range is cut into per-CTA slabs, both
+// operands are streamed K-major, partial products stay in TMEM and are added in CTA order.  Ma <= 128, Nb <= 224.
+extern "C" int kgc_gemm_nt_splitk(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t K, int32_t Ma, int32_t Nb,
+                                  float* C, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_gemm_tn_tc(A, lda, Bt, ldb, K, Ma, Nb, C, workspace, workspace_bytes, 1, stream);
 }

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .conv import MGCNConv, get_param
+from .conv import MGCNConv, get_param, linear_tc, linear_tc_supported
 
 
 class ConvE(nn.Module):
@@ -42,7 +42,9 @@ class ConvE(nn.Module):
         x = self.conv_e(x)
         x = F.relu(self.bn1(x))
         x = self.feature_drop(x)
-        x = self.fc(x.view(-1, self.flat_sz))
+        x = x.view(-1, self.flat_sz)
+        # model.py:173: the 39,200 -> 200 fc layer; fp32-grade tensor-core kernels for the shapes they take
+        x = linear_tc(x, self.fc.weight, self.fc.bias) if linear_tc_supported(x, self.fc.weight) else self.fc(x)
         x = self.hidden_drop(x)
         return F.relu(self.bn2(x))
 

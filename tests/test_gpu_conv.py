@@ -415,3 +415,32 @@ def test_conv_linearity_and_determinism_at_fb15k237_shape(k):
     rows = torch.from_numpy(dst).cuda() + (torch.arange(2 * E, device='cuda') >= E) * N
     ref.index_add_(0, rows, msg)
     close(a1.reshape(2 * N, D), ref.cpu().numpy(), 'fb15k237 agg', rtol=2e-5)
+
+
+@pytest.mark.parametrize('B,F,O', [(128, 39200, 200), (77, 4096, 200), (5, 8192, 32), (128, 5024, 100)])
+def test_linear_tc_fc_layer(k, B, F, O):
+    """ConvE's fc layer (model.py:173) on the 3xTF32 kernels: split-K forward, transposed-operand backward; fp32 accuracy
+    against the fp64 evaluation, deterministic."""
+    g = torch.Generator().manual_seed(B + F + O)
+    x = (torch.randn(B, F, generator=g)).cuda().requires_grad_(True)
+    w = (torch.randn(O, F, generator=g) * 0.01).cuda().requires_grad_(True)
+    b = (torch.randn(O, generator=g) * 0.1).cuda().requires_grad_(True)
+    dy = torch.randn(B, O, generator=g).cuda()
+    assert k.linear_tc_supported(x, w)
+    y = k.linear_tc(x, w, b)
+    y.backward(dy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = xd @ wd.t() + bd
+    yd.backward(dy.double())
+    y32 = (x.detach() @ w.detach().t() + b.detach())
+    for got, ref, ref32, name in ((y.detach(), yd.detach(), y32, 'y'), (x.grad, xd.grad, None, 'dx'), (w.grad, wd.grad, None, 'dw'),
+                                  (b.grad, bd.grad, None, 'db')):
+        scale = float(ref.abs().max())
+        err = float((got.double() - ref).abs().max()) / scale
+        err32 = float((ref32.double() - ref).abs().max()) / scale if ref32 is not None else float('nan')
+        print('linear_tc B={} F={} O={} {}: err {:.2e} (fp32 GEMM {:.2e})'.format(B, F, O, name, err, err32))
+        assert err <= 4e-6, (name, err)
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    y2 = k.linear_tc(x2, w2, b2)
+    y2.backward(dy)
+    assert torch.equal(y2, y) and torch.equal(x2.grad, x.grad) and torch.equal(w2.grad, w.grad)

@@ -218,7 +218,7 @@ def test_score_1n_training_path(k, B, N, D):
     loss_ref.backward()
     # fp32 tolerance: sigmoid output <= 1 -> absolute 2e-6; gradients relative to their largest entry
     assert float((pred.detach().double() - pred_ref.detach()).abs().max()) <= 2e-6
-    assert abs(float(loss) - float(loss_ref)) <= 2e-6 * max(1.0, abs(float(loss_ref)))
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-6 * max(1.0, abs(float(loss_ref.detach())))
     for got, ref, name in ((x.grad, xd.grad, 'x'), (ent.grad, ed.grad, 'ent'), (bias.grad, bd.grad, 'bias')):
         scale = float(ref.abs().max())
         err = float((got.double() - ref).abs().max())
