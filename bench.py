@@ -530,7 +530,16 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush, workload='wn18r
                                        'frac': cp_bytes / (ms_cp * 1e-3) / 1e9 / peak,
                                        'note': 'torch copy of the edge-embedding table, timed the same way: what a plain '
                                                'streaming kernel of this size reaches (launch latency + tail included)'}
-    del cp_dst
+    # what a RANDOM gather of rows of this size reaches: the aggregation reads every edge-embedding row (400 B) and a node
+    # row per edge in sorted-by-endpoint order, i.e. as a permutation of the tables
+    perm = torch.randperm(eed.shape[0], device=x.device)
+    ms_g = time_kernel(lambda: torch.index_select(eed, 0, perm, out=cp_dst), flush)
+    g_bytes = cp_bytes + perm.numel() * 8
+    out['row_gather_same_size_reference'] = {'ms': ms_g, 'algorithmic_bytes': g_bytes, 'achieved_gbs': g_bytes / (ms_g * 1e-3) / 1e9,
+                                             'frac': g_bytes / (ms_g * 1e-3) / 1e9 / peak,
+                                             'note': 'torch.index_select of all edge-embedding rows in a random order (400-byte '
+                                                     'rows): the access pattern of the aggregation kernels without their math'}
+    del cp_dst, perm
     for name, fn in fns.items():
         ms = time_kernel(fn, flush)
         gbs = bytes_[name] / (ms * 1e-3) / 1e9

@@ -155,6 +155,25 @@ int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pr
                        const int64_t* seed, float drop_p, float keep_scale, int32_t training, int64_t n_rows,
                        int64_t n_rows_global, int32_t Dout, float* d_res3, void* stream);
 
+/* ---- K0: parameter-side work of one layer step, batched --------------------------------------------------
+ * kgc_conv_prep (forward): relp = cat(rels, loop_rel) (model.py:86); all_rel = relp @ w_rel (model.py:107, all
+ * n_rels + 1 rows - the caller drops the last); and the hi / lo TF32 packs kgc_gemm_nt needs for the three
+ * transforms of the step and of its backward: packed_fwd = 3 x pack(W_h as [K = D, N = Dout]), packed_bwd =
+ * 3 x pack(W_h^T as [K = Dout, N = D]), h = in, out, loop, each kgc_gemm_packed_b_bytes long, the self-loop weight
+ * pre-scaled by loop_rel . loop_edge (model.py:92-94 folded: (x . lr . le) @ W = x @ diag(lr . le) W).
+ * kgc_conv_param_grads (backward): from m_loop = x^T @ d_res_loop and the type-sorted edge reduction d_relp:
+ *   d_w_loop = diag(lr . le) m_loop;  d_v = rowsum(m_loop . w_loop);  d_loop_edge = d_v . lr;
+ *   d_relp' = d_relp + [g_rel; 0] @ w_rel^T;  d_rels = d_relp'[:-1];  d_loop_rel = d_v . le + d_relp'[-1];
+ *   d_w_rel = relp^T @ [g_rel; 0]   (g_rel may be NULL: no gradient reached all_rel).
+ * Weights are contiguous [D, Dout]; D, Dout <= 256. */
+int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loop_rel, const float* loop_edge, const float* w_in,
+                  const float* w_out, const float* w_loop, const float* w_rel, int32_t D, int32_t Dout, float* relp,
+                  float* all_rel, float* packed_fwd, float* packed_bwd, void* stream);
+int kgc_conv_param_grads(const float* m_loop, const float* w_loop, const float* loop_rel, const float* loop_edge,
+                         const float* relp, const float* w_rel, const float* g_rel, const float* d_relp,
+                         int32_t n_rels, int32_t D, int32_t Dout, float* d_w_loop, float* d_loop_rel,
+                         float* d_loop_edge, float* d_rels, float* d_w_rel, void* stream);
+
 /* ---- K4b: dense transforms on the tensor cores with fp32-grade accuracy (3xTF32) --------------------------
  * Replaces the fp32 matmuls of model.py:116 (x_j_rel @ W, after the aggregate-then-transform reordering
  * agg_h @ W_h) and of its autograd (d_res_h @ W_h^T):   C[M,N] = A[M,K] @ Bt[N,K]^T
@@ -169,6 +188,10 @@ int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_n, int32_t 
                     void* stream);
 int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                 int64_t ldc, void* stream);
+/* n_prob (1..3) products of IDENTICAL shape in one launch (the in / out / self-loop transforms of a layer step):
+ * A[i], packed_b[i], C[i] are HOST arrays of device pointers.  The CTAs are dealt to (problem, column tile) groups. */
+int kgc_gemm_nt_batch(int32_t n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda,
+                      const float* const* packed_b, int32_t N, float* const* C, int64_t ldc, void* stream);
 /* Same kernel with the streamed operand AND the result transposed in memory (the long dimension M contiguous):
  *   Ct[n, m] = sum_k At[k, m] * Bt[n, k],  At: [K, M] row-major, pitch ldat;  Ct: [N, M] row-major, pitch ldct.
  * M % 32 == 0.  Used for the autograd of ConvE's fc layer (model.py:173): d_W[out, flat] = d_y^T @ x_flat and

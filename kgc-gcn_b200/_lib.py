@@ -38,6 +38,9 @@ SIGNATURES = {
     'kgc_gemm_packed_b_bytes': (_sz, [_i32, _i32]),
     'kgc_gemm_pack_b': (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'kgc_gemm_nt': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
+    'kgc_conv_prep': (ctypes.c_int, [_vp, _i32] + [_vp] * 6 + [_i32, _i32] + [_vp] * 5),
+    'kgc_conv_param_grads': (ctypes.c_int, [_vp] * 8 + [_i32, _i32, _i32] + [_vp] * 6),
+    'kgc_gemm_nt_batch': (ctypes.c_int, [_i32, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_gemm_nt_trans': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_gemm_nt_splitk': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     'kgc_gemm_set_debug': (None, [_vp]),

@@ -29,21 +29,22 @@ def _mm(a, b, out):
     return torch.mm(a, b, out=out)
 
 
-def gemm_nt(a, b_kn, out, plan=None, tag='b'):
+def gemm_nt(a, b_kn, out, plan=None, tag='b', packed=None):
     """out[M, N] = a[M, K] @ b_kn[K, N] on the tensor cores with fp32-grade accuracy (K4b, 3xTF32).
     ``a`` and ``out`` are row-major (possibly row-strided views); ``b_kn`` is any strided [K, N] view of the small
     operand (a weight or its transpose): it is split and packed per call (a few KB)."""
     M, K = a.shape
-    N = b_kn.shape[1]
+    N = out.shape[1]
     if a.stride(1) != 1 or out.stride(1) != 1:
         raise ValueError('gemm_nt needs unit inner strides')
-    nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(N, K))
-    if nbytes == 0:
-        raise ValueError('gemm_nt: unsupported shape K={} N={}'.format(K, N))
-    packed = plan.scratch('gemm_pack_' + tag, (nbytes // 4,)) if plan is not None else \
-        torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
     p = _lib.ptr
-    _lib.call('kgc_gemm_pack_b', p(b_kn), b_kn.stride(0), b_kn.stride(1), N, K, p(packed), _lib.stream())
+    if packed is None:                                  # ``packed``: the operand already split by kgc_conv_prep / kgc_gemm_pack_b
+        nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(N, K))
+        if nbytes == 0:
+            raise ValueError('gemm_nt: unsupported shape K={} N={}'.format(K, N))
+        packed = plan.scratch('gemm_pack_' + tag, (nbytes // 4,)) if plan is not None else \
+            torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+        _lib.call('kgc_gemm_pack_b', p(b_kn), b_kn.stride(0), b_kn.stride(1), N, K, p(packed), _lib.stream())
     # C is written by TMA stores: 16-byte aligned rows; an odd pitch goes through a padded buffer
     dst = out if (out.data_ptr() % 16 == 0 and out.stride(0) % 4 == 0) else \
         torch.empty((M, (N + 3) // 4 * 4), dtype=torch.float32, device=a.device)[:, :N]
@@ -51,6 +52,22 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b'):
     if dst is not out:
         out.copy_(dst)
     return out
+
+
+def gemm_nt_batch(a_list, packed_list, out_list):
+    """Up to three products out_i = a_i @ B_i of identical shape in ONE launch (K4b); ``packed_list`` holds the split small
+    operands (kgc_conv_prep / kgc_gemm_pack_b)."""
+    import ctypes
+    n = len(a_list)
+    M, K = a_list[0].shape
+    N = out_list[0].shape[1]
+    lda, ldc = a_list[0].stride(0), out_list[0].stride(0)
+    for a, o in zip(a_list, out_list):
+        if a.shape != (M, K) or o.shape != (M, N) or a.stride() != (lda, 1) or o.stride() != (ldc, 1):
+            raise ValueError('gemm_nt_batch needs operands of identical shape and strides')
+    arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])       # noqa: E731
+    _lib.call('kgc_gemm_nt_batch', n, arr(a_list), M, K, lda, arr(packed_list), N, arr(out_list), ldc, _lib.stream())
+    return out_list
 
 
 def _pack_b(b_kn):
@@ -196,9 +213,22 @@ class _ConvFn(torch.autograd.Function):
         n_global = Nl if coll is None else coll.n_global
         if ee.shape[0] != plan.num_edges2 or Nl != plan.num_dst_rows or n_global != plan.num_nodes:
             raise ValueError('edge_embs / x do not match the graph plan')
-        relp = torch.cat([rels, loop_rel], 0).contiguous()          # model.py:86
-        if relp.shape[0] != plan.num_types:
+        T = rels.shape[0] + 1
+        if T != plan.num_types:
             raise ValueError('rels_embs rows + 1 must equal the number of edge types of the plan')
+        # K0: cat(rels, loop_rel) (model.py:86), relp @ w_rel (model.py:107) and the TF32 packs of the six small GEMM
+        # operands of this step (forward and backward) in one launch
+        nf = int(_lib.lib().kgc_gemm_packed_b_bytes(Dout, D)) // 4
+        nbk = int(_lib.lib().kgc_gemm_packed_b_bytes(D, Dout)) // 4
+        if nf == 0 or nbk == 0:
+            raise ValueError('unsupported layer width {} -> {} (<= 256)'.format(D, Dout))
+        relp = torch.empty((T, D), dtype=torch.float32, device=x.device)
+        all_rel_pad = torch.empty((T, Dout), dtype=torch.float32, device=x.device)
+        packed_f = torch.empty((3, nf), dtype=torch.float32, device=x.device)
+        packed_b = torch.empty((3, nbk), dtype=torch.float32, device=x.device)
+        rels_c, wts = rels.detach().contiguous(), [w.detach().contiguous() for w in (w_in, w_out, w_loop, w_rel)]
+        _lib.call('kgc_conv_prep', p(rels_c), T - 1, p(loop_rel.detach()), p(loop_edge.detach()), p(wts[0]), p(wts[1]), p(wts[2]),
+                  p(wts[3]), D, Dout, p(relp), p(all_rel_pad), p(packed_f), p(packed_b), st())
         # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition); it runs on
         # NCCL's stream while this rank's self-loop transform (which only needs its own rows) runs here
         gather = None
@@ -207,11 +237,9 @@ class _ConvFn(torch.autograd.Function):
         else:
             x_full, gather = coll.all_gather_rows(x, async_op=True)
 
-        v = (loop_rel * loop_edge).reshape(D, 1)                     # self-loop: (x . lr . le) @ W = x @ (diag(v) W)
-        w_loop_s = v * w_loop
         res3 = plan.scratch('res3', (3, Nl, Dout))
-        gemm_nt(x, w_loop_s, res3[2], plan, 'f2')
-        if gather is not None:
+        if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
+            gemm_nt(x, None, res3[2], packed=packed_f[2])          # overlaps the all-gather
             gather.wait()
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
@@ -220,8 +248,10 @@ class _ConvFn(torch.autograd.Function):
                       p(out_final), p(carry), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
 
-        gemm_nt(agg[0], w_in, res3[0], plan, 'f0')
-        gemm_nt(agg[1], w_out, res3[1], plan, 'f1')
+        if gather is not None:
+            gemm_nt_batch([agg[0], agg[1]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
+        else:                                                       # the three transforms of the step in one launch
+            gemm_nt_batch([agg[0], agg[1], x], [packed_f[0], packed_f[1], packed_f[2]], [res3[0], res3[1], res3[2]])
 
         nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
@@ -238,20 +268,20 @@ class _ConvFn(torch.autograd.Function):
         _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
                   p(running_var), p(stats), st())
         _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), st())
-        all_rel = torch.mm(relp, w_rel)[:-1]                          # model.py:107
+        all_rel = all_rel_pad[:-1]
 
         ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias, ctx.coll = plan, bool(training), float(keep_scale), \
             bias is not None, coll
         ctx.drop_p = float(drop_p)
         ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre,
-                              all_ent, stats, mask_in, mask_out, w_loop_s, seed)
+                              all_ent, stats, mask_in, mask_out, packed_b, seed)
         ctx.mark_non_differentiable(stats)
         return all_ent, all_rel, stats
 
     @staticmethod
     def backward(ctx, g_ent, g_rel, _g_stats):
         (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent, stats, mask_in,
-         mask_out, w_loop_s, seed) = ctx.saved_tensors
+         mask_out, packed_b, seed) = ctx.saved_tensors
         plan, coll = ctx.plan, ctx.coll
         Nl, D = x.shape
         n_global = plan.num_nodes
@@ -290,9 +320,7 @@ class _ConvFn(torch.autograd.Function):
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
         g3 = plan.scratch('g3', (3, Nl, D))
-        gemm_nt(d_res3[0], w_in.t(), g3[0], plan, 'g0')
-        gemm_nt(d_res3[1], w_out.t(), g3[1], plan, 'g1')
-        gemm_nt(d_res3[2], w_loop_s.t(), g3[2], plan, 'g2')
+        gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]], [g3[0], g3[1], g3[2]])
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
         d_x_full = torch.empty((n_global, D), dtype=torch.float32, device=dev)
         d_ee = torch.empty_like(ee)
@@ -319,22 +347,16 @@ class _ConvFn(torch.autograd.Function):
             if scatter is not None:
                 scatter.wait()
             d_x += g3[2]                                              # self-loop term of this rank's rows
-        v = (loop_rel * loop_edge).reshape(D, 1)
-        d_w_loop = v * m_loop
-        d_v = (m_loop * w_loop).sum(1).reshape(1, D)
-        d_loop_edge = d_v * loop_rel
-        d_loop_rel = d_v * loop_edge
         d_bias = flat[3 * D * Dout + T * D:] * 3.0 if ctx.has_bias else None
-
-        # ---- relation transform (model.py:107): replicated inputs, identical on every rank
-        if g_rel is not None:
-            g_rel_pad = torch.cat([g_rel, g_rel.new_zeros((1, Dout))], 0)
-            d_relp = d_relp + torch.mm(g_rel_pad, w_rel.t())
-            d_w_rel = torch.mm(relp.t(), g_rel_pad)
-        else:
-            d_w_rel = torch.zeros_like(w_rel)
-        d_rels = d_relp[:-1]
-        d_loop_rel = d_loop_rel + d_relp[-1:]
+        # K0 backward: self-loop vectors, relation transform (model.py:107; replicated inputs, identical on every rank)
+        small = torch.empty((2 * D * Dout + 2 * D + (T - 1) * D,), dtype=torch.float32, device=dev)
+        d_w_loop, d_w_rel = small[:D * Dout].view(D, Dout), small[D * Dout:2 * D * Dout].view(D, Dout)
+        o = 2 * D * Dout
+        d_loop_rel, d_loop_edge, d_rels = small[o:o + D].view(1, D), small[o + D:o + 2 * D].view(1, D), small[o + 2 * D:].view(T - 1, D)
+        g_rel_c = None if g_rel is None else g_rel.contiguous()
+        _lib.call('kgc_conv_param_grads', p(m_loop), p(w_loop.detach().contiguous()), p(loop_rel.detach()), p(loop_edge.detach()),
+                  p(relp), p(w_rel.detach().contiguous()), p(g_rel_c), p(d_relp), T - 1, D, Dout, p(d_w_loop), p(d_loop_rel),
+                  p(d_loop_edge), p(d_rels), p(d_w_rel), st())
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
                 None, None, None, None, None, None, None, None, None, None, None)
 

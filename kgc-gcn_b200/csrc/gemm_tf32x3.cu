@@ -171,8 +171,14 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+constexpr int kMaxBatch = 3;               // problems of one launch (same shapes, different operands): in / out / loop halves
+struct GemmMaps {
+  CUtensorMap a[kMaxBatch], bhi[kMaxBatch], blo[kMaxBatch], c[kMaxBatch], c16[kMaxBatch];
+};
+
 struct GemmParams {
   int64_t M;
+  int32_t n_prob;
   int32_t N, K;
   int32_t n_kb, ksteps, NT, n_ntiles, n_mtiles, stages;
   float* C;
@@ -185,9 +191,7 @@ struct GemmParams {
 };
 
 __global__ void __launch_bounds__(kThreadsG, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
-                   const __grid_constant__ CUtensorMap map_c16, const GemmParams P) {
+gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
   if (P.dbg != nullptr && threadIdx.x == 0) {                      // debug aid: launch-to-exit envelope over all CTAs (ns)
     long long g;
@@ -245,17 +249,24 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   int dbg_n = 0;
 #define KGC_DBG(role) do { if (dbg_on && dbg_n < 64) P.dbg[(role) * 64 + dbg_n++] = clock64(); } while (0)
 
-  // work: this CTA owns column tile nt and the row tiles mt = first, first + step, ...
+  // work: this CTA owns column tile nt of problem prob and the row tiles mt = first, first + step, ...
+  const int groups = P.n_prob * P.n_ntiles;                        // host launches a multiple of groups CTAs
+  const int prob = (blockIdx.x % groups) / P.n_ntiles;
   const int nt = blockIdx.x % P.n_ntiles;
-  const int first = blockIdx.x / P.n_ntiles;
-  const int step = gridDim.x / P.n_ntiles;                         // host launches a multiple of n_ntiles CTAs
+  const int first = blockIdx.x / groups;
+  const int step = gridDim.x / groups;
+  const CUtensorMap* map_a = &maps.a[prob];
+  const CUtensorMap* map_bhi = &maps.bhi[prob];
+  const CUtensorMap* map_blo = &maps.blo[prob];
+  const CUtensorMap* map_c = &maps.c[prob];
+  const CUtensorMap* map_c16 = &maps.c16[prob];
 
   if (warp == 0) {
     if (lane == 0) {
       mb_expect_tx(b_full, 2u * P.n_kb * tile_b);
       for (int kb = 0; kb < P.n_kb; ++kb) {
-        tma_2d(s_bhi + kb * tile_b_al, &map_bhi, b_full, kb * kBK, nt * P.NT);
-        tma_2d(s_blo + kb * tile_b_al, &map_blo, b_full, kb * kBK, nt * P.NT);
+        tma_2d(s_bhi + kb * tile_b_al, map_bhi, b_full, kb * kBK, nt * P.NT);
+        tma_2d(s_blo + kb * tile_b_al, map_blo, b_full, kb * kBK, nt * P.NT);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -264,8 +275,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mb_wait(raw_empty + stage, phase ^ 1);
           KGC_DBG(0);
           mb_expect_tx(raw_full + stage, kTileA);
-          if (P.trans_a) tma_3d(s_a + stage * kTileA, &map_a, raw_full + stage, 0, kb * kBK, mt * (kBM / 32));
-          else tma_2d(s_a + stage * kTileA, &map_a, raw_full + stage, kb * kBK, mt * kBM);
+          if (P.trans_a) tma_3d(s_a + stage * kTileA, map_a, raw_full + stage, 0, kb * kBK, mt * (kBM / 32));
+          else tma_2d(s_a + stage * kTileA, map_a, raw_full + stage, kb * kBK, mt * kBM);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -424,8 +435,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (lane == 0) {
           const int col = nt * P.NT + c0;
           if (m0 < P.M && col < P.N) {
-            if (P.trans_c) tma_store_2d(wide ? &map_c : &map_c16, bb, (int)m0, col);     // Ct: inner coordinate = row of C
-            else tma_store_2d(wide ? &map_c : &map_c16, bb, col, (int)m0);
+            if (P.trans_c) tma_store_2d(wide ? map_c : map_c16, bb, (int)m0, col);     // Ct: inner coordinate = row of C
+            else tma_store_2d(wide ? map_c : map_c16, bb, col, (int)m0);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -461,6 +472,110 @@ __global__ void pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t s
   split_tf32(__float_as_uint(v), h, l);
   hi[i] = __uint_as_float(h);
   lo[i] = __uint_as_float(l);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Parameter-side work of one MGCNConv step, batched.  The layer's small operands (three [D, Dout] weights, the relation
+// table, two [1, D] self-loop vectors) need ~20 tiny tensor operations per step in the reference formulation
+// (model.py:86, 92-94, 107 and their autograd); each costs a launch (~2 us inside a CUDA graph) for a few KB of work.
+struct PrepArgs {
+  const float *rels, *loop_rel, *loop_edge, *w[3], *w_rel;        // w: in, out, loop
+  int n_rels, D, Dout;
+  int n_pad_f, k_pad_f, n_pad_b, k_pad_b;                         // packed layouts of W (N = Dout, K = D) and W^T (N = D, K = Dout)
+  float *relp, *all_rel, *packed_f, *packed_b;
+};
+
+__global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
+  const int T = a.n_rels + 1;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = T * a.D, n1 = T * a.Dout, nf = a.n_pad_f * a.k_pad_f, nb = a.n_pad_b * a.k_pad_b;
+  if (i < n0) {                                                   // relp = cat(rels, loop_rel)   (model.py:86)
+    const int t = i / a.D, c = i % a.D;
+    a.relp[i] = t < a.n_rels ? a.rels[i] : a.loop_rel[c];
+    return;
+  }
+  i -= n0;
+  if (i < n1) {                                                   // all_rel = relp @ w_rel        (model.py:107)
+    const int t = i / a.Dout, o = i % a.Dout;
+    const float* r = t < a.n_rels ? a.rels + (int64_t)t * a.D : a.loop_rel;
+    float acc = 0.f;
+    for (int c = 0; c < a.D; ++c) acc = fmaf(r[c], a.w_rel[(int64_t)c * a.Dout + o], acc);
+    a.all_rel[i] = acc;
+    return;
+  }
+  i -= n1;
+  if (i < 3 * nf) {                                               // Bt[n, k] = W_h[k, n]  (x loop_rel[k] loop_edge[k] for the self-loop)
+    const int h = i / nf, j = i % nf, n = j / a.k_pad_f, k = j % a.k_pad_f;
+    float v = 0.f;
+    if (n < a.Dout && k < a.D) {
+      v = a.w[h][(int64_t)k * a.Dout + n];
+      if (h == 2) v *= a.loop_rel[k] * a.loop_edge[k];
+    }
+    uint32_t hi, lo;
+    split_tf32(__float_as_uint(v), hi, lo);
+    float* dst = a.packed_f + (int64_t)h * 2 * nf;
+    dst[j] = __uint_as_float(hi);
+    dst[nf + j] = __uint_as_float(lo);
+    return;
+  }
+  i -= 3 * nf;
+  if (i < 3 * nb) {                                               // Bt[n, k] = W_h^T[k, n] = W_h[n, k]
+    const int h = i / nb, j = i % nb, n = j / a.k_pad_b, k = j % a.k_pad_b;
+    float v = 0.f;
+    if (n < a.D && k < a.Dout) {
+      v = a.w[h][(int64_t)n * a.Dout + k];
+      if (h == 2) v *= a.loop_rel[n] * a.loop_edge[n];
+    }
+    uint32_t hi, lo;
+    split_tf32(__float_as_uint(v), hi, lo);
+    float* dst = a.packed_b + (int64_t)h * 2 * nb;
+    dst[j] = __uint_as_float(hi);
+    dst[nb + j] = __uint_as_float(lo);
+  }
+}
+
+struct ParamGradArgs {
+  const float *m_loop, *w_loop, *loop_rel, *loop_edge, *relp, *w_rel, *g_rel, *d_relp;
+  int n_rels, D, Dout;
+  float *d_w_loop, *d_loop_rel, *d_loop_edge, *d_rels, *d_w_rel;
+};
+
+__global__ void __launch_bounds__(256) conv_param_grads_kernel(const ParamGradArgs a) {
+  const int T = a.n_rels + 1;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = a.D * a.Dout;
+  if (i < nw) {                                                   // d_w_loop = diag(loop_rel . loop_edge) m_loop
+    const int c = i / a.Dout;
+    a.d_w_loop[i] = a.loop_rel[c] * a.loop_edge[c] * a.m_loop[i];
+    return;
+  }
+  i -= nw;
+  if (i < nw) {                                                   // d_w_rel = relp^T @ [g_rel; 0]
+    const int c = i / a.Dout, o = i % a.Dout;
+    float acc = 0.f;
+    if (a.g_rel != nullptr)
+      for (int t = 0; t < a.n_rels; ++t) acc = fmaf(a.relp[(int64_t)t * a.D + c], a.g_rel[(int64_t)t * a.Dout + o], acc);
+    a.d_w_rel[i] = acc;
+    return;
+  }
+  i -= nw;
+  if (i < T * a.D) {                                              // d_relp + [g_rel; 0] @ w_rel^T; last row -> the self-loop vectors
+    const int t = i / a.D, c = i % a.D;
+    float val = a.d_relp[i];
+    if (t < a.n_rels) {
+      if (a.g_rel != nullptr) {
+        float acc = 0.f;
+        for (int o = 0; o < a.Dout; ++o) acc = fmaf(a.g_rel[(int64_t)t * a.Dout + o], a.w_rel[(int64_t)c * a.Dout + o], acc);
+        val += acc;
+      }
+      a.d_rels[i] = val;
+    } else {
+      float dv = 0.f;                                             // d_v[c] = sum_o m_loop[c, o] w_loop[c, o]
+      for (int o = 0; o < a.Dout; ++o) dv = fmaf(a.m_loop[(int64_t)c * a.Dout + o], a.w_loop[(int64_t)c * a.Dout + o], dv);
+      a.d_loop_edge[c] = dv * a.loop_rel[c];
+      a.d_loop_rel[c] = dv * a.loop_edge[c] + val;
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -828,6 +943,40 @@ using namespace kgc;
 
 static long long* g_gemm_dbg = nullptr;
 
+extern "C" int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loop_rel, const float* loop_edge, const float* w_in,
+                             const float* w_out, const float* w_loop, const float* w_rel, int32_t D, int32_t Dout, float* relp,
+                             float* all_rel, float* packed_fwd, float* packed_bwd, void* stream) {
+  Tiling tf, tb;
+  KGC_REQUIRE(make_tiling(Dout, D, &tf) == 0 && make_tiling(D, Dout, &tb) == 0, "unsupported layer width (<= 256)");
+  KGC_REQUIRE(n_rels >= 0 && rels && loop_rel && loop_edge && w_in && w_out && w_loop && w_rel && relp && all_rel && packed_fwd && packed_bwd,
+              "null buffer");
+  PrepArgs a;
+  a.rels = rels; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.w[0] = w_in; a.w[1] = w_out; a.w[2] = w_loop; a.w_rel = w_rel;
+  a.n_rels = n_rels; a.D = D; a.Dout = Dout;
+  a.n_pad_f = tf.n_pad; a.k_pad_f = tf.k_pad; a.n_pad_b = tb.n_pad; a.k_pad_b = tb.k_pad;
+  a.relp = relp; a.all_rel = all_rel; a.packed_f = packed_fwd; a.packed_b = packed_bwd;
+  const int64_t total = (int64_t)(n_rels + 1) * (D + Dout) + 3 * ((int64_t)tf.n_pad * tf.k_pad + (int64_t)tb.n_pad * tb.k_pad);
+  conv_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(a);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_conv_param_grads(const float* m_loop, const float* w_loop, const float* loop_rel, const float* loop_edge,
+                                    const float* relp, const float* w_rel, const float* g_rel, const float* d_relp,
+                                    int32_t n_rels, int32_t D, int32_t Dout, float* d_w_loop, float* d_loop_rel,
+                                    float* d_loop_edge, float* d_rels, float* d_w_rel, void* stream) {
+  KGC_REQUIRE(m_loop && w_loop && loop_rel && loop_edge && relp && w_rel && d_relp && d_w_loop && d_loop_rel && d_loop_edge && d_rels && d_w_rel,
+              "null buffer");
+  ParamGradArgs a;
+  a.m_loop = m_loop; a.w_loop = w_loop; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.relp = relp; a.w_rel = w_rel;
+  a.g_rel = g_rel; a.d_relp = d_relp; a.n_rels = n_rels; a.D = D; a.Dout = Dout;
+  a.d_w_loop = d_w_loop; a.d_loop_rel = d_loop_rel; a.d_loop_edge = d_loop_edge; a.d_rels = d_rels; a.d_w_rel = d_w_rel;
+  const int64_t total = 2 * (int64_t)D * Dout + (int64_t)(n_rels + 1) * D;
+  conv_param_grads_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(a);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" size_t kgc_gemm_packed_b_bytes(int32_t N, int32_t K) {
   Tiling t;
   if (make_tiling(N, K, &t)) return 0;
@@ -847,35 +996,43 @@ extern "C" int kgc_gemm_pack_b(const float* B, int64_t stride_k, int64_t stride_
 
 extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // device buffer of 9 * 64 int64, or NULL
 
-// C[M, N] = f(A[M, K] @ Bt^T + row_bias) (trans_c = 0) or Ct[N, M] = the same, stored transposed (trans_c = 1)
-static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
-                          int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c, int32_t trans_a, void* stream) {
+// C_i[M, N] = f(A_i[M, K] @ Bt_i^T + row_bias) (trans_c = 0) or Ct_i[N, M] = the same, stored transposed (trans_c = 1),
+// i < n_prob problems of identical shape in ONE launch: the CTAs are dealt to (problem, column tile) groups, so a batch
+// fills the 148 SMs with whole row-tile rounds where a single N x 100 x 200 product leaves a 14% tail
+static int launch_gemm_nt(int n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda, const float* const* packed_b,
+                          int32_t N, float* const* C, int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c,
+                          int32_t trans_a, void* stream) {
   Tiling t;
+  KGC_REQUIRE(n_prob >= 1 && n_prob <= kMaxBatch, "1..3 problems per launch");
   KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
   KGC_REQUIRE(M > 0 && lda >= (trans_a ? M : (int64_t)K) && ldc >= (trans_c ? M : (int64_t)N), "bad leading dimensions");
   KGC_REQUIRE(!trans_a || M % 32 == 0, "a transposed A operand needs M % 32 == 0");
-  KGC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0, "C must be 16-byte aligned with a 16-byte row pitch (TMA store)");
-  CUtensorMap ma, mbh, mbl, mc, mc16;
+  KGC_REQUIRE(ldc % 4 == 0, "C needs a 16-byte row pitch (TMA store)");
+  GemmMaps maps;
   const int total = t.n_pad * t.k_pad;
-  if (trans_c) {     // Ct[N, M]: boxes of 32 rows of C (inner) x 32 / 16 columns of C
-    if (make_map_f32(&mc, C, N, M, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
-    if (make_map_f32(&mc16, C, N, M, ldc, 16, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
-  } else {
-    if (make_map_f32(&mc, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
-    if (make_map_f32(&mc16, C, M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
+  for (int i = 0; i < kMaxBatch; ++i) {
+    const int j = i < n_prob ? i : 0;          // unused slots repeat problem 0 (never dereferenced)
+    KGC_REQUIRE((reinterpret_cast<uintptr_t>(C[j]) & 15) == 0, "C must be 16-byte aligned (TMA store)");
+    if (trans_c) {     // Ct[N, M]: boxes of 32 rows of C (inner) x 32 / 16 columns of C
+      if (make_map_f32(&maps.c[i], C[j], N, M, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+      if (make_map_f32(&maps.c16[i], C[j], N, M, ldc, 16, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+    } else {
+      if (make_map_f32(&maps.c[i], C[j], M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B, 32)) return 1;
+      if (make_map_f32(&maps.c16[i], C[j], M, N, ldc, 32, CU_TENSOR_MAP_SWIZZLE_64B, 16)) return 1;
+    }
+    if (trans_a) {     // At[K, M]: dims (32 m, K, M / 32 groups), one box = 4 groups x 32 k
+      if (make_map_f32_groups(&maps.a[i], A[j], K, (int)(M / 32), lda, kBM / 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else if (make_map_f32(&maps.a[i], A[j], M, K, lda, kBM)) {
+      return 1;
+    }
+    if (make_map_f32(&maps.bhi[i], packed_b[j], t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
+    if (make_map_f32(&maps.blo[i], packed_b[j] + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   }
-  if (trans_a) {     // At[K, M]: dims (32 m, K, M / 32 groups), one box = 4 groups x 32 k
-    if (make_map_f32_groups(&ma, A, K, (int)(M / 32), lda, kBM / 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-  } else if (make_map_f32(&ma, A, M, K, lda, kBM)) {
-    return 1;
-  }
-  if (make_map_f32(&mbh, packed_b, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
-  if (make_map_f32(&mbl, packed_b + total, t.n_pad, t.k_pad, t.k_pad, t.NT)) return 1;
   GemmParams P;
-  P.M = M; P.N = N; P.K = K;
+  P.M = M; P.N = N; P.K = K; P.n_prob = n_prob;
   P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
-  P.C = C; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.trans_a = trans_a; P.dbg = g_gemm_dbg;
+  P.C = C[0]; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.trans_a = trans_a; P.dbg = g_gemm_dbg;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
   const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
@@ -888,25 +1045,32 @@ static int launch_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, con
     KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  // a multiple of n_ntiles CTAs, at most one per SM, never more row-tile owners than row tiles
-  int per = kNumSMs / t.n_ntiles;
+  // a multiple of (problems x column tiles) CTAs, at most one per SM, never more row-tile owners than row tiles
+  const int groups = n_prob * t.n_ntiles;
+  int per = kNumSMs / groups;
   if (per > P.n_mtiles) per = P.n_mtiles;
   if (per < 1) per = 1;
-  gemm_tf32x3_kernel<<<per * t.n_ntiles, kThreadsG, smem, as_stream(stream)>>>(ma, mbh, mbl, mc, mc16, P);
+  gemm_tf32x3_kernel<<<per * groups, kThreadsG, smem, as_stream(stream)>>>(maps, P);
   KGC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* packed_b, int32_t N, float* C,
                            int64_t ldc, void* stream) {
-  return launch_gemm_nt(A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, 0, stream);
+  return launch_gemm_nt(1, &A, M, K, lda, &packed_b, N, &C, ldc, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int kgc_gemm_nt_batch(int32_t n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda,
+                                 const float* const* packed_b, int32_t N, float* const* C, int64_t ldc, void* stream) {
+  KGC_REQUIRE(A && packed_b && C, "null pointer table");
+  return launch_gemm_nt(n_prob, A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, 0, stream);
 }
 
 // Ct[N, M] = (A @ Bt^T)^T with A given transposed, At[K, M] row-major: the long dimension M is contiguous in BOTH the
 // streamed operand and the result (a [K, M] weight or activation matrix and a gradient of the same shape)
 extern "C" int kgc_gemm_nt_trans(const float* At, int64_t M, int32_t K, int64_t ldat, const float* packed_b, int32_t N,
                                  float* Ct, int64_t ldct, void* stream) {
-  return launch_gemm_nt(At, M, K, ldat, packed_b, N, Ct, ldct, nullptr, 0, 1, 1, stream);
+  return launch_gemm_nt(1, &At, M, K, ldat, &packed_b, N, &Ct, ldct, nullptr, 0, 1, 1, stream);
 }
 
 // pred[b, n] = sigmoid(X[b, :] . E[n, :] + bias[n]): the entity table is the streamed operand, the queries the packed
@@ -914,7 +1078,7 @@ extern "C" int kgc_gemm_nt_trans(const float* At, int64_t M, int32_t K, int64_t 
 extern "C" int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
                                 const float* bias, float* pred, int64_t ld_pred, void* stream) {
   KGC_REQUIRE(bias != nullptr, "bias is required");
-  return launch_gemm_nt(ent, n_ent, D, ld_ent, packed_x, B, pred, ld_pred, bias, 1, 1, 0, stream);
+  return launch_gemm_nt(1, &ent, n_ent, D, ld_ent, &packed_x, B, &pred, ld_pred, bias, 1, 1, 0, stream);
 }
 
 extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {
