@@ -223,6 +223,13 @@ int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int
 int kgc_gemm_nt_splitk(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t K, int32_t Ma, int32_t Nb,
                        float* C, void* workspace, size_t workspace_bytes, void* stream);
 
+/* n_prob (1..3) weight-gradient reductions of identical shape in one launch (d_W of the in / out / self-loop
+ * transforms): HOST arrays of device pointers; the CTAs are dealt to (problem, row slab) pairs, so every CTA sweeps
+ * a 3x longer slab than in three separate launches and three times fewer partials are added.  Same workspace size. */
+int kgc_gemm_tn_tc_batch(int32_t n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb,
+                         int64_t M, int32_t Ka, int32_t Nb, float* const* C, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's
  * query ids qid[B] (int64) and the query->objects CSR (ptr int64 [Q+1], idx int32 [nnz]):

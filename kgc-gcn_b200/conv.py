@@ -70,6 +70,29 @@ def gemm_nt_batch(a_list, packed_list, out_list):
     return out_list
 
 
+def gemm_tn_batch(a_list, b_list, out_list, plan=None):
+    """Up to three weight-gradient reductions out_i = a_i^T @ b_i of identical shape in ONE launch (K4c on the tensor
+    cores; Ka <= 128, Nb <= 224 - wider shapes go through gemm_tn one by one)."""
+    import ctypes
+    n = len(a_list)
+    M, Ka = a_list[0].shape
+    Nb = b_list[0].shape[1]
+    lda, ldb = a_list[0].stride(0), b_list[0].stride(0)
+    same = all(a.shape == (M, Ka) and b.shape == (M, Nb) and a.stride() == (lda, 1) and b.stride() == (ldb, 1)
+               and o.is_contiguous() for a, b, o in zip(a_list, b_list, out_list))
+    if not same or Ka > 128 or Nb > 224:
+        for a, b, o in zip(a_list, b_list, out_list):
+            gemm_tn(a, b, o, plan)
+        return out_list
+    nbytes = int(_lib.lib().kgc_gemm_tn_tc_workspace_bytes(M, Ka, Nb))
+    ws = plan.scratch('kgc_gemm_tn_tc_ws', (nbytes // 4,)) if plan is not None else \
+        torch.empty((nbytes // 4,), dtype=torch.float32, device=a_list[0].device)
+    arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])       # noqa: E731
+    _lib.call('kgc_gemm_tn_tc_batch', n, arr(a_list), lda, arr(b_list), ldb, M, Ka, Nb, arr(out_list), _lib.ptr(ws), nbytes,
+              _lib.stream())
+    return out_list
+
+
 def _pack_b(b_kn):
     K, N = b_kn.shape
     nbytes = int(_lib.lib().kgc_gemm_packed_b_bytes(N, K))
@@ -312,9 +335,7 @@ class _ConvFn(torch.autograd.Function):
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
         d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
         # weight-gradient reductions over the node rows (K4c: register-tiled fp32, deterministic)
-        gemm_tn(agg[0], d_res3[0], d_w_in, plan)
-        gemm_tn(agg[1], d_res3[1], d_w_out, plan)
-        gemm_tn(x, d_res3[2], m_loop, plan)                            # [D, Dout]
+        gemm_tn_batch([agg[0], agg[1], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
         if ctx.has_bias:
             torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 

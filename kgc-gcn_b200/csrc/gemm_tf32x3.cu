@@ -680,8 +680,13 @@ constexpr int kTnBox = kTnRows * 128;            // one 32-column x 32-row box: 
 constexpr int kTnStages = 3;
 constexpr int kTnLoStages = 2;
 
+struct GemmTnMaps {                              // per problem of a batched launch
+  CUtensorMap a[kMaxBatch], b[kMaxBatch], a3[kMaxBatch], b3[kMaxBatch], p[kMaxBatch];
+};
+
 struct GemmTnParams {
   int64_t M;
+  int32_t n_prob, n_slabs;                       // CTA = (problem, row slab); partial[problem][slab][Ka][Nb]
   int32_t Ka, Nb, ga, gb, n_pad;                 // ga / gb = 32-column groups of A / B; n_pad = MMA N (multiple of 16)
   int32_t ga_full, gb_full;                      // groups that lie completely inside the operand (fetched by one 3-D TMA)
   int32_t kmajor;                                // split-K product of K-major operands (see kgc_gemm_nt_splitk)
@@ -704,9 +709,7 @@ __device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(kThreadsG, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ CUtensorMap map_a3, const __grid_constant__ CUtensorMap map_b3,
-                  const __grid_constant__ CUtensorMap map_p, const GemmTnParams P) {
+gemm_tn_tc_kernel(const __grid_constant__ GemmTnMaps maps, const GemmTnParams P) {
   extern __shared__ uint8_t smem_raw[];
   if (P.dbg != nullptr && threadIdx.x == 0) {                      // debug aid: launch-to-exit envelope over all CTAs (ns)
     long long g;
@@ -750,7 +753,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0;
   int dbg_n = 0;
 
-  const int64_t m0 = blockIdx.x * P.rows_per_cta;
+  const int prob = blockIdx.x % P.n_prob, slab = blockIdx.x / P.n_prob;
+  const CUtensorMap* map_a = &maps.a[prob];
+  const CUtensorMap* map_b = &maps.b[prob];
+  const CUtensorMap* map_a3 = &maps.a3[prob];
+  const CUtensorMap* map_b3 = &maps.b3[prob];
+  const CUtensorMap* map_p = &maps.p[prob];
+  const int64_t m0 = slab * P.rows_per_cta;
   const int64_t m1 = m0 + P.rows_per_cta < P.M ? m0 + P.rows_per_cta : P.M;
   const int n_kb = m1 > m0 ? (int)((m1 - m0 + kTnRows - 1) / kTnRows) : 0;
 
@@ -767,8 +776,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           // K-major operands A[Ka, K], Bt[Nb, K]: a K block is 32 contraction COLUMNS; A lands as 128 rows x 128 B,
           // Bt as n_pad rows x 128 B (128-byte swizzle), rows past Ka / Nb and columns past K zero-filled by TMA
           mb_expect_tx(raw_full + stage, (uint32_t)(kTileA + P.n_pad * 128));
-          tma_2d(dst, &map_a, raw_full + stage, row, 0);
-          tma_2d(dst + kTileA, &map_b, raw_full + stage, row, 0);
+          tma_2d(dst, map_a, raw_full + stage, row, 0);
+          tma_2d(dst + kTileA, map_b, raw_full + stage, row, 0);
           if (++stage == kTnStages) { stage = 0; phase ^= 1; }
           continue;
         }
@@ -777,10 +786,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // zero-filled by TMA
         // one instruction fetches all the complete 32-column groups of an operand (a TMA issue costs ~170 cycles of the
         // producer thread); the ragged last group and the all-padding groups go through the zero-filling 2-D map
-        if (P.ga_full > 0) tma_3d(dst, &map_a3, raw_full + stage, 0, row, 0);
-        for (int g = P.ga_full; g < P.ga; ++g) tma_2d(dst + g * kTnBox, &map_a, raw_full + stage, g * 32, row);
-        if (P.gb_full > 0) tma_3d(dst + P.ga * kTnBox, &map_b3, raw_full + stage, 0, row, 0);
-        for (int g = P.gb_full; g < P.gb; ++g) tma_2d(dst + (P.ga + g) * kTnBox, &map_b, raw_full + stage, g * 32, row);
+        if (P.ga_full > 0) tma_3d(dst, map_a3, raw_full + stage, 0, row, 0);
+        for (int g = P.ga_full; g < P.ga; ++g) tma_2d(dst + g * kTnBox, map_a, raw_full + stage, g * 32, row);
+        if (P.gb_full > 0) tma_3d(dst + P.ga * kTnBox, map_b3, raw_full + stage, 0, row, 0);
+        for (int g = P.gb_full; g < P.gb; ++g) tma_2d(dst + (P.ga + g) * kTnBox, map_b, raw_full + stage, g * 32, row);
         if (++stage == kTnStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -866,7 +875,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // box in the (now idle) pipeline stages and one lane issues a TMA store, clipped at Ka rows / Nb columns.
     const int quarter = warp % 4;
     const int i = quarter * 32 + lane;
-    float* out = P.partial + ((int64_t)blockIdx.x * P.Ka + i) * P.Nb;
+    float* out = P.partial + (((int64_t)prob * P.n_slabs + slab) * P.Ka + i) * P.Nb;
     if (n_kb > 0) {
       mb_wait(acc_full, 0);                                        // every MMA has retired: shared memory is free
       if (warp == 10 && lane == 0) KGC_DBG(6);
@@ -889,7 +898,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          if (c0 < P.Nb && quarter * 32 < P.Ka) tma_store_3d(&map_p, bb, c0, quarter * 32, (int)blockIdx.x);
+          if (c0 < P.Nb && quarter * 32 < P.Ka) tma_store_3d(map_p, bb, c0, quarter * 32, slab);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         buf ^= 1;
@@ -914,9 +923,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // C[e] = sum over the CTA partials in a FIXED order: 8 part-lanes per element, then their sums in lane order
+struct TnOut { float* c[kMaxBatch]; };
 __global__ void __launch_bounds__(256)
-gemm_tn_partials_reduce(const float* __restrict__ partial, int n_parts, int n_elem, float* __restrict__ C) {
+gemm_tn_partials_reduce(const float* __restrict__ partial_all, int n_parts, int n_elem, const TnOut outs) {
   __shared__ float sm[8][33];
+  const float* partial = partial_all + (int64_t)blockIdx.y * n_parts * n_elem;      // blockIdx.y = problem of the batch
+  float* C = outs.c[blockIdx.y];
   const int e = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (e < n_elem)
@@ -1087,38 +1099,44 @@ extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t 
 }
 
 // C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb] on the tensor cores (3xTF32).  Ka <= 128, Nb <= 224, multiples of 4.
-static int launch_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
-                             float* C, void* workspace, size_t workspace_bytes, int32_t kmajor, void* stream) {
+static int launch_gemm_tn_tc(int n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb, int64_t M,
+                             int32_t Ka, int32_t Nb, float* const* C, void* workspace, size_t workspace_bytes, int32_t kmajor,
+                             void* stream) {
+  KGC_REQUIRE(n_prob >= 1 && n_prob <= kMaxBatch, "1..3 problems per launch");
   KGC_REQUIRE(M > 0 && Ka > 0 && Nb > 0 && Ka <= 128 && Nb <= 224, "supported: Ka <= 128, Nb <= 224");
   KGC_REQUIRE(Nb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && (kmajor || Ka % 4 == 0), "dimensions and leading dimensions must be multiples of 4");
   KGC_REQUIRE(workspace && workspace_bytes >= kgc_gemm_tn_tc_workspace_bytes(M, Ka, Nb), "workspace too small");
-  CUtensorMap ma, mb;
   GemmTnParams P;
   P.n_pad = (Nb + 15) / 16 * 16;
-  if (kmajor) {      // A[Ka, M], Bt[Nb, M] with the contraction index M contiguous
-    if (make_map_f32(&ma, A, Ka, M, lda, kBM) || make_map_f32(&mb, B, Nb, M, ldb, P.n_pad)) return 1;
-  } else if (make_map_f32_mn(&ma, A, M, Ka, lda) || make_map_f32_mn(&mb, B, M, Nb, ldb)) {
-    return 1;
-  }
   P.kmajor = kmajor;
-  P.M = M; P.Ka = Ka; P.Nb = Nb;
+  P.M = M; P.Ka = Ka; P.Nb = Nb; P.n_prob = n_prob;
   P.ga = 4;                                   // the MMA always reads M = 128 rows of D: 4 groups (columns past Ka are zero-filled)
-  P.n_pad = (Nb + 15) / 16 * 16;
   P.gb = (P.n_pad + 31) / 32;
-  int grid = (int)ceil_div(M, 2 * kTnRows);   // at least two K blocks per CTA
-  if (grid > kNumSMs) grid = kNumSMs;
-  if (grid < 1) grid = 1;
-  P.rows_per_cta = ceil_div(ceil_div(M, grid), kTnRows) * kTnRows;     // slabs start on K-block boundaries
-  grid = (int)ceil_div(M, P.rows_per_cta);
+  int slabs = (int)ceil_div(M, 2 * kTnRows);  // at least two K blocks per CTA
+  if (slabs > kNumSMs / n_prob) slabs = kNumSMs / n_prob;
+  if (slabs < 1) slabs = 1;
+  P.rows_per_cta = ceil_div(ceil_div(M, slabs), kTnRows) * kTnRows;     // slabs start on K-block boundaries
+  slabs = (int)ceil_div(M, P.rows_per_cta);
+  P.n_slabs = slabs;
   P.partial = static_cast<float*>(workspace);
   P.dbg = g_gemm_dbg;
-  CUtensorMap mp, ma3, mb3;
-  if (make_map_f32_parts(&mp, P.partial, grid, Ka, Nb)) return 1;
   P.ga_full = kmajor ? 0 : Ka / 32;
   P.gb_full = kmajor ? 0 : Nb / 32;
-  ma3 = ma; mb3 = mb;                         // placeholders when an operand has no complete group
-  if (P.ga_full > 0 && make_map_f32_mn_groups(&ma3, A, M, P.ga_full, lda)) return 1;
-  if (P.gb_full > 0 && make_map_f32_mn_groups(&mb3, B, M, P.gb_full, ldb)) return 1;
+  GemmTnMaps maps;
+  TnOut outs;
+  for (int i = 0; i < kMaxBatch; ++i) {
+    const int j = i < n_prob ? i : 0;          // unused slots repeat problem 0 (never dereferenced)
+    outs.c[i] = C[j];
+    if (kmajor) {      // A[Ka, M], Bt[Nb, M] with the contraction index M contiguous
+      if (make_map_f32(&maps.a[i], A[j], Ka, M, lda, kBM) || make_map_f32(&maps.b[i], B[j], Nb, M, ldb, P.n_pad)) return 1;
+    } else if (make_map_f32_mn(&maps.a[i], A[j], M, Ka, lda) || make_map_f32_mn(&maps.b[i], B[j], M, Nb, ldb)) {
+      return 1;
+    }
+    maps.a3[i] = maps.a[i]; maps.b3[i] = maps.b[i];                      // placeholders when an operand has no complete group
+    if (P.ga_full > 0 && make_map_f32_mn_groups(&maps.a3[i], A[j], M, P.ga_full, lda)) return 1;
+    if (P.gb_full > 0 && make_map_f32_mn_groups(&maps.b3[i], B[j], M, P.gb_full, ldb)) return 1;
+    if (make_map_f32_parts(&maps.p[i], P.partial + (int64_t)j * slabs * Ka * Nb, slabs, Ka, Nb)) return 1;
+  }
   const size_t stage = (size_t)(P.ga + P.gb) * kTnBox;
   const size_t smem = (kTnStages + kTnLoStages) * stage + 512 + 1024;
   KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
@@ -1128,21 +1146,28 @@ static int launch_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_
     attr = smem;
   }
   cudaStream_t st = as_stream(stream);
-  gemm_tn_tc_kernel<<<grid, kThreadsG, smem, st>>>(ma, mb, ma3, mb3, mp, P);
+  gemm_tn_tc_kernel<<<slabs * n_prob, kThreadsG, smem, st>>>(maps, P);
   KGC_LAUNCH_CHECK();
-  gemm_tn_partials_reduce<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(P.partial, grid, Ka * Nb, C);
+  gemm_tn_partials_reduce<<<dim3((Ka * Nb + 31) / 32, n_prob), dim3(32, 8), 0, st>>>(P.partial, slabs, Ka * Nb, outs);
   KGC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int kgc_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb,
                               float* C, void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_gemm_tn_tc(A, lda, B, ldb, M, Ka, Nb, C, workspace, workspace_bytes, 0, stream);
+  return launch_gemm_tn_tc(1, &A, lda, &B, ldb, M, Ka, Nb, &C, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int kgc_gemm_tn_tc_batch(int32_t n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb,
+                                    int64_t M, int32_t Ka, int32_t Nb, float* const* C, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  KGC_REQUIRE(A && B && C, "null pointer table");
+  return launch_gemm_tn_tc(n_prob, A, lda, B, ldb, M, Ka, Nb, C, workspace, workspace_bytes, 0, stream);
 }
 
 // C[Ma, Nb] = A[Ma, K] @ Bt[Nb, K]^T with a LONG contraction (K >> Ma, Nb): the K range is cut into per-CTA slabs, both
 // operands are streamed K-major, partial products stay in TMEM and are added in CTA order.  Ma <= 128, Nb <= 224.
 extern "C" int kgc_gemm_nt_splitk(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t K, int32_t Ma, int32_t Nb,
                                   float* C, void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_gemm_tn_tc(A, lda, Bt, ldb, K, Ma, Nb, C, workspace, workspace_bytes, 1, stream);
+  return launch_gemm_tn_tc(1, &A, lda, &Bt, ldb, K, Ma, Nb, &C, workspace, workspace_bytes, 1, stream);
 }

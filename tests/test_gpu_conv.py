@@ -444,3 +444,28 @@ def test_linear_tc_fc_layer(k, B, F, O):
     y2 = k.linear_tc(x2, w2, b2)
     y2.backward(dy)
     assert torch.equal(y2, y) and torch.equal(x2.grad, x.grad) and torch.equal(w2.grad, w.grad)
+
+
+def test_gemm_batches_match_single_launches(k):
+    """The batched K4b / K4c launches give bit-identical K4b results and fp32-accurate, deterministic K4c results."""
+    from kgc_gcn_b200.conv import gemm_nt_batch, gemm_tn_batch, _pack_b
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 5000, 100, 200
+    a = [torch.randn(M, K, generator=g).cuda() for _ in range(3)]
+    w = [(torch.randn(K, N, generator=g) * 0.1).cuda() for _ in range(3)]
+    single = [k.gemm_nt(a[i], w[i], torch.empty(M, N, device='cuda')) for i in range(3)]
+    for n in (2, 3):
+        outs = [torch.full((M, N), float('nan'), device='cuda') for _ in range(n)]
+        gemm_nt_batch(a[:n], [_pack_b(w[i]) for i in range(n)], outs)
+        for i in range(n):
+            assert torch.equal(outs[i], single[i])
+    b = [torch.randn(M, N, generator=g).cuda() for _ in range(3)]
+    for n in (1, 2, 3):
+        outs = [torch.full((K, N), float('nan'), device='cuda') for _ in range(n)]
+        gemm_tn_batch(a[:n], b[:n], outs)
+        outs2 = [torch.empty((K, N), device='cuda') for _ in range(n)]
+        gemm_tn_batch(a[:n], b[:n], outs2)
+        for i in range(n):
+            truth = a[i].double().t() @ b[i].double()
+            assert float((outs[i].double() - truth).abs().max()) / float(truth.abs().max()) <= 3e-6
+            assert torch.equal(outs[i], outs2[i])
