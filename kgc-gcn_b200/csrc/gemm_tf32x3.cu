@@ -479,7 +479,8 @@ __global__ void pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t s
 // table, two [1, D] self-loop vectors) need ~20 tiny tensor operations per step in the reference formulation
 // (model.py:86, 92-94, 107 and their autograd); each costs a launch (~2 us inside a CUDA graph) for a few KB of work.
 struct PrepArgs {
-  const float *rels, *loop_rel, *loop_edge, *w[3], *w_rel;        // w: in, out, loop
+  const float *rels, *loop_rel, *loop_edge, *w0, *w1, *w2, *w_rel;   // w0..2: in, out, loop (no array: a runtime index
+                                                                     // into a by-value parameter forces a local-memory copy)
   int n_rels, D, Dout;
   int n_pad_f, k_pad_f, n_pad_b, k_pad_b;                         // packed layouts of W (N = Dout, K = D) and W^T (N = D, K = Dout)
   float *relp, *all_rel, *packed_f, *packed_b;
@@ -499,7 +500,8 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
     const int t = i / a.Dout, o = i % a.Dout;
     const float* r = t < a.n_rels ? a.rels + (int64_t)t * a.D : a.loop_rel;
     float acc = 0.f;
-    for (int c = 0; c < a.D; ++c) acc = fmaf(r[c], a.w_rel[(int64_t)c * a.Dout + o], acc);
+#pragma unroll 25
+    for (int c = 0; c < a.D; ++c) acc = fmaf(r[c], a.w_rel[(int64_t)c * a.Dout + o], acc);   // unrolled: 25 loads in flight
     a.all_rel[i] = acc;
     return;
   }
@@ -508,7 +510,8 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
     const int h = i / nf, j = i % nf, n = j / a.k_pad_f, k = j % a.k_pad_f;
     float v = 0.f;
     if (n < a.Dout && k < a.D) {
-      v = a.w[h][(int64_t)k * a.Dout + n];
+      const float* wh = h == 0 ? a.w0 : (h == 1 ? a.w1 : a.w2);
+      v = wh[(int64_t)k * a.Dout + n];
       if (h == 2) v *= a.loop_rel[k] * a.loop_edge[k];
     }
     uint32_t hi, lo;
@@ -523,7 +526,8 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
     const int h = i / nb, j = i % nb, n = j / a.k_pad_b, k = j % a.k_pad_b;
     float v = 0.f;
     if (n < a.D && k < a.Dout) {
-      v = a.w[h][(int64_t)n * a.Dout + k];
+      const float* wh = h == 0 ? a.w0 : (h == 1 ? a.w1 : a.w2);
+      v = wh[(int64_t)n * a.Dout + k];
       if (h == 2) v *= a.loop_rel[n] * a.loop_edge[n];
     }
     uint32_t hi, lo;
@@ -553,27 +557,33 @@ __global__ void __launch_bounds__(256) conv_param_grads_kernel(const ParamGradAr
   if (i < nw) {                                                   // d_w_rel = relp^T @ [g_rel; 0]
     const int c = i / a.Dout, o = i % a.Dout;
     float acc = 0.f;
-    if (a.g_rel != nullptr)
+    if (a.g_rel != nullptr) {
+#pragma unroll 8
       for (int t = 0; t < a.n_rels; ++t) acc = fmaf(a.relp[(int64_t)t * a.D + c], a.g_rel[(int64_t)t * a.Dout + o], acc);
+    }
     a.d_w_rel[i] = acc;
     return;
   }
   i -= nw;
-  if (i < T * a.D) {                                              // d_relp + [g_rel; 0] @ w_rel^T; last row -> the self-loop vectors
-    const int t = i / a.D, c = i % a.D;
-    float val = a.d_relp[i];
-    if (t < a.n_rels) {
-      if (a.g_rel != nullptr) {
-        float acc = 0.f;
-        for (int o = 0; o < a.Dout; ++o) acc = fmaf(a.g_rel[(int64_t)t * a.Dout + o], a.w_rel[(int64_t)c * a.Dout + o], acc);
-        val += acc;
+  // one WARP per (t, c): the lanes stride over Dout (coalesced rows of g_rel / w_rel / m_loop / w_loop), fixed shuffle tree
+  const int pair = i / 32, lane = i % 32;
+  if (pair < T * a.D) {                                           // d_relp + [g_rel; 0] @ w_rel^T; last row -> the self-loop vectors
+    const int t = pair / a.D, c = pair % a.D;
+    const float* u = t < a.n_rels ? a.g_rel + (int64_t)t * a.Dout : a.m_loop + (int64_t)c * a.Dout;
+    const float* w = t < a.n_rels ? a.w_rel + (int64_t)c * a.Dout : a.w_loop + (int64_t)c * a.Dout;
+    float acc = 0.f;
+    if (t == a.n_rels || a.g_rel != nullptr)
+      for (int o = lane; o < a.Dout; o += 32) acc = fmaf(u[o], w[o], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+    if (lane == 0) {
+      const float val = a.d_relp[pair];
+      if (t < a.n_rels) {
+        a.d_rels[pair] = val + acc;
+      } else {                                                    // acc = d_v[c] = sum_o m_loop[c, o] w_loop[c, o]
+        a.d_loop_edge[c] = acc * a.loop_rel[c];
+        a.d_loop_rel[c] = acc * a.loop_edge[c] + val;
       }
-      a.d_rels[i] = val;
-    } else {
-      float dv = 0.f;                                             // d_v[c] = sum_o m_loop[c, o] w_loop[c, o]
-      for (int o = 0; o < a.Dout; ++o) dv = fmaf(a.m_loop[(int64_t)c * a.Dout + o], a.w_loop[(int64_t)c * a.Dout + o], dv);
-      a.d_loop_edge[c] = dv * a.loop_rel[c];
-      a.d_loop_rel[c] = dv * a.loop_edge[c] + val;
     }
   }
 }
@@ -928,7 +938,7 @@ __global__ void __launch_bounds__(256)
 gemm_tn_partials_reduce(const float* __restrict__ partial_all, int n_parts, int n_elem, const TnOut outs) {
   __shared__ float sm[8][33];
   const float* partial = partial_all + (int64_t)blockIdx.y * n_parts * n_elem;      // blockIdx.y = problem of the batch
-  float* C = outs.c[blockIdx.y];
+  float* C = blockIdx.y == 0 ? outs.c[0] : (blockIdx.y == 1 ? outs.c[1] : outs.c[2]);   // no runtime index into a parameter
   const int e = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (e < n_elem)
@@ -963,7 +973,7 @@ extern "C" int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loo
   KGC_REQUIRE(n_rels >= 0 && rels && loop_rel && loop_edge && w_in && w_out && w_loop && w_rel && relp && all_rel && packed_fwd && packed_bwd,
               "null buffer");
   PrepArgs a;
-  a.rels = rels; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.w[0] = w_in; a.w[1] = w_out; a.w[2] = w_loop; a.w_rel = w_rel;
+  a.rels = rels; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.w0 = w_in; a.w1 = w_out; a.w2 = w_loop; a.w_rel = w_rel;
   a.n_rels = n_rels; a.D = D; a.Dout = Dout;
   a.n_pad_f = tf.n_pad; a.k_pad_f = tf.k_pad; a.n_pad_b = tb.n_pad; a.k_pad_b = tb.k_pad;
   a.relp = relp; a.all_rel = all_rel; a.packed_f = packed_fwd; a.packed_b = packed_bwd;
@@ -983,7 +993,7 @@ extern "C" int kgc_conv_param_grads(const float* m_loop, const float* w_loop, co
   a.m_loop = m_loop; a.w_loop = w_loop; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.relp = relp; a.w_rel = w_rel;
   a.g_rel = g_rel; a.d_relp = d_relp; a.n_rels = n_rels; a.D = D; a.Dout = Dout;
   a.d_w_loop = d_w_loop; a.d_loop_rel = d_loop_rel; a.d_loop_edge = d_loop_edge; a.d_rels = d_rels; a.d_w_rel = d_w_rel;
-  const int64_t total = 2 * (int64_t)D * Dout + (int64_t)(n_rels + 1) * D;
+  const int64_t total = 2 * (int64_t)D * Dout + (int64_t)(n_rels + 1) * D * 32;
   conv_param_grads_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(a);
   KGC_LAUNCH_CHECK();
   return 0;

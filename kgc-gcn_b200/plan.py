@@ -114,7 +114,18 @@ class StreamPlan(object):
         self.fill_rows = torch.from_numpy(sp['fill_rows']).to(device)
         self.n_fill = int(sp['fill_rows'].shape[0])
         self.levels = []
-        for it, n_part in sp['levels']:
+        levels = list(sp['levels'])
+        if self.n_fill:
+            # rows without any record ride along in the first fix-up launch as EMPTY final items (out = addend or 0):
+            # one launch less per aggregation than a separate kgc_rows_fill
+            fr = sp['fill_rows'].astype(np.int64)
+            empty = np.stack([np.zeros_like(fr), np.zeros_like(fr), fr, (fr << 1) | 1], 1).astype(np.int32)
+            if levels:
+                levels[0] = (np.concatenate([levels[0][0], empty], 0), levels[0][1])
+            else:
+                levels = [(empty, 0)]
+            self.n_fill = 0
+        for it, n_part in levels:
             # hub rows first (a block each), then the many rows that merely straddle a chunk boundary (a lane group each)
             large = (it[:, 1] - it[:, 0]) > SMALL_ITEM
             order = np.concatenate([np.nonzero(large)[0], np.nonzero(~large)[0]])
