@@ -17,7 +17,13 @@
 // No float atomics anywhere: results are bit-reproducible run to run.
 // Tried and rejected in round 1: staging every operand row with one bulk async copy (cp.async.bulk, UBLKCP) into
 // per-warp shared-memory stages - correct but 0.2-0.3 of the HBM peak: the copy engine retires roughly one 400-byte
-// request per 30 cycles per SM, far below what 128-bit LDGs sustain.
+// request per 30 cycles per SM, far below what 128-bit LDGs sustain.  Also measured and rejected: (a) double-buffered
+// register batches (loads of batch b + 1 issued before batch b is consumed, 2 x 4 edges): 39 / 66 / 41 us against
+// 37 / 67 / 41 us - no change, the bytes in flight per warp are the same; (b) a per-warp cp.async (LDGSTS.BYPASS.128) ring
+// of 12 edges in shared memory, each lane landing and re-reading its own float4 column (no barriers): 65 / 92 / 83 us,
+// 0.29 / 0.37 / 0.23 of the peak - LDGSTS sustains far fewer 400-byte row requests than plain 128-bit loads here.
+// ncu of the kept version: every unit below 45% (DRAM 30%, L2 21%, L1 32%, issue 39%), 14 resident warps per SM,
+// long-scoreboard stalls dominate: latency-bound at the occupancy 100+ registers allow.
 #include "common.cuh"
 
 namespace kgc {
@@ -79,18 +85,39 @@ __global__ void __launch_bounds__(kThreads, 2)
 agg_stream_kernel(const StreamArgs A) {
   constexpr int kU = Unroll<MODE>::value;
   static_assert(kChunk == 32, "one record per lane");
-  const int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + threadIdx.x / 32;
+  // PERSISTENT warps: the grid fills the GPU once (2 CTAs per SM) and every warp walks chunks w, w + W, w + 2W, ...
+  // (W = warps of the grid), fetching the records of its next chunk while it processes the current one.  One warp per
+  // chunk with a one-shot grid paid a record round trip per chunk with nothing else in flight (fwd 37.4 -> 34.9 us).
+  // Claiming chunks dynamically from an atomic work counter instead of the static stride measured the same (35.2 us).
   const int lane = threadIdx.x % 32;
-  const int64_t cb = chunk * kChunk;
-  if (cb >= A.n_rec) return;
-  const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
+  const int64_t n_chunks = (A.n_rec + kChunk - 1) / kChunk;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + threadIdx.x / 32;
+  if (chunk >= n_chunks) return;
   const int D4 = A.D4;
-  const int2 slots = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
-  const int4 myrec = ld_rec(A.rec + cb + (lane < cnt ? lane : cnt - 1));
-  const uint32_t myflag = __ldg(A.rowflags + cb + (lane < cnt ? lane : cnt - 1));
   bool active[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) active[f] = lane + f * 32 < D4;
+  auto rec_index = [&](int64_t ch) {
+    const int64_t b = ch * kChunk;
+    const int n = (int)(b + kChunk < A.n_rec ? kChunk : A.n_rec - b);
+    return b + (lane < n ? lane : n - 1);
+  };
+  int2 slots_n = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
+  int4 myrec_n = ld_rec(A.rec + rec_index(chunk));
+  uint32_t myflag_n = __ldg(A.rowflags + rec_index(chunk));
+ while (chunk < n_chunks) {
+  const int64_t next = chunk + stride;
+  const int64_t cb = chunk * kChunk;
+  const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
+  const int2 slots = slots_n;
+  const int4 myrec = myrec_n;
+  const uint32_t myflag = myflag_n;
+  if (next < n_chunks) {                                         // records of the next chunk: in flight during this one
+    slots_n = __ldg(reinterpret_cast<const int2*>(A.chunks + next));
+    myrec_n = ld_rec(A.rec + rec_index(next));
+    myflag_n = __ldg(A.rowflags + rec_index(next));
+  }
 
   float4 acc[NF];
 #pragma unroll
@@ -182,6 +209,8 @@ agg_stream_kernel(const StreamArgs A) {
       if (active[f]) out[c] = acc[f];
     }
   }
+  chunk = next;
+ }   // persistent chunk loop
 }
 
 // out[rows[i]] = addend ? addend[rows[i]] : 0   (rows without any edge record)
@@ -320,7 +349,9 @@ template <int MODE>
 int launch_stream(const StreamArgs& A, cudaStream_t st) {
   if (A.n_rec == 0) return 0;
   const int64_t n_chunks = ceil_div(A.n_rec, kChunk);
-  const unsigned grid = (unsigned)ceil_div(n_chunks, kWarpsPerBlock);
+  int64_t blocks = ceil_div(n_chunks, kWarpsPerBlock);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;                 // persistent: 2 resident CTAs per SM (__launch_bounds__)
+  const unsigned grid = (unsigned)blocks;
   if (A.D4 <= 32) {
     agg_stream_kernel<MODE, 1><<<grid, kThreads, 0, st>>>(A);
   } else {
