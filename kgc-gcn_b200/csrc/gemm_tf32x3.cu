@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
   }
   i -= n1;
   if (i < 3 * nf) {                                               // Bt[n, k] = W_h[k, n]  (x loop_rel[k] loop_edge[k] for the self-loop)
-    const int h = i / nf, j = i % nf, n = j / a.k_pad_f, k = j % a.k_pad_f;
+    // consecutive threads take consecutive n: coalesced reads of the row-major weight (the strided 4-byte writes are cheap)
+    const int h = i / nf, j0 = i % nf, k = j0 / a.n_pad_f, n = j0 % a.n_pad_f, j = n * a.k_pad_f + k;
     float v = 0.f;
     if (n < a.Dout && k < a.D) {
       const float* wh = h == 0 ? a.w0 : (h == 1 ? a.w1 : a.w2);
