@@ -38,7 +38,7 @@ WORKLOADS = {
 D_IN, D_OUT, BATCH = 100, 200, 128
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this bench command
 # (profiles/r01_ncu_conv_kernels_final.md); below the algorithmic bytes because x / g / rel rows hit L2
-NCU_TRAFFIC = {'wn18rr': {'agg_fwd': 96.55e6, 'agg_bwd_src': 165.89e6, 'agg_bwd_rel': 110.87e6}}
+NCU_TRAFFIC = {'wn18rr': {'agg_fwd': 93.50e6, 'agg_bwd_src': 167.99e6, 'agg_bwd_rel': 113.45e6}}   # profiles/r01_ncu_conv_kernels_final2.md
 
 
 def params_ns():
