@@ -21,7 +21,17 @@
 // register batches (loads of batch b + 1 issued before batch b is consumed, 2 x 4 edges): 39 / 66 / 41 us against
 // 37 / 67 / 41 us - no change, the bytes in flight per warp are the same; (b) a per-warp cp.async (LDGSTS.BYPASS.128) ring
 // of 12 edges in shared memory, each lane landing and re-reading its own float4 column (no barriers): 65 / 92 / 83 us,
-// 0.29 / 0.37 / 0.23 of the peak - LDGSTS sustains far fewer 400-byte row requests than plain 128-bit loads here.
+// 0.29 / 0.37 / 0.23 of the peak - LDGSTS sustains far fewer 400-byte row requests than plain 128-bit loads here; (c) MORE
+// edges in flight per warp - double-buffered batches of 8 / 6 / 4 at 3 x 128-thread CTAs per SM (168 registers): 43 / 107 /
+// 65 us, clearly worse; (d) prefetch.global.L2 of the next chunk's operand rows one chunk ahead: 84 / 131 / 115 us - every
+// extra line request costs as much as a demand request; (e) records broadcast from shared memory (one LDS.128 per edge)
+// instead of warp shuffles, with a bounds-check-free path for full chunks: 128 registers + spills, 73 us; (f) one-warp
+// CTAs (16 per SM), which lets the compiler prove every branch warp-uniform and drops the WARPSYNC / ENDCOLLECTIVE /
+// BSSY bookkeeping around the shuffles (1,376 -> 744 SASS instructions): 55 / 66 / 37 us - slower forward, same backward.
+// tests/gather_probe.py: the kept kernel takes the same 35 us when edge ids AND source rows are perfectly sequential as
+// when both are random, so the ORDER of the row reads is not what bounds it; neither is the instruction count (f) nor
+// the number of requests in flight (a, c).  What the variants have in common is ~130 row requests of 400 bytes (4 partial
+// cache lines each) in flight per SM; the open question for round 2 is the L1 miss path for such partial-line requests.
 // ncu of the kept version: every unit below 45% (DRAM 30%, L2 21%, L1 32%, issue 39%), 14 resident warps per SM,
 // long-scoreboard stalls dominate: latency-bound at the occupancy 100+ registers allow.
 #include "common.cuh"
