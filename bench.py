@@ -537,8 +537,9 @@ def kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush, workload='wn18r
     g_bytes = cp_bytes + perm.numel() * 8
     out['row_gather_same_size_reference'] = {'ms': ms_g, 'algorithmic_bytes': g_bytes, 'achieved_gbs': g_bytes / (ms_g * 1e-3) / 1e9,
                                              'frac': g_bytes / (ms_g * 1e-3) / 1e9 / peak,
-                                             'note': 'torch.index_select of all edge-embedding rows in a random order (400-byte '
-                                                     'rows): the access pattern of the aggregation kernels without their math'}
+                                             'note': 'torch.index_select of all edge-embedding rows in a random order: the LIBRARY gather of '
+                                                     'the same rows (it takes the same time for sequential indices and for any row '
+                                                     'width, tests/gather_probe.py history: bound by its per-row overhead, not by HBM)'}
     del cp_dst, perm
     for name, fn in fns.items():
         ms = time_kernel(fn, flush)
