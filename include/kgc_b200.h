@@ -247,6 +247,24 @@ int kgc_label_build(const int64_t* qid, int64_t B, const int64_t* triples, const
 int kgc_neg_sample(const int64_t* qid, int64_t B, const int64_t* ptr, const int32_t* idx, int64_t n_entity,
                    const uint32_t* draws, int32_t k, int32_t tries, int32_t* neg, void* stream);
 
+/* ---- K7: ConvE feature-map normalisation: BatchNorm2d (+ ReLU) + feature dropout (SURVEY "next" row N2) --------
+ * Replaces model.py:168-170 (x = bn1(x); x = relu(x); x = feature_drop(x)) on the [B, C, H, W] convolution output
+ * (HW = H * W, a multiple of 4; contiguous) and its autograd; with relu = 0 and drop_p = 0 also bn0 (model.py:165),
+ * the ONE-channel BatchNorm2d over the [B, 1, 2 k_w, k_h] input image, which cuDNN gives to a single CTA.
+ * Forward: training != 0 -> batch statistics (fp64 accumulation, fixed-order reduction) + the running-statistics
+ * update of nn.BatchNorm2d (momentum, unbiased variance; running_* may be NULL); else the running statistics.
+ * stats[2][C] = {mean, rstd} is written for the backward.  Dropout (training only, drop_p in [0, 1)): keep mask from a
+ * Philox4x32-10 stream keyed by *seed (device int64), regenerated by the backward - no mask tensor.
+ * Backward: dx; sums[2][C] = {d_beta, d_gamma}.  partials: kgc_bn2d_partials_bytes(C) of scratch. */
+size_t kgc_bn2d_partials_bytes(int32_t C);
+int kgc_bn2d_relu_drop_fwd(const float* x, int64_t B, int32_t C, int32_t HW, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float eps, float momentum, int32_t training,
+                           int32_t relu, const int64_t* seed, float drop_p, double* partials, float* stats, float* y,
+                           void* stream);
+int kgc_bn2d_relu_drop_bwd(const float* dy, const float* x, int64_t B, int32_t C, int32_t HW, const float* gamma,
+                           const float* beta, const float* stats, int32_t training, int32_t relu, const int64_t* seed,
+                           float drop_p, double* partials, float* sums, float* dx, void* stream);
+
 /* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------
  * Replaces model.py:177-179 (x = mm(x, all_ent^T); x += bias; sigmoid) where the caller needs the dense matrix
  * (BCE against the multi-hot label, main.py:63-66).  Forward: the K4b tensor-core kernel (3xTF32, fp32-grade) with

@@ -26,26 +26,6 @@ __device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t idx4, float s)
   return make_float4(v.x ? s : 0.f, v.y ? s : 0.f, v.z ? s : 0.f, v.w ? s : 0.f);
 }
 
-// Counter-based dropout: Philox4x32-10 keyed by the step's seed, counter = (float4 index, plane).  The forward and
-// the backward regenerate the same keep mask from (seed, index), so no mask tensor is written or read.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-// keep-scale per lane of one float4: s where the 32-bit draw >= drop_thr (= p * 2^32), else 0
-__device__ __forceinline__ float4 philox_mask4(int64_t idx4, uint32_t plane, uint64_t seed, uint32_t drop_thr, float s) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), plane, 0u),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  return make_float4(r.x >= drop_thr ? s : 0.f, r.y >= drop_thr ? s : 0.f, r.z >= drop_thr ? s : 0.f,
-                     r.w >= drop_thr ? s : 0.f);
-}
 struct DropCfg {
   const uint8_t* mask_in;     // injected keep masks (tests / replay of recorded draws) ...
   const uint8_t* mask_out;

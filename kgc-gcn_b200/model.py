@@ -11,7 +11,43 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .conv import MGCNConv, get_param, linear_tc, linear_tc_supported
+
+
+class _BnReluDropFn(torch.autograd.Function):
+    """dropout(relu(batch_norm(x))) over [B, C, H, W] (model.py:168-170) on the K7 kernels."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, training, drop_p, seed, relu):
+        x_ = _lib.require_cuda(x.detach(), torch.float32, 'x')
+        B, C = int(x_.shape[0]), int(x_.shape[1])
+        HW = int(x_.shape[2] * x_.shape[3])
+        p = _lib.ptr
+        partials = torch.empty((int(_lib.lib().kgc_bn2d_partials_bytes(C)) // 8,), dtype=torch.float64, device=x.device)
+        stats = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x_)
+        _lib.call('kgc_bn2d_relu_drop_fwd', p(x_), B, C, HW, p(gamma.detach()), p(beta.detach()), p(running_mean),
+                  p(running_var), float(eps), float(momentum), int(training), int(relu), p(seed), float(drop_p), p(partials),
+                  p(stats), p(y), _lib.stream())
+        ctx.save_for_backward(x_, gamma.detach(), beta.detach(), stats, seed if seed is not None else torch.empty(0))
+        ctx.cfg = (bool(training), float(drop_p), seed is not None, int(relu))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats, seed = ctx.saved_tensors
+        training, drop_p, has_seed, relu = ctx.cfg
+        B, C = int(x.shape[0]), int(x.shape[1])
+        HW = int(x.shape[2] * x.shape[3])
+        dy = dy.contiguous()
+        p = _lib.ptr
+        partials = torch.empty((int(_lib.lib().kgc_bn2d_partials_bytes(C)) // 8,), dtype=torch.float64, device=x.device)
+        sums = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        _lib.call('kgc_bn2d_relu_drop_bwd', p(dy), p(x), B, C, HW, p(gamma), p(beta), p(stats), int(training), relu,
+                  p(seed) if has_seed else None, drop_p, p(partials), p(sums), p(dx), _lib.stream())
+        return dx, sums[1], sums[0], None, None, None, None, None, None, None, None
 
 
 class ConvE(nn.Module):
@@ -32,16 +68,52 @@ class ConvE(nn.Module):
         self.flat_sz = flat_sz_h * flat_sz_w * params.num_filter
         self.fc = nn.Linear(self.flat_sz, params.gcn_out_dim)
         self.register_parameter('bias', nn.Parameter(torch.zeros(num_entities)))
+        # dropout stream of the K7 kernel (device-resident counter, not part of the state dict)
+        self.register_buffer('_drop_seed', torch.zeros(1, dtype=torch.int64), persistent=False)
+        self._drop_seeded = False
+
+    @staticmethod
+    def _k7_ok(x, bn, p=0.0):
+        return (x.is_cuda and x.dtype == torch.float32 and (x.shape[2] * x.shape[3]) % 4 == 0 and bn.affine
+                and bn.track_running_stats and bn.momentum is not None and 0.0 <= p < 1.0)
+
+    def _bn0(self, x):
+        """model.py:165 - the ONE-channel BatchNorm2d over the input image (cuDNN: one CTA, 27 us forward + 50 us backward
+        for 51,200 values) - on the K7 kernels."""
+        bn = self.bn0
+        if not self._k7_ok(x, bn):
+            return bn(x)
+        if self.training:
+            bn.num_batches_tracked.add_(1)
+        return _BnReluDropFn.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                                   self.training, 0.0, None, 0)
+
+    def _bn1_relu_drop(self, x):
+        """model.py:168-170 - bn1, relu, feature dropout - on the K7 kernels where they apply (GPU, fp32, H * W % 4 == 0,
+        BatchNorm with running statistics and a fixed momentum); the torch / cuDNN modules otherwise."""
+        bn, p = self.bn1, self.feature_drop.p
+        if not self._k7_ok(x, bn, p):
+            return self.feature_drop(F.relu(bn(x)))
+        seed = None
+        if self.training and p > 0.0:
+            if not self._drop_seeded:
+                self._drop_seed.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+                self._drop_seeded = True
+            self._drop_seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)     # new stream every step (device op: graph-capturable)
+            seed = self._drop_seed.clone()
+        if self.training:
+            bn.num_batches_tracked.add_(1)
+        return _BnReluDropFn.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                                   self.training, p, seed, 1)
 
     def query(self, src_emb, rel_emb):
         """Front end: (src_emb, rel_emb) -> query matrix X[B, Dout] (model.py:161-175)."""
         d = self.params.gcn_out_dim
         stack_inp = torch.cat([src_emb.view(-1, 1, d), rel_emb.view(-1, 1, d)], dim=1)
         x = torch.transpose(stack_inp, 2, 1).reshape(-1, 1, 2 * self.params.k_w, self.params.k_h)
-        x = self.bn0(x)
+        x = self._bn0(x)
         x = self.conv_e(x)
-        x = F.relu(self.bn1(x))
-        x = self.feature_drop(x)
+        x = self._bn1_relu_drop(x)
         x = x.view(-1, self.flat_sz)
         # model.py:173: the 39,200 -> 200 fc layer; fp32-grade tensor-core kernels for the shapes they take
         x = linear_tc(x, self.fc.weight, self.fc.bias) if linear_tc_supported(x, self.fc.weight) else self.fc(x)
