@@ -264,6 +264,8 @@ class _ConvFn(torch.autograd.Function):
         if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
             gemm_nt(x, None, res3[2], packed=packed_f[2])          # overlaps the all-gather
             gather.wait()
+        if max(x_full.shape[0], 3 * Nl, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
+            raise ValueError('kgc_gcn_b200: node / edge tables of 2^32 float4 elements or more are not supported')
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):

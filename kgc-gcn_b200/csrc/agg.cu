@@ -79,6 +79,7 @@ struct StreamArgs {
   int64_t plane;              // n_dst_rows * D4 (bwd)
   int32_t n_edges_in;         // records with eid >= n_edges_in belong to the out half (bwd)
   int32_t D4;
+  int64_t max_rows;           // known bound on the row indices of g3 / outputs (guard of the 32-bit float4 indices)
 };
 
 // One warp walks one chunk of kChunk (= 32) sorted records.  Lane l first loads record cb + l (one coalesced
@@ -223,6 +224,147 @@ agg_stream_kernel(const StreamArgs A) {
  }   // persistent chunk loop
 }
 
+// ---------------------------------------------------------------------------------------------- lean variant
+// Same chunks / carry protocol / arithmetic as agg_stream_kernel.  ncu of that kernel (profiles/r01_ncu_agg_lean.md):
+// 75 warp instructions per edge, 72% of the stall samples spread evenly over them (fixed-latency waits, shuffles,
+// branch bookkeeping) and only 28% on the first use of a loaded row - instruction-latency-bound at 14 warps per SM.
+// This version (i) fully unrolls the 32 edges of a FULL chunk (shuffle lanes and batch slots are compile-time, no
+// per-edge bounds checks; the stream's single partial chunk takes a plain loop), (ii) issues ALL row loads of a batch,
+// the relation row included, in the load phase, so the consume phase is pure arithmetic, (iii) forms addresses from
+// 32-bit float4 indices (one IMAD + one IMAD.WIDE per load), (iv) runs at 3-4 CTAs per SM with small batches.
+template <int MODE, int KU, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+agg_lean_kernel(const StreamArgs A) {
+  static_assert(kChunk == 32, "one record per lane");
+  constexpr bool kHasC = MODE != kFwd;        // third gathered operand
+  constexpr bool kHasR = MODE != kBwdRel;     // relation row
+  const int lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);          // warp-uniform for the compiler
+  const int64_t n_chunks = (A.n_rec + kChunk - 1) / kChunk;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t chunk = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (chunk >= n_chunks) return;
+  const uint32_t D4 = (uint32_t)A.D4;
+  const bool act = lane < (int)D4;
+  const uint32_t c = act ? lane : 0;
+  const float4* __restrict__ ee = A.ee;
+  const float4* __restrict__ xs = A.x;
+  const float4* __restrict__ rel = A.rel;
+  const float4* __restrict__ g3 = A.g3;
+  const uint32_t plane = (uint32_t)A.plane;
+  const uint32_t n_in = (uint32_t)A.n_edges_in;
+  auto rec_index = [&](int64_t ch) {
+    const int64_t b = ch * kChunk;
+    const int n = (int)(b + kChunk < A.n_rec ? kChunk : A.n_rec - b);
+    return b + (lane < n ? lane : n - 1);
+  };
+  int2 slots_n = __ldg(reinterpret_cast<const int2*>(A.chunks + chunk));
+  int4 rec_n = ld_rec(A.rec + rec_index(chunk));
+  uint32_t flag_n = __ldg(A.rowflags + rec_index(chunk));
+
+  float4 va[KU], vb[KU], vc[kHasC ? KU : 1], vr[kHasR ? KU : 1];
+  int4 rec;
+  uint32_t flag;
+  float4 acc;
+  bool started_here;
+  int2 slots;
+  float4* const out_final = A.out_final;
+  float4* const carry = A.carry;
+  float4* const d_ee = A.d_ee;
+  const float4* const addend = A.addend;
+  auto issue = [&](int u, int e) {
+    const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, rec.x, e);
+    const uint32_t ra = (uint32_t)__shfl_sync(0xffffffffu, rec.y, e);
+    const uint32_t rb = (uint32_t)__shfl_sync(0xffffffffu, rec.z, e);
+    if (MODE == kFwd) {
+      if (act) {
+        va[u] = ld_stream(ee + (eid * D4 + c));
+        vb[u] = __ldg(xs + (ra * D4 + c));
+        vr[kHasR ? u : 0] = __ldg(rel + (rb * D4 + c));
+      }
+    } else if (MODE == kBwdSrc) {
+      const uint32_t erow = __shfl_sync(0xffffffffu, flag, e) & kRowMask;
+      if (act) {
+        va[u] = ld_stream(ee + (eid * D4 + c));
+        vb[u] = __ldg(g3 + ((eid >= n_in ? plane : 0u) + ra * D4 + c));
+        vc[kHasC ? u : 0] = __ldg(xs + (erow * D4 + c));
+        vr[kHasR ? u : 0] = __ldg(rel + (rb * D4 + c));
+      }
+    } else {
+      if (act) {
+        va[u] = ld_stream(ee + (eid * D4 + c));
+        vb[u] = __ldg(g3 + ((eid >= n_in ? plane : 0u) + rb * D4 + c));
+        vc[kHasC ? u : 0] = __ldg(xs + (ra * D4 + c));
+      }
+    }
+  };
+  // `last` = this record closes its row (rows are contiguous, so the next record opens one: the accumulator is cleared
+  // here and no per-edge "first" test is needed)
+  auto consume = [&](int u, int e, bool last) {
+    const float nrm = __int_as_float(__shfl_sync(0xffffffffu, rec.w, e));
+    const float4 rv = vr[kHasR ? u : 0];
+    if (MODE == kFwd) {
+      add4(acc, mul3s(nrm, vb[u], rv, va[u]));
+    } else if (MODE == kBwdSrc) {
+      const uint32_t eid = (uint32_t)__shfl_sync(0xffffffffu, rec.x, e);
+      const float4 pe = scale4(nrm, mul4(vb[u], rv));
+      if (act) st_stream(d_ee + (eid * D4 + c), mul4(pe, vc[kHasC ? u : 0]));
+      add4(acc, mul4(pe, va[u]));
+    } else {
+      add4(acc, mul3s(nrm, vb[u], vc[kHasC ? u : 0], va[u]));
+    }
+    if (last) {
+      const uint32_t row = __shfl_sync(0xffffffffu, flag, e) & kRowMask;
+      float4* out = started_here ? out_final + (row * D4 + c) : carry + ((uint32_t)slots.x * D4 + c);
+      if (act) {
+        float4 v = acc;
+        if (MODE == kBwdSrc && started_here && addend != nullptr) add4(v, __ldg(addend + (row * D4 + c)));
+        *out = v;
+      }
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      started_here = true;
+    }
+  };
+
+  while (chunk < n_chunks) {
+    const int64_t next = chunk + stride;
+    const int64_t cb = chunk * kChunk;
+    const int cnt = (int)(cb + kChunk < A.n_rec ? kChunk : A.n_rec - cb);
+    slots = slots_n;
+    rec = rec_n;
+    flag = flag_n;
+    if (next < n_chunks) {                                         // records of the next chunk: in flight during this one
+      slots_n = __ldg(reinterpret_cast<const int2*>(A.chunks + next));
+      rec_n = ld_rec(A.rec + rec_index(next));
+      flag_n = __ldg(A.rowflags + rec_index(next));
+    }
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t valid = cnt == kChunk ? 0xffffffffu : ((1u << cnt) - 1u);
+    const uint32_t last_mask = __ballot_sync(0xffffffffu, (flag & kLast) != 0) & valid;
+    started_here = (__shfl_sync(0xffffffffu, flag, 0) & kFirst) != 0;
+    if (cnt == kChunk) {
+#pragma unroll
+      for (int base = 0; base < kChunk; base += KU) {
+#pragma unroll
+        for (int u = 0; u < KU; ++u)
+          if (base + u < kChunk) issue(u, base + u);
+#pragma unroll
+        for (int u = 0; u < KU; ++u)
+          if (base + u < kChunk) consume(u, base + u, (last_mask >> (base + u)) & 1u);
+      }
+    } else {                                                     // the stream's last, partial chunk
+      for (int e = 0; e < cnt; ++e) {
+        issue(0, e);
+        consume(0, e, (last_mask >> e) & 1u);
+      }
+    }
+    if (!((last_mask >> (cnt - 1)) & 1u)) {                      // the row continues in the next chunk
+      if (act) carry[(uint32_t)slots.y * D4 + c] = acc;
+    }
+    chunk = next;
+  }
+}
+
 // out[rows[i]] = addend ? addend[rows[i]] : 0   (rows without any edge record)
 __global__ void rows_fill_kernel(const int32_t* __restrict__ rows, int64_t n_rows, const float4* __restrict__ addend,
                                  float4* __restrict__ out, int D4) {
@@ -355,17 +497,27 @@ inline int check_dim(int32_t D, int* D4, int* NF) {
     default: { constexpr int NF = 8; __VA_ARGS__; } break; \
   }
 
+// Lean kernel configuration (edges per batch, CTAs per SM), measured on B200 at the WN18RR / FB15k-237 shapes
+// (tests/agg_variants.py history in profiles/r01_agg_variants.md): fwd 4 x 3, bwd_src 3 x 3, bwd_rel 4 x 3 - the largest
+// batches that fit 80 registers without spills; 2 CTAs x 8 edges and 4 CTAs x 2-3 edges were 10-20% slower.
+template <int MODE> struct LeanCfg { static constexpr int ku = 4, minb = 3; };
+template <> struct LeanCfg<kBwdSrc> { static constexpr int ku = 3, minb = 3; };
+
 template <int MODE>
 int launch_stream(const StreamArgs& A, cudaStream_t st) {
   if (A.n_rec == 0) return 0;
   const int64_t n_chunks = ceil_div(A.n_rec, kChunk);
   int64_t blocks = ceil_div(n_chunks, kWarpsPerBlock);
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;                 // persistent: 2 resident CTAs per SM (__launch_bounds__)
-  const unsigned grid = (unsigned)blocks;
-  if (A.D4 <= 32) {
-    agg_stream_kernel<MODE, 1><<<grid, kThreads, 0, st>>>(A);
+  if (A.D4 <= 32) {                                               // D <= 128: one float4 column per lane
+    // 32-bit float4 indices: edge ids are < n_rec, node / output rows < max_rows (the host checks the node table)
+    KGC_REQUIRE((uint64_t)A.n_rec * A.D4 < (1ull << 32) && (uint64_t)A.max_rows * A.D4 < (1ull << 32),
+                "tables of 2^32 float4 or more are not supported (32-bit float4 indices)");
+    constexpr int minb = LeanCfg<MODE>::minb;
+    if (blocks > (int64_t)minb * kNumSMs) blocks = (int64_t)minb * kNumSMs;   // persistent grid
+    agg_lean_kernel<MODE, LeanCfg<MODE>::ku, minb><<<(unsigned)blocks, kThreads, 0, st>>>(A);
   } else {
-    agg_stream_kernel<MODE, 2><<<grid, kThreads, 0, st>>>(A);
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;               // persistent: 2 resident CTAs per SM (__launch_bounds__)
+    agg_stream_kernel<MODE, 2><<<(unsigned)blocks, kThreads, 0, st>>>(A);
   }
   KGC_LAUNCH_CHECK();
   return 0;
@@ -379,10 +531,10 @@ using namespace kgc;
 extern "C" int kgc_agg_fwd(const float* x, const float* rel, int64_t n_types, const float* ee,
                            const kgc_edge_rec_t* rec_dst, const uint32_t* rowflags, const kgc_chunk_t* chunks,
                            int64_t n_rec, float* out_final, float* carry, int32_t D, void* stream) {
-  (void)n_types;
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   StreamArgs A = {};
+  (void)n_types;
   A.x = (const float4*)x; A.rel = (const float4*)rel; A.ee = (const float4*)ee;
   A.rec = rec_dst; A.rowflags = rowflags; A.chunks = chunks;
   A.out_final = (float4*)out_final; A.carry = (float4*)carry;
@@ -396,8 +548,9 @@ extern "C" int kgc_agg_bwd_src(const float* x, const float* rel, int64_t n_types
                                float* d_ee, float* dx_final, float* carry, int32_t D, void* stream) {
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
-  (void)n_types;
   StreamArgs A = {};
+  (void)n_types;
+  A.max_rows = 3 * n_dst_rows;
   A.x = (const float4*)x; A.rel = (const float4*)rel; A.ee = (const float4*)ee; A.g3 = (const float4*)g3;
   A.addend = (const float4*)loop_addend;
   A.rec = rec_src; A.rowflags = rowflags; A.chunks = chunks;
@@ -412,6 +565,7 @@ extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
   int D4, nf;
   KGC_REQUIRE(check_dim(D, &D4, &nf) == 0, "D must be a multiple of 4 and <= 256");
   StreamArgs A = {};
+  A.max_rows = 3 * n_dst_rows;
   A.x = (const float4*)x; A.ee = (const float4*)ee; A.g3 = (const float4*)g3;
   A.rec = rec_type; A.rowflags = rowflags; A.chunks = chunks;
   A.out_final = (float4*)drel_final; A.carry = (float4*)carry;
