@@ -414,7 +414,7 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
         torch.manual_seed(0)
         model = k.MGCN(N, R, E, prm).to(dev)
         model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=(mode == 'graph'))
+        opt = k.ClipAdam(model.parameters(), lr=1e-3, max_norm=1.0)          # clip_grad_norm_ + Adam (K9), main.py:68-71
         batches = loader.batches()
         step = k.GraphedTrainStep(model, opt, graph, ds, BATCH) if mode == 'graph' else None
         ms, n = 0.0, 0
@@ -433,8 +433,7 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
                     pred = model(trip[:, 0], trip[:, 1], graph)
                     loss = model.loss(pred, lab)
                     loss.backward()
-                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-                    opt.step()
+                    opt.step()                                                # clips inside (max_norm = 1.0)
                     loss.item()
                 b.record()
                 torch.cuda.synchronize()
@@ -450,7 +449,7 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
     head = 'graph' if 'graph' in out else 'eager'
     res = {'ms_total': out[head][0], 'steps': out[head][1], 'h2d': BATCH * 8, 'd2h': 4,
            'scope': 'full training step through the public API ({}): host query ids -> K5 batch build -> MGCN forward -> BCE -> '
-                    'backward -> clip_grad_norm -> Adam -> loss.item()'.format(
+                    'backward -> ClipAdam (gradient-norm clip + Adam, K9) -> loss.item()'.format(
                         'GraphedTrainStep, one CUDA-graph replay per step' if head == 'graph' else 'eager loop')}
     if 'eager' in out and head == 'graph':
         res['eager_ms_per_step'] = out['eager'][0] / out['eager'][1]

@@ -265,6 +265,31 @@ int kgc_bn2d_relu_drop_bwd(const float* dy, const float* x, int64_t B, int32_t C
                            const float* beta, const float* stats, int32_t training, int32_t relu, const int64_t* seed,
                            float drop_p, double* partials, float* sums, float* dx, void* stream);
 
+/* ---- K8: ConvE's one-input-channel convolution (SURVEY "next" row N2) ------------------------------------------
+ * Replaces model.py:166 (x = self.conv_e(x): nn.Conv2d(1, F, (K, K), stride 1, padding 0)) and its autograd.
+ * torch layouts, contiguous fp32: x [B, 1, H, W], w [F, 1, K, K], bias [F] or NULL, y / dy [B, F, H-K+1, W-K+1].
+ * Direct fp32 FMA kernels, fixed summation order (deterministic).  kgc_conv1ch_supported: W = 20, K in {3, 5, 7},
+ * K <= H <= 64 and the filters fit shared memory; callers use the library convolution otherwise.
+ * Backward: dx [B, 1, H, W] and/or dw [F, 1, K, K] (either may be NULL); workspace: kgc_conv1ch_bwd_workspace_bytes. */
+int kgc_conv1ch_supported(int32_t F, int32_t K, int32_t H, int32_t W);
+size_t kgc_conv1ch_bwd_workspace_bytes(int64_t B, int32_t F, int32_t K);
+int kgc_conv1ch_fwd(const float* x, const float* w, const float* bias, int64_t B, int32_t F, int32_t K, int32_t H,
+                    int32_t W, float* y, void* stream);
+int kgc_conv1ch_bwd(const float* dy, const float* x, const float* w, int64_t B, int32_t F, int32_t K, int32_t H,
+                    int32_t W, float* dx, float* dw, void* workspace, void* stream);
+
+/* ---- K9: gradient-norm clipping + Adam (the optimiser half of the training step, main.py:68-71, 217) --------------
+ * One call = nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step() (amsgrad off, L2 weight
+ * decay) over fp32 tensors: squared-norm partials (fp64, fixed order), coefficient + step counter + bias corrections on the
+ * device, then the update with coef * g applied in flight (gradients are not modified).
+ * tensors[n]: device table; items[n_items][4] int32 = {tensor, chunk, elements in chunk (<= kgc_opt_chunk_elems()), 0};
+ * hyper[6] (device fp32) = lr, beta1, beta2, eps, weight_decay, max_norm (<= 0: no clipping); state[5] (device fp64) =
+ * step count (in/out), clip coefficient, lr / (1 - b1^t), 1 / sqrt(1 - b2^t), gradient norm (out); partials[n_items]. */
+typedef struct { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; } kgc_opt_tensor_t;
+int32_t kgc_opt_chunk_elems(void);
+int kgc_clip_adam_step(const kgc_opt_tensor_t* tensors, const int32_t* items, int64_t n_items, const float* hyper,
+                       double* state, double* partials, void* stream);
+
 /* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------
  * Replaces model.py:177-179 (x = mm(x, all_ent^T); x += bias; sigmoid) where the caller needs the dense matrix
  * (BCE against the multi-hot label, main.py:63-66).  Forward: the K4b tensor-core kernel (3xTF32, fp32-grade) with

@@ -54,6 +54,12 @@ SIGNATURES = {
     'kgc_bn2d_partials_bytes': (_sz, [_i32]),
     'kgc_bn2d_relu_drop_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _i32, _vp, _f32, _vp, _vp, _vp, _vp]),
     'kgc_bn2d_relu_drop_bwd': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _vp, _vp, _vp]),
+    'kgc_conv1ch_supported': (_i32, [_i32, _i32, _i32, _i32]),
+    'kgc_conv1ch_bwd_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'kgc_conv1ch_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'kgc_conv1ch_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    'kgc_opt_chunk_elems': (_i32, []),
+    'kgc_clip_adam_step': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'kgc_score_1n_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
     'kgc_score_1n_bwd_logit': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

@@ -2,8 +2,8 @@
 
 Same constructors, forward signatures, parameter / state-dict names, so a checkpoint
 written by the reference loads here and vice versa.  The encoder is the CUDA MGCNConv; the ConvE front
-end (bn0 -> 7x7 conv -> bn1 -> relu -> fc -> bn2 -> relu, model.py:161-175) is SURVEY.md "next" row N2 and
-stays on torch/cuDNN; the 1-N scoring tail of ``forward`` (which must return the dense [B,N] matrix to stay
+end (bn0 -> 7x7 conv -> bn1 -> relu -> fc -> bn2 -> relu, model.py:161-175) is SURVEY.md "next" row N2: bn0 / bn1 (K7),
+the convolution (K8) and the fc layer (3xTF32 tensor-core GEMMs) run on our kernels, bn2 on torch; the 1-N scoring tail of ``forward`` (which must return the dense [B,N] matrix to stay
 call-compatible) and its autograd run on the 3xTF32 tensor-core kernels (K6t, scoring.score_1n); ``rank`` uses the
 fused tensor-core scoring + ranking kernel (K6).
 """
@@ -48,6 +48,38 @@ class _BnReluDropFn(torch.autograd.Function):
         _lib.call('kgc_bn2d_relu_drop_bwd', p(dy), p(x), B, C, HW, p(gamma), p(beta), p(stats), int(training), relu,
                   p(seed) if has_seed else None, drop_p, p(partials), p(sums), p(dx), _lib.stream())
         return dx, sums[1], sums[0], None, None, None, None, None, None, None, None
+
+
+class _Conv1chFn(torch.autograd.Function):
+    """nn.Conv2d(1, F, (K, K)) forward / backward (model.py:166) on the K8 direct-convolution kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x_ = _lib.require_cuda(x.detach(), torch.float32, 'x').contiguous()
+        w_ = weight.detach().contiguous()
+        B, H, W = int(x_.shape[0]), int(x_.shape[2]), int(x_.shape[3])
+        F_, K = int(w_.shape[0]), int(w_.shape[2])
+        y = torch.empty((B, F_, H - K + 1, W - K + 1), dtype=torch.float32, device=x.device)
+        p = _lib.ptr
+        _lib.call('kgc_conv1ch_fwd', p(x_), p(w_), p(bias.detach().contiguous()) if bias is not None else None, B, F_, K, H, W,
+                  p(y), _lib.stream())
+        ctx.save_for_backward(x_, w_)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, H, W = int(x.shape[0]), int(x.shape[2]), int(x.shape[3])
+        F_, K = int(w.shape[0]), int(w.shape[2])
+        p = _lib.ptr
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        ws = torch.empty((int(_lib.lib().kgc_conv1ch_bwd_workspace_bytes(B, F_, K)) // 4,), dtype=torch.float32, device=x.device)
+        _lib.call('kgc_conv1ch_bwd', p(dy), p(x), p(w), B, F_, K, H, W, p(dx), p(dw), p(ws), _lib.stream())
+        db = dy.sum((0, 2, 3)) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
 
 
 class ConvE(nn.Module):
@@ -106,13 +138,23 @@ class ConvE(nn.Module):
         return _BnReluDropFn.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
                                    self.training, p, seed, 1)
 
+    def _conv(self, x):
+        """model.py:166 - the one-input-channel k x k convolution - on the K8 kernels for the shapes they take (GPU, fp32,
+        stride 1, no padding, W = 20, k in {3, 5, 7}); the torch / cuDNN module otherwise."""
+        c = self.conv_e
+        if (x.is_cuda and x.dtype == torch.float32 and c.in_channels == 1 and c.kernel_size[0] == c.kernel_size[1]
+                and c.stride == (1, 1) and c.padding == (0, 0) and c.dilation == (1, 1) and c.groups == 1
+                and _lib.lib().kgc_conv1ch_supported(c.out_channels, c.kernel_size[0], x.shape[2], x.shape[3])):
+            return _Conv1chFn.apply(x, c.weight, c.bias)
+        return c(x)
+
     def query(self, src_emb, rel_emb):
         """Front end: (src_emb, rel_emb) -> query matrix X[B, Dout] (model.py:161-175)."""
         d = self.params.gcn_out_dim
         stack_inp = torch.cat([src_emb.view(-1, 1, d), rel_emb.view(-1, 1, d)], dim=1)
         x = torch.transpose(stack_inp, 2, 1).reshape(-1, 1, 2 * self.params.k_w, self.params.k_h)
         x = self._bn0(x)
-        x = self.conv_e(x)
+        x = self._conv(x)
         x = self._bn1_relu_drop(x)
         x = x.view(-1, self.flat_sz)
         # model.py:173: the 39,200 -> 200 fc layer; fp32-grade tensor-core kernels for the shapes they take

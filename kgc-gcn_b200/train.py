@@ -13,7 +13,8 @@ from . import _lib
 class GraphedTrainStep(object):
     """step = GraphedTrainStep(model, optimizer, graph, dataset, batch_size); loss = step(qid).
 
-    ``optimizer`` must be capturable (``torch.optim.Adam(..., capturable=True)``); ``dataset`` is the KBDataset of the
+    ``optimizer`` must be capturable (``kgc_gcn_b200.ClipAdam(..., max_norm=clip_grad)``, which also does the gradient
+    clipping, or ``torch.optim.Adam(..., capturable=True)``); ``dataset`` is the KBDataset of the
     training queries; batches whose size differs from ``batch_size`` (the last one of an epoch) run eagerly."""
 
     def __init__(self, model, optimizer, graph, dataset, batch_size, clip_grad=1.0, warmup=3):
@@ -27,6 +28,8 @@ class GraphedTrainStep(object):
         self.trip = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
         self.label = torch.zeros((self.B, dataset.num_entity), dtype=torch.float32, device=dev)
         self.qid = torch.zeros((self.B,), dtype=torch.int64, device=dev)
+        self._opt_clips = bool(getattr(optimizer, 'param_groups', None)) and \
+            all(g.get('max_norm') for g in optimizer.param_groups)
         self.loss = None
         self.cuda_graph = None
         self._warmup = int(warmup)
@@ -45,7 +48,8 @@ class GraphedTrainStep(object):
         pred = self.model(trip[:, 0], trip[:, 1], self.graph_data)
         loss = self.model.loss(pred, label)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        if not self._opt_clips:                       # ClipAdam(max_norm=...) clips inside its step (K9)
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
         self.opt.step()
         return loss.detach()
 
@@ -75,6 +79,8 @@ class GraphedTrainStep(object):
                 for j, (key, v) in enumerate(st.items()):
                     if torch.is_tensor(v):
                         v.zero_() if fresh else v.copy_(saved_s[i][j])
+        if hasattr(self.opt, 'prepare'):             # ClipAdam: device-side step counter / hyper-parameters
+            self.opt.prepare()
         self.cuda_graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.cuda_graph):
@@ -86,6 +92,8 @@ class GraphedTrainStep(object):
             self.opt.zero_grad(set_to_none=True)
             return self._body(trip, label)
         self._fill(qid)
+        if hasattr(self.opt, 'sync_hyper'):
+            self.opt.sync_hyper()                    # a scheduler may have changed the learning rate (device-side copy)
         if self.cuda_graph is None:
             self._capture()                          # capture records the step; nothing has been executed for this batch yet
         self.cuda_graph.replay()

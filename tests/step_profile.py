@@ -18,7 +18,7 @@ ds = k.KBDataset(bench.synthetic_queries(orc, tri, R), N, prm, training=True)
 loader = k.BatchIterator(ds, bench.BATCH, shuffle=True, device=dev)
 torch.manual_seed(0)
 model = k.MGCN(N, R, E, prm).to(dev); model.train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+opt = k.ClipAdam(model.parameters(), lr=1e-3, max_norm=1.0)
 batches = loader.batches()
 def step():
     qid = next(batches)
@@ -27,7 +27,6 @@ def step():
     pred = model(trip[:, 0], trip[:, 1], graph)
     loss = model.loss(pred, lab)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
     opt.step()
     return loss.item()
 for _ in range(5): step()

@@ -109,12 +109,15 @@ def test_graphed_train_step_matches_eager(toy):
     qids = [list(range(0, 16)), list(range(1, 17)), list(range(0, 16))]
     losses = {}
     finals = {}
-    for mode in ('eager', 'graph'):
+    for mode in ('eager', 'graph', 'graph_clipadam'):
         torch.manual_seed(3)
         m = copy.deepcopy(m0).train()
         m.conv1.drop.p = 0.0
-        opt = torch.optim.Adam(m.parameters(), lr=1e-2, capturable=(mode == 'graph'))
-        step = k.GraphedTrainStep(m, opt, dl.graph, ds, 16, warmup=0) if mode == 'graph' else None
+        if mode == 'graph_clipadam':                 # K9: clip + Adam inside the optimiser, device-side step / lr
+            opt = k.ClipAdam(m.parameters(), lr=1e-2, max_norm=1.0)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-2, capturable=(mode == 'graph'))
+        step = k.GraphedTrainStep(m, opt, dl.graph, ds, 16, warmup=0) if mode != 'eager' else None
         ls = []
         for q in qids:
             if step is not None:
@@ -129,13 +132,15 @@ def test_graphed_train_step_matches_eager(toy):
                 ls.append(float(loss.item()))
         losses[mode] = ls
         finals[mode] = {n: p.detach().clone() for n, p in m.named_parameters()}
-    for a, b in zip(losses['eager'], losses['graph']):
-        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (losses)
+    for other in ('graph', 'graph_clipadam'):
+        for a, b in zip(losses['eager'], losses[other]):
+            assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (losses)
     # Adam divides by sqrt(v): on parameters whose true gradient is zero (a BatchNorm scale feeding another BatchNorm)
     # it turns rounding noise into O(lr) steps, so only parameters with a real gradient signal are compared
     for n in ('entity_embedding', 'relation_embedding', 'edge_embeddings', 'conv1.in_weight', 'conv1.loop_weight',
               'conv2.fc.weight', 'conv2.bias'):
         assert torch.allclose(finals['eager'][n], finals['graph'][n], rtol=1e-3, atol=1e-4), n
+        assert torch.allclose(finals['eager'][n], finals['graph_clipadam'][n], rtol=1e-3, atol=1e-4), n
 
 
 @pytest.mark.parametrize('B,C,H,W', [(128, 200, 14, 14), (7, 5, 2, 2), (33, 16, 6, 6)])
@@ -202,3 +207,91 @@ def test_conve_bn_relu_dropout_kernels(B, C, H, W):
     # a second step draws a different mask
     ya2 = conve._bn1_relu_drop(x.clone())
     assert not torch.equal(ya2 == 0, ya == 0)
+
+
+@pytest.mark.parametrize('B,F,K,H,bias', [(128, 200, 7, 20, False), (5, 3, 3, 20, True), (37, 45, 5, 12, True), (1, 200, 7, 7, False)])
+def test_conve_conv_kernels(B, F, K, H, bias):
+    """K8: ConvE's one-input-channel convolution (model.py:166) against torch's conv2d evaluated in float64: output,
+    input gradient, weight gradient (and bias gradient); bit-identical across two runs (fixed summation order)."""
+    import kgc_gcn_b200 as k
+    W = 20
+    prm = SimpleNamespace(gcn_out_dim=H * W // 2, hidden_drop=0.0, feat_drop=0.0, k_w=H // 2 if H % 2 == 0 else H, k_h=W,
+                          num_filter=F, kernel_size=K, bias=bias)
+    g = torch.Generator().manual_seed(B * 7 + F)
+    conv = torch.nn.Conv2d(1, F, (K, K), bias=bias).cuda()
+    holder = SimpleNamespace(conv_e=conv)
+    x = torch.randn(B, 1, H, W, generator=g).cuda()
+    dy = torch.randn(B, F, H - K + 1, W - K + 1, generator=g).cuda()
+    assert k._lib.lib().kgc_conv1ch_supported(F, K, H, W) == 1
+    outs = []
+    for _ in range(2):
+        xa = x.clone().requires_grad_(True)
+        conv.zero_grad()
+        ya = k.ConvE._conv(holder, xa)
+        assert ya.grad_fn is not None and 'Conv1ch' in type(ya.grad_fn).__name__          # the K8 path, not cuDNN
+        ya.backward(dy)
+        outs.append((ya.detach().clone(), xa.grad.clone(), conv.weight.grad.clone(),
+                     conv.bias.grad.clone() if bias else None))
+    for a, b in zip(outs[0], outs[1]):
+        assert a is None or torch.equal(a, b)
+    x64 = x.double().requires_grad_(True)
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    b64 = conv.bias.detach().double().requires_grad_(True) if bias else None
+    y64 = torch.nn.functional.conv2d(x64, w64, b64)
+    y64.backward(dy.double())
+
+    def close(a, b):
+        return float((a.double() - b).abs().max()) <= 1e-5 * max(1e-30, float(b.abs().max()))
+    assert close(outs[0][0], y64.detach())
+    assert close(outs[0][1], x64.grad)
+    assert close(outs[0][2], w64.grad)
+    if bias:
+        assert close(outs[0][3], b64.grad)
+    assert k._lib.lib().kgc_conv1ch_supported(F, K, H, 19) == 0 and k._lib.lib().kgc_conv1ch_supported(F, 4, H, W) == 0
+
+
+@pytest.mark.parametrize('max_norm,wd', [(1.0, 0.0), (1e6, 0.0), (0.5, 0.01), (None, 0.0)])
+def test_clip_adam_matches_torch(max_norm, wd):
+    """K9: ClipAdam.step() == nn.utils.clip_grad_norm_ + torch.optim.Adam.step() (main.py:68-71, 217) over several steps,
+    on tensors whose sizes are not multiples of the kernel's chunk / vector width; same state_dict layout."""
+    import kgc_gcn_b200 as k
+    g = torch.Generator().manual_seed(5)
+    shapes = [(70001, 3), (16384,), (129, 7), (1,), (333, 100)]
+    pa = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = k.ClipAdam(pa, lr=3e-3, weight_decay=wd, max_norm=max_norm)
+    ob = torch.optim.Adam(pb, lr=3e-3, weight_decay=wd)
+    for it in range(5):
+        scale = 10.0 ** (it - 2)
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda() * scale
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if it == 3:
+            for grp in oa.param_groups + ob.param_groups:
+                grp['lr'] = 1e-3                                    # a scheduler step (main.py:219)
+        if max_norm is not None:
+            ref_norm = torch.nn.utils.clip_grad_norm_(pb, max_norm)
+        oa.step(); ob.step()
+        if max_norm is not None:
+            assert abs(float(oa.last_grad_norm) - float(ref_norm)) <= 1e-5 * float(ref_norm)
+        for a, b in zip(pa, pb):
+            assert float((a - b).detach().abs().max()) <= 2e-6 * max(1.0, float(b.detach().abs().max())), (it, a.shape)
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert set(sa['state'].keys()) == set(sb['state'].keys())
+    for i in sa['state']:
+        assert set(sa['state'][i].keys()) == set(sb['state'][i].keys())
+        assert float(sa['state'][i]['step']) == float(sb['state'][i]['step']) == 5.0
+        for key in ('exp_avg', 'exp_avg_sq'):                       # max-norm relative: two fp32 evaluation orders
+            va, vb = sa['state'][i][key], sb['state'][i][key]
+            assert float((va - vb).abs().max()) <= 2e-6 * float(vb.abs().max()), (i, key)
+    ob.load_state_dict(sa)                                          # a ClipAdam checkpoint loads into torch.optim.Adam ...
+    oc = k.ClipAdam(pa, lr=3e-3, weight_decay=wd, max_norm=max_norm)
+    oc.load_state_dict(sb)                                          # ... and vice versa, continuing at step 6
+    for a in pa:
+        a.grad = torch.ones_like(a)
+    oc.step()
+    assert float(oc.state_dict()['state'][0]['step']) == 6.0
+    cpu = torch.nn.Parameter(torch.zeros(3))
+    cpu.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):                               # no CPU fallback
+        k.ClipAdam([cpu], lr=1e-3).step()
