@@ -281,9 +281,11 @@ def test_clip_adam_matches_torch(max_norm, wd):
     for i in sa['state']:
         assert set(sa['state'][i].keys()) == set(sb['state'][i].keys())
         assert float(sa['state'][i]['step']) == float(sb['state'][i]['step']) == 5.0
-        for key in ('exp_avg', 'exp_avg_sq'):                       # max-norm relative: two fp32 evaluation orders
+        # max-norm relative; torch's clip coefficient comes from an fp32 norm of norms (ours: fp64 partials), the two
+        # coefficients agree to ~1e-5 (checked above on the norm) and exp_avg_sq carries that difference squared
+        for key, tol in (('exp_avg', 2e-5), ('exp_avg_sq', 4e-5)):
             va, vb = sa['state'][i][key], sb['state'][i][key]
-            assert float((va - vb).abs().max()) <= 2e-6 * float(vb.abs().max()), (i, key)
+            assert float((va - vb).abs().max()) <= tol * float(vb.abs().max()), (i, key)
     ob.load_state_dict(sa)                                          # a ClipAdam checkpoint loads into torch.optim.Adam ...
     oc = k.ClipAdam(pa, lr=3e-3, weight_decay=wd, max_norm=max_norm)
     oc.load_state_dict(sb)                                          # ... and vice versa, continuing at step 6
