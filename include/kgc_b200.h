@@ -142,6 +142,15 @@ int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_
 int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, void* stream);
 int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_t Dout, float eps, int32_t training,
                            const float* running_mean, const float* running_var, float* stats, void* stream);
+/* Single-GPU training (no all-reduce between the two steps): kgc_colsum_finalize + kgc_colstats_from_sums + the
+ * running-statistics bookkeeping of nn.BatchNorm1d in ONE launch: running_mean/var (NULL: not tracked) get the momentum
+ * update with the unbiased variance, *num_batches_tracked (NULL: skipped) is incremented; sums (NULL: skipped) as above.
+ * kgc_colsum_finalize2 = kgc_colsum_finalize plus an fp32 copy of the sums (d_beta / d_gamma of the backward). */
+int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
+                          float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                          double* sums, float* stats, void* stream);
+int kgc_colsum_finalize2(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, float* sums32,
+                         void* stream);
 int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
                    int64_t n_rows, int32_t Dout, float* all_ent, void* stream);
 /* Backward of the tail.  kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and

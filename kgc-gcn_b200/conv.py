@@ -226,7 +226,8 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, rels, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, bias,
-                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll, seed, drop_p):
+                plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll, seed, drop_p,
+                bn_track=None):
         # x: this rank's node rows [Nl, D] (all rows on one GPU); ee: the rows of the edges this rank owns
         Nl, D = x.shape
         Dout = w_in.shape[1]
@@ -250,8 +251,13 @@ class _ConvFn(torch.autograd.Function):
         packed_f = torch.empty((3, nf), dtype=torch.float32, device=x.device)
         packed_b = torch.empty((3, nbk), dtype=torch.float32, device=x.device)
         rels_c, wts = rels.detach().contiguous(), [w.detach().contiguous() for w in (w_in, w_out, w_loop, w_rel)]
-        _lib.call('kgc_conv_prep', p(rels_c), T - 1, p(loop_rel.detach()), p(loop_edge.detach()), p(wts[0]), p(wts[1]), p(wts[2]),
-                  p(wts[3]), D, Dout, p(relp), p(all_rel_pad), p(packed_f), p(packed_b), st())
+        # ... on a side stream: the aggregation below reads the relation rows straight from `rels` (real edges never carry
+        # the self-loop type), so K0 leaves the critical path; the main stream joins before the first dense transform
+        main, side = torch.cuda.current_stream(), plan.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call('kgc_conv_prep', p(rels_c), T - 1, p(loop_rel.detach()), p(loop_edge.detach()), p(wts[0]), p(wts[1]),
+                      p(wts[2]), p(wts[3]), D, Dout, p(relp), p(all_rel_pad), p(packed_f), p(packed_b), st())
         # halo exchange: every rank needs the source rows of its edges (all-gather of the row partition); it runs on
         # NCCL's stream while this rank's self-loop transform (which only needs its own rows) runs here
         gather = None
@@ -262,6 +268,7 @@ class _ConvFn(torch.autograd.Function):
 
         res3 = plan.scratch('res3', (3, Nl, Dout))
         if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
+            main.wait_stream(side)
             gemm_nt(x, None, res3[2], packed=packed_f[2])          # overlaps the all-gather
             gather.wait()
         if max(x_full.shape[0], 3 * Nl, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
@@ -269,9 +276,11 @@ class _ConvFn(torch.autograd.Function):
         agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
-            _lib.call('kgc_agg_fwd', p(x_full), p(relp), relp.shape[0], p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
+            _lib.call('kgc_agg_fwd', p(x_full), p(rels_c), T - 1, p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
                       p(out_final), p(carry), D, st())
         plan.run_reduction(plan.fwd, level0, agg, D, tag='f')
+        if gather is None:
+            main.wait_stream(side)                                  # K0's operand packs are needed from here on
 
         if gather is not None:
             gemm_nt_batch([agg[0], agg[1]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
@@ -286,12 +295,19 @@ class _ConvFn(torch.autograd.Function):
         all_ent = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
         _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), p(seed), float(drop_p), float(keep_scale), p(bias),
                   Nl, Dout, p(pre), p(partials), st())
-        if training:
-            _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
-            if coll is not None:
+        if training and coll is None:
+            # one GPU: column sums -> batch statistics -> nn.BatchNorm1d's running-statistics bookkeeping in ONE launch
+            # (bn_track = (momentum, num_batches_tracked) when the module tracks running statistics)
+            mom, nbt = bn_track if bn_track is not None else (0.0, None)
+            _lib.call('kgc_colstats_finalize', p(partials), nb, n_global, Dout, float(eps), float(mom),
+                      p(running_mean) if bn_track is not None else None, p(running_var) if bn_track is not None else None,
+                      p(nbt), None, p(stats), st())
+        else:
+            if training:
+                _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
                 coll.all_reduce(sums)                                # BatchNorm statistics over ALL node rows
-        _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
-                  p(running_var), p(stats), st())
+            _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
+                      p(running_var), p(stats), st())
         _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), st())
         all_rel = all_rel_pad[:-1]
 
@@ -324,12 +340,15 @@ class _ConvFn(torch.autograd.Function):
         sums = torch.empty((2, Dout), dtype=torch.float64, device=dev)
         d_res3 = plan.scratch('d_res3', (3, Nl, Dout))
         _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(all_ent), p(pre), p(stats), Nl, Dout, p(partials), st())
-        _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
-        if coll is not None:
+        if coll is None:
+            sums32 = torch.empty((2, Dout), dtype=torch.float32, device=dev)
+            _lib.call('kgc_colsum_finalize2', p(partials), nb, Dout, p(sums), p(sums32), st())
+        else:
+            _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
             coll.all_reduce(sums)
+            sums32 = sums.float()
         _lib.call('kgc_tail_bwd_apply', p(g_ent), p(all_ent), p(pre), p(stats), p(gamma), p(sums), p(mask_in),
                   p(mask_out), p(seed), ctx.drop_p, ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
-        sums32 = sums.float()
         d_beta, d_gamma = sums32[0], sums32[1]
 
         # replicated-parameter gradients: one flat buffer so that a partitioned run needs ONE all-reduce
@@ -381,7 +400,7 @@ class _ConvFn(torch.autograd.Function):
                   p(relp), p(w_rel.detach().contiguous()), p(g_rel_c), p(d_relp), T - 1, D, Dout, p(d_w_loop), p(d_loop_rel),
                   p(d_loop_edge), p(d_rels), p(d_w_rel), st())
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class MGCNConv(nn.Module):
@@ -460,11 +479,16 @@ class MGCNConv(nn.Module):
         self._last_seed = seed
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
+        # running statistics of nn.BatchNorm1d: updated inside the statistics kernel when the momentum is a number
+        track = self.training and bn.track_running_stats and bn.running_mean is not None
+        fused = track and bn.momentum is not None
         all_ent, all_rel, stats = _ConvFn.apply(
             x, rels_embs, edge_embs, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, plan, m_in, m_out, keep_scale,
-            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None, seed, drop_p)
-        self._update_running_stats(stats, num_ent)
+            use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None, seed, drop_p,
+            (float(bn.momentum), bn.num_batches_tracked) if fused else None)
+        if track and not fused:
+            self._update_running_stats(stats, num_ent)
         return all_ent, all_rel
 
     def _update_running_stats(self, stats, n_rows):

@@ -6,34 +6,35 @@
 //   agg[dst] = sum_e norm_e * x[src_e] (.) rel[type_e] (.) ee[e]      (this file)
 //   res      = agg @ W                                                   (dense GEMM, host side)
 //
-// Streaming design (round 1, second version - the first one gave one 8-lane group a whole output row and
-// was latency-bound at 25-40% of HBM peak, profiles/r01_ncu_agg_kernels.md):
-//   * the sorted edge records are cut into CHUNKS of 32 consecutive records, one warp per chunk, whatever
-//     the row boundaries: every warp has the same amount of work and there is no per-row launch overhead;
-//   * lane l owns float4 columns l and l + 32 of a row (D <= 256), so a 400-byte row is one fully
-//     coalesced 25-lane request; 4 edges are in flight per warp (records prefetched one trip ahead);
-//   * a row that lies inside one chunk is written straight to the output; the (at most two) rows a chunk
-//     shares with its neighbours go to CARRY rows, which kgc_rows_reduce adds in a fixed order.
-// No float atomics anywhere: results are bit-reproducible run to run.
-// Tried and rejected in round 1: staging every operand row with one bulk async copy (cp.async.bulk, UBLKCP) into
-// per-warp shared-memory stages - correct but 0.2-0.3 of the HBM peak: the copy engine retires roughly one 400-byte
-// request per 30 cycles per SM, far below what 128-bit LDGs sustain.  Also measured and rejected: (a) double-buffered
-// register batches (loads of batch b + 1 issued before batch b is consumed, 2 x 4 edges): 39 / 66 / 41 us against
-// 37 / 67 / 41 us - no change, the bytes in flight per warp are the same; (b) a per-warp cp.async (LDGSTS.BYPASS.128) ring
-// of 12 edges in shared memory, each lane landing and re-reading its own float4 column (no barriers): 65 / 92 / 83 us,
-// 0.29 / 0.37 / 0.23 of the peak - LDGSTS sustains far fewer 400-byte row requests than plain 128-bit loads here; (c) MORE
-// edges in flight per warp - double-buffered batches of 8 / 6 / 4 at 3 x 128-thread CTAs per SM (168 registers): 43 / 107 /
-// 65 us, clearly worse; (d) prefetch.global.L2 of the next chunk's operand rows one chunk ahead: 84 / 131 / 115 us - every
-// extra line request costs as much as a demand request; (e) records broadcast from shared memory (one LDS.128 per edge)
-// instead of warp shuffles, with a bounds-check-free path for full chunks: 128 registers + spills, 73 us; (f) one-warp
-// CTAs (16 per SM), which lets the compiler prove every branch warp-uniform and drops the WARPSYNC / ENDCOLLECTIVE /
-// BSSY bookkeeping around the shuffles (1,376 -> 744 SASS instructions): 55 / 66 / 37 us - slower forward, same backward.
-// tests/gather_probe.py: the kept kernel takes the same 35 us when edge ids AND source rows are perfectly sequential as
-// when both are random, so the ORDER of the row reads is not what bounds it; neither is the instruction count (f) nor
-// the number of requests in flight (a, c).  What the variants have in common is ~130 row requests of 400 bytes (4 partial
-// cache lines each) in flight per SM; the open question for round 2 is the L1 miss path for such partial-line requests.
-// ncu of the kept version: every unit below 45% (DRAM 30%, L2 21%, L1 32%, issue 39%), 14 resident warps per SM,
-// long-scoreboard stalls dominate: latency-bound at the occupancy 100+ registers allow.
+// Streaming design: the sorted edge records are cut into CHUNKS of 32 consecutive records, one warp per chunk whatever
+// the row boundaries (every warp has the same amount of work, no per-row launch overhead); lane l owns float4 column l
+// of a row, so a 400-byte row is one fully coalesced 25-lane request; a row that lies inside one chunk is written
+// straight to the output; the (at most two) rows a chunk shares with its neighbours go to CARRY rows, which
+// kgc_rows_reduce adds in a fixed order.  No float atomics anywhere: results are bit-reproducible run to run.
+//
+// Two kernels implement it.  agg_lean_kernel (D <= 128, the product path at the reference's D = 100) and
+// agg_stream_kernel (the earlier version, kept for 128 < D <= 256: two float4 columns per lane).
+//
+// History of the measurements that shaped agg_lean_kernel (profiles/r01_agg_variants.md has every number):
+//   * agg_stream_kernel reached 0.53 / 0.53 / 0.47 of the measured HBM peak (fwd / bwd_src / bwd_rel, WN18RR shape) and
+//     looked latency-bound: every unit below 45% busy, same time for sequential and for random row order
+//     (tests/gather_probe.py), no gain from more loads in flight.  Rejected on the way: per-row bulk async copies
+//     (UBLKCP, 0.2-0.3 - the copy engine retires ~one 400-byte request per 30 cycles per SM), a per-warp cp.async ring
+//     (0.29 / 0.37 / 0.23), double-buffered register batches (no change), L2 prefetch of the next chunk (worse), records
+//     broadcast from shared memory (spills), one-warp CTAs, dynamic chunk claiming (same).
+//   * ncu source-level sampling then showed WHY: 75 warp instructions per edge, only 28% of the stall samples on the first
+//     use of a loaded row, the other 72% spread evenly over ~700 SASS instructions (fixed-latency waits, shuffles, branch
+//     bookkeeping, per-edge bounds checks, 64-bit address arithmetic) at 3.5 warps per scheduler.  The kernel was bound by
+//     the serial instruction latency of each warp, not by memory.
+//   * a continuous register ring (edge e + P issued as soon as edge e is consumed) cut the instruction count to 47 per
+//     edge but ran SLOWER (45 / 88 / 63 us): a warp has six scoreboard slots, the load being waited for shares its slot
+//     with loads issued after it, and the ring degenerates (long-scoreboard stall 3 -> 12 cycles per issue).  Batches -
+//     all loads of kU edges, then all their arithmetic - are the structure the scoreboards reward.
+//   * agg_lean_kernel: 42 instructions per edge, batches of 3-4 edges at 3 CTAs per SM (80 registers, no spills):
+//     35.8 / 64.6 / 39.9 us -> 26.6 / 47.1 / 28.8 us = 0.70 / 0.73 / 0.65 of the measured peak, bit-identical outputs.
+//     Relation rows staged in shared memory and grids balanced to equal chunks per warp changed nothing measurable.
+//     ncu of the kept kernel: DRAM 47%, L1TEX 62%, 19 resident warps per SM, long-scoreboard 9 cycles per issue - it is
+//     now memory-latency-bound; the torch copy of the same bytes, timed the same way, reaches 0.77-0.79.
 #include "common.cuh"
 
 namespace kgc {
@@ -82,7 +83,7 @@ struct StreamArgs {
   int64_t max_rows;           // known bound on the row indices of g3 / outputs (guard of the 32-bit float4 indices)
 };
 
-// One warp walks one chunk of kChunk (= 32) sorted records.  Lane l first loads record cb + l (one coalesced
+// agg_stream_kernel (128 < D <= 256).  One warp walks one chunk of kChunk (= 32) sorted records.  Lane l first loads record cb + l (one coalesced
 // 512-byte + 128-byte request for the whole chunk); every edge's record is then broadcast with warp shuffles,
 // so all gather addresses of the chunk are known after a single memory round trip.  kU edges are in flight per
 // trip: phase 1 issues their DRAM / L2 row loads (edge embedding + the gathered operand), phase 2 consumes them

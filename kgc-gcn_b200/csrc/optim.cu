@@ -3,7 +3,7 @@
 // (main.py:217) - for fp32 parameters: 29.4 M of them at the WN18RR shape (edge embeddings 17.4 M, fc weight 7.8 M, entity
 // embeddings 4.1 M).  torch runs four multi-tensor launches for the clip (norms, norm of norms, scale in place: reads the
 // gradients twice and rewrites them) and two for the fused Adam: 340 us per step.  Here: pass 1 reads the gradients once
-// (squared-norm partials, fp64, fixed order), a one-thread kernel turns them into the clip coefficient, advances the step
+// (squared-norm partials, fp64, fixed order), a one-block kernel turns them into the clip coefficient, advances the step
 // counter and forms the bias corrections, pass 2 applies coef * g inside the Adam update (the clipped gradient is never
 // written back).  Everything the step needs lives in device memory (lr included), so a CUDA graph of the step stays valid
 // when the host changes the learning rate.

@@ -137,6 +137,50 @@ colsum_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, in
   sums[Dout + c] = q;
 }
 
+// the same reduction, with a float copy of the sums (the backward hands d_beta / d_gamma to autograd in fp32)
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+colsum_finalize2_kernel(const double* __restrict__ partials, int64_t n_blocks, int Dout, double* __restrict__ sums,
+                        float* __restrict__ sums32) {
+  __shared__ double sm[2][kFinLanes][kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
+  double s = 0, q = 0;
+  reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
+  if (lane != 0 || c >= Dout) return;
+  sums[c] = s;
+  sums[Dout + c] = q;
+  sums32[c] = (float)s;
+  sums32[Dout + c] = (float)q;
+}
+
+// single-GPU training: partials -> sums -> batch statistics -> nn.BatchNorm1d's running-statistics update, one launch
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+colstats_finalize_kernel(const double* __restrict__ partials, int64_t n_blocks, int64_t n_rows, int Dout, float eps,
+                         float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                         int64_t* __restrict__ n_tracked, double* __restrict__ sums, float* __restrict__ stats) {
+  __shared__ double sm[2][kFinLanes][kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols, lane = threadIdx.x / kFinCols;
+  double s = 0, q = 0;
+  reduce_partials(partials, n_blocks, Dout, c, lane, sm, &s, &q);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n_tracked != nullptr) *n_tracked += 1;
+  if (lane != 0 || c >= Dout) return;
+  if (sums != nullptr) {
+    sums[c] = s;
+    sums[Dout + c] = q;
+  }
+  const double mean = s / (double)n_rows;
+  double var = q / (double)n_rows - mean * mean;
+  if (var < 0) var = 0;
+  const float meanf = (float)mean, varf = (float)var;
+  stats[c] = meanf;
+  stats[Dout + c] = varf;
+  stats[2 * Dout + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean != nullptr && rvar != nullptr) {        // momentum update with the UNBIASED variance (torch semantics, fp32)
+    const float unbias = (float)n_rows / (float)(n_rows > 1 ? n_rows - 1 : 1);
+    rmean[c] = rmean[c] * (1.f - momentum) + momentum * meanf;
+    rvar[c] = rvar[c] * (1.f - momentum) + (momentum * unbias) * varf;
+  }
+}
+
 // stats[0] = mean, stats[1] = biased variance, stats[2] = 1/sqrt(var + eps)
 __global__ void colstats_from_sums_kernel(const double* __restrict__ sums, int64_t n_rows, int Dout, float eps,
                                           int training, const float* __restrict__ rmean,
@@ -297,6 +341,28 @@ extern "C" int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   colsum_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
       partials, n_blocks, Dout, sums);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_colsum_finalize2(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, float* sums32,
+                                    void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  KGC_REQUIRE(partials && sums && sums32 && n_blocks > 0, "null buffer");
+  colsum_finalize2_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
+      partials, n_blocks, Dout, sums, sums32);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_rows, int32_t Dout, float eps,
+                                     float momentum, float* running_mean, float* running_var,
+                                     int64_t* num_batches_tracked, double* sums, float* stats, void* stream) {
+  KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  KGC_REQUIRE(partials && stats && n_blocks > 0 && n_rows > 0, "null buffer");
+  KGC_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var come together");
+  colstats_finalize_kernel<<<(unsigned)ceil_div(Dout, kFinCols), kFinCols * kFinLanes, 0, as_stream(stream)>>>(
+      partials, n_blocks, n_rows, Dout, eps, momentum, running_mean, running_var, num_batches_tracked, sums, stats);
   KGC_LAUNCH_CHECK();
   return 0;
 }

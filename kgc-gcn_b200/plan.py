@@ -201,6 +201,12 @@ class GraphPlan(object):
         self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64), n2), n2, dev)
         self._scratch = {}
 
+    def side_stream(self):
+        """A second stream of this device for work that is off the step's critical path (created once per plan)."""
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def scratch(self, name, shape, dtype=torch.float32):
         """Reusable device workspace (caller-allocated, as the C ABI requires)."""
         key = (name, tuple(shape), dtype)

@@ -15,9 +15,9 @@ def main(path, which=5):
         n = n.replace('kgc::<unnamed>::', '').replace('void ', '')
         return re.sub(r'\(.*', '', n)[:84]
     seq = [(int(r[idc]), short(r[kn]), float(r[mv].replace(',', ''))) for r in data]
-    idx = [i for i, s in enumerate(seq) if s[1].startswith('agg_stream_kernel<0') or s[1].startswith('agg_fwd_kernel')]
+    idx = [i for i, s in enumerate(seq) if s[1].startswith(('agg_lean_kernel<0', 'agg_stream_kernel<0', 'agg_fwd_kernel'))]
     # a step = the launches between two consecutive forward aggregation kernels (shifted to the step's first launch)
-    first = next(i for i, s in enumerate(seq) if s[1].startswith('pack_b_kernel') or 'distribution_elementwise' in s[1])
+    first = next(i for i, s in enumerate(seq) if s[1].startswith(('pack_b_kernel', 'conv_prep_kernel')) or 'distribution_elementwise' in s[1])
     shift = idx[0] - first if first < idx[0] else 0
     a, b = idx[which] - shift, idx[which + 1] - shift
     step = seq[a:b]
