@@ -254,9 +254,10 @@ def run_ours(args, rank, world, local_rank):
         g_ent = g_ent_all.to(dev)
     else:
         part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev)
-        x = p['x'][part.lo:part.hi].to(dev).requires_grad_(True)
+        own = part.owned_nodes.cpu()                     # edge-balanced partition: this rank's node rows (local-row order)
+        x = p['x'][own].to(dev).requires_grad_(True)
         ee = p['edge_embs'][part.owned_eids.cpu()].to(dev).requires_grad_(True)
-        g_ent = g_ent_all[part.lo:part.hi].to(dev)
+        g_ent = g_ent_all[own].to(dev)
     del g_ent_all
     leaves = [x, ee, rl] + list(conv.parameters())
 
@@ -359,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
         'config': {'workload': args.workload + '_shape' + ('' if world == 1 else ' x{} (one shape-sized partition per GPU)'.format(world)), 'N': N, 'R': R, 'E': E, 'directed_edges': 2 * E, 'd_in': D_IN,
                    'd_out': D_OUT, 'dropout': 'p=0.1 keep masks drawn inside the timed region (training mode)',
                    'l2': 'flushed between steps (256 MiB memset + 256 MiB read, outside the timed events)', 'launch': launch_mode,
-                   'parallelism': 'single GPU' if world == 1 else 'dst-range partition over {} GPUs: all-gather x / reduce-scatter d_x / all-reduce BN sums + replicated grads (NCCL)'.format(world)},
+                   'parallelism': 'single GPU' if world == 1 else 'edge-balanced dst partition over {} GPUs (split hub rows): all-gather x / reduce-scatter d_x / all-reduce hub rows, BN sums + replicated grads (NCCL)'.format(world)},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
                 'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1), 'eager_ms_per_step': e2e.get('eager_ms_per_step'),
                 'scope': e2e['scope']},
@@ -463,6 +464,8 @@ def e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist):
     steps, warm = args.steps, max(3, args.warmup)
     rng = np.random.default_rng(0)
     host = torch.empty((BATCH, 2), dtype=torch.int64).pin_memory()
+    local_row = torch.full((N,), -1, dtype=torch.int64, device=dev)
+    local_row[part.owned_nodes] = torch.arange(part.n_loc, device=dev)
     ms, n = 0.0, 0
     for i in range(warm + steps):
         host[:, 0] = torch.from_numpy(rng.integers(0, N, BATCH))
@@ -473,9 +476,9 @@ def e2e_partitioned_step(conv, part, x, ee, rl, leaves, N, R, dev, args, dist):
         for t in leaves:
             t.grad = None
         ent, rel = conv.forward_partitioned(x, part, ee, rl)
-        mine = (batch[:, 0] >= part.lo) & (batch[:, 0] < part.hi)
-        rows = (batch[:, 0] - part.lo).clamp(0, part.hi - part.lo - 1)
-        loss = (ent[rows].mean(1) * mine).sum() + rel[batch[:, 1]].mean() / part.world
+        rows = local_row[batch[:, 0]]                    # -1: the entity lives on another rank
+        mine = rows >= 0
+        loss = (ent[rows.clamp_min(0)].mean(1) * mine).sum() + rel[batch[:, 1]].mean() / part.world
         loss.backward()
         tot = loss.detach().clone()
         dist.all_reduce(tot)

@@ -194,8 +194,31 @@ def gemm_tn(a, b, out, plan=None, tensor_cores=True):
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
-    def __init__(self, group, world, n_global):
+    def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None):
         self.group, self.world, self.n_global = group, int(world), int(n_global)
+        # split hub rows of an edge-balanced partition (partition.py): every rank accumulates a share of a hub's incoming
+        # edges into a private virtual row (local rows n_loc .. n_loc + n_hub); hub_idx_mine / hub_rows_mine = the hubs this
+        # rank owns and their real local rows
+        self.n_hub, self.hub_idx_mine, self.hub_rows_mine = int(n_hub), hub_idx_mine, hub_rows_mine
+
+    def sum_hub_rows(self, planes, n_loc):
+        """planes [P, n_loc + n_hub, D]: virtual rows summed over ranks, result added into the owners' real rows."""
+        if self.n_hub == 0:
+            return
+        buf = planes[:, n_loc:, :].contiguous()
+        self.all_reduce(buf)
+        if self.hub_idx_mine.numel():
+            planes[:, self.hub_rows_mine, :] = buf[:, self.hub_idx_mine, :]
+
+    def spread_hub_rows(self, planes, n_planes, n_loc):
+        """The inverse for the backward: every rank's virtual rows receive planes[:n_planes] of the hubs' real rows."""
+        if self.n_hub == 0:
+            return
+        buf = torch.zeros((n_planes, self.n_hub, planes.shape[2]), dtype=planes.dtype, device=planes.device)
+        if self.hub_idx_mine.numel():
+            buf[:, self.hub_idx_mine, :] = planes[:n_planes, self.hub_rows_mine, :]
+        self.all_reduce(buf)                                   # every entry is non-zero on one rank: exact
+        planes[:n_planes, n_loc:, :] = buf
 
     def all_gather_rows(self, x_local, async_op=False):
         import torch.distributed as dist
@@ -235,7 +258,10 @@ class _ConvFn(torch.autograd.Function):
         x = _lib.require_cuda(x, torch.float32, 'x')
         ee = _lib.require_cuda(ee, torch.float32, 'edge_embs')
         n_global = Nl if coll is None else coll.n_global
-        if ee.shape[0] != plan.num_edges2 or Nl != plan.num_dst_rows or n_global != plan.num_nodes:
+        n_hub = 0 if coll is None else coll.n_hub           # virtual rows of split hubs follow the Nl real rows
+        Nb = Nl + n_hub
+        if ee.shape[0] != plan.num_edges2 or Nb != plan.num_dst_rows or \
+                plan.num_nodes != (Nl if coll is None else Nb * coll.world):
             raise ValueError('edge_embs / x do not match the graph plan')
         T = rels.shape[0] + 1
         if T != plan.num_types:
@@ -264,16 +290,17 @@ class _ConvFn(torch.autograd.Function):
         if coll is None:
             x_full = x
         else:
-            x_full, gather = coll.all_gather_rows(x, async_op=True)
+            x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)     # blocks of Nb rows: ids = rows
+            x_full, gather = coll.all_gather_rows(x_blk, async_op=True)
 
         res3 = plan.scratch('res3', (3, Nl, Dout))
         if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
             main.wait_stream(side)
             gemm_nt(x, None, res3[2], packed=packed_f[2])          # overlaps the all-gather
             gather.wait()
-        if max(x_full.shape[0], 3 * Nl, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
+        if max(x_full.shape[0], 3 * Nb, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
             raise ValueError('kgc_gcn_b200: node / edge tables of 2^32 float4 elements or more are not supported')
-        agg = torch.empty((2, Nl, D), dtype=torch.float32, device=x.device)
+        agg = torch.empty((2, Nb, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
             _lib.call('kgc_agg_fwd', p(x_full), p(rels_c), T - 1, p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
@@ -283,7 +310,8 @@ class _ConvFn(torch.autograd.Function):
             main.wait_stream(side)                                  # K0's operand packs are needed from here on
 
         if gather is not None:
-            gemm_nt_batch([agg[0], agg[1]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
+            coll.sum_hub_rows(agg, Nl)
+            gemm_nt_batch([agg[0, :Nl], agg[1, :Nl]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
         else:                                                       # the three transforms of the step in one launch
             gemm_nt_batch([agg[0], agg[1], x], [packed_f[0], packed_f[1], packed_f[2]], [res3[0], res3[1], res3[2]])
 
@@ -325,7 +353,9 @@ class _ConvFn(torch.autograd.Function):
          mask_out, packed_b, seed) = ctx.saved_tensors
         plan, coll = ctx.plan, ctx.coll
         Nl, D = x.shape
-        n_global = plan.num_nodes
+        n_global = Nl if coll is None else coll.n_global      # BatchNorm rows (real nodes of all ranks)
+        n_hub = 0 if coll is None else coll.n_hub
+        Nb = Nl + n_hub
         Dout = w_in.shape[1]
         T = relp.shape[0]
         p, st = _lib.ptr, _lib.stream
@@ -356,15 +386,18 @@ class _ConvFn(torch.autograd.Function):
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
         d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
         # weight-gradient reductions over the node rows (K4c: register-tiled fp32, deterministic)
-        gemm_tn_batch([agg[0], agg[1], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
+        gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
         if ctx.has_bias:
             torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
-        g3 = plan.scratch('g3', (3, Nl, D))
-        gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]], [g3[0], g3[1], g3[2]])
+        g3 = plan.scratch('g3', (3, Nb, D))
+        gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]],
+                      [g3[0, :Nl], g3[1, :Nl], g3[2, :Nl]])
+        if n_hub:
+            coll.spread_hub_rows(g3, 2, Nl)                          # the virtual rows see their hub's upstream gradient
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
-        d_x_full = torch.empty((n_global, D), dtype=torch.float32, device=dev)
+        d_x_full = torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
         d_ee = torch.empty_like(ee)
         loop_addend = g3[2] if coll is None else None
 
@@ -388,7 +421,7 @@ class _ConvFn(torch.autograd.Function):
             coll.all_reduce(flat)
             if scatter is not None:
                 scatter.wait()
-            d_x += g3[2]                                              # self-loop term of this rank's rows
+            d_x = d_x[:Nl] + g3[2, :Nl]                               # self-loop term of this rank's (real) rows
         d_bias = flat[3 * D * Dout + T * D:] * 3.0 if ctx.has_bias else None
         # K0 backward: self-loop vectors, relation transform (model.py:107; replicated inputs, identical on every rank)
         small = torch.empty((2 * D * Dout + 2 * D + (T - 1) * D,), dtype=torch.float32, device=dev)
@@ -512,7 +545,7 @@ class MGCNConv(nn.Module):
         self._last_seed = seed
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
-        coll = _Collectives(part.group, part.world, part.num_nodes)
+        coll = _Collectives(part.group, part.world, part.num_nodes, part.n_hub, part.hub_idx_mine, part.hub_rows_mine)
         all_ent, all_rel, stats = _ConvFn.apply(
             x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,

@@ -1,9 +1,21 @@
-"""Destination-range partition of the graph for one-process-per-GPU runs.
+"""Destination partition of the graph for one-process-per-GPU runs.
 
-Nodes are split into ``world`` equal contiguous ranges; every directed edge (and its edge_embeddings row
-and optimiser state) belongs to the rank that owns its DESTINATION node; entity_embedding rows belong to
-the owner of the node.  The forward needs the source rows of the owned edges (all-gather of x), the
-backward returns source-row gradients to their owners (reduce-scatter of d_x).
+Every directed edge (its edge_embeddings row and optimiser state) belongs to ONE rank, normally the rank that owns its
+DESTINATION node; entity_embedding rows belong to the owner of the node.  The forward needs the source rows of the owned
+edges (all-gather of x), the backward returns source-row gradients to their owners (reduce-scatter of d_x).
+
+Two ways of choosing the owners:
+  * ``balance='range'``  - ``world`` equal contiguous node ranges (the plain reading of "range-partitioned by destination").
+    On hub-heavy graphs (the Zipf workloads of SURVEY.md 8(d), real KGs) the rank that holds the hubs owns most edges:
+    with the WN18RR-shape generator rank 0 of 2 owns 75% of the edges, rank 0 of 8 owns 56%.
+  * ``balance='edges'`` (default) - the same machinery after a node RENUMBERING: nodes are dealt to ranks by decreasing
+    in-degree, the heaviest to the least-loaded rank (equal node counts, near-equal edge counts), and the few HUB rows
+    whose in-degree alone exceeds half a rank's share are SPLIT: their incoming edges are dealt round-robin to all
+    ranks, every rank accumulates them into a private virtual row, and the virtual rows are summed across ranks (one small all-reduce of
+    [2, n_hub, D]) into the hub's real row; the backward broadcasts the hub rows' upstream gradient the same way.
+    In the renumbered id space rank r owns the contiguous block [r B, (r + 1) B), B = nodes per rank + n_hub (the last
+    n_hub rows of a block are the virtual rows), so the range machinery (K1 with dst_offset, all-gather, reduce-scatter)
+    is used unchanged.
 """
 import numpy as np
 import torch
@@ -11,8 +23,12 @@ import torch
 from .plan import GraphPlan
 
 
+def _half_degrees(ei, E, num_nodes):
+    return np.stack([np.bincount(ei[0, :E], minlength=num_nodes), np.bincount(ei[0, E:], minlength=num_nodes)]).astype(np.int32)
+
+
 def partition_edges(edge_index, edge_type, num_nodes, world, rank):
-    """Pure host integer logic (numpy): which edges rank ``rank`` owns and their local numbering.
+    """Range partition, pure host integer logic (numpy): which edges rank ``rank`` owns and their local numbering.
 
     Returns dict(lo, hi, owned_eids [n_local] int64 (in-half edges first, ascending), n_edges_in,
     src (global ids), dst (local row ids), type, deg [2, N] int32 = GLOBAL per-half out-degree by src
@@ -30,22 +46,132 @@ def partition_edges(edge_index, edge_type, num_nodes, world, rank):
     dst = ei[1]
     owned = np.nonzero((dst >= lo) & (dst < hi))[0]          # ascending: in-half edges (< E) come first
     n_in = int(np.searchsorted(owned, E))
-    deg = np.stack([np.bincount(ei[0, :E], minlength=num_nodes), np.bincount(ei[0, E:], minlength=num_nodes)]).astype(np.int32)
     return {'lo': lo, 'hi': hi, 'owned_eids': owned, 'n_edges_in': n_in, 'src': ei[0, owned], 'dst': dst[owned] - lo,
-            'type': et[owned], 'deg': deg}
+            'type': et[owned], 'deg': _half_degrees(ei, E, num_nodes)}
+
+
+def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs=64, n_greedy=8192):
+    """Edge-balanced node -> (rank, local row) assignment and the hub rows to split; identical on every rank.
+
+    Returns dict(owner [N], slot [N], hubs [n_hub] (node ids, decreasing in-degree), n_loc).  A node is a split hub when
+    its in-degree (edges of both halves that point to it) exceeds ``hub_fraction`` of a rank's mean edge count - no
+    assignment of whole rows could balance such a row (splitting costs two small all-reduces per step, so rows that can
+    be balanced whole are).  The ``n_greedy`` heaviest remaining nodes go, one by one, to the least-loaded rank
+    (LPT); the light tail is dealt in snake order, the lightest nodes filling the ranks that took few heavy ones
+    (every rank ends with exactly N / world nodes)."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    n2 = ei.shape[1]
+    if num_nodes % world != 0:
+        raise ValueError('num_nodes ({}) must be divisible by the number of ranks ({})'.format(num_nodes, world))
+    n_loc = num_nodes // world
+    indeg = np.bincount(ei[1], minlength=num_nodes).astype(np.int64)
+    hubs = np.zeros((0,), dtype=np.int64)
+    if world > 1:
+        thr = max(1.0, hub_fraction * n2 / world)
+        cand = np.nonzero(indeg > thr)[0]
+        cand = cand[np.argsort(-indeg[cand], kind='stable')]
+        hubs = cand[:max_hubs]
+    w = indeg.copy()
+    w[hubs] = 0                                               # their edges are dealt to every rank
+    order = np.argsort(-w, kind='stable')
+    owner = np.empty(num_nodes, dtype=np.int64)
+    k = min(num_nodes, n_greedy)
+    load = np.zeros(world, dtype=np.int64)
+    count = np.zeros(world, dtype=np.int64)
+    for v in order[:k]:                                        # LPT over the heavy head
+        free = count < n_loc
+        r = int(np.argmin(np.where(free, load, np.iinfo(np.int64).max)))
+        owner[v] = r
+        load[r] += w[v]
+        count[r] += 1
+    rest = order[k:]
+    cap = n_loc - count
+    m = int(cap.min())
+    j = np.arange(m * world, dtype=np.int64)
+    rnd, pos = j // world, j % world
+    owner[rest[:m * world]] = np.where(rnd % 2 == 0, pos, world - 1 - pos)    # snake: 0..W-1, W-1..0, ...
+    owner[rest[m * world:]] = np.repeat(np.arange(world, dtype=np.int64), cap - m)   # the lightest nodes fill the gaps
+    slot = np.empty(num_nodes, dtype=np.int64)
+    by_rank = np.argsort(owner[order], kind='stable')          # per rank, nodes in decreasing weight
+    slot[order[by_rank]] = np.arange(num_nodes, dtype=np.int64) - np.repeat(np.arange(world, dtype=np.int64) * n_loc, n_loc)
+    return {'owner': owner, 'slot': slot, 'hubs': hubs, 'n_loc': n_loc}
+
+
+def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_fraction=0.5, max_hubs=64):
+    """Edge-balanced partition with split hub rows (module docstring), pure host integer logic (numpy).
+
+    Returns dict(n_loc, n_hub, block = n_loc + n_hub, owned_nodes [n_loc] (global ids in local-row order), hubs [n_hub],
+    hub_owner [n_hub], hub_row [n_hub] (local row of the hub at its owner), owned_eids (ascending, in half first),
+    n_edges_in, src (ids in the renumbered space = rows of the all-gathered x), dst (local rows, virtual rows are
+    n_loc + h), type, deg [2, world * block] (global per-half degrees in the renumbered space), newid [N])."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    et = np.asarray(edge_type, dtype=np.int64)
+    n2 = ei.shape[1]
+    if n2 % 2 != 0:
+        raise ValueError('edge list must hold an in half and an out half of equal size')
+    E = n2 // 2
+    a = balanced_assignment(ei, num_nodes, world, hub_fraction, max_hubs)
+    owner, slot, hubs, n_loc = a['owner'], a['slot'], a['hubs'], a['n_loc']
+    n_hub = int(hubs.shape[0])
+    block = n_loc + n_hub
+    newid = owner * block + slot
+    dst = ei[1]
+    edge_rank = owner[dst]
+    dst_new = newid[dst]
+    for h, v in enumerate(hubs):                               # deal the hub's incoming edges round-robin, in edge order
+        e = np.nonzero(dst == v)[0]
+        r = np.arange(e.shape[0], dtype=np.int64) % world
+        edge_rank[e] = r
+        dst_new[e] = r * block + n_loc + h
+    owned = np.nonzero(edge_rank == rank)[0]
+    n_in = int(np.searchsorted(owned, E))
+    deg = _half_degrees(ei, E, num_nodes)
+    deg_ext = np.zeros((2, world * block), dtype=np.int32)
+    deg_ext[:, newid] = deg
+    for h, v in enumerate(hubs):
+        deg_ext[:, np.arange(world) * block + n_loc + h] = deg[:, v][:, None]
+    mine = np.nonzero(owner == rank)[0]
+    owned_nodes = mine[np.argsort(slot[mine], kind='stable')]
+    return {'n_loc': n_loc, 'n_hub': n_hub, 'block': block, 'owned_nodes': owned_nodes, 'hubs': hubs,
+            'hub_owner': owner[hubs], 'hub_row': slot[hubs], 'owned_eids': owned, 'n_edges_in': n_in,
+            'src': newid[ei[0, owned]], 'dst': dst_new[owned] - rank * block, 'type': et[owned], 'deg': deg_ext,
+            'newid': newid}
 
 
 class GraphPartition(object):
-    """This rank's share of the graph + its GraphPlan (built by K1 with the global degrees)."""
+    """This rank's share of the graph + its GraphPlan (built by K1 with the global degrees).
 
-    def __init__(self, edge_index, edge_type, num_nodes, num_types, world, rank, device, group=None):
-        info = partition_edges(edge_index.cpu().numpy() if torch.is_tensor(edge_index) else edge_index,
-                               edge_type.cpu().numpy() if torch.is_tensor(edge_type) else edge_type, num_nodes, world, rank)
+    ``owned_nodes`` [n_loc]: global ids of this rank's node rows in local-row order (shard x / masks / upstream gradients
+    with it); ``owned_eids``: global ids of the edges it owns (shard edge_embeddings with it)."""
+
+    def __init__(self, edge_index, edge_type, num_nodes, num_types, world, rank, device, group=None, balance='edges',
+                 hub_fraction=0.5):
+        ei = edge_index.cpu().numpy() if torch.is_tensor(edge_index) else edge_index
+        et = edge_type.cpu().numpy() if torch.is_tensor(edge_type) else edge_type
         self.world, self.rank, self.group, self.num_nodes = int(world), int(rank), group, int(num_nodes)
-        self.lo, self.hi = info['lo'], info['hi']
+        self.balance = balance
+        if balance == 'range':
+            info = partition_edges(ei, et, num_nodes, world, rank)
+            self.lo, self.hi = info['lo'], info['hi']
+            self.n_loc, self.n_hub, self.block = self.hi - self.lo, 0, self.hi - self.lo
+            self.owned_nodes = torch.arange(self.lo, self.hi, dtype=torch.int64, device=device)
+            ext_nodes, offset = num_nodes, self.lo
+            self.hub_idx_mine = self.hub_rows_mine = None
+        elif balance == 'edges':
+            info = partition_edges_balanced(ei, et, num_nodes, world, rank, hub_fraction=hub_fraction)
+            self.lo = self.hi = None
+            self.n_loc, self.n_hub, self.block = info['n_loc'], info['n_hub'], info['block']
+            self.owned_nodes = torch.from_numpy(info['owned_nodes']).to(device)
+            ext_nodes, offset = world * self.block, rank * self.block
+            mine = np.nonzero(info['hub_owner'] == rank)[0]
+            self.hub_idx_mine = torch.from_numpy(mine.astype(np.int64)).to(device)           # which hubs this rank owns
+            self.hub_rows_mine = torch.from_numpy(info['hub_row'][mine].astype(np.int64)).to(device)   # their local rows
+            self.hubs = info['hubs']
+        else:
+            raise ValueError("balance must be 'edges' or 'range'")
         self.owned_eids = torch.from_numpy(info['owned_eids']).to(device)
         self.n_edges_in = info['n_edges_in']
         self.edge_index = torch.from_numpy(np.stack([info['src'], info['dst']])).to(device)
         self.edge_type = torch.from_numpy(info['type']).to(device)
-        self.plan = GraphPlan(self.edge_index, self.edge_type, num_nodes, num_types, n_edges_in=self.n_edges_in,
-                              n_dst_rows=self.hi - self.lo, dst_offset=self.lo, deg=torch.from_numpy(info['deg']).to(device))
+        self.plan = GraphPlan(self.edge_index, self.edge_type, ext_nodes, num_types, n_edges_in=self.n_edges_in,
+                              n_dst_rows=self.block, dst_offset=offset, deg=torch.from_numpy(info['deg']).to(device))

@@ -48,33 +48,43 @@ def main():
     ent, rel = ref(x, ei, et, None, ee, rl)
     torch.autograd.backward([ent, rel], [g_ent.to(dev), g_rel.to(dev)])
 
-    # ---- partitioned layer
-    part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev)
-    lo, hi = part.lo, part.hi
-    conv = make_conv()
-    conv.set_dropout_masks(m_in[lo:hi], m_out[lo:hi])
-    xl = p['x'][lo:hi].to(dev).requires_grad_(True)
-    eel = p['edge_embs'].to(dev)[part.owned_eids].clone().requires_grad_(True)
-    rll = p['rels'].to(dev).requires_grad_(True)
-    ent_l, rel_l = conv.forward_partitioned(xl, part, eel, rll)
-    torch.autograd.backward([ent_l, rel_l], [g_ent[lo:hi].to(dev), g_rel.to(dev)])
-
+    # ---- partitioned layer: the edge-balanced partition with split hub rows, then the plain range partition
     def check(a, b, name, tol=2e-5):
         scale = float(b.abs().max()) + 1e-30
         err = float((a - b).abs().max()) / scale
         assert err < tol, '{} rank {}: {:.3e}'.format(name, rank, err)
         return err
-    errs = {
-        'all_ent': check(ent_l, ent[lo:hi], 'all_ent'), 'all_rel': check(rel_l, rel, 'all_rel'),
-        'd_x': check(xl.grad, x.grad[lo:hi], 'd_x'), 'd_ee': check(eel.grad, ee.grad[part.owned_eids], 'd_ee'),
-        'd_rel': check(rll.grad, rl.grad, 'd_rel'),
-        'running_mean': check(conv.ent_bn.running_mean, ref.ent_bn.running_mean, 'running_mean'),
-        'running_var': check(conv.ent_bn.running_var, ref.ent_bn.running_var, 'running_var'),
-    }
-    for name in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge'):
-        errs['d_' + name] = check(getattr(conv, name).grad, getattr(ref, name).grad, 'd_' + name)
-    errs['d_gamma'] = check(conv.ent_bn.weight.grad, ref.ent_bn.weight.grad, 'd_gamma')
-    errs['d_beta'] = check(conv.ent_bn.bias.grad, ref.ent_bn.bias.grad, 'd_beta', tol=1e-3)   # ~0 in train mode: noise
+    errs = {}
+    for balance, frac in (('edges', 0.1), ('edges', 0.5), ('range', 0.5)):
+        part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev, balance=balance,
+                                hub_fraction=frac)
+        if frac == 0.1:
+            assert part.n_hub >= 1                                 # the Zipf generator's hub must have been split
+        own = part.owned_nodes
+        conv = make_conv()
+        conv.set_dropout_masks(m_in.to(dev)[own], m_out.to(dev)[own])
+        xl = p['x'].to(dev)[own].clone().requires_grad_(True)
+        eel = p['edge_embs'].to(dev)[part.owned_eids].clone().requires_grad_(True)
+        rll = p['rels'].to(dev).requires_grad_(True)
+        ent_l, rel_l = conv.forward_partitioned(xl, part, eel, rll)
+        torch.autograd.backward([ent_l, rel_l], [g_ent.to(dev)[own], g_rel.to(dev)])
+        e = {
+            'all_ent': check(ent_l, ent[own], 'all_ent'), 'all_rel': check(rel_l, rel, 'all_rel'),
+            'd_x': check(xl.grad, x.grad[own], 'd_x'), 'd_ee': check(eel.grad, ee.grad[part.owned_eids], 'd_ee'),
+            'd_rel': check(rll.grad, rl.grad, 'd_rel'),
+            'running_mean': check(conv.ent_bn.running_mean, ref.ent_bn.running_mean, 'running_mean'),
+            'running_var': check(conv.ent_bn.running_var, ref.ent_bn.running_var, 'running_var'),
+        }
+        for name in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge'):
+            e['d_' + name] = check(getattr(conv, name).grad, getattr(ref, name).grad, 'd_' + name)
+        e['d_gamma'] = check(conv.ent_bn.weight.grad, ref.ent_bn.weight.grad, 'd_gamma')
+        e['d_beta'] = check(conv.ent_bn.bias.grad, ref.ent_bn.bias.grad, 'd_beta', tol=1e-3)   # ~0 in train mode: noise
+        n_own = torch.tensor([float(part.owned_eids.numel())], device=dev)
+        dist.all_reduce(n_own, op=dist.ReduceOp.MAX)
+        e['max_edge_share'] = float(n_own) / (2 * E)
+        errs['{}/{}'.format(balance, frac)] = e
+        if balance == 'edges':
+            assert e['max_edge_share'] <= 1.15 / world             # balanced: no rank owns much more than its share
 
     # ---- entity-sharded filtered rank
     B, NE, d = 300, 4096 * world, 200
@@ -93,7 +103,7 @@ def main():
     assert torch.equal(sh['thr'], whole['thr'])
     dist.barrier()
     if rank == 0:
-        print('DIST_OK', {kk: float('{:.2e}'.format(v)) for kk, v in errs.items()})
+        print('DIST_OK', {b: {kk: float('{:.2e}'.format(v)) for kk, v in e.items()} for b, e in errs.items()})
     dist.destroy_process_group()
 
 

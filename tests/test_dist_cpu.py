@@ -73,6 +73,50 @@ def _worker(rank, world, port, ret):
         full = np.zeros((N, D))
         np.add.at(full, ei[0], norm[:, None] * gsel[ei[1]] * rel[et] * ee)
         np.testing.assert_allclose(mine, full[lo:hi], rtol=1e-10, atol=1e-12)
+        # ---- edge-balanced partition with split hub rows (partition.py): renumbered ids, virtual rows, hub exchange
+        from kgc_gcn_b200.partition import partition_edges_balanced
+        b = partition_edges_balanced(ei, et, N, world, rank, hub_fraction=0.05)
+        n_loc, n_hub, blk = b['n_loc'], b['n_hub'], b['block']
+        assert n_hub >= 1 and n_loc == N // world and (b['dst'] < blk).all() and (b['src'] < world * blk).all()
+        own_e, own_n = b['owned_eids'], b['owned_nodes']
+        counts = torch.zeros(2 * E, dtype=torch.int64)
+        counts[torch.from_numpy(own_e)] = 1
+        dist.all_reduce(counts)
+        assert int(counts.min()) == 1 and int(counts.max()) == 1          # every edge owned exactly once
+        ncount = torch.zeros(N, dtype=torch.int64)
+        ncount[torch.from_numpy(own_n)] = 1
+        dist.all_reduce(ncount)
+        assert int(ncount.min()) == 1 and int(ncount.max()) == 1          # every node owned exactly once
+        most = torch.tensor([own_e.shape[0]])
+        dist.all_reduce(most, op=dist.ReduceOp.MAX)
+        assert int(most) <= 1.15 * 2 * E / world                          # edge-balanced
+        np.testing.assert_array_equal(b['deg'][:, b['newid']], info['deg'])        # degrees follow the renumbering
+        mine = np.nonzero(b['hub_owner'] == rank)[0]
+        collb = _Collectives(None, world, N, n_hub, torch.from_numpy(mine), torch.from_numpy(b['hub_row'][mine]))
+        xb = np.concatenate([x[own_n], np.zeros((n_hub, D))])             # block of n_loc real + n_hub virtual rows
+        xb_full = collb.all_gather_rows(torch.from_numpy(xb)).numpy()
+        np.testing.assert_array_equal(xb_full[b['newid']], x)             # renumbered ids = rows of the gathered table
+        n_in = b['n_edges_in']
+        planes = np.zeros((2, blk, D))
+        for h, sl in ((0, slice(0, n_in)), (1, slice(n_in, None))):
+            eids = own_e[sl]
+            planes[h] = _agg_numpy(xb_full, rel, ee[eids], b['src'][sl], b['dst'][sl], b['type'][sl], norm[eids], blk)
+        planes_t = torch.from_numpy(planes)
+        collb.sum_hub_rows(planes_t, n_loc)
+        for h in (0, 1):
+            half = slice(0, E) if h == 0 else slice(E, 2 * E)
+            glob = _agg_numpy(x, rel, ee[half], ei[0, half], ei[1, half], et[half], norm[half], N)
+            np.testing.assert_allclose(planes_t[h, :n_loc].numpy(), glob[own_n], rtol=1e-10, atol=1e-11)
+        # backward: upstream rows of the hubs reach every rank's virtual rows; d_x returns through the reduce-scatter
+        g_loc = np.zeros((1, blk, D))
+        g_loc[0, :n_loc] = gsel[own_n]
+        g_t = torch.from_numpy(g_loc)
+        collb.spread_hub_rows(g_t, 1, n_loc)
+        np.testing.assert_array_equal(g_t[0, n_loc:].numpy(), gsel[b['hubs']])
+        partb = np.zeros((world * blk, D))
+        np.add.at(partb, b['src'], norm[own_e][:, None] * g_t[0].numpy()[b['dst']] * rel[b['type']] * ee[own_e])
+        mine_dx = collb.reduce_scatter_rows(torch.from_numpy(partb)).numpy()
+        np.testing.assert_allclose(mine_dx[:n_loc], full[own_n], rtol=1e-10, atol=1e-12)
         # ---- entity-sharded filtered rank: integer counts all-reduce to the unsharded answer, target logits sum exactly
         B, NE = 16, 64
         scores = rng.integers(-5, 6, (B, NE)).astype(np.float64)
