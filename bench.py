@@ -253,7 +253,8 @@ def run_ours(args, rank, world, local_rank):
         ee = p['edge_embs'].to(dev).requires_grad_(True)
         g_ent = g_ent_all.to(dev)
     else:
-        part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev)
+        part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev,
+                                p2p=False if os.environ.get('KGC_P2P', '1') == '0' else 'auto')      # KGC_P2P=0: NCCL halo exchange (A/B)
         own = part.owned_nodes.cpu()                     # edge-balanced partition: this rank's node rows (local-row order)
         x = p['x'][own].to(dev).requires_grad_(True)
         ee = p['edge_embs'][part.owned_eids.cpu()].to(dev).requires_grad_(True)
@@ -360,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         'config': {'workload': args.workload + '_shape' + ('' if world == 1 else ' x{} (one shape-sized partition per GPU)'.format(world)), 'N': N, 'R': R, 'E': E, 'directed_edges': 2 * E, 'd_in': D_IN,
                    'd_out': D_OUT, 'dropout': 'p=0.1 keep masks drawn inside the timed region (training mode)',
                    'l2': 'flushed between steps (256 MiB memset + 256 MiB read, outside the timed events)', 'launch': launch_mode,
-                   'parallelism': 'single GPU' if world == 1 else 'edge-balanced dst partition over {} GPUs (split hub rows): all-gather x / reduce-scatter d_x / all-reduce hub rows, BN sums + replicated grads (NCCL)'.format(world)},
+                   'parallelism': 'single GPU' if world == 1 else 'edge-balanced dst partition over {} GPUs ({} split hub rows); halo exchange of x / d_x: {}; all-reduce of hub rows, BN sums, replicated grads: NCCL'.format(world, part.n_hub, 'pulls over NVLink peer memory (K10)' if part.p2p(D_IN) is not None else 'NCCL all-gather / reduce-scatter')},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
                 'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1), 'eager_ms_per_step': e2e.get('eager_ms_per_step'),
                 'scope': e2e['scope']},

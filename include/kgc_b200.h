@@ -299,6 +299,29 @@ int32_t kgc_opt_chunk_elems(void);
 int kgc_clip_adam_step(const kgc_opt_tensor_t* tensors, const int32_t* items, int64_t n_items, const float* hyper,
                        double* state, double* partials, void* stream);
 
+/* ---- K10: halo exchange of the dst-partitioned layer over NVLink peer memory -----------------
+ * Replaces the library all-gather of x / reduce-scatter of d_x of the partitioned layer: every rank keeps the gathered
+ * node table and its partial d_x in SYMMETRIC buffers (same size on every rank, peer-mapped); *_ptrs_dev = device array
+ * of `world` pointers to the ranks' buffers.
+ *   kgc_p2p_barrier      flag barrier: flag_ptrs_dev[r] = rank r's uint32[world] flag array (zero-initialised);
+ *                        *epoch (local, zero-initialised) counts barriers; *error is set to 1 on a ~2 s timeout.
+ *   kgc_p2p_halo_gather  pulls the rows `rows[n_rows]` (row ids of the gathered table [world * block_rows, D]; row g is
+ *                        owned by rank g / block_rows) from their owners' tables into this rank's table.
+ *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r whose bit is set in mask[v], in ascending r, of
+ *                        part_r[row0 + v]   (v < n_rows: this rank's rows; deterministic).
+ *   kgc_p2p_allreduce    one-shot sum of a small vector (n_bytes, a multiple of 16; fp32 or fp64) over the ranks: copy
+ *                        into this rank's staging slot (stage_ptrs_dev[r] + offset_bytes), flag barrier, every rank adds
+ *                        all slots in rank order (identical bits everywhere).  in == out is allowed.  One CTA: meant for
+ *                        the BatchNorm sums, the split hub rows and the replicated-parameter gradients (<= ~1 MB). */
+int kgc_p2p_allreduce(void* const* stage_ptrs_dev, int64_t offset_bytes, void* const* flag_ptrs_dev, int32_t rank,
+                      int32_t world, uint32_t* epoch, int32_t* error, const void* in, void* out, int64_t n_bytes,
+                      int32_t is_double, void* stream);
+int kgc_p2p_barrier(void* const* flag_ptrs_dev, int32_t rank, int32_t world, uint32_t* epoch, int32_t* error, void* stream);
+int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, int64_t n_rows, int64_t block_rows,
+                        int32_t D, void* stream);
+int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const uint64_t* mask, int64_t row0, int64_t n_rows,
+                        const float* addend, float* out, int32_t D, void* stream);
+
 /* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------
  * Replaces model.py:177-179 (x = mm(x, all_ent^T); x += bias; sigmoid) where the caller needs the dense matrix
  * (BCE against the multi-hot label, main.py:63-66).  Forward: the K4b tensor-core kernel (3xTF32, fp32-grade) with

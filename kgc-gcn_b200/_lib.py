@@ -62,6 +62,10 @@ SIGNATURES = {
     'kgc_conv1ch_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     'kgc_opt_chunk_elems': (_i32, []),
     'kgc_clip_adam_step': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'kgc_p2p_allreduce': (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    'kgc_p2p_barrier': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp]),
+    'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _vp]),
     'kgc_score_1n_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
     'kgc_score_1n_bwd_logit': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

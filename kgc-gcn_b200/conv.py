@@ -191,11 +191,19 @@ def gemm_tn(a, b, out, plan=None, tensor_cores=True):
     return out
 
 
+class _Done(object):
+    """Stand-in for an async work handle whose work is already ordered on the current stream."""
+
+    def wait(self):
+        return None
+
+
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
-    def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None):
+    def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None, p2p=None):
         self.group, self.world, self.n_global = group, int(world), int(n_global)
+        self.p2p = p2p          # partition._P2PContext: halo exchange over NVLink peer memory (K10) instead of NCCL
         # split hub rows of an edge-balanced partition (partition.py): every rank accumulates a share of a hub's incoming
         # edges into a private virtual row (local rows n_loc .. n_loc + n_hub); hub_idx_mine / hub_rows_mine = the hubs this
         # rank owns and their real local rows
@@ -206,7 +214,7 @@ class _Collectives(object):
         if self.n_hub == 0:
             return
         buf = planes[:, n_loc:, :].contiguous()
-        self.all_reduce(buf)
+        self.all_reduce(buf, 'hub_f')
         if self.hub_idx_mine.numel():
             planes[:, self.hub_rows_mine, :] = buf[:, self.hub_idx_mine, :]
 
@@ -217,7 +225,7 @@ class _Collectives(object):
         buf = torch.zeros((n_planes, self.n_hub, planes.shape[2]), dtype=planes.dtype, device=planes.device)
         if self.hub_idx_mine.numel():
             buf[:, self.hub_idx_mine, :] = planes[:n_planes, self.hub_rows_mine, :]
-        self.all_reduce(buf)                                   # every entry is non-zero on one rank: exact
+        self.all_reduce(buf, 'hub_b')                          # every entry is non-zero on one rank: exact
         planes[:n_planes, n_loc:, :] = buf
 
     def all_gather_rows(self, x_local, async_op=False):
@@ -239,7 +247,11 @@ class _Collectives(object):
         work = dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group, async_op=async_op)
         return (out, work) if async_op else out
 
-    def all_reduce(self, t):
+    def all_reduce(self, t, tag=None):
+        """Sum over the ranks, in place.  With the peer-memory context and a call-site ``tag``: the one-shot K10 kernel
+        (stage + flag barrier + add in rank order, ~1 launch instead of an NCCL ring); otherwise NCCL / gloo."""
+        if self.p2p is not None and tag is not None and self.p2p.all_reduce(t, tag):
+            return t
         import torch.distributed as dist
         dist.all_reduce(t, group=self.group)
         return t
@@ -289,6 +301,9 @@ class _ConvFn(torch.autograd.Function):
         gather = None
         if coll is None:
             x_full = x
+        elif coll.p2p is not None:
+            # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads)
+            x_full, gather = coll.p2p.gather(x), _Done()
         else:
             x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)     # blocks of Nb rows: ids = rows
             x_full, gather = coll.all_gather_rows(x_blk, async_op=True)
@@ -333,7 +348,7 @@ class _ConvFn(torch.autograd.Function):
         else:
             if training:
                 _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
-                coll.all_reduce(sums)                                # BatchNorm statistics over ALL node rows
+                coll.all_reduce(sums, 'bn_f')                        # BatchNorm statistics over ALL node rows
             _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
                       p(running_var), p(stats), st())
         _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), st())
@@ -375,7 +390,7 @@ class _ConvFn(torch.autograd.Function):
             _lib.call('kgc_colsum_finalize2', p(partials), nb, Dout, p(sums), p(sums32), st())
         else:
             _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
-            coll.all_reduce(sums)
+            coll.all_reduce(sums, 'bn_b')
             sums32 = sums.float()
         _lib.call('kgc_tail_bwd_apply', p(g_ent), p(all_ent), p(pre), p(stats), p(gamma), p(sums), p(mask_in),
                   p(mask_out), p(seed), ctx.drop_p, ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
@@ -397,7 +412,8 @@ class _ConvFn(torch.autograd.Function):
         if n_hub:
             coll.spread_hub_rows(g3, 2, Nl)                          # the virtual rows see their hub's upstream gradient
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
-        d_x_full = torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
+        p2p = None if coll is None else coll.p2p
+        d_x_full = p2p.partial if p2p is not None else torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
         d_ee = torch.empty_like(ee)
         loop_addend = g3[2] if coll is None else None
 
@@ -407,7 +423,7 @@ class _ConvFn(torch.autograd.Function):
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
         scatter = None
-        if coll is not None:       # source-row gradients go back to their owners while the d_rel pass runs here
+        if coll is not None and p2p is None:   # source-row gradients go back to their owners while the d_rel pass runs here
             d_x, scatter = coll.reduce_scatter_rows(d_x_full, async_op=True)
 
         def level0_rel(sp, out_final, carry):
@@ -417,8 +433,13 @@ class _ConvFn(torch.autograd.Function):
 
         if coll is None:
             d_x = d_x_full
+        elif p2p is not None:
+            coll.all_reduce(flat, 'flat')
+            # K10: barrier, then every owner pulls the partial rows of the ranks that touched its rows (rank order,
+            # deterministic) and adds the self-loop term - reduce-scatter + add in one kernel over peer memory
+            d_x = p2p.reduce(g3[2, :Nl], Nl)
         else:
-            coll.all_reduce(flat)
+            coll.all_reduce(flat, 'flat')
             if scatter is not None:
                 scatter.wait()
             d_x = d_x[:Nl] + g3[2, :Nl]                               # self-loop term of this rank's (real) rows
@@ -545,7 +566,8 @@ class MGCNConv(nn.Module):
         self._last_seed = seed
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
-        coll = _Collectives(part.group, part.world, part.num_nodes, part.n_hub, part.hub_idx_mine, part.hub_rows_mine)
+        coll = _Collectives(part.group, part.world, part.num_nodes, part.n_hub, part.hub_idx_mine, part.hub_rows_mine,
+                            part.p2p(x_local.shape[1]) if hasattr(part, 'p2p') else None)
         all_ent, all_rel, stats = _ConvFn.apply(
             x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,

@@ -103,7 +103,9 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
     Returns dict(n_loc, n_hub, block = n_loc + n_hub, owned_nodes [n_loc] (global ids in local-row order), hubs [n_hub],
     hub_owner [n_hub], hub_row [n_hub] (local row of the hub at its owner), owned_eids (ascending, in half first),
     n_edges_in, src (ids in the renumbered space = rows of the all-gathered x), dst (local rows, virtual rows are
-    n_loc + h), type, deg [2, world * block] (global per-half degrees in the renumbered space), newid [N])."""
+    n_loc + h), type, deg [2, world * block] (global per-half degrees in the renumbered space), newid [N],
+    halo_rows (sorted renumbered ids of the REMOTE rows this rank's edges read), touch_mask [n_loc] uint64 (bit r: rank r
+    owns an edge whose source is this row))."""
     ei = np.asarray(edge_index, dtype=np.int64)
     et = np.asarray(edge_type, dtype=np.int64)
     n2 = ei.shape[1]
@@ -132,10 +134,19 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
         deg_ext[:, np.arange(world) * block + n_loc + h] = deg[:, v][:, None]
     mine = np.nonzero(owner == rank)[0]
     owned_nodes = mine[np.argsort(slot[mine], kind='stable')]
+    # halo bookkeeping of the peer-memory exchange (K10): the remote rows this rank's records reference, and for each of
+    # its own rows the set of ranks whose edges reference it (bit r = rank r leaves a partial gradient for the row)
+    src_new = newid[ei[0]]
+    touch = np.zeros(world * block, dtype=np.uint64)
+    for r in range(world):
+        touch[np.unique(src_new[edge_rank == r])] |= np.uint64(1 << r)
+    used = np.nonzero((touch >> np.uint64(rank)) & np.uint64(1))[0]
+    halo_rows = used[(used < rank * block) | (used >= (rank + 1) * block)].astype(np.int32)
+    touch_mine = touch[rank * block:rank * block + n_loc].copy()
     return {'n_loc': n_loc, 'n_hub': n_hub, 'block': block, 'owned_nodes': owned_nodes, 'hubs': hubs,
             'hub_owner': owner[hubs], 'hub_row': slot[hubs], 'owned_eids': owned, 'n_edges_in': n_in,
             'src': newid[ei[0, owned]], 'dst': dst_new[owned] - rank * block, 'type': et[owned], 'deg': deg_ext,
-            'newid': newid}
+            'newid': newid, 'halo_rows': halo_rows, 'touch_mask': touch_mine}
 
 
 class GraphPartition(object):
@@ -145,11 +156,13 @@ class GraphPartition(object):
     with it); ``owned_eids``: global ids of the edges it owns (shard edge_embeddings with it)."""
 
     def __init__(self, edge_index, edge_type, num_nodes, num_types, world, rank, device, group=None, balance='edges',
-                 hub_fraction=0.5):
+                 hub_fraction=0.5, p2p='auto'):
         ei = edge_index.cpu().numpy() if torch.is_tensor(edge_index) else edge_index
         et = edge_type.cpu().numpy() if torch.is_tensor(edge_type) else edge_type
         self.world, self.rank, self.group, self.num_nodes = int(world), int(rank), group, int(num_nodes)
         self.balance = balance
+        self.device = torch.device(device)
+        self._p2p_mode, self._p2p = p2p, {}
         if balance == 'range':
             info = partition_edges(ei, et, num_nodes, world, rank)
             self.lo, self.hi = info['lo'], info['hi']
@@ -167,6 +180,8 @@ class GraphPartition(object):
             self.hub_idx_mine = torch.from_numpy(mine.astype(np.int64)).to(device)           # which hubs this rank owns
             self.hub_rows_mine = torch.from_numpy(info['hub_row'][mine].astype(np.int64)).to(device)   # their local rows
             self.hubs = info['hubs']
+            self.halo_rows = torch.from_numpy(info['halo_rows']).to(device)
+            self.touch_mask = torch.from_numpy(info['touch_mask'].view(np.int64)).to(device)
         else:
             raise ValueError("balance must be 'edges' or 'range'")
         self.owned_eids = torch.from_numpy(info['owned_eids']).to(device)
@@ -175,3 +190,112 @@ class GraphPartition(object):
         self.edge_type = torch.from_numpy(info['type']).to(device)
         self.plan = GraphPlan(self.edge_index, self.edge_type, ext_nodes, num_types, n_edges_in=self.n_edges_in,
                               n_dst_rows=self.block, dst_offset=offset, deg=torch.from_numpy(info['deg']).to(device))
+
+    # ------------------------------------------------------------------ peer-memory halo exchange (K10)
+    def p2p(self, D):
+        """Symmetric buffers + peer pointer tables of the halo exchange for feature width ``D`` (allocated and rendezvoused
+        at first use - a collective call), or None when the exchange runs on NCCL: range partitions, CPU / gloo groups,
+        ``p2p=False``, or a torch build / topology without symmetric memory (``p2p='auto'`` falls back silently,
+        ``p2p=True`` raises)."""
+        if D in self._p2p:
+            return self._p2p[D]
+        ctx = None
+        if self._p2p_mode and self.balance == 'edges' and self.world > 1 and self.world <= 8 and self.device.type == 'cuda':
+            try:
+                ctx = _P2PContext(self, D)
+            except Exception:                                   # pragma: no cover (depends on the box)
+                if self._p2p_mode is True:
+                    raise
+                ctx = None
+            ok = torch.tensor([1 if ctx is not None else 0], device=self.device)
+            import torch.distributed as dist
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+            if int(ok) == 0:
+                ctx = None
+        self._p2p[D] = ctx
+        return ctx
+
+
+class _P2PContext(object):
+    """Symmetric memory of one partition and feature width: the gathered node table, the partial d_x table, the staging
+    slots of the small all-reduces and the barrier flags, with the device arrays of peer pointers the K10 kernels take."""
+
+    STAGE_BYTES = 4 << 20
+
+    def __init__(self, part, D):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = part.group if part.group is not None else dist.group.WORLD
+        dev, W, B = part.device, part.world, part.block
+        self.rank, self.world, self.block, self.D = part.rank, W, B, D
+        self.table = symm.empty((W * B, D), dtype=torch.float32, device=dev)       # gathered x (own block + pulled halo rows)
+        self.partial = symm.empty((W * B, D), dtype=torch.float32, device=dev)     # this rank's partial d_x
+        self.flags = symm.empty((64,), dtype=torch.int32, device=dev)
+        self.stage = symm.empty((self.STAGE_BYTES,), dtype=torch.uint8, device=dev)  # slots of the one-shot all-reduces
+        self.table.zero_(); self.partial.zero_(); self.flags.zero_(); self.stage.zero_()
+        self._h_table = symm.rendezvous(self.table, group)
+        self._h_partial = symm.rendezvous(self.partial, group)
+        self._h_flags = symm.rendezvous(self.flags, group)
+        self._h_stage = symm.rendezvous(self.stage, group)
+        self.table_ptrs, self.partial_ptrs, self.flag_ptrs, self.stage_ptrs = (
+            int(h.buffer_ptrs_dev) for h in (self._h_table, self._h_partial, self._h_flags, self._h_stage))
+        self._slots, self._stage_used = {}, 0
+        self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.error = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.halo_rows, self.touch_mask = part.halo_rows, part.touch_mask
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                               # every rank's buffers are zeroed before anyone pulls
+
+    def barrier(self):
+        import ctypes
+        from . import _lib
+        _lib.call('kgc_p2p_barrier', ctypes.c_void_p(self.flag_ptrs), self.rank, self.world, _lib.ptr(self.epoch),
+                  _lib.ptr(self.error), _lib.stream())
+
+    def gather(self, x_local):
+        """x rows of this rank -> its block of the table; barrier; pull the remote rows this rank's edges read."""
+        import ctypes
+        from . import _lib
+        n = x_local.shape[0]
+        self.table[self.rank * self.block:self.rank * self.block + n].copy_(x_local)
+        self.barrier()
+        _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.table_ptrs), self.rank, _lib.ptr(self.halo_rows),
+                  self.halo_rows.numel(), self.block, self.D, _lib.stream())
+        return self.table
+
+    def reduce(self, addend, n_rows):
+        """barrier; d_x of this rank's rows = addend + the partials of the ranks that touched them, in rank order."""
+        import ctypes
+        from . import _lib
+        out = torch.empty((n_rows, self.D), dtype=torch.float32, device=self.table.device)
+        self.barrier()
+        _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.touch_mask),
+                  self.rank * self.block, n_rows, _lib.ptr(addend), _lib.ptr(out), self.D, _lib.stream())
+        return out
+
+    def all_reduce(self, t, tag):
+        """In-place sum of a small contiguous fp32 / fp64 tensor over the ranks (one kernel: stage, flag barrier, add in rank
+        order).  ``tag`` names the call site: every site owns a staging slot, so a slot is rewritten only a full step later.
+        Returns False (caller falls back to NCCL) when the tensor does not fit the kernel's constraints."""
+        import ctypes
+        from . import _lib
+        nbytes = t.numel() * t.element_size()
+        if t.dtype not in (torch.float32, torch.float64) or not t.is_contiguous() or nbytes % 16 or t.data_ptr() % 16 \
+                or nbytes == 0 or nbytes > (1 << 20):
+            return False
+        key = (tag, nbytes, t.dtype)
+        off = self._slots.get(key)
+        if off is None:
+            off = self._stage_used
+            if off + nbytes > self.STAGE_BYTES:
+                return False
+            self._slots[key] = off
+            self._stage_used = (off + nbytes + 255) // 256 * 256
+        _lib.call('kgc_p2p_allreduce', ctypes.c_void_p(self.stage_ptrs), off, ctypes.c_void_p(self.flag_ptrs), self.rank,
+                  self.world, _lib.ptr(self.epoch), _lib.ptr(self.error), _lib.ptr(t), _lib.ptr(t), nbytes,
+                  1 if t.dtype == torch.float64 else 0, _lib.stream())
+        return True
+
+    def check(self):
+        if int(self.error) != 0:
+            raise RuntimeError('kgc_p2p_barrier timed out: a peer rank did not arrive')

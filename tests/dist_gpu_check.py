@@ -55,9 +55,9 @@ def main():
         assert err < tol, '{} rank {}: {:.3e}'.format(name, rank, err)
         return err
     errs = {}
-    for balance, frac in (('edges', 0.1), ('edges', 0.5), ('range', 0.5)):
+    for balance, frac, p2p in (('edges', 0.1, 'auto'), ('edges', 0.5, 'auto'), ('edges', 0.1, False), ('range', 0.5, False)):
         part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev, balance=balance,
-                                hub_fraction=frac)
+                                hub_fraction=frac, p2p=p2p)
         if frac == 0.1:
             assert part.n_hub >= 1                                 # the Zipf generator's hub must have been split
         own = part.owned_nodes
@@ -82,7 +82,11 @@ def main():
         n_own = torch.tensor([float(part.owned_eids.numel())], device=dev)
         dist.all_reduce(n_own, op=dist.ReduceOp.MAX)
         e['max_edge_share'] = float(n_own) / (2 * E)
-        errs['{}/{}'.format(balance, frac)] = e
+        ctx = part.p2p(D)
+        if ctx is not None:
+            ctx.check()                                            # no barrier timed out
+        e['p2p'] = 1.0 if ctx is not None else 0.0
+        errs['{}/{}/{}'.format(balance, frac, p2p)] = e
         if balance == 'edges':
             assert e['max_edge_share'] <= 1.15 / world             # balanced: no rank owns much more than its share
 
