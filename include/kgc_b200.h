@@ -305,10 +305,11 @@ int kgc_clip_adam_step(const kgc_opt_tensor_t* tensors, const int32_t* items, in
  * of `world` pointers to the ranks' buffers.
  *   kgc_p2p_barrier      flag barrier: flag_ptrs_dev[r] = rank r's uint32[world] flag array (zero-initialised);
  *                        *epoch (local, zero-initialised) counts barriers; *error is set to 1 on a ~2 s timeout.
- *   kgc_p2p_halo_gather  pulls the rows `rows[n_rows]` (row ids of the gathered table [world * block_rows, D]; row g is
- *                        owned by rank g / block_rows) from their owners' tables into this rank's table.
- *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r whose bit is set in mask[v], in ascending r, of
- *                        part_r[row0 + v]   (v < n_rows: this rank's rows; deterministic).
+ *   kgc_p2p_halo_gather  every rank's node table = its own block_rows rows, then its halo.  Pulls the remote rows
+ *                        rows[n_rows] (renumbered ids: owner g / block_rows, local row g % block_rows) from the head of
+ *                        their owners' tables into rows block_rows + i of this rank's table.
+ *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r with idx[r * n_rows + v] >= 0, in ascending r, of
+ *                        row idx[r * n_rows + v] of part_r   (v < n_rows: this rank's rows; deterministic).
  *   kgc_p2p_allreduce    one-shot sum of a small vector (n_bytes, a multiple of 16; fp32 or fp64) over the ranks: copy
  *                        into this rank's staging slot (stage_ptrs_dev[r] + offset_bytes), flag barrier, every rank adds
  *                        all slots in rank order (identical bits everywhere).  in == out is allowed.  One CTA: meant for
@@ -319,7 +320,7 @@ int kgc_p2p_allreduce(void* const* stage_ptrs_dev, int64_t offset_bytes, void* c
 int kgc_p2p_barrier(void* const* flag_ptrs_dev, int32_t rank, int32_t world, uint32_t* epoch, int32_t* error, void* stream);
 int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, int64_t n_rows, int64_t block_rows,
                         int32_t D, void* stream);
-int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const uint64_t* mask, int64_t row0, int64_t n_rows,
+int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
                         const float* addend, float* out, int32_t D, void* stream);
 
 /* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------

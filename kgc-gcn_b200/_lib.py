@@ -65,7 +65,7 @@ SIGNATURES = {
     'kgc_p2p_allreduce': (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     'kgc_p2p_barrier': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp]),
-    'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _vp]),
+    'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_score_1n_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
     'kgc_score_1n_bwd_logit': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

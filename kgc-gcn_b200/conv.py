@@ -201,9 +201,13 @@ class _Done(object):
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
-    def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None, p2p=None):
-        self.group, self.world, self.n_global = group, int(world), int(n_global)
+    def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None, p2p=None, rank=0,
+                 halo_rows=None):
+        self.group, self.world, self.n_global, self.rank = group, int(world), int(n_global), int(rank)
         self.p2p = p2p          # partition._P2PContext: halo exchange over NVLink peer memory (K10) instead of NCCL
+        # edge-balanced partitions number a rank's node table COMPACTLY: its own block, then the remote rows it reads
+        # (halo_rows = their ids in the gathered layout); None = range partition (table = all rows, global ids)
+        self.halo_rows = halo_rows
         # split hub rows of an edge-balanced partition (partition.py): every rank accumulates a share of a hub's incoming
         # edges into a private virtual row (local rows n_loc .. n_loc + n_hub); hub_idx_mine / hub_rows_mine = the hubs this
         # rank owns and their real local rows
@@ -234,6 +238,18 @@ class _Collectives(object):
                           device=x_local.device)
         work = dist.all_gather_into_tensor(out, x_local.contiguous(), group=self.group, async_op=async_op)
         return (out, work) if async_op else out
+
+    def gather_compact(self, x_blk):
+        """Library path of the compact node table: all-gather every block, keep own block + the halo rows."""
+        full = self.all_gather_rows(x_blk)
+        return torch.cat([x_blk, full.index_select(0, self.halo_rows)], 0)
+
+    def reduce_compact(self, partial, block):
+        """Library path back: compact partial d_x -> dense gathered layout -> reduce-scatter -> this rank's block."""
+        full = partial.new_zeros((self.world * block, partial.shape[1]))
+        full[self.rank * block:(self.rank + 1) * block] = partial[:block]
+        full[self.halo_rows] = partial[block:block + self.halo_rows.numel()]
+        return self.reduce_scatter_rows(full)
 
     def reduce_scatter_rows(self, full, async_op=False):
         import torch.distributed as dist
@@ -272,8 +288,9 @@ class _ConvFn(torch.autograd.Function):
         n_global = Nl if coll is None else coll.n_global
         n_hub = 0 if coll is None else coll.n_hub           # virtual rows of split hubs follow the Nl real rows
         Nb = Nl + n_hub
-        if ee.shape[0] != plan.num_edges2 or Nb != plan.num_dst_rows or \
-                plan.num_nodes != (Nl if coll is None else Nb * coll.world):
+        compact = coll is not None and coll.halo_rows is not None
+        n_table = Nl if coll is None else (Nb + coll.halo_rows.numel() if compact else Nb * coll.world)
+        if ee.shape[0] != plan.num_edges2 or Nb != plan.num_dst_rows or plan.num_nodes != n_table:
             raise ValueError('edge_embs / x do not match the graph plan')
         T = rels.shape[0] + 1
         if T != plan.num_types:
@@ -304,9 +321,11 @@ class _ConvFn(torch.autograd.Function):
         elif coll.p2p is not None:
             # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads)
             x_full, gather = coll.p2p.gather(x), _Done()
+        elif compact:                                               # library fallback of the compact table
+            x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)
+            x_full, gather = coll.gather_compact(x_blk), _Done()
         else:
-            x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)     # blocks of Nb rows: ids = rows
-            x_full, gather = coll.all_gather_rows(x_blk, async_op=True)
+            x_full, gather = coll.all_gather_rows(x, async_op=True)
 
         res3 = plan.scratch('res3', (3, Nl, Dout))
         if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
@@ -423,7 +442,8 @@ class _ConvFn(torch.autograd.Function):
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
         scatter = None
-        if coll is not None and p2p is None:   # source-row gradients go back to their owners while the d_rel pass runs here
+        compact = coll is not None and coll.halo_rows is not None
+        if coll is not None and p2p is None and not compact:   # source-row gradients go back to their owners while the d_rel pass runs
             d_x, scatter = coll.reduce_scatter_rows(d_x_full, async_op=True)
 
         def level0_rel(sp, out_final, carry):
@@ -438,6 +458,9 @@ class _ConvFn(torch.autograd.Function):
             # K10: barrier, then every owner pulls the partial rows of the ranks that touched its rows (rank order,
             # deterministic) and adds the self-loop term - reduce-scatter + add in one kernel over peer memory
             d_x = p2p.reduce(g3[2, :Nl], Nl)
+        elif compact:
+            coll.all_reduce(flat, 'flat')
+            d_x = coll.reduce_compact(d_x_full, Nb)[:Nl] + g3[2, :Nl]
         else:
             coll.all_reduce(flat, 'flat')
             if scatter is not None:
@@ -567,7 +590,7 @@ class MGCNConv(nn.Module):
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
         coll = _Collectives(part.group, part.world, part.num_nodes, part.n_hub, part.hub_idx_mine, part.hub_rows_mine,
-                            part.p2p(x_local.shape[1]) if hasattr(part, 'p2p') else None)
+                            part.p2p(x_local.shape[1]), part.rank, getattr(part, 'halo_rows64', None))
         all_ent, all_rel, stats = _ConvFn.apply(
             x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,

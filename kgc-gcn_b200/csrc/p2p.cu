@@ -5,11 +5,12 @@
 // reduce-scatter of a dense [N, D] partial - N x 400 bytes in and out per rank whatever the graph.  A rank only ever
 // touches the rows its edges reference (73% / 46% / 26% of the nodes at 2 / 4 / 8 ranks of the WN18RR-shape workload), and
 // every GPU of the NVSwitch domain can load any peer's memory directly, so:
-//   * kgc_p2p_halo_gather  - every rank publishes its row block in a symmetric buffer laid out like the gathered table;
-//                            after a barrier each rank PULLS exactly the remote rows its records reference (one warp per
-//                            400-byte row, 4 rows in flight per warp) into its own copy of the table;
+//   * kgc_p2p_halo_gather  - every rank publishes its row block at the head of a symmetric node table; after a barrier each
+//                            rank PULLS exactly the remote rows its records reference (one warp per 400-byte row, 8 rows
+//                            in flight per warp) into the compact tail of its own table (own rows, then the halo: every
+//                            per-rank structure is O(own rows + halo) whatever the number of ranks);
 //   * kgc_p2p_halo_reduce  - every rank leaves its partial d_x in a symmetric buffer; after a barrier the owner of a row
-//                            pulls the partials of the ranks that touched it (a per-row bit mask built with the partition)
+//                            pulls the partials of the ranks that touched it (a per-row index table built with the partition)
 //                            and adds them IN RANK ORDER (deterministic) together with the self-loop term - the
 //                            reduce-scatter and the add that followed it, in one kernel;
 //   * kgc_p2p_barrier      - flag barrier in symmetric memory (release/acquire at system scope, monotonically increasing
@@ -107,7 +108,8 @@ p2p_allreduce_kernel(char* const* __restrict__ stage, int64_t offset, uint32_t* 
 constexpr int kHaloThreads = 256;
 constexpr int kHaloUnroll = 8;
 
-// table[r] = rank r's copy of the gathered node table [world * block_rows, D]; row g lives in block g / block_rows
+// table[r] = rank r's COMPACT node table: its own block_rows rows, then its halo; rows[i] = renumbered id g of the i-th
+// halo row: owner g / block_rows, local row g % block_rows; it lands in row block_rows + i of this rank's table
 __global__ void __launch_bounds__(kHaloThreads)
 halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* __restrict__ rows, int64_t n_rows,
                    int block_rows, int D4) {
@@ -122,7 +124,8 @@ halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* _
     for (int u = 0; u < kHaloUnroll; ++u) {
       const int64_t i = i0 + u < n_rows ? i0 + u : n_rows - 1;
       g[u] = __ldg(rows + i);
-      const float4* src = table[g[u] / block_rows] + g[u] * D4;
+      const float4* src = table[g[u] / block_rows] + (g[u] % block_rows) * D4;     // the owner's block opens its table
+      g[u] = block_rows + i;                                                        // compact row of this rank's table
       if (lane < D4) v[u][0] = src[lane];
       if (lane + 32 < D4) v[u][1] = src[lane + 32];
     }
@@ -137,26 +140,28 @@ halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* _
   }
 }
 
-// out[v] = addend[v] + sum over ranks r with bit r of mask[v] set (ascending r) of part[r][row0 + v]
+// out[v] = addend[v] + sum over the ranks r with idx[r][v] >= 0 (ascending r) of part[r][idx[r][v]]
 template <int WMAX>
 __global__ void __launch_bounds__(kHaloThreads)
-halo_reduce_kernel(const float4* const* __restrict__ part, int world, const uint64_t* __restrict__ mask, int64_t row0,
-                   int64_t n_rows, const float4* __restrict__ addend, float4* __restrict__ out, int D4) {
+halo_reduce_kernel(const float4* const* __restrict__ part, int world, const int32_t* __restrict__ idx, int64_t n_rows,
+                   const float4* __restrict__ addend, float4* __restrict__ out, int D4) {
   const int lane = threadIdx.x % 32;
   const int64_t warp = (blockIdx.x * (int64_t)kHaloThreads + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * (kHaloThreads / 32);
   constexpr int kRows = WMAX <= 4 ? 4 : 2;                  // rows per warp trip: kRows * WMAX row loads in flight
   for (int64_t v0 = warp * kRows; v0 < n_rows; v0 += n_warps * kRows) {
-    uint64_t m[kRows];
+    int32_t at[kRows][WMAX];
 #pragma unroll
-    for (int u = 0; u < kRows; ++u) m[u] = v0 + u < n_rows ? __ldg(mask + v0 + u) : 0;
+    for (int u = 0; u < kRows; ++u)
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r) at[u][r] = (r < world && v0 + u < n_rows) ? __ldg(idx + (int64_t)r * n_rows + v0 + u) : -1;
     for (int c = lane; c < D4; c += 32) {
       float4 p[kRows][WMAX];
 #pragma unroll
       for (int u = 0; u < kRows; ++u)
 #pragma unroll
         for (int r = 0; r < WMAX; ++r)
-          if (r < world && ((m[u] >> r) & 1)) p[u][r] = part[r][(row0 + v0 + u) * D4 + c];
+          if (at[u][r] >= 0) p[u][r] = part[r][(int64_t)at[u][r] * D4 + c];
 #pragma unroll
       for (int u = 0; u < kRows; ++u) {
         if (v0 + u < n_rows) {
@@ -165,7 +170,7 @@ halo_reduce_kernel(const float4* const* __restrict__ part, int world, const uint
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < WMAX; ++r)
-            if (r < world && ((m[u] >> r) & 1)) { s.x += p[u][r].x; s.y += p[u][r].y; s.z += p[u][r].z; s.w += p[u][r].w; }
+            if (at[u][r] >= 0) { s.x += p[u][r].x; s.y += p[u][r].y; s.z += p[u][r].z; s.w += p[u][r].w; }
           out[v * D4 + c] = make_float4(s.x + acc.x, s.y + acc.y, s.z + acc.z, s.w + acc.w);
         }
       }
@@ -199,22 +204,22 @@ extern "C" int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, co
   return 0;
 }
 
-extern "C" int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const uint64_t* mask, int64_t row0, int64_t n_rows,
+extern "C" int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
                                    const float* addend, float* out, int32_t D, void* stream) {
-  KGC_REQUIRE(part_ptrs_dev && mask && out && world >= 1 && world <= 64 && D > 0 && D % 4 == 0, "bad arguments");
+  KGC_REQUIRE(part_ptrs_dev && idx && out && world >= 1 && world <= 64 && D > 0 && D % 4 == 0, "bad arguments");
   if (n_rows == 0) return 0;
   int64_t blocks = ceil_div(n_rows, (kHaloThreads / 32) * 2);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   const unsigned g = (unsigned)blocks;
   cudaStream_t st = as_stream(stream);
   if (world <= 2) {
-    halo_reduce_kernel<2><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, mask, row0, n_rows,
+    halo_reduce_kernel<2><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else if (world <= 4) {
-    halo_reduce_kernel<4><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, mask, row0, n_rows,
+    halo_reduce_kernel<4><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else if (world <= 8) {
-    halo_reduce_kernel<8><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, mask, row0, n_rows,
+    halo_reduce_kernel<8><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else {
     return fail(__func__, "more than 8 ranks are not supported by this build");

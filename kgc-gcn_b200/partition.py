@@ -102,10 +102,11 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
 
     Returns dict(n_loc, n_hub, block = n_loc + n_hub, owned_nodes [n_loc] (global ids in local-row order), hubs [n_hub],
     hub_owner [n_hub], hub_row [n_hub] (local row of the hub at its owner), owned_eids (ascending, in half first),
-    n_edges_in, src (ids in the renumbered space = rows of the all-gathered x), dst (local rows, virtual rows are
-    n_loc + h), type, deg [2, world * block] (global per-half degrees in the renumbered space), newid [N],
-    halo_rows (sorted renumbered ids of the REMOTE rows this rank's edges read), touch_mask [n_loc] uint64 (bit r: rank r
-    owns an edge whose source is this row))."""
+    n_edges_in, newid [N] (node -> renumbered id = owner * block + local row), halo_rows [n_halo] (ascending renumbered ids
+    of the REMOTE rows this rank's edges read), src (COMPACT ids: [0, block) = own rows, block + i = halo_rows[i]), dst
+    (local rows, virtual rows are n_loc + h), type, deg [2, block + n_halo] (global per-half degrees by compact id),
+    n_halo_max (largest halo of any rank: size of the symmetric tables), peer_idx [world, n_loc] int32 (compact row of this
+    rank's node v in rank r's table, -1 when r's edges never read v: the partial gradients the owner has to add))."""
     ei = np.asarray(edge_index, dtype=np.int64)
     et = np.asarray(edge_type, dtype=np.int64)
     n2 = ei.shape[1]
@@ -140,13 +141,32 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
     touch = np.zeros(world * block, dtype=np.uint64)
     for r in range(world):
         touch[np.unique(src_new[edge_rank == r])] |= np.uint64(1 << r)
-    used = np.nonzero((touch >> np.uint64(rank)) & np.uint64(1))[0]
-    halo_rows = used[(used < rank * block) | (used >= (rank + 1) * block)].astype(np.int32)
-    touch_mine = touch[rank * block:rank * block + n_loc].copy()
+    # COMPACT numbering of this rank's node table: [0, block) = its own rows (real + virtual), then only the remote rows
+    # its edges read (ascending renumbered id) - every per-rank structure is O(own rows + halo), not O(all nodes)
+    ids = np.arange(world * block, dtype=np.int64)
+    peer_idx = np.full((world, n_loc), -1, dtype=np.int32)     # row of MY node v in rank r's partial table, -1: untouched
+    n_halo_all = np.zeros(world, dtype=np.int64)
+    halo_rows = None
+    for r in range(world):
+        bit = ((touch >> np.uint64(r)) & np.uint64(1)).astype(bool)
+        remote = bit & ((ids < r * block) | (ids >= (r + 1) * block))
+        hr = np.nonzero(remote)[0]
+        n_halo_all[r] = hr.shape[0]
+        pos = np.full(world * block, -1, dtype=np.int64)
+        pos[hr] = block + np.arange(hr.shape[0], dtype=np.int64)
+        pos[r * block:(r + 1) * block] = np.where(bit[r * block:(r + 1) * block], np.arange(block, dtype=np.int64), -1)
+        peer_idx[r] = pos[rank * block:rank * block + n_loc]
+        if r == rank:
+            halo_rows = hr
+            cmap = pos.copy()
+            cmap[r * block:(r + 1) * block] = np.arange(block, dtype=np.int64)
+    n_halo = int(halo_rows.shape[0])
+    comp_ids = np.concatenate([np.arange(rank * block, (rank + 1) * block, dtype=np.int64), halo_rows])
     return {'n_loc': n_loc, 'n_hub': n_hub, 'block': block, 'owned_nodes': owned_nodes, 'hubs': hubs,
             'hub_owner': owner[hubs], 'hub_row': slot[hubs], 'owned_eids': owned, 'n_edges_in': n_in,
-            'src': newid[ei[0, owned]], 'dst': dst_new[owned] - rank * block, 'type': et[owned], 'deg': deg_ext,
-            'newid': newid, 'halo_rows': halo_rows, 'touch_mask': touch_mine}
+            'src': cmap[newid[ei[0, owned]]], 'dst': dst_new[owned] - rank * block, 'type': et[owned],
+            'deg': np.ascontiguousarray(deg_ext[:, comp_ids]), 'newid': newid, 'halo_rows': halo_rows.astype(np.int32),
+            'n_halo': n_halo, 'n_halo_max': int(n_halo_all.max()), 'peer_idx': peer_idx}
 
 
 class GraphPartition(object):
@@ -175,13 +195,15 @@ class GraphPartition(object):
             self.lo = self.hi = None
             self.n_loc, self.n_hub, self.block = info['n_loc'], info['n_hub'], info['block']
             self.owned_nodes = torch.from_numpy(info['owned_nodes']).to(device)
-            ext_nodes, offset = world * self.block, rank * self.block
+            ext_nodes, offset = self.block + info['n_halo'], 0      # compact node table: own rows, then the halo
             mine = np.nonzero(info['hub_owner'] == rank)[0]
             self.hub_idx_mine = torch.from_numpy(mine.astype(np.int64)).to(device)           # which hubs this rank owns
             self.hub_rows_mine = torch.from_numpy(info['hub_row'][mine].astype(np.int64)).to(device)   # their local rows
             self.hubs = info['hubs']
             self.halo_rows = torch.from_numpy(info['halo_rows']).to(device)
-            self.touch_mask = torch.from_numpy(info['touch_mask'].view(np.int64)).to(device)
+            self.halo_rows64 = self.halo_rows.to(torch.int64)
+            self.n_halo, self.n_halo_max = info['n_halo'], info['n_halo_max']
+            self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
         else:
             raise ValueError("balance must be 'edges' or 'range'")
         self.owned_eids = torch.from_numpy(info['owned_eids']).to(device)
@@ -228,8 +250,9 @@ class _P2PContext(object):
         group = part.group if part.group is not None else dist.group.WORLD
         dev, W, B = part.device, part.world, part.block
         self.rank, self.world, self.block, self.D = part.rank, W, B, D
-        self.table = symm.empty((W * B, D), dtype=torch.float32, device=dev)       # gathered x (own block + pulled halo rows)
-        self.partial = symm.empty((W * B, D), dtype=torch.float32, device=dev)     # this rank's partial d_x
+        rows = B + part.n_halo_max                                              # same size on every rank (symmetric)
+        self.table = symm.empty((rows, D), dtype=torch.float32, device=dev)     # own block, then the pulled halo rows
+        self.partial = symm.empty((rows, D), dtype=torch.float32, device=dev)   # this rank's partial d_x, same numbering
         self.flags = symm.empty((64,), dtype=torch.int32, device=dev)
         self.stage = symm.empty((self.STAGE_BYTES,), dtype=torch.uint8, device=dev)  # slots of the one-shot all-reduces
         self.table.zero_(); self.partial.zero_(); self.flags.zero_(); self.stage.zero_()
@@ -242,7 +265,7 @@ class _P2PContext(object):
         self._slots, self._stage_used = {}, 0
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.error = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.halo_rows, self.touch_mask = part.halo_rows, part.touch_mask
+        self.halo_rows, self.peer_idx = part.halo_rows, part.peer_idx
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)                               # every rank's buffers are zeroed before anyone pulls
 
@@ -257,7 +280,7 @@ class _P2PContext(object):
         import ctypes
         from . import _lib
         n = x_local.shape[0]
-        self.table[self.rank * self.block:self.rank * self.block + n].copy_(x_local)
+        self.table[:n].copy_(x_local)
         self.barrier()
         _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.table_ptrs), self.rank, _lib.ptr(self.halo_rows),
                   self.halo_rows.numel(), self.block, self.D, _lib.stream())
@@ -269,8 +292,8 @@ class _P2PContext(object):
         from . import _lib
         out = torch.empty((n_rows, self.D), dtype=torch.float32, device=self.table.device)
         self.barrier()
-        _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.touch_mask),
-                  self.rank * self.block, n_rows, _lib.ptr(addend), _lib.ptr(out), self.D, _lib.stream())
+        _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.peer_idx),
+                  n_rows, _lib.ptr(addend), _lib.ptr(out), self.D, _lib.stream())
         return out
 
     def all_reduce(self, t, tag):

@@ -76,8 +76,8 @@ def _worker(rank, world, port, ret):
         # ---- edge-balanced partition with split hub rows (partition.py): renumbered ids, virtual rows, hub exchange
         from kgc_gcn_b200.partition import partition_edges_balanced
         b = partition_edges_balanced(ei, et, N, world, rank, hub_fraction=0.05)
-        n_loc, n_hub, blk = b['n_loc'], b['n_hub'], b['block']
-        assert n_hub >= 1 and n_loc == N // world and (b['dst'] < blk).all() and (b['src'] < world * blk).all()
+        n_loc, n_hub, blk, n_halo = b['n_loc'], b['n_hub'], b['block'], b['n_halo']
+        assert n_hub >= 1 and n_loc == N // world and (b['dst'] < blk).all() and (b['src'] < blk + n_halo).all()
         own_e, own_n = b['owned_eids'], b['owned_nodes']
         counts = torch.zeros(2 * E, dtype=torch.int64)
         counts[torch.from_numpy(own_e)] = 1
@@ -90,17 +90,24 @@ def _worker(rank, world, port, ret):
         most = torch.tensor([own_e.shape[0]])
         dist.all_reduce(most, op=dist.ReduceOp.MAX)
         assert int(most) <= 1.15 * 2 * E / world                          # edge-balanced
-        np.testing.assert_array_equal(b['deg'][:, b['newid']], info['deg'])        # degrees follow the renumbering
+        halo = b['halo_rows'].astype(np.int64)
+        assert (np.diff(halo) > 0).all() and ((halo < rank * blk) | (halo >= (rank + 1) * blk)).all()
+        comp_ids = np.concatenate([np.arange(rank * blk, (rank + 1) * blk), halo])      # compact id -> gathered-layout id
+        old_of = np.full(world * blk, -1)
+        old_of[b['newid']] = np.arange(N)                                 # gathered-layout id -> node (virtual rows: -1)
+        real = old_of[comp_ids] >= 0
+        np.testing.assert_array_equal(b['deg'][:, real], info['deg'][:, old_of[comp_ids][real]])   # degrees follow the ids
         mine = np.nonzero(b['hub_owner'] == rank)[0]
-        collb = _Collectives(None, world, N, n_hub, torch.from_numpy(mine), torch.from_numpy(b['hub_row'][mine]))
+        collb = _Collectives(None, world, N, n_hub, torch.from_numpy(mine), torch.from_numpy(b['hub_row'][mine]), None, rank,
+                             torch.from_numpy(halo))
         xb = np.concatenate([x[own_n], np.zeros((n_hub, D))])             # block of n_loc real + n_hub virtual rows
-        xb_full = collb.all_gather_rows(torch.from_numpy(xb)).numpy()
-        np.testing.assert_array_equal(xb_full[b['newid']], x)             # renumbered ids = rows of the gathered table
+        table = collb.gather_compact(torch.from_numpy(xb)).numpy()        # own block, then the halo rows
+        np.testing.assert_array_equal(table[real], x[old_of[comp_ids][real]])
         n_in = b['n_edges_in']
         planes = np.zeros((2, blk, D))
         for h, sl in ((0, slice(0, n_in)), (1, slice(n_in, None))):
             eids = own_e[sl]
-            planes[h] = _agg_numpy(xb_full, rel, ee[eids], b['src'][sl], b['dst'][sl], b['type'][sl], norm[eids], blk)
+            planes[h] = _agg_numpy(table, rel, ee[eids], b['src'][sl], b['dst'][sl], b['type'][sl], norm[eids], blk)
         planes_t = torch.from_numpy(planes)
         collb.sum_hub_rows(planes_t, n_loc)
         for h in (0, 1):
@@ -113,10 +120,20 @@ def _worker(rank, world, port, ret):
         g_t = torch.from_numpy(g_loc)
         collb.spread_hub_rows(g_t, 1, n_loc)
         np.testing.assert_array_equal(g_t[0, n_loc:].numpy(), gsel[b['hubs']])
-        partb = np.zeros((world * blk, D))
+        partb = np.zeros((blk + n_halo, D))
         np.add.at(partb, b['src'], norm[own_e][:, None] * g_t[0].numpy()[b['dst']] * rel[b['type']] * ee[own_e])
-        mine_dx = collb.reduce_scatter_rows(torch.from_numpy(partb)).numpy()
+        mine_dx = collb.reduce_compact(torch.from_numpy(partb), blk).numpy()
         np.testing.assert_allclose(mine_dx[:n_loc], full[own_n], rtol=1e-10, atol=1e-12)
+        # the owner-side index table of the peer-memory reduce (K10): the same sum, pulled row by row in rank order
+        gathered = [torch.zeros((blk + b['n_halo_max'], D), dtype=torch.float64) for _ in range(world)]
+        padded = torch.zeros((blk + b['n_halo_max'], D), dtype=torch.float64)
+        padded[:blk + n_halo] = torch.from_numpy(partb)
+        dist.all_gather(gathered, padded)
+        pulled = np.zeros((n_loc, D))
+        for r in range(world):
+            at = b['peer_idx'][r]
+            pulled[at >= 0] += gathered[r].numpy()[at[at >= 0]]
+        np.testing.assert_allclose(pulled, full[own_n], rtol=1e-10, atol=1e-12)
         # ---- entity-sharded filtered rank: integer counts all-reduce to the unsharded answer, target logits sum exactly
         B, NE = 16, 64
         scores = rng.integers(-5, 6, (B, NE)).astype(np.float64)
