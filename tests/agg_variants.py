@@ -1,5 +1,7 @@
 """Debug aid (not a test): time the three level-0 aggregation kernels of one graph shape through the C ABI and print a
-digest of their outputs, for the kernel variant selected by KGC_AGG_VARIANT / KGC_AGG_CTAS (probe builds only)."""
+digest of their outputs.  profiles/r01_agg_variants.md was produced with it from probe builds of agg.cu that selected a
+kernel variant through KGC_AGG_VARIANT / KGC_AGG_KU / KGC_AGG_MINB (the variables are ignored by the product build, which
+always runs agg_lean_kernel); the digest is how "bit-identical to the baseline" was checked for every variant."""
 import hashlib, json, os, sys
 import numpy as np
 import torch
