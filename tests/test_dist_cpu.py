@@ -178,3 +178,43 @@ def test_partition_edges_rejects_uneven():
     from kgc_gcn_b200.partition import partition_edges
     with pytest.raises(ValueError):
         partition_edges(np.zeros((2, 4), dtype=np.int64), np.zeros(4, dtype=np.int64), 7, 2, 0)
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_balanced_partition_properties(world):
+    """Host logic of the edge-balanced partition (partition.py) on the hub-heavy generator of SURVEY.md 8(d): equal node
+    counts, every edge and node owned once, near-equal edge counts where the range partition is 1.5x - 4.5x off, hubs split
+    only where no whole-row assignment could balance them, compact tables that hold exactly the rows the edges read."""
+    from kgc_gcn_b200.partition import partition_edges, partition_edges_balanced
+    N, R, E = 2048 * world, 5, 8192 * world
+    tri = orc.synthetic_triples(N, R, E, 11)
+    g = orc.build_graph(tri, N, R)
+    ei, et = g['edge_index'], g['edge_attr'][0]
+    parts = [partition_edges_balanced(ei, et, N, world, r) for r in range(world)]
+    mean = 2 * E / world
+    assert max(p['owned_eids'].shape[0] for p in parts) <= 1.1 * mean
+    assert max(partition_edges(ei, et, N, world, r)['owned_eids'].shape[0] for r in range(world)) >= 1.4 * mean
+    assert sorted(np.concatenate([p['owned_eids'] for p in parts]).tolist()) == list(range(2 * E))
+    assert sorted(np.concatenate([p['owned_nodes'] for p in parts]).tolist()) == list(range(N))
+    n_hub = parts[0]['n_hub']
+    indeg = np.bincount(ei[1], minlength=N)
+    assert n_hub == int((indeg > 0.5 * mean).sum()) and (n_hub > 0) == (indeg.max() > 0.5 * mean)
+    for r, p in enumerate(parts):
+        blk = p['block']
+        assert p['n_loc'] == N // world and blk == N // world + n_hub and p['n_hub'] == n_hub
+        assert p['src'].min() >= 0 and p['src'].max() < blk + p['n_halo'] and p['dst'].max() < blk
+        used = np.unique(p['src'])
+        assert (used[used >= blk] == blk + np.arange(p['n_halo'])).all()          # every halo row is read, none is missing
+        assert p['n_halo'] <= p['n_halo_max'] == max(q['n_halo'] for q in parts)
+        # the owner-side table of the peer-memory reduce: rank q reads my row v <=> peer_idx[q, v] is its compact row there
+        for q, other in enumerate(parts):
+            at = p['peer_idx'][q]
+            ids_mine = r * blk + np.arange(p['n_loc'])                            # my rows in the gathered layout
+            if q == r:
+                read = np.isin(np.arange(p['n_loc']), other['src'][other['src'] < blk])
+                assert ((at >= 0) == read).all() and (at[at >= 0] == np.arange(p['n_loc'])[at >= 0]).all()
+            else:
+                halo = other['halo_rows'].astype(np.int64)
+                pos = np.searchsorted(halo, ids_mine)
+                hit = (pos < halo.shape[0]) & (halo[np.minimum(pos, halo.shape[0] - 1)] == ids_mine)
+                assert ((at >= 0) == hit).all() and (at[hit] == blk + pos[hit]).all()
