@@ -344,6 +344,8 @@ def run_ours(args, rank, world, local_rank):
     roof, kernels = None, None
     if rank == 0 and world == 1:
         roof, kernels = kernel_rooflines(k, conv, x, ee, rl, ei, et, N, R, E, flush, args.workload)
+    if part is not None and part.p2p(D_IN) is not None:
+        part.p2p(D_IN).check()                # a peer-memory barrier that timed out would have produced garbage timings
     if dist is not None:
         # release the CUDA graph (it holds the captured NCCL kernels) before the communicator goes away
         run_step = None

@@ -50,6 +50,8 @@ class ClipAdam(torch.optim.Optimizer):
                 s['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 s['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             step0 = max(step0, float(s['step']))
+        if st is not None:                   # the set of parameters with gradients changed: keep counting from the device
+            step0 = max(step0, float(st['state'][0]))
         st = {
             'key': key,
             'items': torch.tensor(items, dtype=torch.int32, device=dev).reshape(-1, 4),
