@@ -323,6 +323,27 @@ int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t
 int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
                         const float* addend, float* out, int32_t D, void* stream);
 
+/* ---- N4: native text -> id ingest (host C++, no device code; SURVEY "next" row N4) ---------------------------------
+ * Replaces the two per-line passes of DataLoader._load_data (data_loader.py:64-111) over <data_dir>/{train,valid,test}.txt:
+ * ids in first-appearance order (tokens lower-cased for the vocabulary, looked up as written - the reference's quirk),
+ * triple arrays, and the (s, r) -> objects / (o, r + R) -> subjects groups as CSR query sets in the reference's order
+ * (train: one query per group created during the train split, in creation order, train-only objects; valid / test:
+ * one tail and one head query per triple with the objects of ALL splits; objects sorted and unique).
+ * kgc_ingest_open: 0 OK; 1 malformed line (not three tokens); 2 unsupported text (non-ASCII token, relation ending in
+ * "_reverse": the caller runs the reference's Python passes); 3 I/O; 4 unknown token at look-up (kgc_last_error() is the
+ * token: the reference raises KeyError).
+ * kgc_ingest_count what: 0 entities, 1 relations R, 2/3/4 triples of train / valid / test, 5/6 bytes of the entity /
+ * relation token blobs, 10 + 2q queries and 11 + 2q label entries of query set q (0 train, 1 valid_tail, 2 valid_head,
+ * 3 test_tail, 4 test_head).
+ * kgc_ingest_copy array: 5/6 all entity / relation tokens in id order, each followed by '\n'; 2/3/4 split triples int64 [n,3]; 10 + 3q query triples int64 [Q,3] (train: o = -1), 11 + 3q ptr
+ * int64 [Q+1], 12 + 3q idx int32 [nnz].  kgc_ingest_name kind: 0 entity, 1 relation token (lower-cased) of an id. */
+typedef struct kgc_ingest kgc_ingest_t;
+int kgc_ingest_open(const char* data_dir, kgc_ingest_t** out);
+void kgc_ingest_close(kgc_ingest_t* h);
+int64_t kgc_ingest_count(const kgc_ingest_t* h, int32_t what);
+int kgc_ingest_copy(const kgc_ingest_t* h, int32_t array, void* dst, int64_t capacity_bytes);
+const char* kgc_ingest_name(const kgc_ingest_t* h, int32_t kind, int64_t id);
+
 /* ---- K6t: 1-N scoring in TRAINING (dense [B,N] sigmoid scores and their autograd) -------------------------
  * Replaces model.py:177-179 (x = mm(x, all_ent^T); x += bias; sigmoid) where the caller needs the dense matrix
  * (BCE against the multi-hot label, main.py:63-66).  Forward: the K4b tensor-core kernel (3xTF32, fp32-grade) with

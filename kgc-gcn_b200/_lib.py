@@ -66,6 +66,11 @@ SIGNATURES = {
     'kgc_p2p_barrier': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp]),
     'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'kgc_ingest_open': (ctypes.c_int, [ctypes.c_char_p, _vp]),
+    'kgc_ingest_close': (None, [_vp]),
+    'kgc_ingest_count': (_i64, [_vp, _i32]),
+    'kgc_ingest_copy': (ctypes.c_int, [_vp, _i32, _vp, _i64]),
+    'kgc_ingest_name': (ctypes.c_char_p, [_vp, _i32, _i64]),
     'kgc_score_1n_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
     'kgc_score_1n_bwd_logit': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'kgc_score_kpad': (_i32, [_i32]),

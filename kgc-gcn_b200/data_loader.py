@@ -39,24 +39,119 @@ class GraphData(object):
         return self.edge_index.device
 
 
+class QuerySet(object):
+    """One query set as the native ingest delivers it: triples [Q, 3] int64, ptr [Q + 1] int64, idx [nnz] int32 (sorted
+    unique objects of every query).  ``as_list()`` gives the reference's list of dicts (data_loader.py:98-111)."""
+
+    def __init__(self, triples, ptr, idx, train):
+        self.triples, self.ptr, self.idx, self.train = triples, ptr, idx, train
+
+    def __len__(self):
+        return int(self.triples.shape[0])
+
+    def as_list(self):
+        out = []
+        trip, ptr, idx = self.triples.tolist(), self.ptr.tolist(), self.idx.tolist()
+        for q, t in enumerate(trip):
+            d = {'triple': tuple(t), 'label': idx[ptr[q]:ptr[q + 1]]}
+            if self.train:
+                d['sub_samp'] = 1
+            out.append(d)
+        return out
+
+
+class LazyTriplets(dict):
+    """``DataLoader.triplets`` when the data came through the native ingest: the five query sets as QuerySet objects,
+    turned into the reference's lists of dicts on first access of a key."""
+
+    def __init__(self, sets):
+        super(LazyTriplets, self).__init__()
+        self._sets = sets
+        for k in sets:
+            dict.__setitem__(self, k, None)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is None:
+            v = self._sets[key].as_list()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def query_set(self, key):
+        return self._sets[key]
+
+
+def native_ingest(data_dir):
+    """N4 (csrc/ingest.cu): the two text passes of the reference loader in C++.  Returns a dict of numpy arrays and token
+    lists, or None when the text is outside what the native parser reproduces exactly (non-ASCII tokens, relation names
+    ending in ``_reverse``).  Malformed lines raise ValueError, tokens that only match case-insensitively KeyError - the
+    reference's own failures."""
+    import ctypes
+    h = _lib.lib()
+    handle = ctypes.c_void_p()
+    rc = h.kgc_ingest_open(os.fsencode(data_dir), ctypes.byref(handle))
+    if rc != 0:
+        msg = h.kgc_last_error().decode(errors='replace')
+        if rc == 2:
+            return None
+        if rc == 1:
+            raise ValueError(msg)
+        if rc == 4:
+            raise KeyError(msg)
+        raise OSError(msg)
+    try:
+        def arr(array, n, dtype):
+            a = np.empty(n, dtype=dtype)
+            if h.kgc_ingest_copy(handle, array, a.ctypes.data_as(ctypes.c_void_p), a.nbytes) != 0:
+                raise RuntimeError(h.kgc_last_error().decode())
+            return a
+        cnt = lambda what: int(h.kgc_ingest_count(handle, what))      # noqa: E731
+        def names(array):                      # one blob instead of one call per token
+            blob = arr(array, (cnt(array),), np.uint8).tobytes().decode('ascii')
+            return blob.split('\n')[:-1] if blob else []
+        out = {'entities': names(5), 'relations': names(6)}
+        assert len(out['entities']) == cnt(0) and len(out['relations']) == cnt(1)
+        for k, split in enumerate(('train', 'valid', 'test')):
+            out[split] = arr(2 + k, (cnt(2 + k), 3), np.int64)
+        for q, name in enumerate(('train', 'valid_tail', 'valid_head', 'test_tail', 'test_head')):
+            nq, nnz = cnt(10 + 2 * q), cnt(11 + 2 * q)
+            out['q_' + name] = QuerySet(arr(10 + 3 * q, (nq, 3), np.int64), arr(11 + 3 * q, (nq + 1,), np.int64),
+                                        arr(12 + 3 * q, (nnz,), np.int32), train=(q == 0))
+        return out
+    finally:
+        h.kgc_ingest_close(handle)
+
+
 class KBDataset(object):
     """Query set in CSR form.  ``triplets`` is the reference's list of {'triple': (s, r, o), 'label': [objs]}."""
 
     def __init__(self, triplets, num_entity, params, training=False):
-        self.triplets = triplets
         self.num_entity = int(num_entity)
         self.params = params
         self.training = training
-        q = len(triplets)
-        self.triples = np.asarray([t['triple'] for t in triplets], dtype=np.int64).reshape(q, 3)
-        self.ptr = np.zeros(q + 1, dtype=np.int64)
-        idx = []
-        for i, t in enumerate(triplets):
-            objs = sorted(int(o) for o in t['label'])
-            idx.extend(objs)
-            self.ptr[i + 1] = len(idx)
-        self.idx = np.asarray(idx, dtype=np.int32)
+        if isinstance(triplets, QuerySet):                       # CSR arrays straight from the native ingest (N4)
+            self._triplets = None
+            self._lazy = triplets
+            self.triples, self.ptr, self.idx = triplets.triples, triplets.ptr, triplets.idx
+        else:
+            self._triplets = triplets
+            q = len(triplets)
+            self.triples = np.asarray([t['triple'] for t in triplets], dtype=np.int64).reshape(q, 3)
+            self.ptr = np.zeros(q + 1, dtype=np.int64)
+            idx = []
+            for i, t in enumerate(triplets):
+                objs = sorted(int(o) for o in t['label'])
+                idx.extend(objs)
+                self.ptr[i + 1] = len(idx)
+            self.idx = np.asarray(idx, dtype=np.int32)
         self._dev = {}
+
+    @property
+    def triplets(self):
+        """The reference's list of {'triple': ..., 'label': [...]} (materialised on first use when the data came as CSR)."""
+        if self._triplets is None:
+            self._triplets = self._lazy.as_list()
+        return self._triplets
 
     def label_values(self):
         """(pos, add): label = add everywhere, pos on the positives.  Training with lbl_smooth != 0 gives
@@ -105,7 +200,7 @@ class KBDataset(object):
         return torch.stack([b[0] for b in batch], dim=0), torch.stack([b[1] for b in batch], dim=0)
 
     def __len__(self):
-        return len(self.triplets)
+        return int(self.triples.shape[0])
 
     def __getitem__(self, idx):
         raise RuntimeError('KBDataset is batch-built on the GPU; iterate the loaders from get_data_loaders() '
@@ -163,6 +258,20 @@ class DataLoader(object):
         self.graph = self._load_data()
 
     def _load_data(self):
+        native = native_ingest(self.data_dir) if getattr(self.params, 'native_ingest', True) else None
+        if native is not None:                 # N4: both text passes in C++, query sets as CSR arrays
+            n_rel = len(native['relations'])
+            self.entity2id = {name: i for i, name in enumerate(native['entities'])}
+            self.relation2id = {name: i for i, name in enumerate(native['relations'])}
+            self.relation2id.update({name + '_reverse': i + n_rel for i, name in enumerate(native['relations'])})
+            self.num_entity, self.num_relation = len(native['entities']), n_rel
+            self.num_edge = int(native['train'].shape[0])
+            self.triplets = LazyTriplets({k: native['q_' + k] for k in ('train', 'valid_tail', 'valid_head', 'test_tail',
+                                                                          'test_head')})
+            graph = self._build_graph(np.arange(self.num_entity, dtype=np.int64), native['train'], bi_direction=True)
+            logging.info('entity={}, relation={}, train_triplets={}, valid_triplets={}, test_triplets={}'.format(
+                self.num_entity, self.num_relation, native['train'].shape[0], native['valid'].shape[0], native['test'].shape[0]))
+            return graph
         # pass 1 (data_loader.py:64-74): ids in first-appearance order over train, valid, test; tokens lower-cased
         ent2id, rel2id = OrderedDict(), OrderedDict()
         splits = ('train', 'valid', 'test')
@@ -243,11 +352,15 @@ class DataLoader(object):
         data.edge_norm = self._edge_normal(rel, edge_index, len(graph_nodes))
         return data
 
+    def _queries(self, key):
+        t = self.triplets
+        return t.query_set(key) if isinstance(t, LazyTriplets) else t[key]
+
     def _get_dataset(self, data_type, params):
         if data_type == 'train':
-            return KBDataset(self.triplets['train'], len(self.entity2id), params, training=True)
+            return KBDataset(self._queries('train'), len(self.entity2id), params, training=True)
         elif data_type in ['valid_head', 'valid_tail', 'test_head', 'test_tail']:
-            return KBDataset(self.triplets[data_type], len(self.entity2id), params)
+            return KBDataset(self._queries(data_type), len(self.entity2id), params)
         else:
             raise ValueError('Unkown data type')
 

@@ -262,3 +262,95 @@ def test_cpu_tensors_fail_loudly():
     ei = torch.tensor([[0, 1], [1, 0]])
     with pytest.raises(RuntimeError, match='CUDA'):
         conv(torch.zeros(2, 8), ei, torch.tensor([0, 2]), None, torch.zeros(2, 8), torch.zeros(4, 8))
+
+
+def _write_dataset(root, name, files):
+    d = os.path.join(root, 'data', name)
+    os.makedirs(d, exist_ok=True)
+    for split, text in files.items():
+        with open(os.path.join(d, split + '.txt'), 'wb') as f:
+            f.write(text.encode('utf-8'))
+
+
+def _load(root, name, native):
+    import kgc_gcn_b200 as k
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        return k.DataLoader(name, params(native_ingest=native))
+    finally:
+        os.chdir(cwd)
+
+
+def _same_loader(a, b):
+    assert a.entity2id == b.entity2id and a.relation2id == b.relation2id
+    assert list(a.entity2id) == list(b.entity2id) and list(a.relation2id) == list(b.relation2id)     # insertion order too
+    assert (a.num_entity, a.num_relation, a.num_edge) == (b.num_entity, b.num_relation, b.num_edge)
+    assert torch.equal(a.graph.edge_index, b.graph.edge_index) and torch.equal(a.graph.edge_attr, b.graph.edge_attr)
+    assert torch.equal(a.graph.edge_norm, b.graph.edge_norm) and torch.equal(a.graph.entity, b.graph.entity)
+    assert sorted(a.triplets.keys()) == sorted(b.triplets.keys())
+    for key in b.triplets:
+        qa, qb = a._get_dataset(key, params()), b._get_dataset(key, params())
+        np.testing.assert_array_equal(qa.triples, qb.triples)
+        np.testing.assert_array_equal(qa.ptr, qb.ptr)
+        np.testing.assert_array_equal(qa.idx, qb.idx)
+        assert [(tuple(q['triple']), sorted(q['label'])) for q in a.triplets[key]] == \
+            [(tuple(q['triple']), sorted(q['label'])) for q in b.triplets[key]]
+        assert all(('sub_samp' in q) == (key == 'train') for q in a.triplets[key])
+
+
+def test_native_ingest_matches_python_passes(tmp_path, golden_dir):
+    """N4 (csrc/ingest.cu) against the Python restatement of data_loader.py:64-111 on Toy and on random text with duplicate
+    lines, blank lines, tabs / runs of spaces, CRLF and lone CR line ends, entities and relations that first appear in the
+    valid / test files, and no trailing newline."""
+    from kgc_gcn_b200.data_loader import LazyTriplets
+    a, b = _load(golden_dir, 'Toy', True), _load(golden_dir, 'Toy', False)
+    assert isinstance(a.triplets, LazyTriplets) and not isinstance(b.triplets, LazyTriplets)
+    _same_loader(a, b)
+    rng = np.random.default_rng(3)
+    for case in range(4):
+        n_ent, n_rel = int(rng.integers(5, 60)), int(rng.integers(1, 7))
+        seps = [' ', '\t', '  ', ' \t ']
+        ends = ['\n', '\r\n', '\n\n', '\r', '\n \n']
+
+        def lines(n, lo_e, lo_r):
+            out = []
+            for _ in range(n):
+                s, o = rng.integers(lo_e, n_ent, 2)
+                r = rng.integers(lo_r, n_rel)
+                sep = seps[int(rng.integers(len(seps)))]
+                row = sep.join(['e%d' % s, 'rel_%d' % r, 'e%d' % o])
+                out.append(('  ' if rng.random() < 0.2 else '') + row + ends[int(rng.integers(len(ends)))])
+                if rng.random() < 0.15:
+                    out.append(out[-1])                               # duplicate line
+            return ''.join(out)
+        files = {'train': lines(int(rng.integers(20, 200)), n_ent // 3, n_rel // 2),
+                 'valid': lines(int(rng.integers(1, 40)), 0, 0), 'test': lines(int(rng.integers(1, 40)), 0, 0).rstrip()}
+        _write_dataset(str(tmp_path), 'rand%d' % case, files)
+        _same_loader(_load(str(tmp_path), 'rand%d' % case, True), _load(str(tmp_path), 'rand%d' % case, False))
+
+
+def test_native_ingest_failures_and_fallbacks(tmp_path):
+    """The reference's own failures stay: a line without three tokens raises ValueError, a token that only matches
+    case-insensitively KeyError (data_loader.py:69-71 lower-cases, :83-85 does not).  Text the native parser does not
+    reproduce exactly (non-ASCII tokens, relation names ending in _reverse) goes through the Python passes."""
+    from kgc_gcn_b200.data_loader import LazyTriplets, native_ingest
+    root = str(tmp_path)
+    ok = 'a r b\nb r c\n'
+    _write_dataset(root, 'short', {'train': 'a r b\nb r\n', 'valid': ok, 'test': ok})
+    _write_dataset(root, 'case', {'train': 'a r b\nB r c\n', 'valid': ok, 'test': ok})
+    _write_dataset(root, 'uni', {'train': 'a r b\nécole r c\n', 'valid': ok, 'test': ok})
+    _write_dataset(root, 'rev', {'train': 'a r b\nb r_reverse c\n', 'valid': ok, 'test': ok})
+    for native in (True, False):
+        with pytest.raises(ValueError):
+            _load(root, 'short', native)
+        with pytest.raises(KeyError) as err:
+            _load(root, 'case', native)
+        assert 'B' in str(err.value)
+    with pytest.raises(OSError):
+        native_ingest(os.path.join(root, 'data', 'missing'))
+    for name in ('uni', 'rev'):
+        assert native_ingest(os.path.join(root, 'data', name)) is None
+        dl = _load(root, name, True)
+        assert not isinstance(dl.triplets, LazyTriplets)
+        _same_loader(dl, _load(root, name, False))
