@@ -320,7 +320,7 @@ class _ConvFn(torch.autograd.Function):
             x_full = x
         elif coll.p2p is not None:
             # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads)
-            x_full, gather = coll.p2p.gather(x), _Done()
+            x_full, gather = coll.p2p.gather(x, fence=not training), _Done()
         elif compact:                                               # library fallback of the compact table
             x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)
             x_full, gather = coll.gather_compact(x_blk), _Done()

@@ -275,11 +275,16 @@ class _P2PContext(object):
         _lib.call('kgc_p2p_barrier', ctypes.c_void_p(self.flag_ptrs), self.rank, self.world, _lib.ptr(self.epoch),
                   _lib.ptr(self.error), _lib.stream())
 
-    def gather(self, x_local):
-        """x rows of this rank -> its block of the table; barrier; pull the remote rows this rank's edges read."""
+    def gather(self, x_local, fence=False):
+        """x rows of this rank -> its block of the table; barrier; pull the remote rows this rank's edges read.
+        ``fence``: barrier BEFORE the rows are overwritten as well - needed when nothing else synchronises the ranks between
+        two gathers (evaluation-mode forwards: no BatchNorm all-reduce, no backward), so that no peer is still pulling the
+        previous contents."""
         import ctypes
         from . import _lib
         n = x_local.shape[0]
+        if fence:
+            self.barrier()
         self.table[:n].copy_(x_local)
         self.barrier()
         _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.table_ptrs), self.rank, _lib.ptr(self.halo_rows),

@@ -79,6 +79,14 @@ def main():
             e['d_' + name] = check(getattr(conv, name).grad, getattr(ref, name).grad, 'd_' + name)
         e['d_gamma'] = check(conv.ent_bn.weight.grad, ref.ent_bn.weight.grad, 'd_gamma')
         e['d_beta'] = check(conv.ent_bn.bias.grad, ref.ent_bn.bias.grad, 'd_beta', tol=1e-3)   # ~0 in train mode: noise
+        # evaluation mode, two different inputs back to back (no BatchNorm all-reduce between the two halo gathers)
+        conv.eval(); ref.eval()
+        with torch.no_grad():
+            for shift in (0.0, 0.25):
+                want = ref(x.detach() + shift, ei, et, None, ee.detach(), rl.detach())[0]
+                got = conv.forward_partitioned(xl.detach() + shift, part, eel.detach(), rll.detach())[0]
+                e['eval_%g' % shift] = check(got, want[own], 'eval all_ent')
+        conv.train(); ref.train()
         n_own = torch.tensor([float(part.owned_eids.numel())], device=dev)
         dist.all_reduce(n_own, op=dist.ReduceOp.MAX)
         e['max_edge_share'] = float(n_own) / (2 * E)
