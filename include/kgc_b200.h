@@ -332,11 +332,14 @@ int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t
  * kgc_ingest_open: 0 OK; 1 malformed line (not three tokens); 2 unsupported text (non-ASCII token, relation ending in
  * "_reverse": the caller runs the reference's Python passes); 3 I/O; 4 unknown token at look-up (kgc_last_error() is the
  * token: the reference raises KeyError).
+ * Query set q: 0 train, 1 valid_tail, 2 valid_head, 3 test_tail, 4 test_head.  Train: ptr / idx are per query.  Valid / test:
+ * the object lists are stored ONCE per (s, r) group the set references (ptr / idx over groups) plus query -> group, because
+ * a hub group is the filter of thousands of queries.
  * kgc_ingest_count what: 0 entities, 1 relations R, 2/3/4 triples of train / valid / test, 5/6 bytes of the entity /
- * relation token blobs, 10 + 2q queries and 11 + 2q label entries of query set q (0 train, 1 valid_tail, 2 valid_head,
- * 3 test_tail, 4 test_head).
- * kgc_ingest_copy array: 5/6 all entity / relation tokens in id order, each followed by '\n'; 2/3/4 split triples int64 [n,3]; 10 + 3q query triples int64 [Q,3] (train: o = -1), 11 + 3q ptr
- * int64 [Q+1], 12 + 3q idx int32 [nnz].  kgc_ingest_name kind: 0 entity, 1 relation token (lower-cased) of an id. */
+ * relation token blobs, 10 + 2q queries and 11 + 2q stored label entries of set q, 20 + q rows of its ptr array.
+ * kgc_ingest_copy array: 5/6 all entity / relation tokens in id order, each followed by '\n'; 2/3/4 split triples int64 [n,3];
+ * 10 + 3q query triples int64 [Q,3] (train: o = -1), 11 + 3q ptr int64 [rows+1], 12 + 3q idx int32, 30 + q query -> group
+ * int32 [Q] (valid / test).  kgc_ingest_name kind: 0 entity, 1 relation token (lower-cased) of an id. */
 typedef struct kgc_ingest kgc_ingest_t;
 int kgc_ingest_open(const char* data_dir, kgc_ingest_t** out);
 void kgc_ingest_close(kgc_ingest_t* h);

@@ -133,8 +133,12 @@ struct Split {
 
 struct Csr {
   std::vector<int64_t> triples;  // [q][3]
-  std::vector<int64_t> ptr;      // [q + 1]
-  std::vector<int32_t> idx;      // sorted, unique objects of every query
+  // train set: ptr [q + 1] / idx = sorted, unique objects of every query.  valid / test sets: the object lists are kept ONCE
+  // per (s, r) group - ptr [g + 1] / idx over the groups the set references, qg [q] = group of every query - because a hub
+  // group is the filter of thousands of queries (a per-query copy was 12 GB for a 3 M-line Zipf data set)
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> idx;
+  std::vector<int32_t> qg;
 };
 
 }  // namespace
@@ -317,21 +321,24 @@ int ingest(const std::string& dir, kgc_ingest* h) {
     return all_len[g];
   };
   for (int s = 1; s < 3; ++s) {
-    Csr &ct = h->csr[2 * s - 1], &ch = h->csr[2 * s];
     const auto& tr = h->split[s].triples;
-    ct.ptr.assign(1, 0);
-    ch.ptr.assign(1, 0);
-    for (size_t i = 0; i + 2 < tr.size(); i += 3) {
-      const int64_t a = tr[i], r = tr[i + 1], o = tr[i + 2];
-      const int32_t* b;
-      int64_t n = all_objs(a, r, &b);
-      ct.idx.insert(ct.idx.end(), b, b + n);
-      ct.ptr.push_back((int64_t)ct.idx.size());
-      ct.triples.insert(ct.triples.end(), {a, r, o});
-      n = all_objs(o, r + R, &b);
-      ch.idx.insert(ch.idx.end(), b, b + n);
-      ch.ptr.push_back((int64_t)ch.idx.size());
-      ch.triples.insert(ch.triples.end(), {o, r + R, a});
+    for (int head = 0; head < 2; ++head) {
+      Csr& c = h->csr[2 * s - 1 + head];
+      std::vector<int32_t> local(n_groups, -1);             // group id -> its index among this set's groups
+      c.ptr.assign(1, 0);
+      for (size_t i = 0; i + 2 < tr.size(); i += 3) {
+        const int64_t a = head ? tr[i + 2] : tr[i], r = head ? tr[i + 1] + R : tr[i + 1], o = head ? tr[i] : tr[i + 2];
+        const int32_t g = gid.find(((uint64_t)a << 32) | (uint64_t)r);
+        if (local[g] < 0) {
+          const int32_t* b;
+          const int64_t n = all_objs(a, r, &b);
+          local[g] = (int32_t)c.ptr.size() - 1;
+          c.idx.insert(c.idx.end(), b, b + n);
+          c.ptr.push_back((int64_t)c.idx.size());
+        }
+        c.qg.push_back(local[g]);
+        c.triples.insert(c.triples.end(), {a, r, o});
+      }
     }
   }
   return 0;
@@ -362,7 +369,8 @@ extern "C" int kgc_ingest_open(const char* data_dir, kgc_ingest_t** out) {
 extern "C" void kgc_ingest_close(kgc_ingest_t* h) { delete h; }
 
 // what: 0 entities, 1 relations (R, un-doubled), 2/3/4 triples of train / valid / test, 5/6 bytes of the token blobs,
-//       10 + 2q / 11 + 2q = queries / label entries of query set q (0 train, 1 valid_tail, 2 valid_head, 3 test_tail, 4 test_head)
+//       10 + 2q / 11 + 2q = queries / stored label entries of query set q (0 train, 1 valid_tail, 2 valid_head, 3 test_tail,
+//       4 test_head), 20 + q = rows of its ptr array (queries for train, referenced groups for valid / test)
 extern "C" int64_t kgc_ingest_count(const kgc_ingest_t* h, int32_t what) {
   if (!h) return -1;
   if (what == 0) return (int64_t)h->ent_names.size();
@@ -373,14 +381,15 @@ extern "C" int64_t kgc_ingest_count(const kgc_ingest_t* h, int32_t what) {
     for (const auto& t : (what == 5 ? h->ent_names : h->rel_names)) n += (int64_t)t.size() + 1;
     return n;
   }
-  if (what >= 10 && what < 20) {
+  if (what >= 10 && what < 20) {                   // queries / stored label entries of a set
     const Csr& c = h->csr[(what - 10) / 2];
-    return (what - 10) % 2 == 0 ? (int64_t)c.ptr.size() - 1 : (int64_t)c.idx.size();
+    return (what - 10) % 2 == 0 ? (int64_t)c.triples.size() / 3 : (int64_t)c.idx.size();
   }
+  if (what >= 20 && what < 25) return (int64_t)h->csr[what - 20].ptr.size() - 1;     // rows of ptr: queries (train) / groups
   return -1;
 }
 
-// array: 5/6 entity / relation tokens in id order, each followed by '\n'; 2/3/4 triples of a split (int64 [n,3]); 10 + 3q triples (int64 [Q,3]), 11 + 3q ptr (int64 [Q+1]), 12 + 3q idx (int32)
+// array: 5/6 entity / relation tokens in id order, each followed by '\n'; 2/3/4 triples of a split (int64 [n,3]); 10 + 3q triples (int64 [Q,3]), 11 + 3q ptr (int64 [rows+1]), 12 + 3q idx (int32), 30 + q query -> group (int32 [Q], valid / test)
 extern "C" int kgc_ingest_copy(const kgc_ingest_t* h, int32_t array, void* dst, int64_t capacity_bytes) {
   if (!h || !dst) return kgc::fail(__func__, "null argument");
   const void* src = nullptr;
@@ -398,6 +407,9 @@ extern "C" int kgc_ingest_copy(const kgc_ingest_t* h, int32_t array, void* dst, 
   }
   if (array >= 2 && array <= 4) {
     src = h->split[array - 2].triples.data(); bytes = h->split[array - 2].triples.size() * 8;
+  } else if (array >= 30 && array < 35) {          // query -> group of a valid / test set (empty for train)
+    const Csr& c = h->csr[array - 30];
+    src = c.qg.data(); bytes = c.qg.size() * 4;
   } else if (array >= 10 && array < 25) {
     const Csr& c = h->csr[(array - 10) / 3];
     switch ((array - 10) % 3) {

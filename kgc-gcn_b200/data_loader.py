@@ -39,19 +39,49 @@ class GraphData(object):
         return self.edge_index.device
 
 
-class QuerySet(object):
-    """One query set as the native ingest delivers it: triples [Q, 3] int64, ptr [Q + 1] int64, idx [nnz] int32 (sorted
-    unique objects of every query).  ``as_list()`` gives the reference's list of dicts (data_loader.py:98-111)."""
+def _gather_segments(ptr, idx, rows):
+    """Concatenation of idx[ptr[r]:ptr[r + 1]] for r in rows -> (new_ptr [len(rows) + 1], values), vectorised."""
+    rows = np.asarray(rows, dtype=np.int64)
+    lens = ptr[rows + 1] - ptr[rows]
+    out_ptr = np.zeros(rows.shape[0] + 1, dtype=np.int64)
+    np.cumsum(lens, out=out_ptr[1:])
+    total = int(out_ptr[-1])
+    if total == 0:
+        return out_ptr, idx[:0]
+    pos = np.arange(total, dtype=np.int64) - np.repeat(out_ptr[:-1], lens) + np.repeat(ptr[rows], lens)
+    return out_ptr, idx[pos]
 
-    def __init__(self, triples, ptr, idx, train):
-        self.triples, self.ptr, self.idx, self.train = triples, ptr, idx, train
+
+class QuerySet(object):
+    """One query set as the native ingest delivers it: triples [Q, 3] int64 and the sorted unique objects of the queries
+    as CSR.  Train: ``gptr`` / ``gidx`` are per query (``qg`` None).  Valid / test: they hold every referenced (s, r) group
+    ONCE and ``qg`` [Q] maps a query to its group - a hub group is the filter of thousands of queries; the per-query
+    ``ptr`` / ``idx`` form is expanded only when somebody asks for it (dense label batches).
+    ``as_list()`` gives the reference's list of dicts (data_loader.py:98-111)."""
+
+    def __init__(self, triples, gptr, gidx, train, qg=None):
+        self.triples, self.gptr, self.gidx, self.train, self.qg = triples, gptr, gidx, train, qg
+        self._flat = None
 
     def __len__(self):
         return int(self.triples.shape[0])
 
+    def segments(self, qid):
+        """(ptr [len(qid) + 1], idx) of the queries ``qid`` without expanding the whole set."""
+        qid = np.asarray(qid, dtype=np.int64)
+        return _gather_segments(self.gptr, self.gidx, qid if self.qg is None else self.qg[qid])
+
+    @property
+    def flat(self):
+        """Per-query (ptr, idx) of the whole set."""
+        if self._flat is None:
+            self._flat = (self.gptr, self.gidx) if self.qg is None else self.segments(np.arange(len(self)))
+        return self._flat
+
     def as_list(self):
         out = []
-        trip, ptr, idx = self.triples.tolist(), self.ptr.tolist(), self.idx.tolist()
+        ptr, idx = self.flat
+        trip, ptr, idx = self.triples.tolist(), ptr.tolist(), idx.tolist()
         for q, t in enumerate(trip):
             d = {'triple': tuple(t), 'label': idx[ptr[q]:ptr[q + 1]]}
             if self.train:
@@ -114,9 +144,10 @@ def native_ingest(data_dir):
         for k, split in enumerate(('train', 'valid', 'test')):
             out[split] = arr(2 + k, (cnt(2 + k), 3), np.int64)
         for q, name in enumerate(('train', 'valid_tail', 'valid_head', 'test_tail', 'test_head')):
-            nq, nnz = cnt(10 + 2 * q), cnt(11 + 2 * q)
-            out['q_' + name] = QuerySet(arr(10 + 3 * q, (nq, 3), np.int64), arr(11 + 3 * q, (nq + 1,), np.int64),
-                                        arr(12 + 3 * q, (nnz,), np.int32), train=(q == 0))
+            nq, nnz, rows = cnt(10 + 2 * q), cnt(11 + 2 * q), cnt(20 + q)
+            out['q_' + name] = QuerySet(arr(10 + 3 * q, (nq, 3), np.int64), arr(11 + 3 * q, (rows + 1,), np.int64),
+                                        arr(12 + 3 * q, (nnz,), np.int32), train=(q == 0),
+                                        qg=None if q == 0 else arr(30 + q, (nq,), np.int32))
         return out
     finally:
         h.kgc_ingest_close(handle)
@@ -132,19 +163,33 @@ class KBDataset(object):
         if isinstance(triplets, QuerySet):                       # CSR arrays straight from the native ingest (N4)
             self._triplets = None
             self._lazy = triplets
-            self.triples, self.ptr, self.idx = triplets.triples, triplets.ptr, triplets.idx
+            self.triples = triplets.triples
+            self._ptr = self._idx = None                           # per-query form: expanded on first use
         else:
             self._triplets = triplets
+            self._lazy = None
             q = len(triplets)
             self.triples = np.asarray([t['triple'] for t in triplets], dtype=np.int64).reshape(q, 3)
-            self.ptr = np.zeros(q + 1, dtype=np.int64)
+            self._ptr = np.zeros(q + 1, dtype=np.int64)
             idx = []
             for i, t in enumerate(triplets):
                 objs = sorted(int(o) for o in t['label'])
                 idx.extend(objs)
-                self.ptr[i + 1] = len(idx)
-            self.idx = np.asarray(idx, dtype=np.int32)
+                self._ptr[i + 1] = len(idx)
+            self._idx = np.asarray(idx, dtype=np.int32)
         self._dev = {}
+
+    @property
+    def ptr(self):
+        if self._ptr is None:
+            self._ptr, self._idx = self._lazy.flat
+        return self._ptr
+
+    @property
+    def idx(self):
+        if self._idx is None:
+            self._ptr, self._idx = self._lazy.flat
+        return self._idx
 
     @property
     def triplets(self):
@@ -190,10 +235,10 @@ class KBDataset(object):
     def sparse_batch(self, qid):
         """Host CSR slice for the fused scorer: (triple[B,3], filt_ptr[B+1] int64, filt_idx[nnz] int32), numpy."""
         qid = np.asarray(qid, dtype=np.int64)
-        lens = self.ptr[qid + 1] - self.ptr[qid]
-        fptr = np.zeros(qid.shape[0] + 1, dtype=np.int64)
-        np.cumsum(lens, out=fptr[1:])
-        fidx = np.concatenate([self.idx[self.ptr[q]:self.ptr[q + 1]] for q in qid]) if qid.size else self.idx[:0]
+        if self._lazy is not None and self._ptr is None:           # group-indirect sets: no per-query copy of hub lists
+            fptr, fidx = self._lazy.segments(qid)
+        else:
+            fptr, fidx = _gather_segments(self.ptr, self.idx, qid)
         return self.triples[qid], fptr, fidx.astype(np.int32)
 
     def collate_fn(self, batch):

@@ -297,6 +297,17 @@ def _same_loader(a, b):
         assert [(tuple(q['triple']), sorted(q['label'])) for q in a.triplets[key]] == \
             [(tuple(q['triple']), sorted(q['label'])) for q in b.triplets[key]]
         assert all(('sub_samp' in q) == (key == 'train') for q in a.triplets[key])
+        # sparse (CSR) batches for the fused scorer: same slices, and the group-indirect valid / test sets of the native
+        # ingest serve them without expanding a per-query copy of every filter list
+        fresh = a._get_dataset(key, params())
+        rng = np.random.default_rng(len(qb))
+        for _ in range(3):
+            qid = rng.integers(0, len(qb), size=min(5, len(qb)))
+            for x, y in zip(fresh.sparse_batch(qid), qb.sparse_batch(qid)):
+                np.testing.assert_array_equal(x, y)
+                assert x.dtype == y.dtype
+        if getattr(fresh, '_lazy', None) is not None and key != 'train':
+            assert fresh._ptr is None and fresh._lazy.qg is not None
 
 
 def test_native_ingest_matches_python_passes(tmp_path, golden_dir):
