@@ -365,3 +365,15 @@ def test_native_ingest_failures_and_fallbacks(tmp_path):
         dl = _load(root, name, True)
         assert not isinstance(dl.triplets, LazyTriplets)
         _same_loader(dl, _load(root, name, False))
+
+
+def test_gather_segments_edge_cases():
+    from kgc_gcn_b200.data_loader import _gather_segments
+    ptr = np.asarray([0, 0, 3, 3, 4], dtype=np.int64)          # rows of length 0, 3, 0, 1
+    idx = np.asarray([7, 8, 9, 5], dtype=np.int32)
+    p, v = _gather_segments(ptr, idx, [])
+    assert p.tolist() == [0] and v.shape == (0,)
+    p, v = _gather_segments(ptr, idx, [0, 2])
+    assert p.tolist() == [0, 0, 0] and v.shape == (0,)
+    p, v = _gather_segments(ptr, idx, [3, 1, 1, 0])
+    assert p.tolist() == [0, 1, 4, 7, 7] and v.tolist() == [5, 7, 8, 9, 7, 8, 9] and v.dtype == np.int32
