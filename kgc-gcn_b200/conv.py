@@ -419,10 +419,16 @@ class _ConvFn(torch.autograd.Function):
         flat = torch.empty((3 * D * Dout + T * D + (Dout if ctx.has_bias else 0),), dtype=torch.float32, device=dev)
         d_w_in, d_w_out, m_loop = (flat[k * D * Dout:(k + 1) * D * Dout].view(D, Dout) for k in range(3))
         d_relp = flat[3 * D * Dout:3 * D * Dout + T * D].view(T, D)
-        # weight-gradient reductions over the node rows (K4c: register-tiled fp32, deterministic)
-        gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
-        if ctx.has_bias:
-            torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
+        # weight-gradient reductions over the node rows (K4c on the tensor cores, deterministic).  Nothing on the d_x / d_ee /
+        # d_rel chain below needs them: on one GPU they run on the side stream next to that chain (a K4c CTA leaves room for
+        # one aggregation CTA per SM) and the main stream joins before the parameter-gradient kernel
+        main, side = torch.cuda.current_stream(), (plan.side_stream() if coll is None else None)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
+            if ctx.has_bias:
+                torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
         g3 = plan.scratch('g3', (3, Nb, D))
@@ -466,6 +472,8 @@ class _ConvFn(torch.autograd.Function):
             if scatter is not None:
                 scatter.wait()
             d_x = d_x[:Nl] + g3[2, :Nl]                               # self-loop term of this rank's (real) rows
+        if side is not None:
+            main.wait_stream(side)
         d_bias = flat[3 * D * Dout + T * D:] * 3.0 if ctx.has_bias else None
         # K0 backward: self-loop vectors, relation transform (model.py:107; replicated inputs, identical on every rank)
         small = torch.empty((2 * D * Dout + 2 * D + (T - 1) * D,), dtype=torch.float32, device=dev)
