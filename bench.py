@@ -370,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
                    'l2': 'flushed between steps (256 MiB memset + 256 MiB read, outside the timed events)', 'launch': launch_mode,
                    'parallelism': 'single GPU' if world == 1 else 'edge-balanced dst partition over {} GPUs ({} split hub rows); halo exchange of x / d_x: {}; all-reduce of hub rows, BN sums, replicated grads: NCCL'.format(world, part.n_hub, 'pulls over NVLink peer memory (K10)' if part.p2p(D_IN) is not None else 'NCCL all-gather / reduce-scatter')},
         'e2e': {'value': e2e_value, 'unit': 'edges/s', 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
-                'ms_per_step': e2e['ms_total'] / max(e2e['steps'], 1), 'eager_ms_per_step': e2e.get('eager_ms_per_step'),
+                'ms_per_step': e2e['ms_total'] / e2e['steps'] if e2e['steps'] else None, 'eager_ms_per_step': e2e.get('eager_ms_per_step'),
                 'scope': e2e['scope']},
         'gpu_launches': launches_per_step * args.steps,
         'clocks': clocks.summary(),
