@@ -362,6 +362,24 @@ int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent,
 int kgc_score_1n_bwd_logit(const float* d_pred, int64_t ld_dp, const float* pred, int64_t ld_p, int64_t n_ent,
                            int32_t B, int32_t ldt, float* d_logitT, float* d_bias, void* stream);
 
+/* ---- N1: training loss against SPARSE positives ------------------------------------------
+ * Replaces the dense label build (data_loader.py:34-43), its host-to-device copy (main.py:60), BCELoss (model.py:42-44,
+ * main.py:62) and the loss's backward down to the logit gradient, for the batch's query ids and the query->objects CSR
+ * that kgc_label_build takes.  kgc_label_mask_build: mask[b, w] (uint32 [B, kgc_label_mask_words(N)], zeroed here) gets
+ * bit (j & 31) of word (j >> 5) set for every positive j of query qid[b]; triple_out as in kgc_label_build (may be NULL).
+ * kgc_bce_1n_bwd_logit: with y[b, n] = pos where the bit is set, add elsewhere, and p = pred[b, n] (kgc_score_1n_fwd):
+ *   loss[0]        = mean_{b,n} ((y - 1) * max(log1p(-p), -100) - y * max(log(p), -100))       (torch BCELoss, mean)
+ *   d_logitT[n, b] = (p - y) / max((1 - p) p, 1e-12) / (B N) * p * (1 - p)   ([n_ent, ldt], columns [B, ldt) zeroed)
+ *   d_bias[n]      = sum_b d_logitT[n, b]
+ * i.e. the gradient of the loss for a unit upstream gradient, in the layout kgc_score_1n_bwd_logit produces.
+ * loss_partial: double [kgc_label_mask_words(n_ent)] workspace; sums are formed in a fixed order (deterministic). */
+int64_t kgc_label_mask_words(int64_t n_entity);
+int kgc_label_mask_build(const int64_t* qid, int64_t B, const int64_t* triples, const int64_t* ptr, const int32_t* idx,
+                         int64_t n_entity, uint32_t* mask, int64_t* triple_out, void* stream);
+int kgc_bce_1n_bwd_logit(const float* pred, int64_t ld_p, const uint32_t* mask, int64_t n_ent, int32_t B, int32_t ldt,
+                         float pos, float add, float* d_logitT, float* d_bias, double* loss_partial, float* loss,
+                         void* stream);
+
 /* ---- K6: fused 1-N scoring + filter + rank (tcgen05 / TMA) --------------------------------------------
  * Replaces model.py:177-178 (X @ all_ent^T + bias) and main.py:122-126 (filter, rank) without
  * materialising the [B,N] score matrix.  Ranking is on the logit (sigmoid is monotone and saturates,

@@ -219,6 +219,24 @@ class MGCN(nn.Module):
     def loss(self, pred, label):
         return self.loss_fn(pred, label)
 
+    def loss_sparse(self, qid, dataset, data):
+        """``loss(forward(src, rel, data), label)`` for the training queries ``qid`` of ``dataset`` (a KBDataset) without the
+        dense [B, N] label or the BCE tensors: src / rel are the queries' triples and the label is read
+        as sparse positives from the dataset's CSR with its ``label_values()`` (label smoothing as data_loader.py:41-43).
+        Same value and gradients as the dense route within fp32 rounding (tests/test_gpu_zz_loss.py)."""
+        from .scoring import score_1n_bce, score_1n_supported
+        dev = self.entity_embedding.device
+        triples, ptr, idx = dataset.device_csr(dev)
+        qid = torch.as_tensor(qid, dtype=torch.int64).to(dev, non_blocking=True)
+        trip = torch.index_select(triples, 0, qid)
+        all_ent, all_rel = self.encode(data)
+        x = self.conv2.query(torch.index_select(all_ent, 0, trip[:, 0]), torch.index_select(all_rel, 0, trip[:, 1]))
+        if not score_1n_supported(x, all_ent):
+            raise RuntimeError('loss_sparse: shape not taken by the tensor-core scorer (B <= 256, Dout <= 224, Dout % 4 == 0); '
+                               'use loss(forward(...), label)')
+        pos, add = dataset.label_values()
+        return score_1n_bce(x, all_ent, self.conv2.bias, qid, ptr, idx, pos, add)
+
     def rank(self, src, rel, obj, filt_ptr, filt_idx, data, count_eq=False):
         """Filtered rank of obj among all entities for the queries (src, rel) without materialising the
         [B, N] scores (K6): what main.py:121-126 computes from model(sub, rel, graph)."""

@@ -70,6 +70,64 @@ def score_1n(x, all_ent, bias):
     return _Score1N.apply(x, all_ent, bias)
 
 
+class _Score1NBCE(torch.autograd.Function):
+    """loss = BCELoss(sigmoid(x @ all_ent^T + bias), label) with the label given as SPARSE positives:
+    model.py:177-179 + model.py:42-44 + the label build of data_loader.py:34-43 in one differentiable call.  The forward
+    runs the K6t scorer, sets one bit per positive and makes ONE pass over pred that yields the mean loss, the logit
+    gradient (transposed) and the bias gradient for a unit upstream gradient; the backward scales by the upstream scalar
+    and runs the two gradient GEMMs.  The dense label and the BCE forward / backward tensors are never built."""
+
+    @staticmethod
+    def forward(ctx, x, all_ent, bias, qid, ptr, idx, pos, add):
+        x = _lib.require_cuda(x.detach(), torch.float32, 'x')
+        ent = _lib.require_cuda(all_ent.detach(), torch.float32, 'all_ent')
+        bias_ = _lib.require_cuda(bias.detach(), torch.float32, 'bias')
+        qid = _lib.require_cuda(qid, torch.int64, 'qid')
+        ptr = _lib.require_cuda(ptr, torch.int64, 'ptr')
+        idx = _lib.require_cuda(idx, torch.int32, 'idx')
+        B, D = int(x.shape[0]), int(x.shape[1])
+        N = int(ent.shape[0])
+        if int(qid.numel()) != B:
+            raise ValueError('qid has {} entries for {} queries'.format(int(qid.numel()), B))
+        ldp, ldt = (N + 3) // 4 * 4, (B + 3) // 4 * 4
+        p, dev = _lib.ptr, x.device
+        packed = torch.empty((int(_lib.lib().kgc_gemm_packed_b_bytes(B, D)) // 4,), dtype=torch.float32, device=dev)
+        pred = torch.empty((B, ldp), dtype=torch.float32, device=dev)
+        _lib.call('kgc_gemm_pack_b', p(x), x.stride(1), x.stride(0), B, D, p(packed), _lib.stream())
+        _lib.call('kgc_score_1n_fwd', p(ent), N, D, ent.stride(0), p(packed), B, p(bias_), p(pred), ldp, _lib.stream())
+        words = int(_lib.lib().kgc_label_mask_words(N))
+        mask = torch.empty((B, words), dtype=torch.int32, device=dev)            # uint32 bits; zeroed by the call
+        _lib.call('kgc_label_mask_build', p(qid), B, None, p(ptr), p(idx), N, p(mask), None, _lib.stream())
+        d_logit_t = torch.empty((N, ldt), dtype=torch.float32, device=dev)
+        d_bias = torch.empty((N,), dtype=torch.float32, device=dev)
+        partial = torch.empty((words,), dtype=torch.float64, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        _lib.call('kgc_bce_1n_bwd_logit', p(pred), ldp, p(mask), N, B, ldt, float(pos), float(add), p(d_logit_t), p(d_bias),
+                  p(partial), p(loss), _lib.stream())
+        ctx.save_for_backward(x, ent, d_logit_t, d_bias)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        from .conv import gemm_nt, gemm_tn
+        x, ent, d_logit_t, d_bias = ctx.saved_tensors
+        B, D = int(x.shape[0]), int(x.shape[1])
+        N, ldt = int(ent.shape[0]), int(d_logit_t.shape[1])
+        d_x = d_ent = None
+        if ctx.needs_input_grad[0]:
+            d_x = gemm_tn(d_logit_t, ent, torch.empty((ldt, D), dtype=torch.float32, device=x.device))[:B] * g
+        if ctx.needs_input_grad[1]:                      # the upstream scalar rides on the small operand
+            d_ent = gemm_nt(d_logit_t[:, :B], (x * g).contiguous(), torch.empty((N, D), dtype=torch.float32, device=x.device))
+        return d_x, d_ent, (d_bias * g if ctx.needs_input_grad[2] else None), None, None, None, None, None
+
+
+def score_1n_bce(x, all_ent, bias, qid, ptr, idx, pos=1.0, add=0.0):
+    """Mean BCE of sigmoid(x @ all_ent^T + bias) against the labels of queries ``qid`` (device int64 [B]) given as the
+    query -> objects CSR (``ptr`` int64, ``idx`` int32, on the device): label = ``pos`` on the positives, ``add`` elsewhere
+    (``KBDataset.label_values()``).  Differentiable in x, all_ent and bias; same shapes as ``score_1n_supported``."""
+    return _Score1NBCE.apply(x, all_ent, bias, qid, ptr, idx, pos, add)
+
+
 def score_kpad(d):
     kpad = int(_lib.lib().kgc_score_kpad(int(d)))
     if kpad < 0:

@@ -15,9 +15,11 @@ class GraphedTrainStep(object):
 
     ``optimizer`` must be capturable (``kgc_gcn_b200.ClipAdam(..., max_norm=clip_grad)``, which also does the gradient
     clipping, or ``torch.optim.Adam(..., capturable=True)``); ``dataset`` is the KBDataset of the
-    training queries; batches whose size differs from ``batch_size`` (the last one of an epoch) run eagerly."""
+    training queries; batches whose size differs from ``batch_size`` (the last one of an epoch) run eagerly.
+    ``fused_loss=True`` (opt-in) trains through ``MGCN.loss_sparse``: the label stays a sparse list of positives and the
+    dense [B, N] label, its build and the BCE tensors drop out of the step."""
 
-    def __init__(self, model, optimizer, graph, dataset, batch_size, clip_grad=1.0, warmup=3):
+    def __init__(self, model, optimizer, graph, dataset, batch_size, clip_grad=1.0, warmup=3, fused_loss=False):
         self.model, self.opt, self.graph_data, self.ds = model, optimizer, graph, dataset
         self.clip, self.B = float(clip_grad), int(batch_size)
         dev = graph.edge_index.device
@@ -26,7 +28,8 @@ class GraphedTrainStep(object):
         self.dev = dev
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.trip = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
-        self.label = torch.zeros((self.B, dataset.num_entity), dtype=torch.float32, device=dev)
+        self.fused_loss = bool(fused_loss)
+        self.label = None if self.fused_loss else torch.zeros((self.B, dataset.num_entity), dtype=torch.float32, device=dev)
         self.qid = torch.zeros((self.B,), dtype=torch.int64, device=dev)
         self._opt_clips = bool(getattr(optimizer, 'param_groups', None)) and \
             all(g.get('max_norm') for g in optimizer.param_groups)
@@ -38,15 +41,20 @@ class GraphedTrainStep(object):
         """Host ids -> static device buffers (H2D of B int64), then K5 into the static triple / label buffers."""
         host = torch.as_tensor(qid, dtype=torch.int64)
         self.qid.copy_(host, non_blocking=True)
+        if self.fused_loss:                           # the graph reads the triples and the positives through qid
+            return
         triples, ptr, idx = self.ds.device_csr(self.dev)
         pos, add = self.ds.label_values()
         p = _lib.ptr
         _lib.call('kgc_label_build', p(self.qid), self.B, p(triples), p(ptr), p(idx), self.ds.num_entity, pos, add,
                   p(self.trip), p(self.label), _lib.stream())
 
-    def _body(self, trip, label):
-        pred = self.model(trip[:, 0], trip[:, 1], self.graph_data)
-        loss = self.model.loss(pred, label)
+    def _body(self, trip, label, qid=None):
+        if qid is not None:
+            loss = self.model.loss_sparse(qid, self.ds, self.graph_data)
+        else:
+            pred = self.model(trip[:, 0], trip[:, 1], self.graph_data)
+            loss = self.model.loss(pred, label)
         loss.backward()
         if not self._opt_clips:                       # ClipAdam(max_norm=...) clips inside its step (K9)
             torch.nn.utils.clip_grad_norm_(self.params, self.clip)
@@ -67,7 +75,7 @@ class GraphedTrainStep(object):
         with torch.cuda.stream(side):
             for _ in range(max(self._warmup, 1)):
                 self.opt.zero_grad(set_to_none=True)
-                self._body(self.trip, self.label)
+                self._body(self.trip, self.label, self.qid if self.fused_loss else None)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -84,12 +92,14 @@ class GraphedTrainStep(object):
         self.cuda_graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.cuda_graph):
-            self.loss = self._body(self.trip, self.label)
+            self.loss = self._body(self.trip, self.label, self.qid if self.fused_loss else None)
 
     def __call__(self, qid):
         if len(qid) != self.B:                       # ragged last batch: the eager path (same arithmetic)
-            trip, label = self.ds.build_batch(qid, self.dev)
             self.opt.zero_grad(set_to_none=True)
+            if self.fused_loss:
+                return self._body(None, None, torch.as_tensor(qid, dtype=torch.int64).to(self.dev))
+            trip, label = self.ds.build_batch(qid, self.dev)
             return self._body(trip, label)
         self._fill(qid)
         if hasattr(self.opt, 'sync_hyper'):

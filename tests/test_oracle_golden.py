@@ -175,3 +175,37 @@ def test_stable_csr():
     perm, rowptr = orc.stable_csr(keys, 7)
     assert perm.tolist() == [3, 1, 4, 0, 2, 5, 6]
     assert rowptr.tolist() == [0, 1, 3, 3, 6, 6, 7, 7]
+
+
+@pytest.mark.parametrize('smooth', [0.0, 0.1])
+def test_sparse_bce_matches_torch_bce_on_dense_labels(toy_ds, smooth):
+    """N1 pin: the sparse-positives loss restatement == the reference's loss path (dense label of data_loader.py:34-43,
+    nn.BCELoss of model.py:42-44, autograd through the sigmoid of model.py:179).  Without smoothing on the Toy training
+    queries; with smoothing on 50 entities (on Toy 0.9 + 1/7 > 1 and BCELoss rejects the label).
+    A saturated-logit pair exercises the clamps of torch's BCE.  float64: 1e-12, float32: 1e-6."""
+    if smooth:
+        n, rng = 50, np.random.default_rng(3)
+        queries = [{'triple': (i, 0, -1), 'label': set(rng.choice(n, size=1 + i % 5, replace=False).tolist())} for i in range(12)]
+    else:
+        queries, n = toy_ds['queries']['train'], toy_ds['num_entity']
+    ptr, idx = orc.queries_to_csr(queries)
+    qid = list(range(len(queries)))[::-1]
+    _, lab = orc.make_batch(queries, qid, n, smooth, training=True)
+    pos, add = float(lab.max()), float(lab.min())               # the two float32 label values (1, 0 without smoothing)
+    gen = torch.Generator().manual_seed(5)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 1e-6)):
+        z = torch.randn((len(qid), n), generator=gen, dtype=torch.float64) * 4.0
+        z[0, 0], z[1, 1] = 40.0, -120.0
+        z = z.to(dtype).requires_grad_(True)
+        pred = torch.sigmoid(z)
+        ref = torch.nn.BCELoss()(pred, torch.from_numpy(lab).to(dtype))
+        ref.backward()
+        loss, d_logit, d_bias = orc.bce_1n_sparse(pred.detach(), ptr, idx, qid, pos, add)
+        assert abs(float(loss) - float(ref.detach())) <= tol * abs(float(ref.detach()))
+        scale = float(z.grad.abs().max())
+        assert float((d_logit - z.grad).abs().max()) <= tol * scale
+        assert float((d_bias - z.grad.sum(0)).abs().max()) <= 10 * tol * scale
+    mask = orc.label_mask(ptr, idx, qid, n)                     # bit form of the same labels
+    cols = np.arange(n)
+    dense = ((mask[:, cols >> 5] >> (cols & 31).astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(dense, lab == pos)
