@@ -7,6 +7,8 @@ the convolution (K8) and the fc layer (3xTF32 tensor-core GEMMs) run on our kern
 call-compatible) and its autograd run on the 3xTF32 tensor-core kernels (K6t, scoring.score_1n); ``rank`` uses the
 fused tensor-core scoring + ranking kernel (K6).
 """
+import weakref
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -184,17 +186,23 @@ class MGCN(nn.Module):
         self.loss_fn = nn.BCELoss()
         self._arange_cache = {}
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_arange_cache'] = {}                      # weak references do not pickle; the cache refills on first use
+        return state
+
     def _is_arange(self, idx, n):
         """data.entity / edge_ids are arange in every graph the reference builds (data_loader.py:145-153);
         the identity gathers of model.py:29-30 are then skipped (they copy 16 MB + 70 MB per WN18RR step).
         The check costs one device sync, so it is cached on the identity + version of the index tensor."""
         key = (idx.data_ptr(), idx._version, idx.numel(), n, str(idx.device))
-        ok = self._arange_cache.get(key)
-        if ok is None:
-            ok = idx.numel() == n and bool((idx == torch.arange(n, device=idx.device)).all())
-            if len(self._arange_cache) > 16:
-                self._arange_cache.clear()
-            self._arange_cache[key] = ok
+        hit = self._arange_cache.get(key)
+        if hit is not None and hit[1]() is idx:          # same live tensor object: the address cannot have been recycled
+            return hit[0]
+        ok = idx.numel() == n and bool((idx == torch.arange(n, device=idx.device)).all())
+        if len(self._arange_cache) > 16:
+            self._arange_cache.clear()
+        self._arange_cache[key] = (ok, weakref.ref(idx))
         return ok
 
     def encode(self, data):
