@@ -10,9 +10,11 @@
 // mentions it, "tail" key before "head" key within a line.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -20,110 +22,118 @@
 
 namespace {
 
-// open-addressing hash tables (linear probing, power-of-two capacity, load <= 0.5): the per-line work of both passes is
-// two to three look-ups, and std::unordered_map's node allocations dominated the first version
+// open-addressing hash tables (linear probing, power-of-two capacity, load <= 0.5).  A look-up is ONE cache line: key / hash,
+// id and (for tokens of <= 16 bytes, i.e. every id of WN18RR / FB15k-237 / Wikidata) the lower-cased token itself sit in the
+// slot.  The tables of a real data set are far bigger than the caches, so both passes work on blocks of lines: hash the
+// block, prefetch its slots, then resolve in order (std::unordered_map's node allocations dominated the first version, the
+// cache misses of dependent probes the second).
 struct KeyTable {                // uint64 key -> dense id in insertion order
-  std::vector<uint64_t> keys;
-  std::vector<int32_t> ids;      // -1 = empty
+  struct Slot { uint64_t key; int32_t id; int32_t pad; };     // id -1 = empty
+  std::vector<Slot> slots;
   size_t n = 0;
-  KeyTable() : keys(1 << 16), ids(1 << 16, -1) {}
+  KeyTable() : slots(1 << 16, Slot{0, -1, 0}) {}
   static inline uint64_t mix(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
     return x;
   }
   void grow() {
-    std::vector<uint64_t> ok; std::vector<int32_t> oi;
-    ok.swap(keys); oi.swap(ids);
-    keys.assign(ok.size() * 2, 0); ids.assign(oi.size() * 2, -1);
-    const size_t mask = keys.size() - 1;
-    for (size_t i = 0; i < ok.size(); ++i)
-      if (oi[i] >= 0) {
-        size_t p = mix(ok[i]) & mask;
-        while (ids[p] >= 0) p = (p + 1) & mask;
-        keys[p] = ok[i]; ids[p] = oi[i];
+    std::vector<Slot> old(slots.size() * 2, Slot{0, -1, 0});
+    old.swap(slots);
+    const size_t mask = slots.size() - 1;
+    for (const Slot& o : old)
+      if (o.id >= 0) {
+        size_t p = mix(o.key) & mask;
+        while (slots[p].id >= 0) p = (p + 1) & mask;
+        slots[p] = o;
       }
   }
+  inline void prefetch(uint64_t key) const { __builtin_prefetch(&slots[mix(key) & (slots.size() - 1)]); }
   int32_t find(uint64_t key) const {
-    const size_t mask = keys.size() - 1;
+    const size_t mask = slots.size() - 1;
     size_t p = mix(key) & mask;
-    while (ids[p] >= 0) {
-      if (keys[p] == key) return ids[p];
+    while (slots[p].id >= 0) {
+      if (slots[p].key == key) return slots[p].id;
       p = (p + 1) & mask;
     }
     return -1;
   }
   int32_t find_or_insert(uint64_t key) {           // new keys get id n, n + 1, ...
-    if (2 * (n + 1) > keys.size()) grow();
-    const size_t mask = keys.size() - 1;
+    if (2 * (n + 1) > slots.size()) grow();
+    const size_t mask = slots.size() - 1;
     size_t p = mix(key) & mask;
-    while (ids[p] >= 0) {
-      if (keys[p] == key) return ids[p];
+    while (slots[p].id >= 0) {
+      if (slots[p].key == key) return slots[p].id;
       p = (p + 1) & mask;
     }
-    keys[p] = key; ids[p] = (int32_t)n;
+    slots[p].key = key; slots[p].id = (int32_t)n;
     return (int32_t)n++;
   }
 };
 
-struct TokenTable {              // token bytes -> dense id in insertion order; the tokens live in `names`
-  std::vector<uint64_t> hashes;
-  std::vector<int32_t> ids;
+struct Token {                   // one whitespace-separated token of a line, hashed over its lower-cased bytes
+  const char* p;
+  uint32_t len;
+  bool upper;                    // holds an ASCII upper-case letter: the reference's case-sensitive look-up will not find it
+  uint64_t hash;
+  char low[16];                  // lower-cased bytes, zero padded (len <= 16)
+};
+
+struct TokenTable {              // lower-cased token bytes -> dense id in insertion order; the tokens live in `names`
+  struct Slot { uint64_t hash; int32_t id; uint32_t len; char low[16]; };       // 32 bytes; id -1 = empty
+  std::vector<Slot> slots;
   std::vector<std::string>* names;
-  explicit TokenTable(std::vector<std::string>* nm) : hashes(1 << 16), ids(1 << 16, -1), names(nm) {}
-  static inline uint64_t hash(const char* p, size_t n, bool fold) {
-    uint64_t h = 1469598103934665603ull;             // FNV-1a over the (optionally lower-cased) bytes
+  explicit TokenTable(std::vector<std::string>* nm) : slots(1 << 16, Slot{0, -1, 0, {0}}), names(nm) {}
+  static inline void scan(const char* p, size_t n, Token* t) {
+    uint64_t h = 1469598103934665603ull;             // FNV-1a over the lower-cased bytes
+    bool up = false;
+    memset(t->low, 0, sizeof(t->low));
     for (size_t i = 0; i < n; ++i) {
       unsigned char c = (unsigned char)p[i];
-      if (fold && c >= 'A' && c <= 'Z') c = (unsigned char)(c - 'A' + 'a');
+      if (c >= 'A' && c <= 'Z') { c = (unsigned char)(c - 'A' + 'a'); up = true; }
+      if (i < sizeof(t->low)) t->low[i] = (char)c;
       h = (h ^ c) * 1099511628211ull;
     }
-    return KeyTable::mix(h);
+    t->p = p; t->len = (uint32_t)n; t->upper = up; t->hash = KeyTable::mix(h);
   }
-  static inline bool same(const std::string& a, const char* p, size_t n, bool fold) {
-    if (a.size() != n) return false;
-    for (size_t i = 0; i < n; ++i) {
-      unsigned char c = (unsigned char)p[i];
-      if (fold && c >= 'A' && c <= 'Z') c = (unsigned char)(c - 'A' + 'a');
+  inline bool same(const Slot& s, const Token& t) const {
+    if (s.hash != t.hash || s.len != t.len) return false;
+    if (t.len <= sizeof(t.low)) return memcmp(s.low, t.low, sizeof(t.low)) == 0;
+    const std::string& a = (*names)[s.id];             // long token: compare the stored lower-cased name
+    for (size_t i = 0; i < t.len; ++i) {
+      unsigned char c = (unsigned char)t.p[i];
+      if (c >= 'A' && c <= 'Z') c = (unsigned char)(c - 'A' + 'a');
       if ((unsigned char)a[i] != c) return false;
     }
     return true;
   }
   void grow() {
-    std::vector<uint64_t> oh; std::vector<int32_t> oi;
-    oh.swap(hashes); oi.swap(ids);
-    hashes.assign(oh.size() * 2, 0); ids.assign(oi.size() * 2, -1);
-    const size_t mask = hashes.size() - 1;
-    for (size_t i = 0; i < oh.size(); ++i)
-      if (oi[i] >= 0) {
-        size_t q = oh[i] & mask;
-        while (ids[q] >= 0) q = (q + 1) & mask;
-        hashes[q] = oh[i]; ids[q] = oi[i];
+    std::vector<Slot> old(slots.size() * 2, Slot{0, -1, 0, {0}});
+    old.swap(slots);
+    const size_t mask = slots.size() - 1;
+    for (const Slot& o : old)
+      if (o.id >= 0) {
+        size_t q = o.hash & mask;
+        while (slots[q].id >= 0) q = (q + 1) & mask;
+        slots[q] = o;
       }
   }
-  // fold = true: compare / store the lower-cased token (pass 1); fold = false: the bytes as written (pass 2)
-  int32_t find(const char* p, size_t n, bool fold) const {
-    const uint64_t h = hash(p, n, fold);
-    const size_t mask = hashes.size() - 1;
-    size_t q = h & mask;
-    while (ids[q] >= 0) {
-      if (hashes[q] == h && same((*names)[ids[q]], p, n, fold)) return ids[q];
+  inline void prefetch(const Token& t) const { __builtin_prefetch(&slots[t.hash & (slots.size() - 1)]); }
+  int32_t intern(const Token& t) {                   // id of the lower-cased token; new tokens get the next id
+    if (2 * (names->size() + 1) > slots.size()) grow();
+    const size_t mask = slots.size() - 1;
+    size_t q = t.hash & mask;
+    while (slots[q].id >= 0) {
+      if (same(slots[q], t)) return slots[q].id;
       q = (q + 1) & mask;
     }
-    return -1;
-  }
-  void intern_lower(const char* p, size_t n) {
-    if (2 * (names->size() + 1) > hashes.size()) grow();
-    const uint64_t h = hash(p, n, true);
-    const size_t mask = hashes.size() - 1;
-    size_t q = h & mask;
-    while (ids[q] >= 0) {
-      if (hashes[q] == h && same((*names)[ids[q]], p, n, true)) return;
-      q = (q + 1) & mask;
-    }
-    hashes[q] = h; ids[q] = (int32_t)names->size();
-    names->emplace_back(p, n);
-    for (auto& c : names->back())
-      if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+    Slot& s = slots[q];
+    s.hash = t.hash; s.id = (int32_t)names->size(); s.len = t.len;
+    memcpy(s.low, t.low, sizeof(s.low));
+    names->emplace_back(t.p, t.len);
+    if (t.upper)
+      for (auto& c : names->back())
+        if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+    return s.id;
   }
 };
 
@@ -207,7 +217,19 @@ int for_each_line(const std::string& text, std::string* err, Fn fn) {
   return 0;
 }
 
+struct PhaseTimer {               // KGC_INGEST_TIMING=1: wall time per phase on stderr
+  bool on = getenv("KGC_INGEST_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[kgc_ingest] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 int ingest(const std::string& dir, kgc_ingest* h) {
+  PhaseTimer timer;
   static const char* kNames[3] = {"train.txt", "valid.txt", "test.txt"};
   std::string text[3];
   for (int s = 0; s < 3; ++s)
@@ -215,20 +237,45 @@ int ingest(const std::string& dir, kgc_ingest* h) {
       h->error = "cannot read " + dir + "/" + kNames[s];
       return 3;
     }
-  // ---- pass 1: ids in first-appearance order, tokens lower-cased
+  timer.lap("read files");
+  // ---- pass 1: ids in first-appearance order over the lower-cased tokens, and with them the triples.  The reference looks
+  // the tokens up a second time AS WRITTEN (data_loader.py:83-85) in the lower-cased vocabulary: a token without an ASCII
+  // upper-case letter is its own lower-cased form (found, same id), any other token cannot be in the vocabulary (KeyError) -
+  // so the second text pass reduces to remembering the first such token in reading order.
   TokenTable ent(&h->ent_names), rel(&h->rel_names);
+  constexpr size_t kWindow = 32;                       // lines between a slot prefetch and its use
+  std::vector<Token> win(3 * kWindow);
+  std::string first_upper;
+  bool any_upper = false;
   for (int s = 0; s < 3; ++s) {
+    std::vector<int64_t>& tri = h->split[s].triples;
+    tri.reserve(3 * (text[s].size() / 12 + 1));        // a line of three tokens holds >= 6 bytes; typical lines 15-40
+    size_t seen = 0, done = 0;
+    auto resolve = [&](const Token* t) {
+      const int64_t a = ent.intern(t[0]), r = rel.intern(t[1]), o = ent.intern(t[2]);
+      tri.insert(tri.end(), {a, r, o});
+      if (!any_upper && (t[0].upper || t[1].upper || t[2].upper)) {
+        const Token& u = t[0].upper ? t[0] : (t[1].upper ? t[1] : t[2]);
+        first_upper.assign(u.p, u.len);
+        any_upper = true;
+      }
+    };
     const int rc = for_each_line(text[s], &h->error, [&](const char** tok, const size_t* len) {
-      ent.intern_lower(tok[0], len[0]);
-      rel.intern_lower(tok[1], len[1]);
-      ent.intern_lower(tok[2], len[2]);
+      if (seen - done == kWindow) resolve(&win[3 * (done++ % kWindow)]);
+      Token* t = &win[3 * (seen++ % kWindow)];
+      for (int k = 0; k < 3; ++k) TokenTable::scan(tok[k], len[k], &t[k]);
+      ent.prefetch(t[0]);
+      ent.prefetch(t[2]);
       return 0;
     });
     if (rc) {
       h->error = std::string(kNames[s]) + ": " + h->error;
       return rc;
     }
+    while (done < seen) resolve(&win[3 * (done++ % kWindow)]);
+    tri.shrink_to_fit();
   }
+  timer.lap("pass 1 (vocabulary, ids)");
   const int64_t R = (int64_t)h->rel_names.size();
   for (const auto& name : h->rel_names)
     if (name.size() >= 8 && name.compare(name.size() - 8, 8, "_reverse") == 0) {
@@ -240,39 +287,44 @@ int ingest(const std::string& dir, kgc_ingest* h) {
     h->error = "more than 2^31 entities or relations";
     return 3;
   }
-  // ---- pass 2: triples (tokens as written); every line adds o to group (s, r) and s to group (o, r + R).  Groups get
-  // dense ids in creation order (= Python's dict insertion order); memberships are kept as flat (group, value) pairs
+  if (any_upper) {
+    h->error = first_upper;                              // the reference raises KeyError(token) here
+    return 4;
+  }
+  // ---- pass 2 (over the id triples): every line adds o to group (s, r) and s to group (o, r + R).  Groups get dense ids in
+  // creation order (= Python's dict insertion order); memberships are kept as flat (group, value) pairs
   KeyTable gid;
   std::vector<int32_t> pair_g, pair_v;
   size_t n_train_groups = 0, n_train_pairs = 0;
+  {
+    size_t total = 0;
+    for (int s = 0; s < 3; ++s) total += h->split[s].triples.size() / 3;
+    pair_g.reserve(2 * total);
+    pair_v.reserve(2 * total);
+  }
   for (int s = 0; s < 3; ++s) {
-    const int rc = for_each_line(text[s], &h->error, [&](const char** tok, const size_t* len) {
-      int64_t id[3];
-      for (int k = 0; k < 3; ++k) {
-        const int32_t found = (k == 1 ? rel : ent).find(tok[k], len[k], false);
-        if (found < 0) {
-          h->error = std::string(tok[k], len[k]);        // the reference raises KeyError(token) here
-          return 4;
-        }
-        id[k] = found;
-      }
-      h->split[s].triples.insert(h->split[s].triples.end(), {id[0], id[1], id[2]});
-      pair_g.push_back(gid.find_or_insert(((uint64_t)id[0] << 32) | (uint64_t)id[1]));
-      pair_v.push_back((int32_t)id[2]);
-      pair_g.push_back(gid.find_or_insert(((uint64_t)id[2] << 32) | (uint64_t)(id[1] + R)));
-      pair_v.push_back((int32_t)id[0]);
-      return 0;
-    });
-    if (rc) return rc;
+    const std::vector<int64_t>& tri = h->split[s].triples;
+    const size_t n_line = tri.size() / 3;
+    auto key_tail = [&](size_t i) { return ((uint64_t)tri[3 * i] << 32) | (uint64_t)tri[3 * i + 1]; };
+    auto key_head = [&](size_t i) { return ((uint64_t)tri[3 * i + 2] << 32) | (uint64_t)(tri[3 * i + 1] + R); };
+    for (size_t i = 0; i < n_line && i < kWindow; ++i) { gid.prefetch(key_tail(i)); gid.prefetch(key_head(i)); }
+    for (size_t i = 0; i < n_line; ++i) {
+      if (i + kWindow < n_line) { gid.prefetch(key_tail(i + kWindow)); gid.prefetch(key_head(i + kWindow)); }
+      pair_g.push_back(gid.find_or_insert(key_tail(i)));
+      pair_v.push_back((int32_t)tri[3 * i + 2]);
+      pair_g.push_back(gid.find_or_insert(key_head(i)));
+      pair_v.push_back((int32_t)tri[3 * i]);
+    }
     if (s == 0) {
       n_train_groups = gid.n;
       n_train_pairs = pair_g.size();
     }
   }
+  timer.lap("pass 2 (ids, groups)");
   const size_t n_groups = gid.n;
   std::vector<uint64_t> group_key(n_groups);
-  for (size_t p = 0; p < gid.keys.size(); ++p)
-    if (gid.ids[p] >= 0) group_key[gid.ids[p]] = gid.keys[p];
+  for (const KeyTable::Slot& sl : gid.slots)
+    if (sl.id >= 0) group_key[sl.id] = sl.key;
   // counting sort of the pairs by group: segment [ptr[g], ptr[g + 1]) holds group g's values in arrival order
   auto bucket = [&](size_t n_pairs, size_t n_g, std::vector<int64_t>* ptr, std::vector<int32_t>* val) {
     ptr->assign(n_g + 1, 0);
@@ -303,12 +355,14 @@ int ingest(const std::string& dir, kgc_ingest* h) {
       c.triples[3 * g + 2] = -1;
     }
   }
+  timer.lap("train query set");
   // ---- valid / test queries: the objects of ALL splits; a group is sorted the first time a query needs it and shared
   // by every later query (a hub group is referenced by thousands of queries)
   std::vector<int64_t> all_ptr, all_len;
   std::vector<int32_t> all_val;
   bucket(pair_g.size(), n_groups, &all_ptr, &all_val);
   all_len.assign(n_groups, -1);
+  timer.lap("all-split buckets");
   auto all_objs = [&](int64_t a, int64_t r, const int32_t** b) -> int64_t {
     const int32_t g = gid.find(((uint64_t)a << 32) | (uint64_t)r);
     int32_t* lo = all_val.data() + all_ptr[g];
@@ -341,6 +395,7 @@ int ingest(const std::string& dir, kgc_ingest* h) {
       }
     }
   }
+  timer.lap("valid / test query sets");
   return 0;
 }
 

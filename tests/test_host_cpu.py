@@ -367,6 +367,39 @@ def test_native_ingest_failures_and_fallbacks(tmp_path):
         _same_loader(dl, _load(root, name, False))
 
 
+def test_native_ingest_long_tokens_and_first_keyerror(tmp_path):
+    """Tokens longer than the 16 bytes a hash slot stores inline (same 16-byte prefix, same length, differing only in the
+    tail; a 16-byte token next to its 17-byte extension) keep distinct ids; the KeyError names the FIRST case-mismatched
+    token in the reference's look-up order (train before valid before test; subject, relation, object within a line), and a
+    malformed line anywhere wins over it (the vocabulary pass fails first, data_loader.py:64-71)."""
+    root = str(tmp_path)
+    pre = 'x' * 16
+    names = [pre, pre + 'a', pre + 'b', pre + 'ab', pre + 'ba', 'x' * 15, 'y' * 40, 'y' * 39 + 'z']
+    rng = np.random.default_rng(11)
+    def lines(n):
+        return ''.join('%s rel_%s_%d %s\n' % (names[rng.integers(len(names))], 'q' * 20, rng.integers(3), names[rng.integers(len(names))])
+                       for _ in range(n))
+    _write_dataset(root, 'long', {'train': lines(60), 'valid': lines(10), 'test': lines(10)})
+    a = _load(root, 'long', True)
+    _same_loader(a, _load(root, 'long', False))
+    assert a.num_entity == len(set(names)) and a.num_relation == 3
+    ok = 'a r b\nb r c\n'
+    cases = {'k_rel': ({'train': 'a r b\nb R C\n', 'valid': ok, 'test': ok}, 'R'),
+             'k_obj': ({'train': 'a r b\nb r C\nA r b\n', 'valid': ok, 'test': ok}, 'C'),
+             'k_valid': ({'train': ok, 'valid': 'a r b\nb r Cc\n', 'test': 'Zz r b\n'}, 'Cc'),
+             'k_long': ({'train': 'a r b\n' + pre + 'Tail r b\n', 'valid': ok, 'test': ok}, pre + 'Tail')}
+    for name, (files, token) in cases.items():
+        _write_dataset(root, name, files)
+        for native in (True, False):
+            with pytest.raises(KeyError) as err:
+                _load(root, name, native)
+            assert err.value.args[0] == token, (name, native, err.value.args)
+    _write_dataset(root, 'k_short', {'train': 'A r b\n', 'valid': ok, 'test': 'a r\n'})
+    for native in (True, False):
+        with pytest.raises(ValueError):
+            _load(root, 'k_short', native)
+
+
 def test_gather_segments_edge_cases():
     from kgc_gcn_b200.data_loader import _gather_segments
     ptr = np.asarray([0, 0, 3, 3, 4], dtype=np.int64)          # rows of length 0, 3, 0, 1
