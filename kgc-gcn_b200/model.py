@@ -196,13 +196,16 @@ class MGCN(nn.Module):
         the identity gathers of model.py:29-30 are then skipped (they copy 16 MB + 70 MB per WN18RR step).
         The check costs one device sync, so it is cached on the identity + version of the index tensor."""
         key = (idx.data_ptr(), idx._version, idx.numel(), n, str(idx.device))
+        # ``edge_type, edge_ids = data.edge_attr`` (model.py:26) makes a NEW view object per call: the owner of the memory is
+        # the view's base.  While that object is alive the address cannot have been recycled for another tensor.
+        owner = idx._base if idx._base is not None else idx
         hit = self._arange_cache.get(key)
-        if hit is not None and hit[1]() is idx:          # same live tensor object: the address cannot have been recycled
+        if hit is not None and hit[1]() is owner:
             return hit[0]
         ok = idx.numel() == n and bool((idx == torch.arange(n, device=idx.device)).all())
         if len(self._arange_cache) > 16:
             self._arange_cache.clear()
-        self._arange_cache[key] = (ok, weakref.ref(idx))
+        self._arange_cache[key] = (ok, weakref.ref(owner))
         return ok
 
     def encode(self, data):

@@ -234,6 +234,31 @@ def test_state_dict_names():
     assert m.edge_embeddings.shape == (20, 8) and m.conv2.fc.weight.shape == (200, 14 * 14 * 2)
 
 
+def test_arange_check_is_cached_per_owner_tensor(monkeypatch):
+    """MGCN skips the identity gathers of model.py:29-30 when the index is arange; the (synchronising) check runs once per
+    index tensor - also for ``edge_type, edge_ids = data.edge_attr`` (model.py:26), which makes a new view object per call -
+    and again for a different tensor, whatever its address."""
+    import kgc_gcn_b200 as k
+    m = k.MGCN(7, 5, 10, params())
+    evaluations = [0]
+    real = torch.arange
+
+    def counting(*a, **kw):
+        evaluations[0] += 1
+        return real(*a, **kw)
+    attr = torch.stack([torch.zeros(20, dtype=torch.int64), real(20)])
+    monkeypatch.setattr(torch, 'arange', counting)
+    for _ in range(4):
+        _, edge_ids = attr
+        assert m._is_arange(edge_ids, 20)
+    assert evaluations[0] == 1
+    del attr, edge_ids
+    for _ in range(3):                                  # new tensors (the allocator may hand out the old address again)
+        _, edge_ids = torch.stack([torch.zeros(20, dtype=torch.int64), real(20).flip(0)])
+        assert not m._is_arange(edge_ids, 20)
+    assert not m._is_arange(real(5), 20) and m._is_arange(real(7), 7)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'kgc-gcn_b200')
     for fn in os.listdir(pkg):
