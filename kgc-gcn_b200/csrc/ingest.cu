@@ -243,7 +243,7 @@ int ingest(const std::string& dir, kgc_ingest* h) {
   // upper-case letter is its own lower-cased form (found, same id), any other token cannot be in the vocabulary (KeyError) -
   // so the second text pass reduces to remembering the first such token in reading order.
   TokenTable ent(&h->ent_names), rel(&h->rel_names);
-  constexpr size_t kWindow = 32;                       // lines between a slot prefetch and its use
+  constexpr size_t kWindow = 16;                       // lines between a slot prefetch and its use
   std::vector<Token> win(3 * kWindow);
   std::string first_upper;
   bool any_upper = false;
