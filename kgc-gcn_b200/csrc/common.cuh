@@ -33,6 +33,24 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE setting of a kernel: remember, per device, the largest value
+// this process has set, so that the attribute call stays off the launch path without breaking a process that drives several
+// GPUs.  (Concurrent first launches from two host threads may both set it: harmless.)
+struct SmemAttrCache {
+  size_t set[64] = {0};
+  template <typename Kernel>
+  cudaError_t ensure(Kernel kern, size_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && smem <= set[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && tracked) set[dev] = smem;
+    return e;
+  }
+};
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // 128-bit streaming load that does not allocate in L1 (the edge-embedding stream is read once).

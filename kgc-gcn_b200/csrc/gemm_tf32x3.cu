@@ -1063,11 +1063,8 @@ static int launch_gemm_nt(int n_prob, const float* const* A, int64_t M, int32_t 
   KGC_REQUIRE(stages >= 2, "shared-memory plan does not fit");
   P.stages = stages;
   const size_t smem = fixed + (size_t)stages * kTileA;
-  static size_t attr = 0;
-  if (smem > attr) {
-    KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static SmemAttrCache attr;
+  KGC_CUDA_TRY(attr.ensure(gemm_tf32x3_kernel, smem));
   // a multiple of (problems x column tiles) CTAs, at most one per SM, never more row-tile owners than row tiles
   const int groups = n_prob * t.n_ntiles;
   int per = kNumSMs / groups;
@@ -1151,11 +1148,8 @@ static int launch_gemm_tn_tc(int n_prob, const float* const* A, int64_t lda, con
   const size_t stage = (size_t)(P.ga + P.gb) * kTnBox;
   const size_t smem = (kTnStages + kTnLoStages) * stage + 512 + 1024;
   KGC_REQUIRE(smem <= 227 * 1024, "shared-memory plan does not fit");
-  static size_t attr = 0;
-  if (smem > attr) {
-    KGC_CUDA_TRY(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static SmemAttrCache attr;
+  KGC_CUDA_TRY(attr.ensure(gemm_tn_tc_kernel, smem));
   cudaStream_t st = as_stream(stream);
   gemm_tn_tc_kernel<<<slabs * n_prob, kThreadsG, smem, st>>>(maps, P);
   KGC_LAUNCH_CHECK();

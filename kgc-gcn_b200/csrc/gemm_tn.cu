@@ -132,11 +132,8 @@ int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t 
   const int64_t rows_per_cta = ceil_div(M, g);
   const size_t smem = (size_t)2 * kRowsPerStage * (8 * TI + 32 * TO) * sizeof(float);
   auto kern = gemm_tn_partial_kernel<TI, TO>;
-  static bool attr = false;
-  if (!attr) {
-    KGC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static SmemAttrCache attr;                           // one per <TI, TO> instantiation
+  KGC_CUDA_TRY(attr.ensure(kern, smem));
   kern<<<g, kThreadsTN, smem, st>>>(A, lda, B, ldb, M, Ka, Nb, rows_per_cta, ws);
   KGC_LAUNCH_CHECK();
   gemm_tn_reduce_kernel<<<(Ka * Nb + 31) / 32, dim3(32, 8), 0, st>>>(ws, g, Ka * Nb, C);

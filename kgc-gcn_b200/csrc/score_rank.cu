@@ -488,11 +488,8 @@ inline int check_kpad(int kpad) { return (kpad < 16 || kpad % 16 != 0 || kpad > 
 template <bool kPairs, bool kCountEq>
 int launch_score(const CUtensorMap& ma, const CUtensorMap& mb, const ScoreParams& P, cudaStream_t st) {
   auto kern = score_kernel<kPairs, kCountEq>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    KGC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  static SmemAttrCache attr;                           // one per <kPairs, kCountEq> instantiation
+  KGC_CUDA_TRY(attr.ensure(kern, (size_t)kSmemBytes));
   const int grid = P.n_items < kNumSMs ? P.n_items : kNumSMs;
   kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, P);
   KGC_LAUNCH_CHECK();
