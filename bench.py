@@ -461,8 +461,8 @@ def e2e_train_step(k, orc, tri, g, N, R, E, dev, args):
     per = {m: v[0] / v[1] for m, v in out.items() if v[1]}
     graphed = [m for m in ('graph', 'graph_fused') if m in per]
     head = min(graphed, key=per.get) if graphed else 'eager'
-    how = {'graph': 'GraphedTrainStep, one CUDA-graph replay per step): host query ids -> K5 dense label build -> MGCN forward -> BCE',
-           'graph_fused': 'GraphedTrainStep(fused_loss=True), one CUDA-graph replay per step): host query ids -> MGCN encoder + ConvE '
+    how = {'graph': 'GraphedTrainStep, one CUDA-graph replay per step): host query ids (pinned staging buffer) -> K5 dense label build -> MGCN forward -> BCE',
+           'graph_fused': 'GraphedTrainStep(fused_loss=True), one CUDA-graph replay per step): host query ids (pinned staging buffer) -> MGCN encoder + ConvE '
                           '-> 1-N scores -> BCE against the sparse positives fused with the logit gradient (N1)',
            'eager': 'eager loop): host query ids -> K5 dense label build -> MGCN forward -> BCE'}[head]
     res = {'ms_total': out[head][0], 'steps': out[head][1], 'h2d': BATCH * 8, 'd2h': 4,

@@ -33,6 +33,13 @@ class GraphedTrainStep(object):
         self.qid = torch.zeros((self.B,), dtype=torch.int64, device=dev)
         self._opt_clips = bool(getattr(optimizer, 'param_groups', None)) and \
             all(g.get('max_norm') for g in optimizer.param_groups)
+        # pinned staging buffer of the batch's query ids (the only per-step host -> device traffic) and the event that says
+        # the previous step's copy has left it
+        try:
+            self._pin = torch.empty((self.B,), dtype=torch.int64, pin_memory=True)
+            self._pin_done = torch.cuda.Event()
+        except RuntimeError:                          # no pinned memory to be had: stage from pageable memory
+            self._pin = self._pin_done = None
         self.loss = None
         self.cuda_graph = None
         self._warmup = int(warmup)
@@ -40,7 +47,13 @@ class GraphedTrainStep(object):
     def _fill(self, qid):
         """Host ids -> static device buffers (H2D of B int64), then K5 into the static triple / label buffers."""
         host = torch.as_tensor(qid, dtype=torch.int64)
-        self.qid.copy_(host, non_blocking=True)
+        if self._pin is not None and not host.is_cuda:
+            self._pin_done.synchronize()
+            self._pin.copy_(host)
+            self.qid.copy_(self._pin, non_blocking=True)
+            self._pin_done.record()
+        else:
+            self.qid.copy_(host, non_blocking=True)
         if self.fused_loss:                           # the graph reads the triples and the positives through qid
             return
         triples, ptr, idx = self.ds.device_csr(self.dev)
