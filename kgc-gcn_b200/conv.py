@@ -202,8 +202,11 @@ class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
     def __init__(self, group, world, n_global, n_hub=0, hub_idx_mine=None, hub_rows_mine=None, p2p=None, rank=0,
-                 halo_rows=None):
+                 halo_rows=None, n_loc=None):
         self.group, self.world, self.n_global, self.rank = group, int(world), int(n_global), int(rank)
+        # row stride of a rank's block of real rows (None: the caller's x has exactly that many rows).  When the node count
+        # is not a multiple of the number of ranks some ranks hold n_loc - 1 real rows; rows n_real .. n_loc do not exist
+        self.n_loc = None if n_loc is None else int(n_loc)
         self.p2p = p2p          # partition._P2PContext: halo exchange over NVLink peer memory (K10) instead of NCCL
         # edge-balanced partitions number a rank's node table COMPACTLY: its own block, then the remote rows it reads
         # (halo_rows = their ids in the gathered layout); None = range partition (table = all rows, global ids)
@@ -286,8 +289,11 @@ class _ConvFn(torch.autograd.Function):
         x = _lib.require_cuda(x, torch.float32, 'x')
         ee = _lib.require_cuda(ee, torch.float32, 'edge_embs')
         n_global = Nl if coll is None else coll.n_global
-        n_hub = 0 if coll is None else coll.n_hub           # virtual rows of split hubs follow the Nl real rows
-        Nb = Nl + n_hub
+        n_hub = 0 if coll is None else coll.n_hub           # virtual rows of split hubs follow the block of real rows
+        n_loc = Nl if coll is None or coll.n_loc is None else coll.n_loc      # block stride: Nl or Nl + 1 (uneven counts)
+        if not 0 <= n_loc - Nl <= 1:
+            raise ValueError('x has {} rows, the partition expects {} or {}'.format(Nl, n_loc, n_loc - 1))
+        Nb = n_loc + n_hub
         compact = coll is not None and coll.halo_rows is not None
         n_table = Nl if coll is None else (Nb + coll.halo_rows.numel() if compact else Nb * coll.world)
         if ee.shape[0] != plan.num_edges2 or Nb != plan.num_dst_rows or plan.num_nodes != n_table:
@@ -322,10 +328,11 @@ class _ConvFn(torch.autograd.Function):
             # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads)
             x_full, gather = coll.p2p.gather(x, fence=not training), _Done()
         elif compact:                                               # library fallback of the compact table
-            x_blk = x if n_hub == 0 else torch.cat([x, x.new_zeros((n_hub, D))], 0)
+            x_blk = x if Nb == Nl else torch.cat([x, x.new_zeros((Nb - Nl, D))], 0)
             x_full, gather = coll.gather_compact(x_blk), _Done()
         else:
-            x_full, gather = coll.all_gather_rows(x, async_op=True)
+            x_full, gather = coll.all_gather_rows(x if Nb == Nl else torch.cat([x, x.new_zeros((Nb - Nl, D))], 0),
+                                                  async_op=True)
 
         res3 = plan.scratch('res3', (3, Nl, Dout))
         if gather is not None:                                      # self-loop: (x . lr . le) @ W = x @ (diag(lr . le) W)
@@ -344,7 +351,7 @@ class _ConvFn(torch.autograd.Function):
             main.wait_stream(side)                                  # K0's operand packs are needed from here on
 
         if gather is not None:
-            coll.sum_hub_rows(agg, Nl)
+            coll.sum_hub_rows(agg, n_loc)
             gemm_nt_batch([agg[0, :Nl], agg[1, :Nl]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
         else:                                                       # the three transforms of the step in one launch
             gemm_nt_batch([agg[0], agg[1], x], [packed_f[0], packed_f[1], packed_f[2]], [res3[0], res3[1], res3[2]])
@@ -389,7 +396,8 @@ class _ConvFn(torch.autograd.Function):
         Nl, D = x.shape
         n_global = Nl if coll is None else coll.n_global      # BatchNorm rows (real nodes of all ranks)
         n_hub = 0 if coll is None else coll.n_hub
-        Nb = Nl + n_hub
+        n_loc = Nl if coll is None or coll.n_loc is None else coll.n_loc
+        Nb = n_loc + n_hub
         Dout = w_in.shape[1]
         T = relp.shape[0]
         p, st = _lib.ptr, _lib.stream
@@ -435,7 +443,7 @@ class _ConvFn(torch.autograd.Function):
         gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]],
                       [g3[0, :Nl], g3[1, :Nl], g3[2, :Nl]])
         if n_hub:
-            coll.spread_hub_rows(g3, 2, Nl)                          # the virtual rows see their hub's upstream gradient
+            coll.spread_hub_rows(g3, 2, n_loc)                       # the virtual rows see their hub's upstream gradient
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
         p2p = None if coll is None else coll.p2p
         d_x_full = p2p.partial if p2p is not None else torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
@@ -598,7 +606,7 @@ class MGCNConv(nn.Module):
         bn = self.ent_bn
         use_batch_stats = self.training or bn.running_mean is None
         coll = _Collectives(part.group, part.world, part.num_nodes, part.n_hub, part.hub_idx_mine, part.hub_rows_mine,
-                            part.p2p(x_local.shape[1]), part.rank, getattr(part, 'halo_rows64', None))
+                            part.p2p(x_local.shape[1]), part.rank, getattr(part, 'halo_rows64', None), part.n_loc)
         all_ent, all_rel, stats = _ConvFn.apply(
             x_local, rels_embs, edge_embs_local, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, part.plan, m_in, m_out, keep_scale,

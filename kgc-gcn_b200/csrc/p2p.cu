@@ -14,8 +14,11 @@
 //                            and adds them IN RANK ORDER (deterministic) together with the self-loop term - the
 //                            reduce-scatter and the add that followed it, in one kernel;
 //   * kgc_p2p_barrier      - flag barrier in symmetric memory (release/acquire at system scope, monotonically increasing
-//                            epoch, one flag slot per peer).  A rank that waits longer than ~2 s raises *error instead of
-//                            hanging the GPU.
+//                            epoch, one flag slot per peer).  Ranks may skew by any amount a training loop produces
+//                            (evaluation, checkpoint writes, logging): the wait has NO data-path time-out.  A watchdog
+//                            of ~2 minutes (a peer process is gone) sets *error and TRAPS - the context dies and every
+//                            later CUDA call of the process raises; the kernels after the barrier never run on
+//                            unpublished peer data.
 // Hazards: a buffer a peer reads in step t is overwritten by its owner in step t + 1 only after another barrier of the same
 // sequence has been passed by every rank (forward barrier between two backward uses and vice versa).
 #include "common.cuh"
@@ -53,10 +56,12 @@ __device__ __forceinline__ void cta_barrier_across_ranks(uint32_t* const* __rest
     const uint32_t* mine = flags[rank] + r;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-      if (clock64() - t0 > 4000000000ll) {                  // ~2 s: a peer is gone
+      if (clock64() - t0 > 240000000000ll) {                // ~2 min at 1.9 GHz: a peer process is gone
         *error = 1;
-        break;
+        __threadfence_system();
+        __trap();                                           // never continue on peer buffers that were not published
       }
+      __nanosleep(64);
     }
   }
   __syncthreads();

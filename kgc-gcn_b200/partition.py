@@ -32,22 +32,22 @@ def partition_edges(edge_index, edge_type, num_nodes, world, rank):
 
     Returns dict(lo, hi, owned_eids [n_local] int64 (in-half edges first, ascending), n_edges_in,
     src (global ids), dst (local row ids), type, deg [2, N] int32 = GLOBAL per-half out-degree by src
-    (model.py:73-75)).  ``num_nodes`` must be divisible by ``world`` (equal all-gather blocks)."""
+    (model.py:73-75), padded to world * per columns).  Blocks are ``per = ceil(num_nodes / world)`` rows wide (equal
+    all-gather blocks); when ``num_nodes`` is not a multiple of ``world`` the last block(s) end in rows that do not exist:
+    no edge refers to them and the layer never touches them (``hi - lo`` real rows, possibly fewer than ``per``)."""
     ei = np.asarray(edge_index, dtype=np.int64)
     et = np.asarray(edge_type, dtype=np.int64)
     n2 = ei.shape[1]
     if n2 % 2 != 0:
         raise ValueError('edge list must hold an in half and an out half of equal size')
-    if num_nodes % world != 0:
-        raise ValueError('num_nodes ({}) must be divisible by the number of ranks ({})'.format(num_nodes, world))
     E = n2 // 2
-    per = num_nodes // world
-    lo, hi = rank * per, (rank + 1) * per
+    per = -(-num_nodes // world)
+    lo, hi = min(rank * per, num_nodes), min((rank + 1) * per, num_nodes)
     dst = ei[1]
     owned = np.nonzero((dst >= lo) & (dst < hi))[0]          # ascending: in-half edges (< E) come first
     n_in = int(np.searchsorted(owned, E))
-    return {'lo': lo, 'hi': hi, 'owned_eids': owned, 'n_edges_in': n_in, 'src': ei[0, owned], 'dst': dst[owned] - lo,
-            'type': et[owned], 'deg': _half_degrees(ei, E, num_nodes)}
+    return {'lo': lo, 'hi': hi, 'per': per, 'owned_eids': owned, 'n_edges_in': n_in, 'src': ei[0, owned],
+            'dst': dst[owned] - lo, 'type': et[owned], 'deg': _half_degrees(ei, E, world * per)}
 
 
 def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs=64, n_greedy=8192):
@@ -57,13 +57,14 @@ def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs
     its in-degree (edges of both halves that point to it) exceeds ``hub_fraction`` of a rank's mean edge count - no
     assignment of whole rows could balance such a row (splitting costs two small all-reduces per step, so rows that can
     be balanced whole are).  The ``n_greedy`` heaviest remaining nodes go, one by one, to the least-loaded rank
-    (LPT); the light tail is dealt in snake order, the lightest nodes filling the ranks that took few heavy ones
-    (every rank ends with exactly N / world nodes)."""
+    (LPT); the light tail is dealt in snake order, the lightest nodes filling the ranks that took few heavy ones.
+    Rank r ends with ``count[r]`` = N // world (+ 1 for the first N % world ranks) nodes; ``n_loc`` = the largest count is
+    the row stride of a rank's block, so ranks with one node less carry one row that does not exist (never referenced)."""
     ei = np.asarray(edge_index, dtype=np.int64)
     n2 = ei.shape[1]
-    if num_nodes % world != 0:
-        raise ValueError('num_nodes ({}) must be divisible by the number of ranks ({})'.format(num_nodes, world))
-    n_loc = num_nodes // world
+    base, rem = divmod(num_nodes, world)
+    cap_all = base + (np.arange(world, dtype=np.int64) < rem)  # nodes per rank
+    n_loc = int(cap_all.max())
     indeg = np.bincount(ei[1], minlength=num_nodes).astype(np.int64)
     hubs = np.zeros((0,), dtype=np.int64)
     if world > 1:
@@ -79,13 +80,13 @@ def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs
     load = np.zeros(world, dtype=np.int64)
     count = np.zeros(world, dtype=np.int64)
     for v in order[:k]:                                        # LPT over the heavy head
-        free = count < n_loc
+        free = count < cap_all
         r = int(np.argmin(np.where(free, load, np.iinfo(np.int64).max)))
         owner[v] = r
         load[r] += w[v]
         count[r] += 1
     rest = order[k:]
-    cap = n_loc - count
+    cap = cap_all - count
     m = int(cap.min())
     j = np.arange(m * world, dtype=np.int64)
     rnd, pos = j // world, j % world
@@ -93,19 +94,20 @@ def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs
     owner[rest[m * world:]] = np.repeat(np.arange(world, dtype=np.int64), cap - m)   # the lightest nodes fill the gaps
     slot = np.empty(num_nodes, dtype=np.int64)
     by_rank = np.argsort(owner[order], kind='stable')          # per rank, nodes in decreasing weight
-    slot[order[by_rank]] = np.arange(num_nodes, dtype=np.int64) - np.repeat(np.arange(world, dtype=np.int64) * n_loc, n_loc)
-    return {'owner': owner, 'slot': slot, 'hubs': hubs, 'n_loc': n_loc}
+    slot[order[by_rank]] = np.arange(num_nodes, dtype=np.int64) - np.repeat(np.cumsum(cap_all) - cap_all, cap_all)
+    return {'owner': owner, 'slot': slot, 'hubs': hubs, 'n_loc': n_loc, 'count': cap_all}
 
 
 def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_fraction=0.5, max_hubs=64):
     """Edge-balanced partition with split hub rows (module docstring), pure host integer logic (numpy).
 
-    Returns dict(n_loc, n_hub, block = n_loc + n_hub, owned_nodes [n_loc] (global ids in local-row order), hubs [n_hub],
+    Returns dict(n_loc (row stride of the real rows: the largest node count of any rank), n_hub, block = n_loc + n_hub,
+    owned_nodes [n_real <= n_loc] (global ids in local-row order; n_real = N // world or that + 1), hubs [n_hub],
     hub_owner [n_hub], hub_row [n_hub] (local row of the hub at its owner), owned_eids (ascending, in half first),
     n_edges_in, newid [N] (node -> renumbered id = owner * block + local row), halo_rows [n_halo] (ascending renumbered ids
     of the REMOTE rows this rank's edges read), src (COMPACT ids: [0, block) = own rows, block + i = halo_rows[i]), dst
     (local rows, virtual rows are n_loc + h), type, deg [2, block + n_halo] (global per-half degrees by compact id),
-    n_halo_max (largest halo of any rank: size of the symmetric tables), peer_idx [world, n_loc] int32 (compact row of this
+    n_halo_max (largest halo of any rank: size of the symmetric tables), peer_idx [world, n_real] int32 (compact row of this
     rank's node v in rank r's table, -1 when r's edges never read v: the partial gradients the owner has to add))."""
     ei = np.asarray(edge_index, dtype=np.int64)
     et = np.asarray(edge_type, dtype=np.int64)
@@ -140,11 +142,14 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
     src_new = newid[ei[0]]
     touch = np.zeros(world * block, dtype=np.uint64)
     for r in range(world):
-        touch[np.unique(src_new[edge_rank == r])] |= np.uint64(1 << r)
+        seen = np.zeros(world * block, dtype=bool)
+        seen[src_new[edge_rank == r]] = True                   # boolean scatter: no sort of the 2E source ids
+        touch[seen] |= np.uint64(1 << r)
     # COMPACT numbering of this rank's node table: [0, block) = its own rows (real + virtual), then only the remote rows
     # its edges read (ascending renumbered id) - every per-rank structure is O(own rows + halo), not O(all nodes)
     ids = np.arange(world * block, dtype=np.int64)
-    peer_idx = np.full((world, n_loc), -1, dtype=np.int32)     # row of MY node v in rank r's partial table, -1: untouched
+    n_real = int(a['count'][rank])                             # this rank's real rows (n_loc or n_loc - 1)
+    peer_idx = np.full((world, n_real), -1, dtype=np.int32)    # row of MY node v in rank r's partial table, -1: untouched
     n_halo_all = np.zeros(world, dtype=np.int64)
     halo_rows = None
     for r in range(world):
@@ -155,14 +160,14 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
         pos = np.full(world * block, -1, dtype=np.int64)
         pos[hr] = block + np.arange(hr.shape[0], dtype=np.int64)
         pos[r * block:(r + 1) * block] = np.where(bit[r * block:(r + 1) * block], np.arange(block, dtype=np.int64), -1)
-        peer_idx[r] = pos[rank * block:rank * block + n_loc]
+        peer_idx[r] = pos[rank * block:rank * block + n_real]
         if r == rank:
             halo_rows = hr
             cmap = pos.copy()
             cmap[r * block:(r + 1) * block] = np.arange(block, dtype=np.int64)
     n_halo = int(halo_rows.shape[0])
     comp_ids = np.concatenate([np.arange(rank * block, (rank + 1) * block, dtype=np.int64), halo_rows])
-    return {'n_loc': n_loc, 'n_hub': n_hub, 'block': block, 'owned_nodes': owned_nodes, 'hubs': hubs,
+    return {'n_loc': n_loc, 'n_real': n_real, 'n_hub': n_hub, 'block': block, 'owned_nodes': owned_nodes, 'hubs': hubs,
             'hub_owner': owner[hubs], 'hub_row': slot[hubs], 'owned_eids': owned, 'n_edges_in': n_in,
             'src': cmap[newid[ei[0, owned]]], 'dst': dst_new[owned] - rank * block, 'type': et[owned],
             'deg': np.ascontiguousarray(deg_ext[:, comp_ids]), 'newid': newid, 'halo_rows': halo_rows.astype(np.int32),
@@ -172,11 +177,13 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
 class GraphPartition(object):
     """This rank's share of the graph + its GraphPlan (built by K1 with the global degrees).
 
-    ``owned_nodes`` [n_loc]: global ids of this rank's node rows in local-row order (shard x / masks / upstream gradients
-    with it); ``owned_eids``: global ids of the edges it owns (shard edge_embeddings with it)."""
+    ``owned_nodes`` [n_real]: global ids of this rank's node rows in local-row order (shard x / masks / upstream gradients
+    with it); ``owned_eids``: global ids of the edges it owns (shard edge_embeddings with it).  ``n_loc`` = the row stride
+    of a block (largest node count of any rank; ``n_real`` is n_loc or, when num_nodes is not a multiple of the number of
+    ranks, one less: the missing row is never referenced), virtual hub rows are local rows n_loc .. n_loc + n_hub."""
 
     def __init__(self, edge_index, edge_type, num_nodes, num_types, world, rank, device, group=None, balance='edges',
-                 hub_fraction=0.5, p2p='auto'):
+                 hub_fraction=0.1, p2p='auto'):
         ei = edge_index.cpu().numpy() if torch.is_tensor(edge_index) else edge_index
         et = edge_type.cpu().numpy() if torch.is_tensor(edge_type) else edge_type
         self.world, self.rank, self.group, self.num_nodes = int(world), int(rank), group, int(num_nodes)
@@ -186,14 +193,14 @@ class GraphPartition(object):
         if balance == 'range':
             info = partition_edges(ei, et, num_nodes, world, rank)
             self.lo, self.hi = info['lo'], info['hi']
-            self.n_loc, self.n_hub, self.block = self.hi - self.lo, 0, self.hi - self.lo
+            self.n_loc, self.n_hub, self.block, self.n_real = info['per'], 0, info['per'], self.hi - self.lo
             self.owned_nodes = torch.arange(self.lo, self.hi, dtype=torch.int64, device=device)
-            ext_nodes, offset = num_nodes, self.lo
+            ext_nodes, offset = world * info['per'], rank * info['per']      # gathered layout: equal blocks of `per` rows
             self.hub_idx_mine = self.hub_rows_mine = None
         elif balance == 'edges':
             info = partition_edges_balanced(ei, et, num_nodes, world, rank, hub_fraction=hub_fraction)
             self.lo = self.hi = None
-            self.n_loc, self.n_hub, self.block = info['n_loc'], info['n_hub'], info['block']
+            self.n_loc, self.n_hub, self.block, self.n_real = info['n_loc'], info['n_hub'], info['block'], info['n_real']
             self.owned_nodes = torch.from_numpy(info['owned_nodes']).to(device)
             ext_nodes, offset = self.block + info['n_halo'], 0      # compact node table: own rows, then the halo
             mine = np.nonzero(info['hub_owner'] == rank)[0]
@@ -325,5 +332,8 @@ class _P2PContext(object):
         return True
 
     def check(self):
+        """The barrier has no data-path time-out (ranks may skew freely); its ~2-minute watchdog for a vanished peer sets
+        the error word and traps, so a failure surfaces as a CUDA error on the next synchronising call.  This reads the
+        error word for callers that want the explicit message."""
         if int(self.error) != 0:
-            raise RuntimeError('kgc_p2p_barrier timed out: a peer rank did not arrive')
+            raise RuntimeError('kgc_p2p_barrier: a peer rank did not arrive within the watchdog period')

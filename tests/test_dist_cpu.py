@@ -174,10 +174,72 @@ def test_partition_and_collectives_world2():
     assert dict(ret) == {0: 'ok', 1: 'ok'}
 
 
-def test_partition_edges_rejects_uneven():
-    from kgc_gcn_b200.partition import partition_edges
-    with pytest.raises(ValueError):
-        partition_edges(np.zeros((2, 4), dtype=np.int64), np.zeros(4, dtype=np.int64), 7, 2, 0)
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_partitions_with_uneven_node_counts(world):
+    """num_nodes not a multiple of the number of ranks (the Wikidata5M shape: 4,594,485 nodes on 2 / 4 / 8 GPUs): blocks
+    keep the stride ceil(N / world), some ranks hold one real row less, no edge refers to a row that does not exist, and
+    the per-rank aggregation / owner-side gradient pull (emulated in numpy, one rank after the other) give the global
+    answer."""
+    from kgc_gcn_b200.partition import partition_edges, partition_edges_balanced
+    N, R, E, D = 64 * world + 3, 3, 400 * world, 4
+    tri = orc.synthetic_triples(N, R, E, 13)
+    g = orc.build_graph(tri, N, R)
+    ei, et = g['edge_index'], g['edge_attr'][0]
+    rng = np.random.default_rng(1)
+    x, ee, rel = rng.standard_normal((N, D)), rng.standard_normal((2 * E, D)), rng.standard_normal((2 * R + 1, D))
+    gsel = rng.standard_normal((N, D))
+    glob = _agg_numpy(x, rel, ee, ei[0], ei[1], et, np.ones(2 * E), N)
+    full = np.zeros((N, D))
+    np.add.at(full, ei[0], gsel[ei[1]] * rel[et] * ee)
+    per = -(-N // world)
+    # ---- range partition
+    infos = [partition_edges(ei, et, N, world, r) for r in range(world)]
+    assert sorted(np.concatenate([i['owned_eids'] for i in infos]).tolist()) == list(range(2 * E))
+    assert [i['hi'] - i['lo'] for i in infos] == [min(per, max(0, N - r * per)) for r in range(world)]
+    for r, i in enumerate(infos):
+        assert i['per'] == per and i['deg'].shape == (2, world * per) and (i['deg'][:, N:] == 0).all()
+        assert (i['dst'] >= 0).all() and (i['dst'] < i['hi'] - i['lo']).all()
+        loc = _agg_numpy(x, rel, ee[i['owned_eids']], i['src'], i['dst'], i['type'], np.ones(i['owned_eids'].shape[0]), per)
+        np.testing.assert_allclose(loc[:i['hi'] - i['lo']], glob[i['lo']:i['hi']], rtol=1e-12, atol=1e-12)
+    # ---- edge-balanced partition with split hubs
+    parts = [partition_edges_balanced(ei, et, N, world, r, hub_fraction=0.1) for r in range(world)]
+    assert sorted(np.concatenate([p['owned_eids'] for p in parts]).tolist()) == list(range(2 * E))
+    assert sorted(np.concatenate([p['owned_nodes'] for p in parts]).tolist()) == list(range(N))
+    counts = [p['owned_nodes'].shape[0] for p in parts]
+    assert max(counts) == per and min(counts) >= per - 1 and sum(counts) == N
+    blk, n_loc, n_hub = parts[0]['block'], parts[0]['n_loc'], parts[0]['n_hub']
+    assert n_loc == per and blk == per + n_hub
+    tables, partials = [], []
+    for r, p in enumerate(parts):
+        assert p['n_real'] == counts[r] and p['peer_idx'].shape == (world, counts[r])
+        comp_ids = np.concatenate([np.arange(r * blk, (r + 1) * blk), p['halo_rows'].astype(np.int64)])
+        old_of = np.full(world * blk, -1)
+        old_of[p['newid']] = np.arange(N)
+        table = np.zeros((blk + p['n_halo'], D))
+        real = old_of[comp_ids] >= 0
+        table[real] = x[old_of[comp_ids][real]]
+        assert real[p['src']].all()                                     # no edge reads a row that does not exist
+        assert ((p['dst'] < counts[r]) | (p['dst'] >= n_loc)).all()      # ... or writes one
+        own_e = p['owned_eids']
+        planes = _agg_numpy(table, rel, ee[own_e], p['src'], p['dst'], p['type'], np.ones(own_e.shape[0]), blk)
+        tables.append(planes)
+        g_loc = np.zeros((blk, D))
+        g_loc[:counts[r]] = gsel[p['owned_nodes']]
+        g_loc[n_loc:] = gsel[p['hubs']]
+        part = np.zeros((blk + p['n_halo_max'], D))
+        np.add.at(part, p['src'], g_loc[p['dst']] * rel[p['type']] * ee[own_e])
+        partials.append(part)
+    hub_sum = sum(t[n_loc:] for t in tables)                            # virtual rows summed over ranks
+    for r, p in enumerate(parts):
+        out = tables[r][:counts[r]].copy()
+        mine = np.nonzero(p['hub_owner'] == r)[0]
+        out[p['hub_row'][mine]] = hub_sum[mine]
+        np.testing.assert_allclose(out, glob[p['owned_nodes']], rtol=1e-10, atol=1e-11)
+        pulled = np.zeros((counts[r], D))
+        for q in range(world):
+            at = p['peer_idx'][q]
+            pulled[at >= 0] += partials[q][at[at >= 0]]
+        np.testing.assert_allclose(pulled, full[p['owned_nodes']], rtol=1e-10, atol=1e-11)
 
 
 @pytest.mark.parametrize('world', [2, 4, 8])
