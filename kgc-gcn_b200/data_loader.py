@@ -253,12 +253,14 @@ class KBDataset(object):
 
 
 def epoch_permutation(n, shuffle=True):
-    """Order of one epoch.  Restates torch.utils.data.RandomSampler (what the reference's shuffle=True
-    DataLoaders use, data_loader.py:169-176): one int64 seed drawn from the global torch generator, then
-    torch.randperm under a fresh generator seeded with it - so under the same torch.manual_seed the batches
-    come out in the reference's order."""
+    """Order of one epoch.  Restates what iterating the reference's shuffle=True torch DataLoaders does to the global torch
+    generator (data_loader.py:169-176): ``iter(DataLoader)`` first draws its ``_base_seed`` (one int64, consumed whatever
+    num_workers is), then RandomSampler draws one int64 seed and runs torch.randperm under a fresh generator seeded with
+    it - so under the same torch.manual_seed the batches of every epoch come out in the reference's order
+    (tests/test_host_cpu.py compares with a real torch DataLoader)."""
     if not shuffle:
         return np.arange(n, dtype=np.int64)
+    torch.empty((), dtype=torch.int64).random_()                  # DataLoader.__iter__: _base_seed (drawn and not used here)
     seed = int(torch.empty((), dtype=torch.int64).random_().item())
     gen = torch.Generator()
     gen.manual_seed(seed)

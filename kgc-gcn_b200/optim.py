@@ -67,9 +67,24 @@ class ClipAdam(torch.optim.Optimizer):
         self._dev[gi] = st
         return st
 
-    def prepare(self):
+    def _sync_steps(self):
+        """Live device-side step counter -> ``state[p]['step']`` (what torch.optim.Adam keeps per parameter)."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._dev.get(gi)
+            if st is None:
+                continue
+            step = st['state'][0].to(torch.float32)
+            for p in group['params']:
+                if p in self.state and 'step' in self.state[p]:
+                    self.state[p]['step'].copy_(step)
+
+    def prepare(self, from_state=False):
         """Build the device-side state for every parameter that requires a gradient and push the hyper-parameters and the
-        step count (taken from ``state[p]['step']``) - call before capturing ``step()`` into a CUDA graph."""
+        step count - call before capturing ``step()`` into a CUDA graph.  The count continues from the live device counter
+        (eager steps taken so far); ``from_state=True`` takes it from ``state[p]['step']`` instead (a caller that has just
+        restored the optimiser state, e.g. GraphedTrainStep after its warm-up)."""
+        if not from_state:
+            self._sync_steps()
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group['params'] if p.requires_grad]
             if params:
@@ -135,14 +150,7 @@ class ClipAdam(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ torch.optim.Adam-compatible checkpoints
     def state_dict(self):
-        for gi, group in enumerate(self.param_groups):
-            st = self._dev.get(gi)
-            if st is None:
-                continue
-            step = st['state'][0].to(torch.float32)
-            for p in group['params']:
-                if p in self.state and 'step' in self.state[p]:
-                    self.state[p]['step'].copy_(step)
+        self._sync_steps()
         return super(ClipAdam, self).state_dict()
 
     def load_state_dict(self, state_dict):

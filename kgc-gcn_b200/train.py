@@ -79,8 +79,20 @@ class GraphedTrainStep(object):
         # warm-up iterations (allocator, cuBLAS / cuDNN handles, lazy optimiser state) must not change the training
         # trajectory: parameters, buffers and optimiser state are restored afterwards
         fresh = len(self.opt.state) == 0
-        saved_p = [p.detach().clone() for p in self.params]
-        saved_b = [b.detach().clone() for b in self.model.buffers()]
+        if hasattr(self.opt, '_sync_steps'):         # ClipAdam: eager steps taken so far -> state[p]['step'] before the snapshot
+            self.opt._sync_steps()
+        # a fresh optimiser warms up with lr = 0: the parameters then stay bit-identical without a second copy of the model
+        # (the edge table alone is 16.5 GB at the Wikidata5M shape) and the moments are zeroed afterwards; an optimiser
+        # that already holds state gets parameters and state snapshotted and restored
+        saved_p = None if fresh else [p.detach().clone() for p in self.params]
+        saved_lr = [g['lr'] for g in self.opt.param_groups]
+        if fresh:
+            for g in self.opt.param_groups:
+                g['lr'] = 0.0
+        # the non-persistent dropout-stream buffers (_drop_seed) are NOT restored: they were drawn from torch's generator
+        # during the first warm-up forward and keep advancing (restoring them would pin the stream to seed 0)
+        named_b = [(n, b) for n, b in self.model.named_buffers() if not n.endswith('_drop_seed')]
+        saved_b = [b.detach().clone() for _, b in named_b]
         saved_s = None if fresh else [[v.detach().clone() if torch.is_tensor(v) else v for v in st.values()]
                                       for st in self.opt.state.values()]
         side = torch.cuda.Stream()
@@ -91,17 +103,23 @@ class GraphedTrainStep(object):
                 self._body(self.trip, self.label, self.qid if self.fused_loss else None)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        for g, lr in zip(self.opt.param_groups, saved_lr):
+            g['lr'] = lr
         with torch.no_grad():
-            for p, sp in zip(self.params, saved_p):
-                p.copy_(sp)
-            for b, sb in zip(self.model.buffers(), saved_b):
+            if saved_p is not None:
+                for p, sp in zip(self.params, saved_p):
+                    p.copy_(sp)
+            for (_, b), sb in zip(named_b, saved_b):
                 b.copy_(sb)
             for i, st in enumerate(self.opt.state.values()):
                 for j, (key, v) in enumerate(st.items()):
                     if torch.is_tensor(v):
                         v.zero_() if fresh else v.copy_(saved_s[i][j])
-        if hasattr(self.opt, 'prepare'):             # ClipAdam: device-side step counter / hyper-parameters
-            self.opt.prepare()
+        del saved_p, saved_b, saved_s
+        self.opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()                      # the warm-up's activations go back to the driver before the graph pool grows
+        if hasattr(self.opt, 'prepare'):             # ClipAdam: device-side step counter (from the restored state) / hyper-parameters
+            self.opt.prepare(from_state=True)
         self.cuda_graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.cuda_graph):

@@ -1,0 +1,55 @@
+"""Build oracle/_ref/ from the reference where it lies.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/build_ref.py            (also called by __graft_entry__.build())
+
+The reference (weilonghu/KGC-GCN) is pure Python; its four modules are byte-compiled from /root/reference into
+``oracle/_ref/{model,data_loader,main,utils}.pyc`` (sourceless modules: a BUILT artefact like a .so - git-ignored, it
+travels to the GPU box with the snapshot; no reference source is copied into the repository).  With ``oracle/shims`` on
+the path (stand-ins for the reference's absent third-party imports) they import unmodified, which is what
+``bench.py --impl reference`` times (cpu_baseline.kind = "reference") and what tests/test_oracle_golden.py cross-checks
+the port against when the directory is present.  /root/reference does not exist on the GPU box: there the prebuilt
+files are used as they are; when they are missing everything falls back to the pinned port (oracle/mgcn_oracle.py).
+"""
+import os
+import py_compile
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, '_ref')
+MODULES = ('model', 'data_loader', 'main', 'utils')
+
+
+def build_ref(ref_dir=None):
+    """-> list of written files ([] when the reference tree is absent)."""
+    ref_dir = ref_dir or os.environ.get('KGC_REFERENCE_DIR', '/root/reference')
+    if not all(os.path.exists(os.path.join(ref_dir, m + '.py')) for m in MODULES):
+        return []
+    os.makedirs(OUT, exist_ok=True)
+    written = []
+    for m in MODULES:
+        dst = os.path.join(OUT, m + '.pyc')
+        py_compile.compile(os.path.join(ref_dir, m + '.py'), cfile=dst, dfile='reference/' + m + '.py', doraise=True)
+        written.append(dst)
+    return written
+
+
+def load_reference():
+    """(model, data_loader, main) modules of the UNMODIFIED reference from oracle/_ref, or None when it was not built
+    (or was built by another interpreter version).  Puts oracle/shims and oracle/_ref on sys.path."""
+    if not all(os.path.exists(os.path.join(OUT, m + '.pyc')) for m in MODULES):
+        return None
+    for d in (os.path.join(HERE, 'shims'), OUT):
+        if d not in sys.path:
+            sys.path.insert(0, d)
+    try:
+        import importlib
+        mods = [importlib.import_module(m) for m in ('model', 'data_loader', 'main')]
+    except Exception:                       # stale bytecode (other interpreter), missing third-party module, ...
+        return None
+    if not all(getattr(m, '__file__', '').startswith(OUT) for m in mods):
+        return None                         # some other 'model' / 'main' module shadowed them
+    return tuple(mods)
+
+
+if __name__ == '__main__':
+    print(build_ref() or 'reference tree not found: nothing built')

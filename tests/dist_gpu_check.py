@@ -22,7 +22,7 @@ def main():
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', rank)))
     torch.cuda.set_device(dev)
     dist.init_process_group('nccl', device_id=dev)
-    N, R, E, D, Dout = 3000 * world, 6, 9000 * world, 100, 200
+    N, R, E, D, Dout = 3000 * world + 1, 6, 9000 * world, 100, 200      # node count NOT a multiple of the rank count
     tri = orc.synthetic_triples(N, R, E, 77)
     g = orc.build_graph(tri, N, R)
     p = orc.conv_params(N, R, E, D, Dout, seed=3)

@@ -1,6 +1,6 @@
 """bench.py contract checks that need no GPU: the algorithmic-byte model against SURVEY.md 8(d)'s totals, and the reference
-arm (the oracle port of the training step on the host cores) printing ONE JSON line with the contract's keys - alone on rank
-0 when launched with WORLD_SIZE > 1."""
+arm (the reference's layer and training step on the host cores, bounded sample) printing ONE JSON line with the contract's
+keys - alone on rank 0 when launched with WORLD_SIZE > 1."""
 import importlib.util
 import json
 import os
@@ -42,10 +42,46 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'edges/sec GCN fwd+bwd' and d['unit'] == 'edges/s'
     assert d['n_gpus'] == 1 and d['steps'] == 1 and d['higher_is_better'] is True and d['gpu_launches'] == 0
-    assert d['value'] > 0 and abs(d['value'] - 2 * 86835 / (d['ms_per_step'] * 1e-3)) <= 1e-6 * d['value']
-    assert d['config']['workload'] == 'wn18rr_shape'
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
-    assert d['e2e'] == {'value': d['value'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # the default workload is the GPU arm's (Wikidata5M shape); the CPU runs a bounded sample of it and says which
+    assert d['config']['workload'] == 'wikidata5m_shape' and 'divided by 64' in d['config']['sample']
+    e_sample = 20614279 // 64
+    assert d['value'] > 0 and abs(d['value'] - 2 * e_sample / (d['ms_per_step'] * 1e-3)) <= 1e-6 * d['value']
+    cb = d['cpu_baseline']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'divided by 64' in cb['sample']
+    # same scopes as the GPU arm: value = the layer's forward + backward, e2e = the whole training step (slower)
+    e = d['e2e']
+    assert e['unit'] == 'edges/s' and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
+    assert 0 < e['value'] < d['value'] and abs(e['value'] - 2 * e_sample / (e['ms_per_step'] * 1e-3)) <= 1e-6 * e['value']
+
+
+def test_reference_bytecode_is_the_reference():
+    """oracle/_ref (built by oracle/build_ref.py from /root/reference when that tree exists) imports as the reference's own
+    modules; the port and the unmodified reference give the same layer outputs on a small graph (the golden fixtures pin
+    the same thing; this checks the artefact bench.py --impl reference actually runs)."""
+    import pytest
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import build_ref
+    if os.path.isdir('/root/reference'):
+        assert build_ref.build_ref()
+    ref = build_ref.load_reference()
+    if ref is None:
+        pytest.skip('oracle/_ref was not built (no reference tree on this machine)')
+    import mgcn_oracle as orc
+    ref_model = ref[0]
+    N, R, E = 50, 3, 200
+    tri = orc.synthetic_triples(N, R, E, 1)
+    g = orc.build_graph(tri, N, R)
+    torch.manual_seed(0)
+    conv = ref_model.MGCNConv(8, 12, 2 * R, dropout=0.0).double()
+    p = orc.conv_params(N, R, E, 8, 12, seed=2)
+    ei, et = torch.from_numpy(g['edge_index']), torch.from_numpy(g['edge_attr'][0])
+    ent, rel = conv(p['x'].double(), ei, et, None, p['edge_embs'].double(), p['rels'].double())
+    w = {k: getattr(conv, k).detach() for k in ('loop_weight', 'in_weight', 'out_weight', 'rels_weight', 'loop_rel', 'loop_edge')}
+    w.update({'ent_bn.weight': conv.ent_bn.weight.detach(), 'ent_bn.bias': conv.ent_bn.bias.detach(),
+              'ent_bn.running_mean': torch.zeros(12).double(), 'ent_bn.running_var': torch.ones(12).double()})
+    ent_o, rel_o, _ = orc.conv_forward(p['x'].double(), ei, et, p['edge_embs'].double(), p['rels'].double(), w, training=True)
+    assert float((ent.detach() - ent_o).abs().max()) < 1e-12 and float((rel.detach() - rel_o).abs().max()) < 1e-12
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -469,3 +469,38 @@ def test_gemm_batches_match_single_launches(k):
             truth = a[i].double().t() @ b[i].double()
             assert float((outs[i].double() - truth).abs().max()) / float(truth.abs().max()) <= 3e-6
             assert torch.equal(outs[i], outs2[i])
+
+
+@pytest.mark.parametrize('workload', ['wn18rr', 'fb15k237', 'wikidata5m'])
+def test_layer_parity_at_baseline_shapes(k, workload):
+    """The WHOLE layer - forward outputs and every gradient - at BASELINE.json's full shapes (configs[1..3]) against the
+    float64 restatement of the reference (oracle.conv_fwd_bwd_big: edge-chunked, pinned on the CPU to the reference-order
+    oracle), run on the same GPU as the checker.  Dropout p = 0.1 with injected keep masks.  Uses bench.py's own case
+    builder and parity routine, so the number bench.py prints under `parity` is this one.  Bar: max-norm-relative error
+    below 2e-5 for every tensor (two fp32 evaluations of the reference differ by 5e-6 .. 1e-4)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('kgc_bench', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    if workload == 'wikidata5m' and torch.cuda.get_device_properties(0).total_memory < 120 * (1 << 30):
+        pytest.skip('needs a 180 GB B200')
+    case = bench.LayerCase(k, orc, workload, torch.device('cuda', 0))
+    try:
+        par = bench.parity_vs_float64(case, orc)
+        print(workload, {n: float('{:.2e}'.format(v)) for n, v in par['per_tensor'].items()})
+        assert par['ok'], par
+        # determinism at full size: a second step with the same masks gives the same bits
+        m_in, m_out = case.masks(case.node_ids)
+        case.conv.set_dropout_masks(m_in, m_out)
+        ent1, _ = case.step()
+        g1 = {n: v.clone() for n, v in case.grads().items()}
+        ent1 = ent1.clone()
+        ent2, _ = case.step()
+        assert torch.equal(ent1, ent2)
+        for n, v in case.grads().items():
+            assert torch.equal(g1[n], v), n
+    finally:
+        del case
+        k.plan._PLAN_CACHE.clear()
+        torch.cuda.empty_cache()

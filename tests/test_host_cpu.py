@@ -200,15 +200,19 @@ def test_dataset_csr_and_label_values(toy_loader):
         ds.build_batch([0, 1], 'cpu')                  # no CPU fallback
 
 
-def test_epoch_permutation_matches_torch_random_sampler():
-    """Under the same torch.manual_seed the batch order equals the reference's shuffle=True DataLoader order."""
+def test_epoch_permutation_matches_torch_dataloader():
+    """Under the same torch.manual_seed the batch order equals the order of the reference's shuffle=True torch DataLoaders
+    (data_loader.py:169-176) - a REAL DataLoader, whose iterator draws a base seed before the sampler draws its own - over
+    several epochs, with and without worker processes."""
     from kgc_gcn_b200 import epoch_permutation
     n = 17
-    torch.manual_seed(123)
-    ref = [list(torch.utils.data.RandomSampler(range(n))) for _ in range(2)]
-    torch.manual_seed(123)
-    got = [epoch_permutation(n).tolist() for _ in range(2)]
-    assert got == ref
+    for workers in (0, 2):
+        dl = torch.utils.data.DataLoader(list(range(n)), batch_size=4, shuffle=True, num_workers=workers)
+        torch.manual_seed(123)
+        ref = [[int(v) for b in dl for v in b] for _ in range(3)]
+        torch.manual_seed(123)
+        got = [epoch_permutation(n).tolist() for _ in range(3)]
+        assert got == ref, workers
     assert sorted(got[0]) == list(range(n))
 
 

@@ -209,3 +209,38 @@ def test_sparse_bce_matches_torch_bce_on_dense_labels(toy_ds, smooth):
     cols = np.arange(n)
     dense = ((mask[:, cols >> 5] >> (cols & 31).astype(np.uint32)) & 1).astype(bool)
     assert np.array_equal(dense, lab == pos)
+
+
+def test_chunked_float64_oracle_matches_the_pinned_one():
+    """conv_fwd_bwd_big (edge-chunked, hand-derived backward: the checker of the Wikidata5M-shape GPU tests) against
+    conv_fwd_bwd (reference operation order + autograd, pinned to the reference's golden vectors above): every output and
+    gradient to float64 rounding, with dropout masks, with and without the optional bias, chunk boundaries inside halves."""
+    import torch
+    N, R, E, D, Do = 300, 4, 1500, 12, 20
+    tri = orc.synthetic_triples(N, R, E, 3)
+    g = orc.build_graph(tri, N, R)
+    p = orc.conv_params(N, R, E, D, Do, seed=1)
+    gen = torch.Generator().manual_seed(2)
+    g_ent, g_rel = torch.randn(N, Do, generator=gen), torch.randn(2 * R, Do, generator=gen)
+    m_in = (torch.rand(N, Do, generator=gen) > 0.1).float()
+    m_out = (torch.rand(N, Do, generator=gen) > 0.1).float()
+    ei, et = torch.from_numpy(g['edge_index']), torch.from_numpy(g['edge_attr'][0])
+    w = dict(p['w'])
+    w['ent_bn.weight'] = torch.rand(Do, generator=gen) + 0.5
+    w['ent_bn.bias'] = torch.randn(Do, generator=gen)
+    for bias, masks in ((None, (m_in, m_out)), (torch.randn(Do, generator=gen), (m_in, m_out)), (None, (None, None))):
+        w['bias'] = bias
+        w64 = {k: (v.double() if v is not None else None) for k, v in w.items()}
+        ent, rel, grads, _ = orc.conv_fwd_bwd(p['x'].double(), ei, et, p['edge_embs'].double(), p['rels'].double(), w64,
+                                              g_ent, g_rel, mask_in=masks[0], mask_out=masks[1])
+        big = orc.conv_fwd_bwd_big(p['x'], ei, et, p['edge_embs'], p['rels'], w, g_ent, g_rel, mask_in=masks[0],
+                                   mask_out=masks[1], chunk=333, d_ee_check=grads['edge_embeddings'])
+        scale = lambda t: float(t.abs().max()) + 1e-30                                   # noqa: E731
+        assert float((big['all_ent'] - ent).abs().max()) < 1e-12 * scale(ent)
+        assert float((big['all_rel'] - rel).abs().max()) < 1e-12 * scale(rel)
+        assert big['d_ee_max_abs_err'] < 1e-12 * big['d_ee_max_abs']
+        for k, v in grads.items():
+            if k == 'edge_embeddings':
+                continue
+            tol = 1e-12 * scale(v) if k != 'conv1.bias' else 1e-12 * scale(grads['conv1.ent_bn.weight'])   # ~0 in training mode
+            assert float((big[k] - v).abs().max()) < tol, k
