@@ -462,8 +462,8 @@ class LayerCase(object):
 
 
 def rel_err(a, b):
-    b = b.to(torch.float64)
-    return float((a.to(torch.float64) - b).abs().max() / (b.abs().max() + 1e-300))
+    b = b.detach().to(torch.float64)
+    return float((a.detach().to(torch.float64) - b).abs().max() / (b.abs().max() + 1e-300))
 
 
 def parity_vs_float64(case, orc):

@@ -933,24 +933,32 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmTnMaps maps, const GemmTnParams P)
   }
 }
 
-// C[e] = sum over the CTA partials in a FIXED order: 8 part-lanes per element, then their sums in lane order
+// C[e] = sum over the CTA partials in a FIXED order: 8 part-lanes per element, then their sums in lane order; the
+// partials (up to thousands at 4.6 M rows) are added in double precision and rounded once
 struct TnOut { float* c[kMaxBatch]; };
 __global__ void __launch_bounds__(256)
 gemm_tn_partials_reduce(const float* __restrict__ partial_all, int n_parts, int n_elem, const TnOut outs) {
-  __shared__ float sm[8][33];
+  __shared__ double sm[8][33];
   const float* partial = partial_all + (int64_t)blockIdx.y * n_parts * n_elem;      // blockIdx.y = problem of the batch
   float* C = blockIdx.y == 0 ? outs.c[0] : (blockIdx.y == 1 ? outs.c[1] : outs.c[2]);   // no runtime index into a parameter
   const int e = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (e < n_elem)
-    for (int g = threadIdx.y; g < n_parts; g += 8) s += partial[(int64_t)g * n_elem + e];
+  double s = 0.0;
+  if (e < n_elem) {
+    int g = threadIdx.y;
+    for (; g + 24 < n_parts; g += 32) {                      // four independent loads in flight, added in part order
+      const float v0 = partial[(int64_t)g * n_elem + e], v1 = partial[(int64_t)(g + 8) * n_elem + e];
+      const float v2 = partial[(int64_t)(g + 16) * n_elem + e], v3 = partial[(int64_t)(g + 24) * n_elem + e];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; g < n_parts; g += 8) s += (double)partial[(int64_t)g * n_elem + e];
+  }
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && e < n_elem) {
-    float t = sm[0][threadIdx.x];
+    double t = sm[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < 8; ++k) t += sm[k][threadIdx.x];
-    C[e] = t;
+    C[e] = (float)t;
   }
 }
 
@@ -1101,9 +1109,29 @@ extern "C" int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int6
   return launch_gemm_nt(1, &ent, n_ent, D, ld_ent, &packed_x, B, &pred, ld_pred, bias, 1, 1, 0, stream);
 }
 
+// Rows a CTA accumulates into ONE fp32 TMEM partial.  With one slab per SM a 4.6 M-row reduction (Wikidata5M shape) kept
+// 31 k rows (11.6 k dependent MMAs) in one accumulator and the weight gradients came out 3e-4 .. 7e-4 (max-norm-relative)
+// off the float64 result - the sums cancel heavily, so the rounding of the long fp32 chain shows; slabs of <= 4,096 rows
+// added in double precision bring it to the error of the 3xTF32 products themselves.  Beyond one wave the extra CTAs cost
+// ~3 us of set-up per 4.9 MB slab (3%) and 80 KB of partial each (+3% traffic).
+constexpr int64_t kTnMaxSlabRows = 4096;
+
+static int64_t tn_slabs(int64_t M, int n_prob) {
+  const int64_t per_wave = kNumSMs / n_prob > 0 ? kNumSMs / n_prob : 1;
+  int64_t slabs = ceil_div(M, (int64_t)2 * kTnRows);        // at least two K blocks per CTA
+  if (slabs > per_wave) slabs = per_wave;
+  const int64_t need = ceil_div(M, kTnMaxSlabRows);
+  if (slabs < need) slabs = ceil_div(need, per_wave) * per_wave;      // whole waves
+  return slabs < 1 ? 1 : slabs;
+}
+
 extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {
-  (void)M;
-  return (size_t)kNumSMs * Ka * Nb * sizeof(float);
+  int64_t parts = kNumSMs;                                  // covers 1..3 problems of one launch
+  for (int n = 1; n <= kMaxBatch; ++n) {
+    const int64_t s = tn_slabs(M > 0 ? M : 1, n) * n;
+    if (s > parts) parts = s;
+  }
+  return (size_t)parts * Ka * Nb * sizeof(float);
 }
 
 // C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb] on the tensor cores (3xTF32).  Ka <= 128, Nb <= 224, multiples of 4.
@@ -1120,9 +1148,7 @@ static int launch_gemm_tn_tc(int n_prob, const float* const* A, int64_t lda, con
   P.M = M; P.Ka = Ka; P.Nb = Nb; P.n_prob = n_prob;
   P.ga = 4;                                   // the MMA always reads M = 128 rows of D: 4 groups (columns past Ka are zero-filled)
   P.gb = (P.n_pad + 31) / 32;
-  int slabs = (int)ceil_div(M, 2 * kTnRows);  // at least two K blocks per CTA
-  if (slabs > kNumSMs / n_prob) slabs = kNumSMs / n_prob;
-  if (slabs < 1) slabs = 1;
+  int slabs = (int)tn_slabs(M, n_prob);       // one wave of CTAs, more when a slab would exceed kTnMaxSlabRows rows
   P.rows_per_cta = ceil_div(ceil_div(M, slabs), kTnRows) * kTnRows;     // slabs start on K-block boundaries
   slabs = (int)ceil_div(M, P.rows_per_cta);
   P.n_slabs = slabs;
