@@ -359,6 +359,11 @@ const char* kgc_ingest_name(const kgc_ingest_t* h, int32_t kind, int64_t id);
  * d_E = kgc_gemm_nt(d_logitT, X) stream it row-major; d_bias[n] = sum_b d_logitT[n, b] in a fixed order. */
 int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
                      const float* bias, float* pred, int64_t ld_pred, void* stream);
+/* The same product without the sigmoid: logits[b, n] = X[b,:] . E[n,:] + bias[n] (fp32-grade).  Exact-mode evaluation
+ * (main.py:121-126 ranks fp32 scores; the fused bf16 scorer K6 can move a rank between two entities whose logits lie
+ * within 2^-7 relative of each other): rank on these with kgc_rank_count_dense + kgc_rank_finalize. */
+int kgc_score_1n_logits(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                        const float* bias, float* logits, int64_t ld_logits, void* stream);
 int kgc_score_1n_bwd_logit(const float* d_pred, int64_t ld_dp, const float* pred, int64_t ld_p, int64_t n_ent,
                            int32_t B, int32_t ldt, float* d_logitT, float* d_bias, void* stream);
 
@@ -406,6 +411,10 @@ int kgc_score_pairs(const uint16_t* q_bf16, const uint16_t* e_bf16, const int32_
                     void* stream);
 int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, int64_t b, int64_t n, int32_t kpad,
                    const float* thr, int32_t* count_gt, int32_t* count_eq, void* stream);
+/* Exact-mode counts over DENSE fp32 logits [b, ld] (kgc_score_1n_logits): count_gt[q] += #{j < n_ent : logit[q,j] > thr[q]},
+ * count_eq likewise (may be NULL); caller zeroes the counters; integer atomics only.  b <= 65,535 per call. */
+int kgc_rank_count_dense(const float* logits, int64_t ld, int64_t n_ent, int64_t b, const float* thr,
+                         int32_t* count_gt, int32_t* count_eq, void* stream);
 int kgc_rank_finalize(const int32_t* count_gt, const int32_t* count_eq, const float* thr, const float* s_filt,
                       const int64_t* filt_ptr, const int32_t* filt_idx, const int64_t* obj, int64_t b,
                       int32_t* ranks, int32_t* eq_out, double* sums13, void* stream);

@@ -72,6 +72,8 @@ SIGNATURES = {
     'kgc_ingest_copy': (ctypes.c_int, [_vp, _i32, _vp, _i64]),
     'kgc_ingest_name': (ctypes.c_char_p, [_vp, _i32, _i64]),
     'kgc_score_1n_fwd': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
+    'kgc_score_1n_logits': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
+    'kgc_rank_count_dense': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     'kgc_score_1n_bwd_logit': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'kgc_label_mask_words': (_i64, [_i64]),
     'kgc_label_mask_build': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
@@ -115,6 +117,22 @@ def call(name, *args):
     rc = getattr(h, name)(*args)
     if rc != 0:
         raise RuntimeError('{} failed: {}'.format(name, h.kgc_last_error().decode('utf-8', 'replace')))
+
+
+_WARNED = set()
+
+
+def library_path(site, reason):
+    """A call site is about to leave the hand-written kernels for a torch / cuDNN / cuBLAS library operation (a shape or
+    dtype the kernel does not take).  Never silent: raises under KGC_STRICT=1 (the GPU tests run that way), otherwise warns
+    once per site."""
+    msg = 'kgc_gcn_b200: {} is running on the torch library path ({})'.format(site, reason)
+    if os.environ.get('KGC_STRICT', '0') not in ('', '0'):
+        raise RuntimeError(msg + ' and KGC_STRICT=1 forbids it')
+    if site not in _WARNED:
+        _WARNED.add(site)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
 
 def ptr(t):

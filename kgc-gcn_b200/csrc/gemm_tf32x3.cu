@@ -1109,12 +1109,12 @@ extern "C" int kgc_score_1n_fwd(const float* ent, int64_t n_ent, int32_t D, int6
   return launch_gemm_nt(1, &ent, n_ent, D, ld_ent, &packed_x, B, &pred, ld_pred, bias, 1, 1, 0, stream);
 }
 
-// Rows a CTA accumulates into ONE fp32 TMEM partial.  With one slab per SM a 4.6 M-row reduction (Wikidata5M shape) kept
-// 31 k rows (11.6 k dependent MMAs) in one accumulator and the weight gradients came out 3e-4 .. 7e-4 (max-norm-relative)
-// off the float64 result - the sums cancel heavily, so the rounding of the long fp32 chain shows; slabs of <= 4,096 rows
-// added in double precision bring it to the error of the 3xTF32 products themselves.  Beyond one wave the extra CTAs cost
-// ~3 us of set-up per 4.9 MB slab (3%) and 80 KB of partial each (+3% traffic).
-constexpr int64_t kTnMaxSlabRows = 4096;
+// Rows a CTA accumulates into ONE fp32 TMEM partial.  The tensor core's fp32 accumulation error grows about linearly with
+// the length of the dependent MMA chain (measured on the weight gradients of the Wikidata5M shape, 4.6 M rows, whose sums
+// cancel heavily; max-norm-relative error against float64): one slab per SM = 31 k rows per partial -> 7.4e-4; 4,096 rows
+// -> 5.7e-5; the WN18RR shape's 836 rows -> 1.0e-5.  Slabs of <= 1,024 rows, partials added in double precision by the
+// reduce kernel.  Beyond one wave every extra CTA costs its set-up and epilogue (~4 us per 1.2 MB slab) and 80 KB of partial.
+constexpr int64_t kTnMaxSlabRows = 1024;
 
 static int64_t tn_slabs(int64_t M, int n_prob) {
   const int64_t per_wave = kNumSMs / n_prob > 0 ? kNumSMs / n_prob : 1;
@@ -1123,6 +1123,14 @@ static int64_t tn_slabs(int64_t M, int n_prob) {
   const int64_t need = ceil_div(M, kTnMaxSlabRows);
   if (slabs < need) slabs = ceil_div(need, per_wave) * per_wave;      // whole waves
   return slabs < 1 ? 1 : slabs;
+}
+
+// The same product WITHOUT the sigmoid: logit[b, n] = X[b, :] . E[n, :] + bias[n] (fp32-grade, 3xTF32) - the exact-mode
+// evaluation scorer (scoring.filtered_rank(precision='fp32')) ranks on these where bf16-rounded operands could move a rank
+extern "C" int kgc_score_1n_logits(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                                   const float* bias, float* logits, int64_t ld_logits, void* stream) {
+  KGC_REQUIRE(bias != nullptr, "bias is required");
+  return launch_gemm_nt(1, &ent, n_ent, D, ld_ent, &packed_x, B, &logits, ld_logits, bias, 0, 1, 0, stream);
 }
 
 extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t Nb) {

@@ -428,6 +428,42 @@ __global__ void rank_finalize_kernel(const int32_t* __restrict__ count_gt, const
   ranks[q] = 1 + gt;
   if (eq_out) eq_out[q] = eq;
 }
+// Exact-mode counts over DENSE fp32 logits z[B, ld] (kgc_score_1n_logits): gt[q] += #{j < n : z[q, j] > thr[q]}, eq likewise.
+// grid = (column chunks, queries); integer partial sums -> one integer atomic per CTA (order-independent).
+constexpr int kDenseThreads = 256, kDenseCols = 8 * kDenseThreads;
+__global__ void __launch_bounds__(kDenseThreads)
+rank_count_dense_kernel(const float* __restrict__ z, int64_t ld, int64_t n, const float* __restrict__ thr,
+                        int32_t* __restrict__ count_gt, int32_t* __restrict__ count_eq) {
+  const int64_t q = blockIdx.y;
+  const float t = thr[q];
+  const float* row = z + q * ld;
+  int gt = 0, eq = 0;
+  const int64_t c0 = (int64_t)blockIdx.x * kDenseCols;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t c = c0 + i * kDenseThreads + threadIdx.x;
+    if (c < n) {
+      const float s = __ldg(row + c);
+      gt += s > t ? 1 : 0;
+      eq += s == t ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gt += __shfl_xor_sync(0xFFFFFFFFu, gt, o);
+    eq += __shfl_xor_sync(0xFFFFFFFFu, eq, o);
+  }
+  __shared__ int sg[kDenseThreads / 32], se[kDenseThreads / 32];
+  if (threadIdx.x % 32 == 0) { sg[threadIdx.x / 32] = gt; se[threadIdx.x / 32] = eq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int g = 0, e = 0;
+    for (int w = 0; w < kDenseThreads / 32; ++w) { g += sg[w]; e += se[w]; }
+    if (g) atomicAdd(count_gt + q, g);
+    if (count_eq != nullptr && e) atomicAdd(count_eq + q, e);
+  }
+}
+
 // sums13 = {count, sum rank, sum 1/rank, hits@1..10}; one block, fixed order -> deterministic
 __global__ void rank_sums_kernel(const int32_t* __restrict__ ranks, int64_t b, double* __restrict__ sums13) {
   __shared__ double sm[13][256];
@@ -597,6 +633,16 @@ extern "C" int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, in
   P.count_eq = count_eq;
   if (count_eq) return launch_score<false, true>(ma, mb, P, st);
   return launch_score<false, false>(ma, mb, P, st);
+}
+
+extern "C" int kgc_rank_count_dense(const float* logits, int64_t ld, int64_t n_ent, int64_t b, const float* thr,
+                                    int32_t* count_gt, int32_t* count_eq, void* stream) {
+  if (b == 0 || n_ent == 0) return 0;
+  KGC_REQUIRE(logits && thr && count_gt && ld >= n_ent && b <= 65535, "bad arguments (at most 65,535 queries per call)");
+  rank_count_dense_kernel<<<dim3((unsigned)ceil_div(n_ent, kDenseCols), (unsigned)b), kDenseThreads, 0, as_stream(stream)>>>(
+      logits, ld, n_ent, thr, count_gt, count_eq);
+  KGC_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int kgc_rank_finalize(const int32_t* count_gt, const int32_t* count_eq, const float* thr, const float* s_filt,

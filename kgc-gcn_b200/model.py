@@ -116,6 +116,8 @@ class ConvE(nn.Module):
         for 51,200 values) - on the K7 kernels."""
         bn = self.bn0
         if not self._k7_ok(x, bn):
+            _lib.library_path('ConvE.bn0', 'K7 takes CUDA fp32 maps with H * W % 4 == 0 and an affine BatchNorm with running '
+                                           'statistics and a fixed momentum')
             return bn(x)
         if self.training:
             bn.num_batches_tracked.add_(1)
@@ -127,6 +129,8 @@ class ConvE(nn.Module):
         BatchNorm with running statistics and a fixed momentum); the torch / cuDNN modules otherwise."""
         bn, p = self.bn1, self.feature_drop.p
         if not self._k7_ok(x, bn, p):
+            _lib.library_path('ConvE.bn1', 'K7 takes CUDA fp32 maps with H * W % 4 == 0 and an affine BatchNorm with running '
+                                           'statistics and a fixed momentum')
             return self.feature_drop(F.relu(bn(x)))
         seed = None
         if self.training and p > 0.0:
@@ -148,6 +152,7 @@ class ConvE(nn.Module):
                 and c.stride == (1, 1) and c.padding == (0, 0) and c.dilation == (1, 1) and c.groups == 1
                 and _lib.lib().kgc_conv1ch_supported(c.out_channels, c.kernel_size[0], x.shape[2], x.shape[3])):
             return _Conv1chFn.apply(x, c.weight, c.bias)
+        _lib.library_path('ConvE.conv_e', 'K8 takes CUDA fp32, one input channel, stride 1, no padding, W = 20, k in {3, 5, 7}')
         return c(x)
 
     def query(self, src_emb, rel_emb):
@@ -160,7 +165,11 @@ class ConvE(nn.Module):
         x = self._bn1_relu_drop(x)
         x = x.view(-1, self.flat_sz)
         # model.py:173: the 39,200 -> 200 fc layer; fp32-grade tensor-core kernels for the shapes they take
-        x = linear_tc(x, self.fc.weight, self.fc.bias) if linear_tc_supported(x, self.fc.weight) else self.fc(x)
+        if linear_tc_supported(x, self.fc.weight):
+            x = linear_tc(x, self.fc.weight, self.fc.bias)
+        else:
+            _lib.library_path('ConvE.fc', 'the tensor-core fc kernels take CUDA fp32, B <= 128, out <= 224, flat % 32 == 0, flat >= 4096')
+            x = self.fc(x)
         x = self.hidden_drop(x)
         return F.relu(self.bn2(x))
 
@@ -170,6 +179,7 @@ class ConvE(nn.Module):
         from .scoring import score_1n, score_1n_supported
         if score_1n_supported(x, all_ent):
             return score_1n(x, all_ent, self.bias)
+        _lib.library_path('ConvE 1-N scoring', 'K6t takes CUDA fp32 with Dout <= 224, Dout % 4 == 0 and 16-byte aligned entity rows')
         return torch.sigmoid(torch.addmm(self.bias, x, all_ent.transpose(1, 0)))
 
 
@@ -243,7 +253,7 @@ class MGCN(nn.Module):
         all_ent, all_rel = self.encode(data)
         x = self.conv2.query(torch.index_select(all_ent, 0, trip[:, 0]), torch.index_select(all_rel, 0, trip[:, 1]))
         if not score_1n_supported(x, all_ent):
-            raise RuntimeError('loss_sparse: shape not taken by the tensor-core scorer (B <= 256, Dout <= 224, Dout % 4 == 0); '
+            raise RuntimeError('loss_sparse: shape not taken by the tensor-core scorer (Dout <= 224, Dout % 4 == 0); '
                                'use loss(forward(...), label)')
         pos, add = dataset.label_values()
         return score_1n_bce(x, all_ent, self.conv2.bias, qid, ptr, idx, pos, add)

@@ -9,6 +9,8 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+# the GPU tests must run on the hand-written kernels: any drop to a torch / cuDNN library path raises (kgc_gcn_b200._lib.library_path)
+os.environ.setdefault('KGC_STRICT', '1')
 
 
 def pytest_configure(config):

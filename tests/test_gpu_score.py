@@ -197,7 +197,7 @@ def test_toy_predict_identical_metrics(k, golden_dir):
     np.testing.assert_array_equal(out['ranks'].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize('B,N,D', [(128, 40943, 200), (77, 1001, 200), (5, 14, 32), (256, 3000, 100), (1, 130, 8)])
+@pytest.mark.parametrize('B,N,D', [(128, 40943, 200), (77, 1001, 200), (5, 14, 32), (256, 3000, 100), (1, 130, 8), (300, 2000, 200), (600, 777, 64)])
 def test_score_1n_training_path(k, B, N, D):
     """K6t: dense sigmoid scores (model.py:177-179) and their autograd on the 3xTF32 tensor-core kernels agree with the
     fp64 evaluation of the same expression to fp32 accuracy; nothing is written outside [B, N]."""
@@ -228,3 +228,100 @@ def test_score_1n_training_path(k, B, N, D):
     x2, e2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, ent, bias))
     torch.nn.functional.binary_cross_entropy(score_1n(x2, e2, b2), label).backward()
     assert torch.equal(x2.grad, x.grad) and torch.equal(e2.grad, ent.grad) and torch.equal(b2.grad, bias.grad)
+
+
+def test_filtered_rank_exact_mode(k):
+    """precision='fp32' (exact mode): ranks computed from fp32-grade dense logits (what the reference ranks, main.py:121-126)
+    at a realistic entity count with CLOSELY spaced logits.  Against float64 scores every rank must lie in the interval
+    allowed by an fp32-sized error band (1e-5 of the score scale) - where bf16-rounded operands (2^-7 relative) move ranks;
+    on integer-valued inputs (exact in every precision) the two precisions agree bit for bit."""
+    g = torch.Generator().manual_seed(11)
+    B, N, d = 300, 40943, 200
+    xq = torch.randn(B, d, generator=g).abs().cuda()
+    tab = (torch.rand(N, d, generator=g) * 2 - 1).cuda()
+    bias = (torch.randn(N, generator=g) * 0.1).cuda()
+    obj = torch.randint(0, N, (B,), generator=g).cuda()
+    fptr = torch.arange(0, 3 * B + 1, 3, dtype=torch.int64).cuda()
+    fidx = torch.randint(0, N, (B, 3), generator=g).sort(1).values.reshape(-1).to(torch.int32).cuda()
+    s64 = xq.double() @ tab.double().t() + bias.double()
+    thr = s64[torch.arange(B, device='cuda'), obj]
+    keep = torch.ones((B, N), dtype=torch.bool, device='cuda')
+    keep[torch.arange(B, device='cuda').repeat_interleave(3), fidx.long()] = False
+    keep[torch.arange(B, device='cuda'), obj] = False
+    band = 1e-5 * float(s64.abs().max())
+    lo = ((s64 > (thr + band)[:, None]) & keep).sum(1)
+    hi = ((s64 > (thr - band)[:, None]) & keep).sum(1)
+    exact = k.filtered_rank(xq, tab, bias, obj, fptr, fidx, count_eq=True, precision='fp32')
+    r = exact['ranks'].long() - 1
+    assert bool(((r >= lo) & (r <= hi)).all()), 'fp32-mode ranks outside the fp32 error band'
+    gt64 = ((s64 > thr[:, None]) & keep).sum(1)
+    fast = k.filtered_rank(xq, tab, bias, obj, fptr, fidx, count_eq=True)
+    moved_fast = int((fast['ranks'].long() - 1 != gt64).sum())
+    moved_exact = int((r != gt64).sum())
+    print('ranks that differ from the float64 ranking: bf16 sweep {} / {}, fp32 mode {} / {}'.format(moved_fast, B, moved_exact, B))
+    assert moved_exact <= moved_fast and moved_exact <= B // 50
+    assert float((exact['thr'].double() - thr).abs().max()) <= 2e-6 * float(s64.abs().max())
+    # integer-valued inputs: both precisions are exact, so they must agree bit for bit (incl. ties)
+    xi = torch.randint(-3, 4, (B, d), generator=g).float().cuda()
+    ti = torch.randint(-3, 4, (N, d), generator=g).float().cuda()
+    bi = torch.randint(-2, 3, (N,), generator=g).float().cuda()
+    a = k.filtered_rank(xi, ti, bi, obj, fptr, fidx, count_eq=True)
+    b = k.filtered_rank(xi, ti, bi, obj, fptr, fidx, count_eq=True, precision='fp32')
+    assert torch.equal(a['ranks'], b['ranks']) and torch.equal(a['count_eq'], b['count_eq']) and torch.equal(a['thr'], b['thr'])
+    assert int(a['count_eq'].sum()) > 0                      # the integer case does contain ties
+    from kgc_gcn_b200.scoring import tie_adjusted_sums
+    opt = tie_adjusted_sums(a['ranks'], a['count_eq'], 'optimistic')
+    assert torch.allclose(opt, a['sums'], rtol=1e-12, atol=1e-9)
+    pes, mean = tie_adjusted_sums(a['ranks'], a['count_eq'], 'pessimistic'), tie_adjusted_sums(a['ranks'], a['count_eq'], 'mean')
+    assert float(pes[1]) > float(mean[1]) > float(opt[1]) and float(pes[2]) < float(mean[2]) < float(opt[2])
+
+
+def test_predict_against_the_reference_at_realistic_size(k, tmp_path):
+    """The reference's OWN predict() / evaluate() (main.py:80-135, run on the CPU from oracle/_ref through oracle/shims)
+    against ours on a synthetic data set of realistic size (8,000 entities, 24,000 training triples, 400 validation
+    triples) written as text files both loaders read, with the same state dict: MR / MRR / hits@k of the exact mode
+    (precision='fp32') must equal the reference's to the 5 places evaluate() rounds to unless a rank sits on an fp32 tie;
+    the bf16 sweep is reported next to it.  Skipped when oracle/_ref was not built."""
+    import build_ref
+    ref = build_ref.load_reference()
+    if ref is None:
+        pytest.skip('oracle/_ref not built')
+    ref_model, ref_dl, ref_main = ref
+    N, R, E = 8000, 12, 24000
+    tri = orc.synthetic_triples(N, R, E + 800, 21)
+    root = tmp_path / 'data' / 'Synth'
+    root.mkdir(parents=True)
+    for name, rows in (('train', tri[:E]), ('valid', tri[E:E + 400]), ('test', tri[E + 400:])):
+        (root / (name + '.txt')).write_text('\n'.join('e{} r{} e{}'.format(s, r, o) for s, r, o in rows.tolist()) + '\n')
+    prm = SimpleNamespace(gcn_in_dim=100, gcn_out_dim=200, gcn_drop=0.3, hidden_drop=0.3, feat_drop=0.3, k_w=10, k_h=20,
+                          num_filter=8, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=128, device='cuda')
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        dl = k.DataLoader('Synth', prm)
+        rdl = ref_dl.DataLoader('Synth', prm)
+    finally:
+        os.chdir(cwd)
+    assert dl.num_entity == rdl.num_entity and dl.num_edge == rdl.num_edge
+    torch.manual_seed(3)
+    rm = ref_model.MGCN(rdl.num_entity, rdl.num_relation, rdl.num_edge, prm)
+    with torch.no_grad():                                    # spread the scores: a trained model is not at its xavier init
+        rm.conv2.bias.normal_(0, 0.5)
+        rm.entity_embedding.mul_(30.0)
+    rm.eval()
+    m = k.MGCN(dl.num_entity, dl.num_relation, dl.num_edge, prm)
+    m.load_state_dict(rm.state_dict(), strict=True)
+    m = m.cuda()
+    dl.graph.to('cuda')
+    prm_cpu = SimpleNamespace(**dict(vars(prm), device='cpu'))
+    torch.manual_seed(4)
+    ref_iters = rdl.get_data_loaders(128, 0, prm_cpu)
+    ref_ev = ref_main.evaluate(rm, ref_iters, rdl.graph, prm_cpu, 'valid')
+    iters = dl.get_data_loaders(128, 0, prm)
+    ours = {p_: k.evaluate(m, iters, dl.graph, prm, 'valid', precision=p_) for p_ in ('fp32', 'bf16')}
+    print('reference', ref_ev, 'fp32 mode', ours['fp32'], 'bf16 sweep', ours['bf16'])
+    # the GCN / ConvE front end run in fp32 on both sides with different summation orders (1e-6-level differences in the
+    # logits), so a handful of near-tied ranks may differ by one place: MR within 0.05%, MRR / hits within 2.5e-3 (1 of 800 queries = 1.25e-3)
+    for key, v in ref_ev.items():
+        tol = 5e-4 * abs(v) if key == 'mr' else 2.5e-3
+        assert abs(float(ours['fp32'][key]) - float(v)) <= tol, (key, ours['fp32'][key], v)
