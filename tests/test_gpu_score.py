@@ -294,7 +294,7 @@ def test_predict_against_the_reference_at_realistic_size(k, tmp_path):
     for name, rows in (('train', tri[:E]), ('valid', tri[E:E + 400]), ('test', tri[E + 400:])):
         (root / (name + '.txt')).write_text('\n'.join('e{} r{} e{}'.format(s, r, o) for s, r, o in rows.tolist()) + '\n')
     prm = SimpleNamespace(gcn_in_dim=100, gcn_out_dim=200, gcn_drop=0.3, hidden_drop=0.3, feat_drop=0.3, k_w=10, k_h=20,
-                          num_filter=8, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=128, device='cuda')
+                          num_filter=32, kernel_size=7, bias=False, lbl_smooth=0.1, batch_size=128, device='cuda')
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
