@@ -461,9 +461,18 @@ class LayerCase(object):
                 'd_loop_rel': c.loop_rel.grad, 'd_loop_edge': c.loop_edge.grad, 'd_gamma': c.ent_bn.weight.grad}
 
 
-def rel_err(a, b):
-    b = b.detach().to(torch.float64)
-    return float((a.detach().to(torch.float64) - b).abs().max() / (b.abs().max() + 1e-300))
+def rel_err(a, b, chunk=1 << 26):
+    """max |a - b| / max |b|, both maxima in float64, evaluated in slices of <= 64 Mi elements (the operands are up to
+    16 GB at the Wikidata5M shape: whole-tensor float64 copies do not fit next to the layer's own buffers)."""
+    a, b = a.detach().reshape(-1), b.detach().reshape(-1)
+    num = den = 0.0
+    for i in range(0, max(a.numel(), 1), chunk):
+        bb = b[i:i + chunk].to(torch.float64)
+        if bb.numel() == 0:
+            break
+        num = max(num, float((a[i:i + chunk].to(torch.float64) - bb).abs().max()))
+        den = max(den, float(bb.abs().max()))
+    return num / (den + 1e-300)
 
 
 def parity_vs_float64(case, orc):
@@ -504,8 +513,13 @@ def parity_vs_single_gpu(case, dist):
         ent_l, rel_l = case.step()
     finally:
         case.conv.set_dropout_masks(None, None)
-    got = {kk: v.detach().clone() for kk, v in case.grads().items()}
-    got['all_ent'], got['all_rel'] = ent_l.detach().clone(), rel_l.detach().clone()
+    got = {kk: v.detach() for kk, v in case.grads().items()}      # the leaves' .grad tensors themselves (no second copy)
+    got['all_ent'], got['all_rel'] = ent_l.detach(), rel_l.detach()
+    del ent_l, rel_l
+    for t_ in case.leaves:
+        t_.grad = None
+    k.plan._PLAN_CACHE.clear()
+    torch.cuda.empty_cache()
     # bit-equality of the replicated tensors across ranks: all-gather an integer checksum
     rep = [n for n in got if n not in ('d_x', 'd_ee', 'all_ent')]
     sums = torch.stack([got[n].contiguous().view(torch.int32).to(torch.int64).sum() for n in rep])
@@ -525,14 +539,20 @@ def parity_vs_single_gpu(case, dist):
     et = torch.from_numpy(case.g['edge_attr'][0]).to(dev)
     ent, rel = ref_conv(x, ei, et, None, ee, rl)
     torch.autograd.backward([ent, rel], [case.rows('g_ent', all_nodes), case.g_rel])
-    own, oe = case.node_ids, case.edge_ids
-    want = {'all_ent': ent[own], 'all_rel': rel, 'd_x': x.grad[own], 'd_ee': ee.grad[oe], 'd_rel': rl.grad,
-            'd_loop_weight': ref_conv.loop_weight.grad, 'd_in_weight': ref_conv.in_weight.grad,
-            'd_out_weight': ref_conv.out_weight.grad, 'd_rels_weight': ref_conv.rels_weight.grad,
-            'd_loop_rel': ref_conv.loop_rel.grad, 'd_loop_edge': ref_conv.loop_edge.grad, 'd_gamma': ref_conv.ent_bn.weight.grad}
-    errs = {n: rel_err(got[n], want[n]) for n in want}
-    del want, ent, rel, x, ee, ei, et, ref_conv, fm_in, fm_out
+    ref_conv.set_dropout_masks(None, None)
+    del fm_in, fm_out, ei, et
     k.plan._PLAN_CACHE.clear()                       # the whole-graph plan and its scratch planes (tens of GB at this shape)
+    torch.cuda.empty_cache()
+    own, oe = case.node_ids, case.edge_ids
+    want = {'all_ent': lambda: ent[own], 'all_rel': lambda: rel, 'd_x': lambda: x.grad[own], 'd_ee': lambda: ee.grad[oe],
+            'd_rel': lambda: rl.grad, 'd_loop_weight': lambda: ref_conv.loop_weight.grad,
+            'd_in_weight': lambda: ref_conv.in_weight.grad, 'd_out_weight': lambda: ref_conv.out_weight.grad,
+            'd_rels_weight': lambda: ref_conv.rels_weight.grad, 'd_loop_rel': lambda: ref_conv.loop_rel.grad,
+            'd_loop_edge': lambda: ref_conv.loop_edge.grad, 'd_gamma': lambda: ref_conv.ent_bn.weight.grad}
+    errs = {}
+    for n in want:                                   # one tensor at a time: the row selections are copies of up to 8 GB
+        errs[n] = rel_err(got.pop(n), want[n]())
+    del want, ent, rel, x, ee, ref_conv, got
     torch.cuda.empty_cache()
     t = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
