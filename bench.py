@@ -140,20 +140,55 @@ def small_weights(R, seed=0):
 
 
 class ClockSampler(object):
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  In-process NVML (a 5 ms
+    poll on a thread: a 100 ms timed region on 8 ranks still gets samples); `nvidia-smi -lms 100` when NVML cannot be loaded."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.thread, self.stop, self.source = [], None, index, None, False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                                               # the CUDA device's own UUID: immune to CUDA_VISIBLE_DEVICES renumbering
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, nv, h):
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while True:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(sm), str(mx), ''] + ['Active' if r & b else 'Not Active' for b, _ in bits])
+            except Exception:
+                pass
+            if self.stop:
+                break
+            time.sleep(0.005)
 
     def __enter__(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = 'nvml'
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            self.source = 'nvidia-smi'
         except Exception:
             self.proc = None
         return self
@@ -163,7 +198,10 @@ class ClockSampler(object):
             self.rows.append([c.strip() for c in line.split(',')])
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.source == 'nvml':
+            self.stop = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
             try:
@@ -173,19 +211,19 @@ class ClockSampler(object):
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm),
+                'source': self.source}
 
 
 def synthetic_query_set(k, tri, R):
@@ -413,8 +451,10 @@ class LayerCase(object):
             self.node_ids = torch.arange(N, dtype=torch.int64, device=dev)
             self.edge_ids = torch.arange(2 * E, dtype=torch.int64, device=dev)
         else:
+            p2p_on = os.environ.get('KGC_P2P', '1') != '0'
             self.part = k.GraphPartition(self.g['edge_index'], self.g['edge_attr'][0], N, 2 * R + 1, world, rank, dev,
-                                         p2p=False if os.environ.get('KGC_P2P', '1') == '0' else 'auto')
+                                         balance=os.environ.get('KGC_BALANCE', 'hybrid' if p2p_on else 'edges'),
+                                         p2p='auto' if p2p_on else False)
             self.node_ids, self.edge_ids = self.part.owned_nodes, self.part.owned_eids
         self.x = self.rows('x', self.node_ids).requires_grad_(True)
         self.ee = self.rows('ee', self.edge_ids).requires_grad_(True)
@@ -785,11 +825,17 @@ def run_ours(args, rank, world, local_rank):
         launch_mode = t['launch_mode']
         part = case.part
         p2p = part.p2p(D_IN)
-        par = ('edge-balanced dst partition over {} GPUs ({} split hub rows, largest edge share {:.3f}x the mean); halo exchange of '
-               'x / d_x: {}; all-reduce of hub rows, BN sums, replicated grads: {}'
-               .format(world, part.n_hub, float(part.owned_eids.numel()) * world / (2 * E),
-                       'pulls over NVLink peer memory (K10)' if p2p is not None else 'NCCL all-gather / reduce-scatter',
-                       'one-shot peer-memory kernel (K10)' if p2p is not None else 'NCCL'))
+        if getattr(part, 'hybrid', False):
+            par = ('hybrid cut over {} GPUs: an edge lives with the owner of its lower-degree endpoint (largest edge share {:.3f}x the '
+                   'mean, {} remote rows of {} on rank 0); x rows in, partial aggregates to their owners, upstream rows in, partial '
+                   'd_x to their owners: pulls over NVLink peer memory (K10); BN sums, replicated grads: one-shot peer-memory kernel'
+                   .format(world, float(part.owned_eids.numel()) * world / (2 * E), part.n_halo, N))
+        else:
+            par = ('edge-balanced dst partition over {} GPUs ({} split hub rows, largest edge share {:.3f}x the mean); halo exchange of '
+                   'x / d_x: {}; all-reduce of hub rows, BN sums, replicated grads: {}'
+                   .format(world, part.n_hub, float(part.owned_eids.numel()) * world / (2 * E),
+                           'pulls over NVLink peer memory (K10)' if p2p is not None else 'NCCL all-gather / reduce-scatter',
+                           'one-shot peer-memory kernel (K10)' if p2p is not None else 'NCCL'))
         if p2p is not None:
             p2p.check()
         line.update({'value': value, 'ms_per_step': ms, 'scaling': 'weak' if weak else 'strong',

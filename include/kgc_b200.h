@@ -304,10 +304,12 @@ int kgc_clip_adam_step(const kgc_opt_tensor_t* tensors, const int32_t* items, in
  * node table and its partial d_x in SYMMETRIC buffers (same size on every rank, peer-mapped); *_ptrs_dev = device array
  * of `world` pointers to the ranks' buffers.
  *   kgc_p2p_barrier      flag barrier: flag_ptrs_dev[r] = rank r's uint32[world] flag array (zero-initialised);
- *                        *epoch (local, zero-initialised) counts barriers; *error is set to 1 on a ~2 s timeout.
+ *                        *epoch (local, zero-initialised) counts barriers; no data-path time-out: a ~2 minute watchdog sets
+ *                        *error = 1 and traps.  Barriers issued on different streams need their own flag array + epoch.
  *   kgc_p2p_halo_gather  every rank's node table = its own block_rows rows, then its halo.  Pulls the remote rows
  *                        rows[n_rows] (renumbered ids: owner g / block_rows, local row g % block_rows) from the head of
- *                        their owners' tables into rows block_rows + i of this rank's table.
+ *                        their owners' tables into rows block_rows + i of this rank's table.  order (optional): a permutation of
+ *                        the list positions = the sequence in which they are pulled (spreads every reader over all owners).
  *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r with idx[r * n_rows + v] >= 0, in ascending r, of
  *                        row idx[r * n_rows + v] of part_r   (v < n_rows: this rank's rows; deterministic).
  *   kgc_p2p_allreduce    one-shot sum of a small vector (n_bytes, a multiple of 16; fp32 or fp64) over the ranks: copy
@@ -318,8 +320,8 @@ int kgc_p2p_allreduce(void* const* stage_ptrs_dev, int64_t offset_bytes, void* c
                       int32_t world, uint32_t* epoch, int32_t* error, const void* in, void* out, int64_t n_bytes,
                       int32_t is_double, void* stream);
 int kgc_p2p_barrier(void* const* flag_ptrs_dev, int32_t rank, int32_t world, uint32_t* epoch, int32_t* error, void* stream);
-int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, int64_t n_rows, int64_t block_rows,
-                        int32_t D, void* stream);
+int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, const int32_t* order, int64_t n_rows,
+                        int64_t block_rows, int32_t D, void* stream);
 int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
                         const float* addend, float* out, int32_t D, void* stream);
 

@@ -64,7 +64,7 @@ SIGNATURES = {
     'kgc_clip_adam_step': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'kgc_p2p_allreduce': (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     'kgc_p2p_barrier': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
-    'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp]),
+    'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp]),
     'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_ingest_open': (ctypes.c_int, [ctypes.c_char_p, _vp]),
     'kgc_ingest_close': (None, [_vp]),

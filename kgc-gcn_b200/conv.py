@@ -198,6 +198,16 @@ class _Done(object):
         return None
 
 
+class _StreamJoin(object):
+    """Work handle of kernels issued on another CUDA stream: wait() makes the current stream wait for them."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 class _Collectives(object):
     """The four exchanges of the dst-partitioned layer; ``None`` context = single GPU."""
 
@@ -296,7 +306,10 @@ class _ConvFn(torch.autograd.Function):
         Nb = n_loc + n_hub
         compact = coll is not None and coll.halo_rows is not None
         n_table = Nl if coll is None else (Nb + coll.halo_rows.numel() if compact else Nb * coll.world)
-        if ee.shape[0] != plan.num_edges2 or Nb != plan.num_dst_rows or plan.num_nodes != n_table:
+        # hybrid cut (partition.partition_edges_hybrid): remote rows are destinations too - every table row can be written
+        hybrid = coll is not None and coll.p2p is not None and coll.p2p.hybrid
+        n_dst = n_table if hybrid else Nb
+        if ee.shape[0] != plan.num_edges2 or n_dst != plan.num_dst_rows or plan.num_nodes != n_table:
             raise ValueError('edge_embs / x do not match the graph plan')
         T = rels.shape[0] + 1
         if T != plan.num_types:
@@ -325,8 +338,13 @@ class _ConvFn(torch.autograd.Function):
         if coll is None:
             x_full = x
         elif coll.p2p is not None:
-            # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads)
-            x_full, gather = coll.p2p.gather(x, fence=not training), _Done()
+            # K10: publish this rank's rows, barrier, pull exactly the remote rows its records reference (peer loads) - on the
+            # exchange stream, next to K0 and the self-loop transform of this rank's own rows (NVLink-bound vs tensor-bound)
+            ex = coll.p2p.exchange_stream
+            ex.wait_stream(main)
+            with torch.cuda.stream(ex):
+                x_full = coll.p2p.gather(x, fence=not training)
+            gather = _StreamJoin(ex)
         elif compact:                                               # library fallback of the compact table
             x_blk = x if Nb == Nl else torch.cat([x, x.new_zeros((Nb - Nl, D))], 0)
             x_full, gather = coll.gather_compact(x_blk), _Done()
@@ -339,9 +357,9 @@ class _ConvFn(torch.autograd.Function):
             main.wait_stream(side)
             gemm_nt(x, None, res3[2], packed=packed_f[2])          # overlaps the all-gather
             gather.wait()
-        if max(x_full.shape[0], 3 * Nb, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
+        if max(x_full.shape[0], 3 * n_dst, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
             raise ValueError('kgc_gcn_b200: node / edge tables of 2^32 float4 elements or more are not supported')
-        agg = torch.empty((2, Nb, D), dtype=torch.float32, device=x.device)
+        agg = coll.p2p.agg_planes() if hybrid else torch.empty((2, Nb, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
             _lib.call('kgc_agg_fwd', p(x_full), p(rels_c), T - 1, p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
@@ -350,6 +368,8 @@ class _ConvFn(torch.autograd.Function):
         if gather is None:
             main.wait_stream(side)                                  # K0's operand packs are needed from here on
 
+        if hybrid:
+            coll.p2p.reduce_agg(Nl)                                 # K10: the owners add the partial rows of all ranks (rank order)
         if gather is not None:
             coll.sum_hub_rows(agg, n_loc)
             gemm_nt_batch([agg[0, :Nl], agg[1, :Nl]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
@@ -430,20 +450,22 @@ class _ConvFn(torch.autograd.Function):
         # weight-gradient reductions over the node rows (K4c on the tensor cores, deterministic).  Nothing on the d_x / d_ee /
         # d_rel chain below needs them: on one GPU they run on the side stream next to that chain (a K4c CTA leaves room for
         # one aggregation CTA per SM) and the main stream joins before the parameter-gradient kernel
-        main, side = torch.cuda.current_stream(), (plan.side_stream() if coll is None else None)
-        if side is not None:
-            side.wait_stream(main)
-        with torch.cuda.stream(side if side is not None else main):
+        main, side = torch.cuda.current_stream(), plan.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
             gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
             if ctx.has_bias:
                 torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
-        g3 = plan.scratch('g3', (3, Nb, D))
+        hybrid = coll is not None and coll.p2p is not None and coll.p2p.hybrid
+        g3 = coll.p2p.g3_planes() if hybrid else plan.scratch('g3', (3, Nb, D))
         gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]],
                       [g3[0, :Nl], g3[1, :Nl], g3[2, :Nl]])
         if n_hub:
             coll.spread_hub_rows(g3, 2, n_loc)                       # the virtual rows see their hub's upstream gradient
+        if hybrid:
+            coll.p2p.gather_g()                                      # K10: upstream rows of the remote destinations, from their owners
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
         p2p = None if coll is None else coll.p2p
         d_x_full = p2p.partial if p2p is not None else torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
@@ -456,6 +478,15 @@ class _ConvFn(torch.autograd.Function):
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
         scatter = None
+        if p2p is not None:
+            # K10 on the exchange stream, next to the d_rel pass and the replicated-gradient all-reduce of the main stream:
+            # barrier (own channel), then every owner pulls the partial rows of the ranks that touched its rows (rank order,
+            # deterministic) and adds the self-loop term - reduce-scatter + add in one kernel over peer memory
+            d_x = torch.empty((Nl, D), dtype=torch.float32, device=dev)
+            ex = p2p.exchange_stream
+            ex.wait_stream(main)
+            with torch.cuda.stream(ex):
+                p2p.reduce(g3[2, :Nl], Nl, out=d_x, channel=1)
         compact = coll is not None and coll.halo_rows is not None
         if coll is not None and p2p is None and not compact:   # source-row gradients go back to their owners while the d_rel pass runs
             d_x, scatter = coll.reduce_scatter_rows(d_x_full, async_op=True)
@@ -465,13 +496,12 @@ class _ConvFn(torch.autograd.Function):
                       plan.num_dst_rows, plan.num_edges_in, p(out_final), p(carry), D, st())
         plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
 
+        main.wait_stream(side)                                        # the weight gradients are part of `flat`
         if coll is None:
             d_x = d_x_full
         elif p2p is not None:
             coll.all_reduce(flat, 'flat')
-            # K10: barrier, then every owner pulls the partial rows of the ranks that touched its rows (rank order,
-            # deterministic) and adds the self-loop term - reduce-scatter + add in one kernel over peer memory
-            d_x = p2p.reduce(g3[2, :Nl], Nl)
+            main.wait_stream(p2p.exchange_stream)
         elif compact:
             coll.all_reduce(flat, 'flat')
             d_x = coll.reduce_compact(d_x_full, Nb)[:Nl] + g3[2, :Nl]
@@ -480,8 +510,6 @@ class _ConvFn(torch.autograd.Function):
             if scatter is not None:
                 scatter.wait()
             d_x = d_x[:Nl] + g3[2, :Nl]                               # self-loop term of this rank's (real) rows
-        if side is not None:
-            main.wait_stream(side)
         d_bias = flat[3 * D * Dout + T * D:] * 3.0 if ctx.has_bias else None
         # K0 backward: self-loop vectors, relation transform (model.py:107; replicated inputs, identical on every rank)
         small = torch.empty((2 * D * Dout + 2 * D + (T - 1) * D,), dtype=torch.float32, device=dev)

@@ -9,6 +9,10 @@
 //                            rank PULLS exactly the remote rows its records reference (one warp per 400-byte row, 8 rows
 //                            in flight per warp) into the compact tail of its own table (own rows, then the halo: every
 //                            per-rank structure is O(own rows + halo) whatever the number of ranks);
+//                            The list is ascending by owner, so ranks that walk it front to back all read the SAME owner at
+//                            the same time (one GPU's NVLink egress shared by seven readers); `order` is a permutation
+//                            of the list positions that deals 8-row trips to the owners in turn, starting behind the
+//                            reader's own rank - every peer link of every GPU carries traffic from the first trip on.
 //   * kgc_p2p_halo_reduce  - every rank leaves its partial d_x in a symmetric buffer; after a barrier the owner of a row
 //                            pulls the partials of the ranks that touched it (a per-row index table built with the partition)
 //                            and adds them IN RANK ORDER (deterministic) together with the self-loop term - the
@@ -116,8 +120,8 @@ constexpr int kHaloUnroll = 8;
 // table[r] = rank r's COMPACT node table: its own block_rows rows, then its halo; rows[i] = renumbered id g of the i-th
 // halo row: owner g / block_rows, local row g % block_rows; it lands in row block_rows + i of this rank's table
 __global__ void __launch_bounds__(kHaloThreads)
-halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* __restrict__ rows, int64_t n_rows,
-                   int block_rows, int D4) {
+halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* __restrict__ rows,
+                   const int32_t* __restrict__ order, int64_t n_rows, int block_rows, int D4) {
   const int lane = threadIdx.x % 32;
   const int64_t warp = (blockIdx.x * (int64_t)kHaloThreads + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * (kHaloThreads / 32);
@@ -127,7 +131,8 @@ halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* _
     int64_t g[kHaloUnroll];
 #pragma unroll
     for (int u = 0; u < kHaloUnroll; ++u) {
-      const int64_t i = i0 + u < n_rows ? i0 + u : n_rows - 1;
+      int64_t i = i0 + u < n_rows ? i0 + u : n_rows - 1;
+      if (order != nullptr) i = __ldg(order + i);                                   // pull schedule (see kgc_p2p_halo_gather)
       g[u] = __ldg(rows + i);
       const float4* src = table[g[u] / block_rows] + (g[u] % block_rows) * D4;     // the owner's block opens its table
       g[u] = block_rows + i;                                                        // compact row of this rank's table
@@ -196,15 +201,15 @@ extern "C" int kgc_p2p_barrier(void* const* flag_ptrs_dev, int32_t rank, int32_t
   return 0;
 }
 
-extern "C" int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, int64_t n_rows,
-                                   int64_t block_rows, int32_t D, void* stream) {
+extern "C" int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, const int32_t* order,
+                                   int64_t n_rows, int64_t block_rows, int32_t D, void* stream) {
   KGC_REQUIRE(table_ptrs_dev && block_rows > 0 && D > 0 && D % 4 == 0 && D <= 256, "bad arguments");
   if (n_rows == 0) return 0;
   KGC_REQUIRE(rows != nullptr, "null row list");
   int64_t blocks = ceil_div(n_rows, (kHaloThreads / 32) * kHaloUnroll);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  halo_gather_kernel<<<(unsigned)blocks, kHaloThreads, 0, as_stream(stream)>>>((float4* const*)table_ptrs_dev, rank, rows, n_rows,
-                                                                               (int)block_rows, D / 4);
+  halo_gather_kernel<<<(unsigned)blocks, kHaloThreads, 0, as_stream(stream)>>>((float4* const*)table_ptrs_dev, rank, rows, order,
+                                                                               n_rows, (int)block_rows, D / 4);
   KGC_LAUNCH_CHECK();
   return 0;
 }

@@ -17,6 +17,8 @@ Two ways of choosing the owners:
     n_hub rows of a block are the virtual rows), so the range machinery (K1 with dst_offset, all-gather, reduce-scatter)
     is used unchanged.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -50,7 +52,7 @@ def partition_edges(edge_index, edge_type, num_nodes, world, rank):
             'dst': dst[owned] - lo, 'type': et[owned], 'deg': _half_degrees(ei, E, world * per)}
 
 
-def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs=64, n_greedy=8192):
+def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs=64, n_greedy=8192, weights=None):
     """Edge-balanced node -> (rank, local row) assignment and the hub rows to split; identical on every rank.
 
     Returns dict(owner [N], slot [N], hubs [n_hub] (node ids, decreasing in-degree), n_loc).  A node is a split hub when
@@ -65,9 +67,11 @@ def balanced_assignment(edge_index, num_nodes, world, hub_fraction=0.5, max_hubs
     base, rem = divmod(num_nodes, world)
     cap_all = base + (np.arange(world, dtype=np.int64) < rem)  # nodes per rank
     n_loc = int(cap_all.max())
-    indeg = np.bincount(ei[1], minlength=num_nodes).astype(np.int64)
+    # ``weights``: the load a node brings to its owner (default: its in-degree = the edges that point to it); with explicit
+    # weights no row is split
+    indeg = np.bincount(ei[1], minlength=num_nodes).astype(np.int64) if weights is None else np.asarray(weights, dtype=np.int64)
     hubs = np.zeros((0,), dtype=np.int64)
-    if world > 1:
+    if world > 1 and weights is None:
         thr = max(1.0, hub_fraction * n2 / world)
         cand = np.nonzero(indeg > thr)[0]
         cand = cand[np.argsort(-indeg[cand], kind='stable')]
@@ -174,6 +178,105 @@ def partition_edges_balanced(edge_index, edge_type, num_nodes, world, rank, hub_
             'n_halo': n_halo, 'n_halo_max': int(n_halo_all.max()), 'peer_idx': peer_idx}
 
 
+def partition_edges_hybrid(edge_index, edge_type, num_nodes, world, rank):
+    """Hybrid cut (degree-based edge placement), pure host integer logic (numpy).
+
+    The destination partition moves one x row in and one d_x row out per DISTINCT remote source of a rank's edges; on a
+    hub-heavy graph almost every source of an edge that points to a hub is remote (Wikidata5M shape, 8 ranks: 1.75 M halo
+    rows per rank, 700 MB each way per step).  Here an edge lives with the owner of its LOWER-degree endpoint (its
+    anchor; ties go to the destination, so a graph without skew degenerates to the destination partition): the
+    high-degree endpoint is the remote one, and there are few distinct high-degree nodes.  A rank therefore holds
+      * edges whose destination is its own row and whose source may be remote      (as in the destination partition), and
+      * edges whose SOURCE is its own row and whose destination is remote: their messages are accumulated into a private
+        partial row per remote destination, and the owner of the destination adds the partial rows of all ranks in rank
+        order (forward); the upstream gradient rows of those destinations are pulled from their owners (backward).
+    Both roles share one compact numbering of a rank's node table: [0, n_loc) = its own rows, n_loc + i = remote[i]
+    (ascending renumbered id of every remote node its edges touch as source or destination).  Nodes are dealt to ranks
+    by decreasing anchored-edge count (LPT head, snake tail): equal node counts, near-equal edge counts, no split rows.
+
+    Returns dict(n_loc, n_real, n_hub = 0, block = n_loc, owned_nodes, owned_eids (ascending, in half first), n_edges_in,
+    newid [N] (= owner * n_loc + local row), halo_rows [n_remote] int32 (the remote list), n_halo, n_halo_max, n_remote_all
+    [world], src / dst (compact ids), type, deg [2, n_loc + n_remote], peer_idx [world, n_real] int32 (row of this rank's
+    node v in rank r's table when r's edges read it as a SOURCE, else -1; r = rank: v), peer_dst_idx [world, n_real]
+    (the same for r's edges that point to v: where r keeps its partial aggregate of v))."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    et = np.asarray(edge_type, dtype=np.int64)
+    n2 = ei.shape[1]
+    if n2 % 2 != 0:
+        raise ValueError('edge list must hold an in half and an out half of equal size')
+    E = n2 // 2
+    src, dst = ei[0], ei[1]
+    tot = np.bincount(src, minlength=num_nodes) + np.bincount(dst, minlength=num_nodes)
+    anchor = np.where(tot[src] < tot[dst], src, dst)
+    w = np.bincount(anchor, minlength=num_nodes).astype(np.int64)
+    a = balanced_assignment(ei, num_nodes, world, weights=w)
+    owner, slot, n_loc = a['owner'], a['slot'], a['n_loc']
+    block = n_loc
+    newid = owner * block + slot
+    edge_rank = owner[anchor]
+    owned = np.nonzero(edge_rank == rank)[0]
+    n_in = int(np.searchsorted(owned, E))
+    src_new, dst_new = newid[src], newid[dst]
+    n_real = int(a['count'][rank])
+    mine = np.nonzero(owner == rank)[0]
+    owned_nodes = mine[np.argsort(slot[mine], kind='stable')]
+    my_ids = np.arange(rank * block, rank * block + n_real, dtype=np.int64)
+    ids = np.arange(world * block, dtype=np.int64)
+    peer_src = np.full((world, n_real), -1, dtype=np.int32)
+    peer_dst = np.full((world, n_real), -1, dtype=np.int32)
+    n_remote_all = np.zeros(world, dtype=np.int64)
+    remote_mine = cmap = None
+    for r in range(world):
+        sel = edge_rank == r
+        seen_s = np.zeros(world * block, dtype=bool)
+        seen_d = np.zeros(world * block, dtype=bool)
+        seen_s[src_new[sel]] = True
+        seen_d[dst_new[sel]] = True
+        outside = (ids < r * block) | (ids >= (r + 1) * block)
+        remote = np.nonzero((seen_s | seen_d) & outside)[0]
+        n_remote_all[r] = remote.shape[0]
+        pos = np.full(world * block, -1, dtype=np.int64)
+        pos[remote] = block + np.arange(remote.shape[0], dtype=np.int64)
+        if r == rank:
+            peer_src[r] = peer_dst[r] = np.arange(n_real, dtype=np.int32)       # its own partial rows
+            remote_mine = remote
+            cmap = pos
+            cmap[r * block:(r + 1) * block] = np.arange(block, dtype=np.int64)
+        else:
+            peer_src[r] = np.where(seen_s[my_ids], pos[my_ids], -1)
+            peer_dst[r] = np.where(seen_d[my_ids], pos[my_ids], -1)
+    deg = _half_degrees(ei, E, num_nodes)
+    deg_ext = np.zeros((2, world * block), dtype=np.int32)
+    deg_ext[:, newid] = deg
+    comp_ids = np.concatenate([np.arange(rank * block, (rank + 1) * block, dtype=np.int64), remote_mine])
+    return {'n_loc': n_loc, 'n_real': n_real, 'n_hub': 0, 'block': block, 'owned_nodes': owned_nodes,
+            'hubs': np.zeros((0,), dtype=np.int64), 'owned_eids': owned, 'n_edges_in': n_in,
+            'src': cmap[src_new[owned]], 'dst': cmap[dst_new[owned]], 'type': et[owned],
+            'deg': np.ascontiguousarray(deg_ext[:, comp_ids]), 'newid': newid, 'halo_rows': remote_mine.astype(np.int32),
+            'n_halo': int(remote_mine.shape[0]), 'n_halo_max': int(n_remote_all.max()), 'n_remote_all': n_remote_all,
+            'peer_idx': peer_src, 'peer_dst_idx': peer_dst}
+
+
+def halo_pull_order(halo_rows, block, rank, world, trip=8):
+    """The sequence in which kgc_p2p_halo_gather pulls the positions of ``halo_rows`` (ascending renumbered ids, i.e.
+    ascending owner): trips of ``trip`` consecutive positions are dealt to the owners in turn - first trip of owner
+    rank + 1, of rank + 2, ..., then their second trips, ... - so that every reader spreads over all owners from the first
+    trip on and no owner's NVLink egress is shared by all readers at once.  Pure host integer logic; a permutation."""
+    hr = np.asarray(halo_rows, dtype=np.int64)
+    n = int(hr.shape[0])
+    if n == 0:
+        return np.zeros((0,), dtype=np.int32)
+    n_trips = -(-n // trip)
+    first = np.arange(n_trips, dtype=np.int64) * trip
+    owner = hr[first] // block                                  # a trip belongs to the owner of its first row
+    turn = (owner - rank - 1) % world                           # 0 for the owner right behind this rank
+    start = np.searchsorted(owner, owner, side='left')          # first trip of that owner (owners ascend)
+    k = np.arange(n_trips, dtype=np.int64) - start              # number of the trip within its owner
+    trips = np.lexsort((turn, k))                               # by k, then by turn
+    pos = (first[trips][:, None] + np.arange(trip, dtype=np.int64)[None, :]).reshape(-1)
+    return pos[pos < n].astype(np.int32)
+
+
 class GraphPartition(object):
     """This rank's share of the graph + its GraphPlan (built by K1 with the global degrees).
 
@@ -209,16 +312,36 @@ class GraphPartition(object):
             self.hubs = info['hubs']
             self.halo_rows = torch.from_numpy(info['halo_rows']).to(device)
             self.halo_rows64 = self.halo_rows.to(torch.int64)
+            self.halo_order = torch.from_numpy(halo_pull_order(info['halo_rows'], self.block, rank, world)).to(device)
             self.n_halo, self.n_halo_max = info['n_halo'], info['n_halo_max']
             self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
+        elif balance == 'hybrid':
+            # an edge lives with its lower-degree endpoint (partition_edges_hybrid): remote rows are few; they are read as
+            # sources AND written as destinations (partial aggregates the owners add up), one compact numbering for both
+            info = partition_edges_hybrid(ei, et, num_nodes, world, rank)
+            self.lo = self.hi = None
+            self.n_loc, self.n_hub, self.block, self.n_real = info['n_loc'], 0, info['block'], info['n_real']
+            self.owned_nodes = torch.from_numpy(info['owned_nodes']).to(device)
+            ext_nodes, offset = self.block + info['n_halo'], 0
+            self.hub_idx_mine = self.hub_rows_mine = None
+            self.hubs = info['hubs']
+            self.halo_rows = torch.from_numpy(info['halo_rows']).to(device)
+            self.halo_rows64 = self.halo_rows.to(torch.int64)
+            self.halo_order = torch.from_numpy(halo_pull_order(info['halo_rows'], self.block, rank, world)).to(device)
+            self.n_halo, self.n_halo_max = info['n_halo'], info['n_halo_max']
+            self.n_remote_all = [int(v) for v in info['n_remote_all']]
+            self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
+            self.peer_dst_idx = torch.from_numpy(info['peer_dst_idx']).to(device)
         else:
-            raise ValueError("balance must be 'edges' or 'range'")
+            raise ValueError("balance must be 'hybrid', 'edges' or 'range'")
+        self.hybrid = balance == 'hybrid'
         self.owned_eids = torch.from_numpy(info['owned_eids']).to(device)
         self.n_edges_in = info['n_edges_in']
         self.edge_index = torch.from_numpy(np.stack([info['src'], info['dst']])).to(device)
         self.edge_type = torch.from_numpy(info['type']).to(device)
         self.plan = GraphPlan(self.edge_index, self.edge_type, ext_nodes, num_types, n_edges_in=self.n_edges_in,
-                              n_dst_rows=self.block, dst_offset=offset, deg=torch.from_numpy(info['deg']).to(device))
+                              n_dst_rows=ext_nodes if self.hybrid else self.block, dst_offset=offset,
+                              deg=torch.from_numpy(info['deg']).to(device))
 
     # ------------------------------------------------------------------ peer-memory halo exchange (K10)
     def p2p(self, D):
@@ -229,11 +352,13 @@ class GraphPartition(object):
         if D in self._p2p:
             return self._p2p[D]
         ctx = None
-        if self._p2p_mode and self.balance == 'edges' and self.world > 1 and self.world <= 8 and self.device.type == 'cuda':
+        if self.hybrid and not self._p2p_mode:
+            raise RuntimeError("balance='hybrid' exchanges partial aggregates over peer memory (K10): it needs p2p")
+        if self._p2p_mode and self.balance in ('edges', 'hybrid') and self.world > 1 and self.world <= 8 and self.device.type == 'cuda':
             try:
                 ctx = _P2PContext(self, D)
             except Exception:                                   # pragma: no cover (depends on the box)
-                if self._p2p_mode is True:
+                if self._p2p_mode is True or self.hybrid:
                     raise
                 ctx = None
             ok = torch.tensor([1 if ctx is not None else 0], device=self.device)
@@ -261,25 +386,51 @@ class _P2PContext(object):
         self.table = symm.empty((rows, D), dtype=torch.float32, device=dev)     # own block, then the pulled halo rows
         self.partial = symm.empty((rows, D), dtype=torch.float32, device=dev)   # this rank's partial d_x, same numbering
         self.flags = symm.empty((64,), dtype=torch.int32, device=dev)
+        self.flags2 = symm.empty((64,), dtype=torch.int32, device=dev)          # second barrier channel (exchange stream)
         self.stage = symm.empty((self.STAGE_BYTES,), dtype=torch.uint8, device=dev)  # slots of the one-shot all-reduces
-        self.table.zero_(); self.partial.zero_(); self.flags.zero_(); self.stage.zero_()
+        self.table.zero_(); self.partial.zero_(); self.flags.zero_(); self.flags2.zero_(); self.stage.zero_()
         self._h_table = symm.rendezvous(self.table, group)
         self._h_partial = symm.rendezvous(self.partial, group)
         self._h_flags = symm.rendezvous(self.flags, group)
+        self._h_flags2 = symm.rendezvous(self.flags2, group)
         self._h_stage = symm.rendezvous(self.stage, group)
         self.table_ptrs, self.partial_ptrs, self.flag_ptrs, self.stage_ptrs = (
             int(h.buffer_ptrs_dev) for h in (self._h_table, self._h_partial, self._h_flags, self._h_stage))
+        self.flag2_ptrs = int(self._h_flags2.buffer_ptrs_dev)
+        self.hybrid = bool(getattr(part, 'hybrid', False))
+        if self.hybrid:
+            # partial aggregates [2, rows_r, D] and upstream gradient planes [3, rows_r, D] of every rank, rows_r = its own
+            # rows + ITS remote rows (plane stride differs per rank: per-plane peer pointer tables)
+            self.agg_buf = symm.empty((2 * rows * D,), dtype=torch.float32, device=dev)
+            self.g3_buf = symm.empty((3 * rows * D,), dtype=torch.float32, device=dev)
+            self.agg_buf.zero_(); self.g3_buf.zero_()
+            self._h_agg = symm.rendezvous(self.agg_buf, group)
+            self._h_g3 = symm.rendezvous(self.g3_buf, group)
+            rows_r = [B + n for n in part.n_remote_all]
+            self.rows_mine = rows_r[part.rank]
+            mk = lambda h_, plane: torch.tensor([int(p) + plane * rows_r[r] * D * 4 for r, p in enumerate(h_.buffer_ptrs)],   # noqa: E731
+                                                dtype=torch.int64, device=dev)
+            self.agg_plane_ptrs = [mk(self._h_agg, h) for h in (0, 1)]
+            self.g3_plane_ptrs = [mk(self._h_g3, h) for h in (0, 1)]
+            self.peer_dst_idx = part.peer_dst_idx
         self._slots, self._stage_used = {}, 0
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.epoch2 = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.exchange_stream = torch.cuda.Stream(device=dev)     # halo pulls next to rank-local kernels of the main stream
+        self.halo_order = getattr(part, 'halo_order', None)
         self.error = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.halo_rows, self.peer_idx = part.halo_rows, part.peer_idx
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)                               # every rank's buffers are zeroed before anyone pulls
 
-    def barrier(self):
+    def barrier(self, channel=0):
+        """Flag barrier on the current stream.  Barriers of ONE channel must be ordered by stream dependencies (they share an
+        epoch counter); channel 1 belongs to the exchange stream's backward pulls, which run next to the main stream's
+        one-shot all-reduces (channel 0)."""
         import ctypes
         from . import _lib
-        _lib.call('kgc_p2p_barrier', ctypes.c_void_p(self.flag_ptrs), self.rank, self.world, _lib.ptr(self.epoch),
+        flags, epoch = (self.flag_ptrs, self.epoch) if channel == 0 else (self.flag2_ptrs, self.epoch2)
+        _lib.call('kgc_p2p_barrier', ctypes.c_void_p(flags), self.rank, self.world, _lib.ptr(epoch),
                   _lib.ptr(self.error), _lib.stream())
 
     def gather(self, x_local, fence=False):
@@ -294,19 +445,49 @@ class _P2PContext(object):
             self.barrier()
         self.table[:n].copy_(x_local)
         self.barrier()
-        _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.table_ptrs), self.rank, _lib.ptr(self.halo_rows),
+        order = None if os.environ.get('KGC_HALO_ORDER', '1') == '0' else self.halo_order     # measurement knob
+        _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.table_ptrs), self.rank, _lib.ptr(self.halo_rows), _lib.ptr(order),
                   self.halo_rows.numel(), self.block, self.D, _lib.stream())
         return self.table
 
-    def reduce(self, addend, n_rows):
+    def reduce(self, addend, n_rows, out=None, channel=0):
         """barrier; d_x of this rank's rows = addend + the partials of the ranks that touched them, in rank order."""
         import ctypes
         from . import _lib
-        out = torch.empty((n_rows, self.D), dtype=torch.float32, device=self.table.device)
-        self.barrier()
+        if out is None:
+            out = torch.empty((n_rows, self.D), dtype=torch.float32, device=self.table.device)
+        self.barrier(channel)
         _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.peer_idx),
                   n_rows, _lib.ptr(addend), _lib.ptr(out), self.D, _lib.stream())
         return out
+
+    # ---- hybrid cut: partial aggregates to their owners (forward), upstream gradient rows to the ranks that need them (backward)
+    def agg_planes(self):
+        """This rank's [2, rows, D] aggregate planes in symmetric memory (rows = own + remote rows)."""
+        return self.agg_buf[:2 * self.rows_mine * self.D].view(2, self.rows_mine, self.D)
+
+    def g3_planes(self):
+        return self.g3_buf[:3 * self.rows_mine * self.D].view(3, self.rows_mine, self.D)
+
+    def reduce_agg(self, n_rows):
+        """barrier; own rows of both aggregate planes += the partial rows the other ranks accumulated for them, rank order
+        (in place: peers only read the rows BEHIND a rank's own block)."""
+        import ctypes
+        from . import _lib
+        agg = self.agg_planes()
+        self.barrier()
+        for h in (0, 1):
+            _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.agg_plane_ptrs[h].data_ptr()), self.world,
+                      _lib.ptr(self.peer_dst_idx), n_rows, None, _lib.ptr(agg[h]), self.D, _lib.stream())
+
+    def gather_g(self):
+        """barrier; rows of the remote destinations of planes 0 / 1 of g3 <- their owners' rows."""
+        import ctypes
+        from . import _lib
+        self.barrier()
+        for h in (0, 1):
+            _lib.call('kgc_p2p_halo_gather', ctypes.c_void_p(self.g3_plane_ptrs[h].data_ptr()), self.rank, _lib.ptr(self.halo_rows),
+                      _lib.ptr(self.halo_order), self.halo_rows.numel(), self.block, self.D, _lib.stream())
 
     def all_reduce(self, t, tag):
         """In-place sum of a small contiguous fp32 / fp64 tensor over the ranks (one kernel: stage, flag barrier, add in rank

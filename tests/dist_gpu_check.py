@@ -55,10 +55,10 @@ def main():
         assert err < tol, '{} rank {}: {:.3e}'.format(name, rank, err)
         return err
     errs = {}
-    for balance, frac, p2p in (('edges', 0.1, 'auto'), ('edges', 0.5, 'auto'), ('edges', 0.1, False), ('range', 0.5, False)):
+    for balance, frac, p2p in (('hybrid', 0.5, 'auto'), ('edges', 0.1, 'auto'), ('edges', 0.5, 'auto'), ('edges', 0.1, False), ('range', 0.5, False)):
         part = k.GraphPartition(g['edge_index'], g['edge_attr'][0], N, 2 * R + 1, world, rank, dev, balance=balance,
                                 hub_fraction=frac, p2p=p2p)
-        if frac == 0.1:
+        if frac == 0.1 and balance == 'edges':
             assert part.n_hub >= 1                                 # the Zipf generator's hub must have been split
         own = part.owned_nodes
         conv = make_conv()
@@ -95,7 +95,7 @@ def main():
             ctx.check()                                            # no barrier timed out
         e['p2p'] = 1.0 if ctx is not None else 0.0
         errs['{}/{}/{}'.format(balance, frac, p2p)] = e
-        if balance == 'edges':
+        if balance in ('edges', 'hybrid'):
             assert e['max_edge_share'] <= 1.15 / world             # balanced: no rank owns much more than its share
 
     # ---- entity-sharded filtered rank

@@ -134,6 +134,69 @@ def _worker(rank, world, port, ret):
             at = b['peer_idx'][r]
             pulled[at >= 0] += gathered[r].numpy()[at[at >= 0]]
         np.testing.assert_allclose(pulled, full[own_n], rtol=1e-10, atol=1e-12)
+        # ---- hybrid cut (partition_edges_hybrid): an edge lives with its lower-degree endpoint; remote rows are sources AND
+        # destinations; partial aggregates go to their owners through peer_dst_idx, partial d_x through peer_idx
+        from kgc_gcn_b200.partition import partition_edges_hybrid
+        hb = partition_edges_hybrid(ei, et, N, world, rank)
+        hl, hrem = hb['n_loc'], hb['n_halo']
+        rows_h, rows_max = hl + hrem, hl + hb['n_halo_max']
+        assert hb['block'] == hl and hb['n_hub'] == 0 and int(hb['n_remote_all'][rank]) == hrem
+        he, hn = hb['owned_eids'], hb['owned_nodes']
+        counts = torch.zeros(2 * E, dtype=torch.int64)
+        counts[torch.from_numpy(he)] = 1
+        dist.all_reduce(counts)
+        assert int(counts.min()) == 1 and int(counts.max()) == 1          # every edge owned exactly once
+        ncount = torch.zeros(N, dtype=torch.int64)
+        ncount[torch.from_numpy(hn)] = 1
+        dist.all_reduce(ncount)
+        assert int(ncount.min()) == 1 and int(ncount.max()) == 1          # every node owned exactly once
+        most = torch.tensor([he.shape[0]])
+        dist.all_reduce(most, op=dist.ReduceOp.MAX)
+        assert int(most) <= 1.15 * 2 * E / world                          # edge-balanced without split rows
+        rem = hb['halo_rows'].astype(np.int64)
+        assert (np.diff(rem) > 0).all() and ((rem < rank * hl) | (rem >= (rank + 1) * hl)).all()
+        assert hrem < b['n_halo']                                         # fewer remote rows than the destination partition's halo
+        old_h = np.full(world * hl, -1)
+        old_h[hb['newid']] = np.arange(N)
+        comp_h = np.concatenate([np.arange(rank * hl, (rank + 1) * hl), rem])
+        valid = old_h[comp_h] >= 0
+        assert valid[hl:].all() and (hb['src'] < rows_h).all() and (hb['dst'] < rows_h).all()
+        # an edge's anchor (an endpoint this rank owns) is its lower-degree endpoint, ties to the destination
+        tot = np.bincount(ei[0], minlength=N) + np.bincount(ei[1], minlength=N)
+        anchor_is_src = tot[ei[0, he]] < tot[ei[1, he]]
+        assert (np.where(anchor_is_src, hb['src'], hb['dst']) < hl).all()
+        np.testing.assert_array_equal(hb['deg'][:, valid], info['deg'][:, old_h[comp_h][valid]])
+        table_h = np.zeros((rows_h, D))
+        table_h[valid] = x[old_h[comp_h][valid]]
+        n_in_h = hb['n_edges_in']
+        planes_h = np.zeros((2, rows_max, D))
+        for h, sl in ((0, slice(0, n_in_h)), (1, slice(n_in_h, None))):
+            eids = he[sl]
+            planes_h[h, :rows_h] = _agg_numpy(table_h, rel, ee[eids], hb['src'][sl], hb['dst'][sl], hb['type'][sl], norm[eids], rows_h)
+        everyone = [torch.zeros((2, rows_max, D), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(everyone, torch.from_numpy(planes_h))
+        n_real_h = hb['n_real']
+        assert (hb['peer_dst_idx'][rank] == np.arange(n_real_h)).all() and (hb['peer_idx'][rank] == np.arange(n_real_h)).all()
+        for h in (0, 1):
+            summed = np.zeros((n_real_h, D))
+            for r in range(world):                                         # the owner adds the partial rows in rank order
+                at = hb['peer_dst_idx'][r]
+                summed[at >= 0] += everyone[r].numpy()[h][at[at >= 0]]
+            half = slice(0, E) if h == 0 else slice(E, 2 * E)
+            glob = _agg_numpy(x, rel, ee[half], ei[0, half], ei[1, half], et[half], norm[half], N)
+            np.testing.assert_allclose(summed, glob[hn], rtol=1e-10, atol=1e-11)
+        # backward: the upstream rows of the remote destinations come from their owners; partial d_x goes back through peer_idx
+        g_tab = np.zeros((rows_h, D))
+        g_tab[valid] = gsel[old_h[comp_h][valid]]
+        part_h = np.zeros((rows_max, D))
+        np.add.at(part_h, hb['src'], norm[he][:, None] * g_tab[hb['dst']] * rel[hb['type']] * ee[he])
+        everyone = [torch.zeros((rows_max, D), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(everyone, torch.from_numpy(part_h))
+        pulled = np.zeros((n_real_h, D))
+        for r in range(world):
+            at = hb['peer_idx'][r]
+            pulled[at >= 0] += everyone[r].numpy()[at[at >= 0]]
+        np.testing.assert_allclose(pulled, full[hn], rtol=1e-10, atol=1e-12)
         # ---- entity-sharded filtered rank: integer counts all-reduce to the unsharded answer, target logits sum exactly
         B, NE = 16, 64
         scores = rng.integers(-5, 6, (B, NE)).astype(np.float64)
@@ -280,3 +343,24 @@ def test_balanced_partition_properties(world):
                 pos = np.searchsorted(halo, ids_mine)
                 hit = (pos < halo.shape[0]) & (halo[np.minimum(pos, halo.shape[0] - 1)] == ids_mine)
                 assert ((at >= 0) == hit).all() and (at[hit] == blk + pos[hit]).all()
+
+
+def test_halo_pull_order_is_a_permutation_that_rotates_owners():
+    """partition.halo_pull_order: every position once; consecutive 8-row trips go to different owners, starting with the
+    owner behind the reader's rank (no owner is read by every rank at the same time)."""
+    import numpy as np
+    from kgc_gcn_b200.partition import halo_pull_order
+    rng = np.random.default_rng(5)
+    block, world = 1000, 8
+    for rank in (0, 3, 7):
+        remote = np.setdiff1d(np.arange(world * block), np.arange(rank * block, (rank + 1) * block))
+        ids = np.sort(rng.choice(remote, 3001, replace=False))
+        order = halo_pull_order(ids, block, rank, world)
+        assert order.dtype == np.int32 and sorted(order.tolist()) == list(range(ids.shape[0]))
+        owners = ids[order[order % 8 == 0]] // block
+        first = owners[:world - 1].tolist()
+        assert first == [(rank + 1 + j) % world for j in range(world - 1)]
+        assert (owners[1:world - 1] != owners[:world - 2]).all()
+        inner = np.nonzero(order % 8 != 0)[0]                            # a trip is 8 consecutive list positions
+        assert (order[inner] == order[inner - 1] + 1).all()
+    assert halo_pull_order(np.zeros((0,), dtype=np.int64), block, 0, world).shape == (0,)
