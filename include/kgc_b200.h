@@ -168,12 +168,15 @@ int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pr
  * kgc_conv_prep (forward): relp = cat(rels, loop_rel) (model.py:86); all_rel = relp @ w_rel (model.py:107, all
  * n_rels + 1 rows - the caller drops the last); and the hi / lo TF32 packs kgc_gemm_nt needs for the three
  * transforms of the step and of its backward: packed_fwd = 3 x pack(W_h as [K = D, N = Dout]), packed_bwd =
- * 3 x pack(W_h^T as [K = Dout, N = D]), h = in, out, loop, each kgc_gemm_packed_b_bytes long, the self-loop weight
+ * 4 x pack(W_h^T as [K = Dout, N = D]), h = in, out, loop, rel, each kgc_gemm_packed_b_bytes long, the self-loop weight
  * pre-scaled by loop_rel . loop_edge (model.py:92-94 folded: (x . lr . le) @ W = x @ diag(lr . le) W).
  * kgc_conv_param_grads (backward): from m_loop = x^T @ d_res_loop and the type-sorted edge reduction d_relp:
  *   d_w_loop = diag(lr . le) m_loop;  d_v = rowsum(m_loop . w_loop);  d_loop_edge = d_v . lr;
  *   d_relp' = d_relp + [g_rel; 0] @ w_rel^T;  d_rels = d_relp'[:-1];  d_loop_rel = d_v . le + d_relp'[-1];
  *   d_w_rel = relp^T @ [g_rel; 0]   (g_rel may be NULL: no gradient reached all_rel).
+ * rel_add (optional, [n_rels, D]): the caller already holds g_rel @ w_rel^T (kgc_gemm_nt with packed_bwd[3]) and has written
+ * d_w_rel itself (kgc_gemm_tn_tc) - the two products over the relation rows then run on the tensor cores instead of
+ * this kernel's per-thread loops (0.29 ms at 1,644 relation rows).
  * Weights are contiguous [D, Dout]; D, Dout <= 256. */
 int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loop_rel, const float* loop_edge, const float* w_in,
                   const float* w_out, const float* w_loop, const float* w_rel, int32_t D, int32_t Dout, float* relp,
@@ -181,7 +184,7 @@ int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loop_rel, cons
 int kgc_conv_param_grads(const float* m_loop, const float* w_loop, const float* loop_rel, const float* loop_edge,
                          const float* relp, const float* w_rel, const float* g_rel, const float* d_relp,
                          int32_t n_rels, int32_t D, int32_t Dout, float* d_w_loop, float* d_loop_rel,
-                         float* d_loop_edge, float* d_rels, float* d_w_rel, void* stream);
+                         float* d_loop_edge, float* d_rels, float* d_w_rel, const float* rel_add, void* stream);
 
 /* ---- K4b: dense transforms on the tensor cores with fp32-grade accuracy (3xTF32) --------------------------
  * Replaces the fp32 matmuls of model.py:116 (x_j_rel @ W, after the aggregate-then-transform reordering
@@ -310,19 +313,22 @@ int kgc_clip_adam_step(const kgc_opt_tensor_t* tensors, const int32_t* items, in
  *                        rows[n_rows] (renumbered ids: owner g / block_rows, local row g % block_rows) from the head of
  *                        their owners' tables into rows block_rows + i of this rank's table.  order (optional): a permutation of
  *                        the list positions = the sequence in which they are pulled (spreads every reader over all owners).
- *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r with idx[r * n_rows + v] >= 0, in ascending r, of
- *                        row idx[r * n_rows + v] of part_r   (v < n_rows: this rank's rows; deterministic).
+ *   kgc_p2p_halo_reduce  out[v] = addend[v] + sum over the ranks r with idx[r * n_rows + j] >= 0, in ascending r, of
+ *                        row idx[r * n_rows + j] of part_r   (deterministic); v = j for all j < n_rows (row_ids NULL: every
+ *                        row of this rank) or v = row_ids[j] (only the rows other ranks contributed to); addend == out
+ *                        is allowed (in-place add of the remote partials).
  *   kgc_p2p_allreduce    one-shot sum of a small vector (n_bytes, a multiple of 16; fp32 or fp64) over the ranks: copy
  *                        into this rank's staging slot (stage_ptrs_dev[r] + offset_bytes), flag barrier, every rank adds
- *                        all slots in rank order (identical bits everywhere).  in == out is allowed.  One CTA: meant for
- *                        the BatchNorm sums, the split hub rows and the replicated-parameter gradients (<= ~1 MB). */
+ *                        all slots in rank order (identical bits everywhere).  in == out is allowed.  One CTA up to 64 KB
+ *                        (BatchNorm sums, split hub rows); wider payloads (the replicated-parameter gradients, ~1 MB)
+ *                        stage / meet / add in three launches with many CTAs. */
 int kgc_p2p_allreduce(void* const* stage_ptrs_dev, int64_t offset_bytes, void* const* flag_ptrs_dev, int32_t rank,
                       int32_t world, uint32_t* epoch, int32_t* error, const void* in, void* out, int64_t n_bytes,
                       int32_t is_double, void* stream);
 int kgc_p2p_barrier(void* const* flag_ptrs_dev, int32_t rank, int32_t world, uint32_t* epoch, int32_t* error, void* stream);
 int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, const int32_t* rows, const int32_t* order, int64_t n_rows,
                         int64_t block_rows, int32_t D, void* stream);
-int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
+int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, const int32_t* row_ids, int64_t n_rows,
                         const float* addend, float* out, int32_t D, void* stream);
 
 /* ---- N4: native text -> id ingest (host C++, no device code; SURVEY "next" row N4) ---------------------------------

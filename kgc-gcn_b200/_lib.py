@@ -41,7 +41,7 @@ SIGNATURES = {
     'kgc_gemm_pack_b': (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'kgc_gemm_nt': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_conv_prep': (ctypes.c_int, [_vp, _i32] + [_vp] * 6 + [_i32, _i32] + [_vp] * 5),
-    'kgc_conv_param_grads': (ctypes.c_int, [_vp] * 8 + [_i32, _i32, _i32] + [_vp] * 6),
+    'kgc_conv_param_grads': (ctypes.c_int, [_vp] * 8 + [_i32, _i32, _i32] + [_vp] * 7),
     'kgc_gemm_nt_batch': (ctypes.c_int, [_i32, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_gemm_nt_trans': (ctypes.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     'kgc_gemm_nt_splitk': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
@@ -65,7 +65,7 @@ SIGNATURES = {
     'kgc_p2p_allreduce': (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     'kgc_p2p_barrier': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     'kgc_p2p_halo_gather': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp]),
-    'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'kgc_p2p_halo_reduce': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_ingest_open': (ctypes.c_int, [ctypes.c_char_p, _vp]),
     'kgc_ingest_close': (None, [_vp]),
     'kgc_ingest_count': (_i64, [_vp, _i32]),
@@ -106,7 +106,7 @@ def lib():
 
 
 LAUNCHES = 0     # kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {'kgc_csr_build': 16, 'kgc_label_mask_build': 2, 'kgc_bce_1n_bwd_logit': 2, 'kgc_score_pairs': 3, 'kgc_rank_finalize': 2, 'kgc_gemm_tn': 2, 'kgc_gemm_tn_tc': 2}
+_KERNELS_PER_CALL = {'kgc_csr_build': 16, 'kgc_label_mask_build': 2, 'kgc_bce_1n_bwd_logit': 2, 'kgc_score_pairs': 3, 'kgc_rank_finalize': 2, 'kgc_gemm_tn': 2, 'kgc_gemm_tn_tc': 2}   # (kgc_p2p_allreduce: 1 or 3)
 
 
 def call(name, *args):

@@ -323,7 +323,7 @@ class _ConvFn(torch.autograd.Function):
         relp = torch.empty((T, D), dtype=torch.float32, device=x.device)
         all_rel_pad = torch.empty((T, Dout), dtype=torch.float32, device=x.device)
         packed_f = torch.empty((3, nf), dtype=torch.float32, device=x.device)
-        packed_b = torch.empty((3, nbk), dtype=torch.float32, device=x.device)
+        packed_b = torch.empty((4, nbk), dtype=torch.float32, device=x.device)
         rels_c, wts = rels.detach().contiguous(), [w.detach().contiguous() for w in (w_in, w_out, w_loop, w_rel)]
         # ... on a side stream: the aggregation below reads the relation rows straight from `rels` (real edges never carry
         # the self-loop type), so K0 leaves the critical path; the main stream joins before the first dense transform
@@ -359,7 +359,7 @@ class _ConvFn(torch.autograd.Function):
             gather.wait()
         if max(x_full.shape[0], 3 * n_dst, ee.shape[0]) * (D // 4) >= 1 << 32:      # K2/K3 use 32-bit float4 indices
             raise ValueError('kgc_gcn_b200: node / edge tables of 2^32 float4 elements or more are not supported')
-        agg = coll.p2p.agg_planes() if hybrid else torch.empty((2, Nb, D), dtype=torch.float32, device=x.device)
+        agg = torch.empty((2, n_dst, D), dtype=torch.float32, device=x.device)
 
         def level0(sp, out_final, carry):
             _lib.call('kgc_agg_fwd', p(x_full), p(rels_c), T - 1, p(ee), p(plan.rec_dst), p(sp.rowflags), p(sp.chunks), sp.n_rec,
@@ -369,7 +369,7 @@ class _ConvFn(torch.autograd.Function):
             main.wait_stream(side)                                  # K0's operand packs are needed from here on
 
         if hybrid:
-            coll.p2p.reduce_agg(Nl)                                 # K10: the owners add the partial rows of all ranks (rank order)
+            coll.p2p.reduce_agg(agg)                                # K10: the owners add the partial rows of the other ranks (rank order)
         if gather is not None:
             coll.sum_hub_rows(agg, n_loc)
             gemm_nt_batch([agg[0, :Nl], agg[1, :Nl]], [packed_f[0], packed_f[1]], [res3[0], res3[1]])
@@ -468,9 +468,11 @@ class _ConvFn(torch.autograd.Function):
             coll.p2p.gather_g()                                      # K10: upstream rows of the remote destinations, from their owners
         # ---- K3: d_x (+ self-loop term) and d_ee over src-sorted rows, d_rel over type-sorted rows
         p2p = None if coll is None else coll.p2p
-        d_x_full = p2p.partial if p2p is not None else torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
+        d_x_full = p2p.partial if (p2p is not None and not hybrid) else torch.empty((plan.num_nodes, D), dtype=torch.float32, device=dev)
         d_ee = torch.empty_like(ee)
-        loop_addend = g3[2] if coll is None else None
+        # self-loop term: added by the aggregation itself when its output rows are final (one GPU; hybrid cut: the remote rows
+        # of plane 2 are zero), otherwise by the owner-side reduction
+        loop_addend = g3[2] if (coll is None or hybrid) else None
 
         def level0_src(sp, out_final, carry):
             _lib.call('kgc_agg_bwd_src', p(x_full), p(relp), relp.shape[0], p(ee), p(g3), p(plan.rec_src), p(sp.rowflags), p(sp.chunks),
@@ -478,7 +480,15 @@ class _ConvFn(torch.autograd.Function):
                       D, st())
         plan.run_reduction(plan.bwd_src, level0_src, d_x_full, D, addend=loop_addend, tag='s')
         scatter = None
-        if p2p is not None:
+        if hybrid:
+            # K10 on the exchange stream: partial rows of the remote sources to symmetric memory, barrier (own channel), the
+            # owners add the other ranks' partial rows to the few rows that have any - next to the d_rel pass
+            ex = p2p.exchange_stream
+            ex.wait_stream(main)
+            with torch.cuda.stream(ex):
+                p2p.reduce_dx(d_x_full, channel=1)
+            d_x = d_x_full[:Nl]
+        elif p2p is not None:
             # K10 on the exchange stream, next to the d_rel pass and the replicated-gradient all-reduce of the main stream:
             # barrier (own channel), then every owner pulls the partial rows of the ranks that touched its rows (rank order,
             # deterministic) and adds the self-loop term - reduce-scatter + add in one kernel over peer memory
@@ -517,9 +527,14 @@ class _ConvFn(torch.autograd.Function):
         o = 2 * D * Dout
         d_loop_rel, d_loop_edge, d_rels = small[o:o + D].view(1, D), small[o + D:o + 2 * D].view(1, D), small[o + 2 * D:].view(T - 1, D)
         g_rel_c = None if g_rel is None else g_rel.contiguous()
+        rel_add = None
+        if g_rel_c is not None and T - 1 >= 256 and g_rel_c.data_ptr() % 16 == 0 and Dout % 4 == 0 and (D * Dout) % 32 == 0:
+            # many relations (Wikidata5M shape: 1,644 rows): the two products over the relation rows on the tensor cores
+            rel_add = gemm_nt(g_rel_c, None, torch.empty((T - 1, D), dtype=torch.float32, device=dev), packed=packed_b[3])
+            gemm_tn(relp[:T - 1], g_rel_c, d_w_rel, plan)
         _lib.call('kgc_conv_param_grads', p(m_loop), p(w_loop.detach().contiguous()), p(loop_rel.detach()), p(loop_edge.detach()),
                   p(relp), p(w_rel.detach().contiguous()), p(g_rel_c), p(d_relp), T - 1, D, Dout, p(d_w_loop), p(d_loop_rel),
-                  p(d_loop_edge), p(d_rels), p(d_w_rel), st())
+                  p(d_loop_edge), p(d_rels), p(d_w_rel), p(rel_add), st())
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
                 None, None, None, None, None, None, None, None, None, None, None, None)
 

@@ -524,11 +524,11 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepArgs a) {
     return;
   }
   i -= 3 * nf;
-  if (i < 3 * nb) {                                               // Bt[n, k] = W_h^T[k, n] = W_h[n, k]
+  if (i < 4 * nb) {                                               // Bt[n, k] = W_h^T[k, n] = W_h[n, k]; h = 3: the relation transform
     const int h = i / nb, j = i % nb, n = j / a.k_pad_b, k = j % a.k_pad_b;
     float v = 0.f;
     if (n < a.D && k < a.Dout) {
-      const float* wh = h == 0 ? a.w0 : (h == 1 ? a.w1 : a.w2);
+      const float* wh = h == 0 ? a.w0 : (h == 1 ? a.w1 : (h == 2 ? a.w2 : a.w_rel));
       v = wh[(int64_t)n * a.Dout + k];
       if (h == 2) v *= a.loop_rel[n] * a.loop_edge[n];
     }
@@ -586,6 +586,38 @@ __global__ void __launch_bounds__(256) conv_param_grads_kernel(const ParamGradAr
         a.d_loop_edge[c] = acc * a.loop_rel[c];
         a.d_loop_rel[c] = acc * a.loop_edge[c] + val;
       }
+    }
+  }
+}
+
+// The same gradients when the two products over the relation rows - d_w_rel = relp^T [g_rel; 0] and rel_add = g_rel w_rel^T -
+// were computed by K4c / K4b (at 1,644 relation rows the loops above are 0.29 ms of serial work per thread).
+__global__ void __launch_bounds__(256) conv_param_grads2_kernel(const ParamGradArgs a, const float* __restrict__ rel_add) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = a.D * a.Dout;
+  if (i < nw) {
+    const int c = i / a.Dout;
+    a.d_w_loop[i] = a.loop_rel[c] * a.loop_edge[c] * a.m_loop[i];
+    return;
+  }
+  i -= nw;
+  const int n_el = a.n_rels * a.D, n_el_pad = (n_el + 31) & ~31;  // the warps of the last region must be whole hardware warps
+  if (i < n_el_pad) {
+    if (i < n_el) a.d_rels[i] = a.d_relp[i] + rel_add[i];
+    return;
+  }
+  i -= n_el_pad;
+  const int c = i / 32, lane = i % 32;
+  if (c < a.D) {                                                  // self-loop row: d_v[c] = sum_o m_loop[c, o] w_loop[c, o]
+    const float* u = a.m_loop + (int64_t)c * a.Dout;
+    const float* w = a.w_loop + (int64_t)c * a.Dout;
+    float acc = 0.f;
+    for (int o = lane; o < a.Dout; o += 32) acc = fmaf(u[o], w[o], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+    if (lane == 0) {
+      a.d_loop_edge[c] = acc * a.loop_rel[c];
+      a.d_loop_rel[c] = acc * a.loop_edge[c] + a.d_relp[(int64_t)a.n_rels * a.D + c];
     }
   }
 }
@@ -987,7 +1019,7 @@ extern "C" int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loo
   a.n_rels = n_rels; a.D = D; a.Dout = Dout;
   a.n_pad_f = tf.n_pad; a.k_pad_f = tf.k_pad; a.n_pad_b = tb.n_pad; a.k_pad_b = tb.k_pad;
   a.relp = relp; a.all_rel = all_rel; a.packed_f = packed_fwd; a.packed_b = packed_bwd;
-  const int64_t total = (int64_t)(n_rels + 1) * (D + Dout) + 3 * ((int64_t)tf.n_pad * tf.k_pad + (int64_t)tb.n_pad * tb.k_pad);
+  const int64_t total = (int64_t)(n_rels + 1) * (D + Dout) + 3 * (int64_t)tf.n_pad * tf.k_pad + 4 * (int64_t)tb.n_pad * tb.k_pad;
   conv_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(a);
   KGC_LAUNCH_CHECK();
   return 0;
@@ -996,13 +1028,20 @@ extern "C" int kgc_conv_prep(const float* rels, int32_t n_rels, const float* loo
 extern "C" int kgc_conv_param_grads(const float* m_loop, const float* w_loop, const float* loop_rel, const float* loop_edge,
                                     const float* relp, const float* w_rel, const float* g_rel, const float* d_relp,
                                     int32_t n_rels, int32_t D, int32_t Dout, float* d_w_loop, float* d_loop_rel,
-                                    float* d_loop_edge, float* d_rels, float* d_w_rel, void* stream) {
+                                    float* d_loop_edge, float* d_rels, float* d_w_rel, const float* rel_add, void* stream) {
   KGC_REQUIRE(m_loop && w_loop && loop_rel && loop_edge && relp && w_rel && d_relp && d_w_loop && d_loop_rel && d_loop_edge && d_rels && d_w_rel,
               "null buffer");
   ParamGradArgs a;
   a.m_loop = m_loop; a.w_loop = w_loop; a.loop_rel = loop_rel; a.loop_edge = loop_edge; a.relp = relp; a.w_rel = w_rel;
   a.g_rel = g_rel; a.d_relp = d_relp; a.n_rels = n_rels; a.D = D; a.Dout = Dout;
   a.d_w_loop = d_w_loop; a.d_loop_rel = d_loop_rel; a.d_loop_edge = d_loop_edge; a.d_rels = d_rels; a.d_w_rel = d_w_rel;
+  if (rel_add != nullptr) {                                       // d_w_rel and rel_add = g_rel w_rel^T come from the GEMM kernels
+    KGC_REQUIRE((D * Dout) % 32 == 0, "D * Dout must be a multiple of 32");
+    const int64_t total2 = (int64_t)D * Dout + (((int64_t)n_rels * D + 31) & ~31ll) + (int64_t)D * 32;
+    conv_param_grads2_kernel<<<(unsigned)ceil_div(total2, 256), 256, 0, as_stream(stream)>>>(a, rel_add);
+    KGC_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t total = 2 * (int64_t)D * Dout + (int64_t)(n_rels + 1) * D * 32;
   conv_param_grads_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(a);
   KGC_LAUNCH_CHECK();

@@ -114,6 +114,30 @@ p2p_allreduce_kernel(char* const* __restrict__ stage, int64_t offset, uint32_t* 
   }
 }
 
+// The same sum for payloads one CTA is too slow for (the replicated-parameter gradients: ~1 MB from each of 8 ranks):
+// stage with many CTAs, ONE CTA meets the other ranks, many CTAs add - three launches on the same stream.
+template <typename T4>
+__global__ void __launch_bounds__(256) p2p_stage_kernel(char* const* __restrict__ stage, int64_t offset, int rank,
+                                                        const T4* __restrict__ in, int64_t n4) {
+  T4* mine = reinterpret_cast<T4*>(stage[rank] + offset);
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) mine[i] = in[i];
+}
+template <typename T4, int WMAX>
+__global__ void __launch_bounds__(256) p2p_sum_kernel(char* const* __restrict__ stage, int64_t offset, int world,
+                                                      T4* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
+    T4 v[WMAX];
+#pragma unroll
+    for (int r = 0; r < WMAX; ++r)
+      if (r < world) v[r] = reinterpret_cast<const T4*>(stage[r] + offset)[i];
+    T4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < WMAX; ++r)
+      if (r < world) acc = add_vec(acc, v[r]);
+    out[i] = acc;
+  }
+}
+
 constexpr int kHaloThreads = 256;
 constexpr int kHaloUnroll = 8;
 
@@ -150,11 +174,12 @@ halo_gather_kernel(float4* const* __restrict__ table, int rank, const int32_t* _
   }
 }
 
-// out[v] = addend[v] + sum over the ranks r with idx[r][v] >= 0 (ascending r) of part[r][idx[r][v]]
+// out[v] = addend[v] + sum over the ranks r with idx[r][j] >= 0 (ascending r) of part[r][idx[r][j]];  v = row_ids[j], or j
+// when row_ids is NULL (all rows).  addend == out is allowed (in-place add of the remote partials).
 template <int WMAX>
 __global__ void __launch_bounds__(kHaloThreads)
-halo_reduce_kernel(const float4* const* __restrict__ part, int world, const int32_t* __restrict__ idx, int64_t n_rows,
-                   const float4* __restrict__ addend, float4* __restrict__ out, int D4) {
+halo_reduce_kernel(const float4* const* __restrict__ part, int world, const int32_t* __restrict__ idx,
+                   const int32_t* __restrict__ row_ids, int64_t n_rows, const float4* addend, float4* out, int D4) {
   const int lane = threadIdx.x % 32;
   const int64_t warp = (blockIdx.x * (int64_t)kHaloThreads + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * (kHaloThreads / 32);
@@ -175,8 +200,8 @@ halo_reduce_kernel(const float4* const* __restrict__ part, int world, const int3
 #pragma unroll
       for (int u = 0; u < kRows; ++u) {
         if (v0 + u < n_rows) {
-          const int64_t v = v0 + u;
-          const float4 acc = addend != nullptr ? __ldg(addend + v * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t v = row_ids != nullptr ? (int64_t)__ldg(row_ids + v0 + u) : v0 + u;    // addend may alias out: plain load
+          const float4 acc = addend != nullptr ? addend[v * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < WMAX; ++r)
@@ -214,8 +239,8 @@ extern "C" int kgc_p2p_halo_gather(void* const* table_ptrs_dev, int32_t rank, co
   return 0;
 }
 
-extern "C" int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, int64_t n_rows,
-                                   const float* addend, float* out, int32_t D, void* stream) {
+extern "C" int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, const int32_t* idx, const int32_t* row_ids,
+                                   int64_t n_rows, const float* addend, float* out, int32_t D, void* stream) {
   KGC_REQUIRE(part_ptrs_dev && idx && out && world >= 1 && world <= 64 && D > 0 && D % 4 == 0, "bad arguments");
   if (n_rows == 0) return 0;
   int64_t blocks = ceil_div(n_rows, (kHaloThreads / 32) * 2);
@@ -223,13 +248,13 @@ extern "C" int kgc_p2p_halo_reduce(void* const* part_ptrs_dev, int32_t world, co
   const unsigned g = (unsigned)blocks;
   cudaStream_t st = as_stream(stream);
   if (world <= 2) {
-    halo_reduce_kernel<2><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
+    halo_reduce_kernel<2><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, row_ids, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else if (world <= 4) {
-    halo_reduce_kernel<4><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
+    halo_reduce_kernel<4><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, row_ids, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else if (world <= 8) {
-    halo_reduce_kernel<8><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, n_rows,
+    halo_reduce_kernel<8><<<g, kHaloThreads, 0, st>>>((const float4* const*)part_ptrs_dev, world, idx, row_ids, n_rows,
                                                       (const float4*)addend, (float4*)out, D / 4);
   } else {
     return fail(__func__, "more than 8 ranks are not supported by this build");
@@ -247,6 +272,23 @@ extern "C" int kgc_p2p_allreduce(void* const* stage_ptrs_dev, int64_t offset_byt
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0, "buffers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int64_t n4 = n_bytes / 16;
+  if (n_bytes > (64 << 10)) {                                  // wide payload: stage / barrier / add with many CTAs
+    const unsigned g = (unsigned)(ceil_div(n4, 256) < 2 * kNumSMs ? ceil_div(n4, 256) : 2 * kNumSMs);
+#define KGC_AR_WIDE(T4, WM)                                                                                                \
+  do {                                                                                                                     \
+    p2p_stage_kernel<T4><<<g, 256, 0, st>>>((char* const*)stage_ptrs_dev, offset_bytes, rank, (const T4*)in, n4);          \
+    p2p_barrier_kernel<<<1, 64, 0, st>>>((uint32_t* const*)flag_ptrs_dev, rank, world, epoch, error);                      \
+    p2p_sum_kernel<T4, WM><<<g, 256, 0, st>>>((char* const*)stage_ptrs_dev, offset_bytes, world, (T4*)out, n4);            \
+  } while (0)
+    if (is_double) {
+      if (world <= 2) KGC_AR_WIDE(double2, 2); else if (world <= 4) KGC_AR_WIDE(double2, 4); else KGC_AR_WIDE(double2, 8);
+    } else {
+      if (world <= 2) KGC_AR_WIDE(float4, 2); else if (world <= 4) KGC_AR_WIDE(float4, 4); else KGC_AR_WIDE(float4, 8);
+    }
+#undef KGC_AR_WIDE
+    KGC_LAUNCH_CHECK();
+    return 0;
+  }
 #define KGC_AR_LAUNCH(T4, WM)                                                                                              \
   p2p_allreduce_kernel<T4, WM><<<1, kArThreads, 0, st>>>((char* const*)stage_ptrs_dev, offset_bytes,                       \
                                                           (uint32_t* const*)flag_ptrs_dev, rank, world, epoch, error,      \

@@ -257,6 +257,16 @@ def partition_edges_hybrid(edge_index, edge_type, num_nodes, world, rank):
             'peer_idx': peer_src, 'peer_dst_idx': peer_dst}
 
 
+def sparse_peer_table(peer, rank):
+    """[world, n_real] table of partial-row positions (-1: none) -> (rows [n_list] int32: the own rows some OTHER rank holds
+    a partial row for, idx [world, n_list] int32: the table restricted to them, this rank's own line set to -1)."""
+    peer = np.asarray(peer)
+    others = peer.copy()
+    others[rank] = -1
+    rows = np.nonzero((others >= 0).any(0))[0].astype(np.int32)
+    return torch.from_numpy(rows), torch.from_numpy(np.ascontiguousarray(others[:, rows]).astype(np.int32))
+
+
 def halo_pull_order(halo_rows, block, rank, world, trip=8):
     """The sequence in which kgc_p2p_halo_gather pulls the positions of ``halo_rows`` (ascending renumbered ids, i.e.
     ascending owner): trips of ``trip`` consecutive positions are dealt to the owners in turn - first trip of owner
@@ -332,6 +342,10 @@ class GraphPartition(object):
             self.n_remote_all = [int(v) for v in info['n_remote_all']]
             self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
             self.peer_dst_idx = torch.from_numpy(info['peer_dst_idx']).to(device)
+            # only the rows OTHER ranks contributed to take part in the two reductions: (row list, [world, n_list] index
+            # table with -1 in this rank's own line - its own value is already in place)
+            self.sparse_src = tuple(t.to(device) for t in sparse_peer_table(info['peer_idx'], rank))
+            self.sparse_dst = tuple(t.to(device) for t in sparse_peer_table(info['peer_dst_idx'], rank))
         else:
             raise ValueError("balance must be 'hybrid', 'edges' or 'range'")
         self.hybrid = balance == 'hybrid'
@@ -412,7 +426,7 @@ class _P2PContext(object):
                                                 dtype=torch.int64, device=dev)
             self.agg_plane_ptrs = [mk(self._h_agg, h) for h in (0, 1)]
             self.g3_plane_ptrs = [mk(self._h_g3, h) for h in (0, 1)]
-            self.peer_dst_idx = part.peer_dst_idx
+            self.sparse_src, self.sparse_dst = part.sparse_src, part.sparse_dst
         self._slots, self._stage_used = {}, 0
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.epoch2 = torch.zeros((1,), dtype=torch.int32, device=dev)
@@ -457,28 +471,42 @@ class _P2PContext(object):
         if out is None:
             out = torch.empty((n_rows, self.D), dtype=torch.float32, device=self.table.device)
         self.barrier(channel)
-        _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.peer_idx),
+        _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.partial_ptrs), self.world, _lib.ptr(self.peer_idx), None,
                   n_rows, _lib.ptr(addend), _lib.ptr(out), self.D, _lib.stream())
         return out
 
     # ---- hybrid cut: partial aggregates to their owners (forward), upstream gradient rows to the ranks that need them (backward)
-    def agg_planes(self):
-        """This rank's [2, rows, D] aggregate planes in symmetric memory (rows = own + remote rows)."""
-        return self.agg_buf[:2 * self.rows_mine * self.D].view(2, self.rows_mine, self.D)
-
     def g3_planes(self):
+        """This rank's [3, rows, D] upstream-gradient planes in symmetric memory (rows = own + remote rows; peers read the
+        own rows of planes 0 / 1).  Rows of plane 2 behind the real rows are zero and stay zero (the self-loop addend)."""
         return self.g3_buf[:3 * self.rows_mine * self.D].view(3, self.rows_mine, self.D)
 
-    def reduce_agg(self, n_rows):
-        """barrier; own rows of both aggregate planes += the partial rows the other ranks accumulated for them, rank order
-        (in place: peers only read the rows BEHIND a rank's own block)."""
+    def _reduce_sparse(self, ptr_table, sparse, local, channel):
+        """Remote rows of ``local`` [rows, D] -> this rank's symmetric copy (what the owners read); barrier; own rows that
+        other ranks hold partial rows for += those rows, in rank order, in place."""
         import ctypes
         from . import _lib
-        agg = self.agg_planes()
+        rows, idx = sparse
+        if rows.numel():
+            _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(ptr_table), self.world, _lib.ptr(idx), _lib.ptr(rows), rows.numel(),
+                      _lib.ptr(local), _lib.ptr(local), self.D, _lib.stream())
+
+    def reduce_agg(self, agg):
+        """Forward of the hybrid cut: agg [2, rows, D] (rank-local).  The partial aggregates of the remote destinations go
+        to symmetric memory, the ranks meet, and every owner adds the partial rows the others hold for its rows."""
+        B, R, D = self.block, self.rows_mine, self.D
+        sym = self.agg_buf[:2 * R * D].view(2, R, D)
+        sym[:, B:].copy_(agg[:, B:])
         self.barrier()
         for h in (0, 1):
-            _lib.call('kgc_p2p_halo_reduce', ctypes.c_void_p(self.agg_plane_ptrs[h].data_ptr()), self.world,
-                      _lib.ptr(self.peer_dst_idx), n_rows, None, _lib.ptr(agg[h]), self.D, _lib.stream())
+            self._reduce_sparse(self.agg_plane_ptrs[h].data_ptr(), self.sparse_dst, agg[h], 0)
+
+    def reduce_dx(self, d_x_full, channel=1):
+        """Backward of the hybrid cut: d_x_full [rows, D] (rank-local; own rows complete but for the other ranks' partial rows)."""
+        B, R = self.block, self.rows_mine
+        self.partial[B:R].copy_(d_x_full[B:R])
+        self.barrier(channel)
+        self._reduce_sparse(self.partial_ptrs, self.sparse_src, d_x_full, channel)
 
     def gather_g(self):
         """barrier; rows of the remote destinations of planes 0 / 1 of g3 <- their owners' rows."""
