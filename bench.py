@@ -741,6 +741,11 @@ def bench_layer(k, orc, workload, dev, args, flush, with_roofline=True):
     """value / parity / rooflines of one workload on ONE GPU."""
     case = LayerCase(k, orc, workload, dev)
     res = {'N': case.N, 'R': case.R, 'E': case.E, 'setup_s': case.setup_s}
+    torch.cuda.synchronize()
+    t0 = time.time()
+    k.get_plan(case.ei, case.et, case.N, 2 * case.R + 1)          # K1 (three sorted CSRs) + the streaming schedules: once per graph
+    torch.cuda.synchronize()
+    res['plan_build_s'] = time.time() - t0
     if not args.no_parity:
         try:
             res['parity'] = parity_vs_float64(case, orc)
@@ -788,6 +793,7 @@ def run_ours(args, rank, world, local_rank):
         value, ms = res['value'], res['ms_per_step']
         N, E = case.N, case.E
         line.update({'value': value, 'ms_per_step': ms, 'scaling': 'weak', 'gpu_launches': res['launches_per_step'] * args.steps,
+                     'plan_build_s': res.get('plan_build_s'),
                      'clocks': res['clocks'], 'roofline': res.get('roofline'), 'kernels': res.get('kernels'),
                      'step_hbm': res['step_hbm'], 'parity': res.get('parity')})
         launch_mode, par = res['launch'], 'single GPU'

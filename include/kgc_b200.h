@@ -259,6 +259,14 @@ int kgc_label_build(const int64_t* qid, int64_t B, const int64_t* triples, const
 int kgc_neg_sample(const int64_t* qid, int64_t B, const int64_t* ptr, const int32_t* idx, int64_t n_entity,
                    const uint32_t* draws, int32_t k, int32_t tries, int32_t* neg, void* stream);
 
+/* Edge sampler, likewise an extension without a reference counterpart (the reference always convolves over the full
+ * edge list built at data_loader.py:132-157).  m triples drawn with replacement, t_j = (draws[j] * n_triples) >> 32; the
+ * sampled sub-graph keeps the reference's layout: columns 0..m-1 = in-half edges t_j, m..2m-1 = their reverses
+ * t_j + n_triples.  src / dst / type = the rows of edge_index and edge_attr[0] (int64 [2 n_triples]); outputs int64 [2m];
+ * eids = the chosen columns (the rows of edge_embeddings the sub-graph uses). */
+int kgc_edge_sample(const int64_t* src, const int64_t* dst, const int64_t* type, int64_t n_triples, const uint32_t* draws,
+                    int64_t m, int64_t* sub_src, int64_t* sub_dst, int64_t* sub_type, int64_t* eids, void* stream);
+
 /* ---- K7: ConvE feature-map normalisation: BatchNorm2d (+ ReLU) + feature dropout (SURVEY "next" row N2) --------
  * Replaces model.py:168-170 (x = bn1(x); x = relu(x); x = feature_drop(x)) on the [B, C, H, W] convolution output
  * (HW = H * W, a multiple of 4; contiguous) and its autograd; with relu = 0 and drop_p = 0 also bn0 (model.py:165),

@@ -15,8 +15,10 @@ from .scoring import (EntityTable, filtered_rank, pack_queries, pair_scores, pre
 from .partition import GraphPartition, partition_edges   # noqa: F401
 from .train import GraphedTrainStep             # noqa: F401
 from .optim import ClipAdam                      # noqa: F401
+from .utils import save_checkpoint, load_checkpoint   # noqa: F401
 from . import _lib                               # noqa: F401
 
 __all__ = ['MGCN', 'MGCNConv', 'ConvE', 'DataLoader', 'KBDataset', 'GraphData', 'BatchIterator', 'GraphPlan',
            'get_plan', 'build_levels', 'build_stream_plan', 'get_param', 'gemm_nt', 'gemm_tn', 'gemm_nt_trans', 'gemm_nt_splitk', 'linear_tc', 'linear_tc_supported', 'epoch_permutation', 'EntityTable', 'filtered_rank', 'pack_queries',
-           'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges', 'GraphedTrainStep', 'ClipAdam']
+           'pair_scores', 'predict', 'evaluate', 'score_kpad', 'GraphPartition', 'partition_edges', 'GraphedTrainStep', 'ClipAdam',
+           'save_checkpoint', 'load_checkpoint']

@@ -66,10 +66,39 @@ __global__ void neg_sample_kernel(const int64_t* __restrict__ qid, int64_t B, co
   neg[t] = out;
 }
 
+// Edge sampler (extension, no reference counterpart): triple t_j = (draws[j] * E) >> 32 contributes its in-half edge t_j to
+// column j and its out-half edge t_j + E to column m + j of the sampled sub-graph - the layout MGCNConv expects (in half
+// first).  A pure function of the caller's draws (sampling with replacement).
+__global__ void edge_sample_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                   const int64_t* __restrict__ type, int64_t n_triples, const uint32_t* __restrict__ draws,
+                                   int64_t m, int64_t* __restrict__ sub_src, int64_t* __restrict__ sub_dst,
+                                   int64_t* __restrict__ sub_type, int64_t* __restrict__ eids) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= 2 * m) return;
+  const int64_t t = (int64_t)(((uint64_t)draws[j < m ? j : j - m] * (uint64_t)n_triples) >> 32);
+  const int64_t e = j < m ? t : t + n_triples;
+  sub_src[j] = src[e];
+  sub_dst[j] = dst[e];
+  sub_type[j] = type[e];
+  eids[j] = e;
+}
+
 }  // namespace
 }  // namespace kgc
 
 using namespace kgc;
+
+extern "C" int kgc_edge_sample(const int64_t* src, const int64_t* dst, const int64_t* type, int64_t n_triples,
+                               const uint32_t* draws, int64_t m, int64_t* sub_src, int64_t* sub_dst, int64_t* sub_type,
+                               int64_t* eids, void* stream) {
+  KGC_REQUIRE(n_triples > 0 && n_triples < (1ll << 31) && m >= 0, "bad sizes");
+  if (m == 0) return 0;
+  KGC_REQUIRE(src && dst && type && draws && sub_src && sub_dst && sub_type && eids, "null buffer");
+  edge_sample_kernel<<<(unsigned)ceil_div(2 * m, kThreads), kThreads, 0, as_stream(stream)>>>(src, dst, type, n_triples, draws,
+                                                                                         m, sub_src, sub_dst, sub_type, eids);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int kgc_label_build(const int64_t* qid, int64_t B, const int64_t* triples, const int64_t* ptr,
                                const int32_t* idx, int64_t n_entity, float pos, float add, int64_t* triple_out,

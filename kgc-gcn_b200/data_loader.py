@@ -39,6 +39,17 @@ class GraphData(object):
         return self.edge_index.device
 
 
+def _u32_bits(draws):
+    """uint32 draws as the int32 bit patterns the C ABI reads (int32 / uint32 tensors are taken as they are, wider
+    integer tensors are reduced modulo 2^32)."""
+    if draws.dtype == torch.int32:
+        return draws.contiguous()
+    if draws.dtype == torch.uint32:
+        return draws.contiguous().view(torch.int32)
+    d = draws.to(torch.int64) & 0xFFFFFFFF
+    return torch.where(d >= (1 << 31), d - (1 << 32), d).to(torch.int32).contiguous()
+
+
 def _gather_segments(ptr, idx, rows):
     """Concatenation of idx[ptr[r]:ptr[r + 1]] for r in rows -> (new_ptr [len(rows) + 1], values), vectorised."""
     rows = np.asarray(rows, dtype=np.int64)
@@ -232,6 +243,29 @@ class KBDataset(object):
                       p(label), _lib.stream())
         return triple, label
 
+    def negatives(self, qid, k, draws=None, tries=4, device='cuda', generator=None):
+        """GPU negative sampler (extension: the reference trains 1-N and ships no sampler).  ``k``
+        entities per query of ``qid`` that are NOT among the query's known objects -> int32 [B, k] on ``device``; -1 where
+        all ``tries`` candidates of a slot collided.  A pure function of ``draws`` (uint32 [B, k, tries], candidate =
+        (u * N) >> 32); when omitted they come from torch's generator (``generator`` or the global one on the device)."""
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('the negative sampler runs on the GPU only (no CPU fallback)')
+        _, ptr, idx = self.device_csr(device)
+        qid = torch.as_tensor(qid, dtype=torch.int64).to(device)
+        b = int(qid.numel())
+        if draws is None:
+            draws = torch.randint(0, 1 << 32, (b, int(k), int(tries)), dtype=torch.int64, device=device, generator=generator)
+        draws = torch.as_tensor(draws).to(device)
+        if tuple(draws.shape) != (b, int(k), int(tries)):
+            raise ValueError('draws must be [len(qid), k, tries]')
+        d32 = _u32_bits(draws)
+        neg = torch.empty((b, int(k)), dtype=torch.int32, device=device)
+        p = _lib.ptr
+        with torch.cuda.device(device):
+            _lib.call('kgc_neg_sample', p(qid), b, p(ptr), p(idx), self.num_entity, p(d32), int(k), int(tries), p(neg), _lib.stream())
+        return neg
+
     def sparse_batch(self, qid):
         """Host CSR slice for the fused scorer: (triple[B,3], filt_ptr[B+1] int64, filt_idx[nnz] int32), numpy."""
         qid = np.asarray(qid, dtype=np.int64)
@@ -397,6 +431,34 @@ class DataLoader(object):
         data.entity = torch.from_numpy(graph_nodes)
         data.num_nodes = len(graph_nodes)
         data.edge_norm = self._edge_normal(rel, edge_index, len(graph_nodes))
+        return data
+
+    def sample_edges(self, m, draws=None, generator=None):
+        """GPU edge sampler (extension without a reference counterpart: the reference convolves over the full edge list every
+        step, main.py:61).  ``m`` training triples drawn with replacement -> a GraphData in the reference's layout
+        (edge_index [2, 2m]: the m sampled edges, then their reverses; edge_attr = [types; columns of the full edge list],
+        i.e. ``edge_attr[1]`` indexes ``edge_embeddings`` as in model.py:30) on the graph's device.  A pure function of
+        ``draws`` (uint32 [m], triple = (u * E) >> 32); when omitted they come from torch's generator."""
+        g = self.graph
+        dev = g.edge_index.device
+        if dev.type != 'cuda':
+            raise RuntimeError('the edge sampler runs on the GPU only (no CPU fallback); move the graph with graph.to("cuda")')
+        m = int(m)
+        if draws is None:
+            draws = torch.randint(0, 1 << 32, (m,), dtype=torch.int64, device=dev, generator=generator)
+        draws = torch.as_tensor(draws).to(dev)
+        if tuple(draws.shape) != (m,):
+            raise ValueError('draws must be [m]')
+        d32 = _u32_bits(draws)
+        ei = g.edge_index.contiguous()
+        et = g.edge_attr[0].contiguous()
+        sub = torch.empty((4, 2 * m), dtype=torch.int64, device=dev)
+        p = _lib.ptr
+        with torch.cuda.device(dev):
+            _lib.call('kgc_edge_sample', p(ei[0]), p(ei[1]), p(et), self.num_edge, p(d32), m, p(sub[0]), p(sub[1]), p(sub[2]),
+                      p(sub[3]), _lib.stream())
+        data = GraphData(edge_index=sub[:2], edge_attr=sub[2:])
+        data.entity, data.num_nodes = g.entity, g.num_nodes
         return data
 
     def _queries(self, key):

@@ -214,6 +214,46 @@ def test_label_build_bit_exact(k, golden_dir, toy_dir):
     np.testing.assert_array_equal(lab.cpu().numpy(), l0)
 
 
+def test_samplers_through_the_python_api(k):
+    """KBDataset.negatives / DataLoader.sample_edges (extensions, parity unpinned): bit-exact against the oracle's
+    restatements for the caller's draws; negatives never hit a known object; the sampled sub-graph convolves."""
+    rng = np.random.default_rng(11)
+    N, Q, K, TR = 97, 60, 5, 3
+    qs = [{'triple': (0, 0, -1), 'label': sorted(set(rng.integers(0, N, 30).tolist()))} for _ in range(Q)]
+    kb = k.KBDataset(qs, N, None)
+    qid = rng.permutation(Q)[:23]
+    draws = rng.integers(0, 2 ** 32, (23, K, TR), dtype=np.uint64)
+    neg = kb.negatives(qid, K, draws=torch.from_numpy(draws.astype(np.int64)), tries=TR)
+    exp = orc.neg_sample([q['label'] for q in qs], qid, N, draws)
+    np.testing.assert_array_equal(neg.cpu().numpy(), exp)
+    drawn = kb.negatives(qid, K, tries=8).cpu().numpy()                  # draws from torch's generator
+    for b in range(23):
+        assert not (set(drawn[b][drawn[b] >= 0].tolist()) & set(qs[int(qid[b])]['label']))
+    # edge sampler on a synthetic graph
+    Ng, R, E = 500, 4, 3000
+    tri = orc.synthetic_triples(Ng, R, E, 9)
+    g = orc.build_graph(tri, Ng, R)
+    dl = k.DataLoader.__new__(k.DataLoader)
+    dl.num_edge, dl.num_relation = E, R
+    dl.graph = k.GraphData(edge_index=torch.from_numpy(g['edge_index']).cuda(),
+                                       edge_attr=torch.from_numpy(g['edge_attr']).cuda())
+    dl.graph.entity, dl.graph.num_nodes = torch.arange(Ng).cuda(), Ng
+    ed = rng.integers(0, 2 ** 32, 700, dtype=np.uint64)
+    sub = dl.sample_edges(700, draws=torch.from_numpy(ed.astype(np.int64)))
+    ei, et, cols = orc.edge_sample(g['edge_index'], g['edge_attr'][0], E, ed)
+    np.testing.assert_array_equal(sub.edge_index.cpu().numpy(), ei)
+    np.testing.assert_array_equal(sub.edge_attr[0].cpu().numpy(), et)
+    np.testing.assert_array_equal(sub.edge_attr[1].cpu().numpy(), cols)
+    assert (sub.edge_attr[0][:700] < R).all() and (sub.edge_attr[0][700:] >= R).all()       # in half first, then reverses
+    p = orc.conv_params(Ng, R, E, 100, 200, seed=1)
+    conv = k.MGCNConv(100, 200, 2 * R).cuda().train()
+    x = p['x'].cuda().requires_grad_(True)
+    ee = p['edge_embs'].cuda()[sub.edge_attr[1]].requires_grad_(True)
+    ent, rel = conv(x, sub.edge_index, sub.edge_attr[0], None, ee, p['rels'].cuda())
+    ent.sum().backward()
+    assert torch.isfinite(ent).all() and torch.isfinite(x.grad).all() and ent.shape == (Ng, 200)
+
+
 def test_neg_sampler_matches_restatement(k):
     """Extension without a reference counterpart (parity unpinned): checked against its own restatement."""
     import ctypes

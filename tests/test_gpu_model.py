@@ -297,3 +297,33 @@ def test_clip_adam_matches_torch(max_norm, wd):
     cpu.grad = torch.ones(3)
     with pytest.raises(RuntimeError):                               # no CPU fallback
         k.ClipAdam([cpu], lr=1e-3).step()
+
+
+def test_checkpoint_round_trip_from_the_device(toy, tmp_path, monkeypatch):
+    """utils.save_checkpoint / load_checkpoint (reference utils.py:121-155) with the model and the ClipAdam state in HBM:
+    the staged device -> host copies (several chunks, both staging buffers) give the bytes torch.save would, the file
+    loads back bit for bit into a fresh model + optimiser on the device, and plain torch.load reads it."""
+    k, dl, m, z = toy
+    from kgc_gcn_b200 import utils as ku
+    monkeypatch.setattr(ku, 'CHUNK_BYTES', 4096)                       # force multi-chunk tensors through the staging ring
+    opt = k.ClipAdam(m.parameters(), lr=1e-3, max_norm=1.0)
+    for p_ in m.parameters():
+        p_.grad = torch.randn_like(p_) * 1e-2
+    opt.step()
+    for p_ in m.parameters():
+        p_.grad = None
+    state = {'epoch': 1, 'state_dict': m.state_dict(), 'optim_dict': opt.state_dict(), 'measure': {'mrr': 0.5}}
+    d = str(tmp_path / 'ckpt')
+    k.save_checkpoint(state, True, d)
+    plain = torch.load(os.path.join(d, 'best.ckpt'), weights_only=False)
+    for name, t in m.state_dict().items():
+        assert plain['state_dict'][name].device.type == 'cpu' and torch.equal(plain['state_dict'][name], t.cpu()), name
+    m2 = k.MGCN(dl.num_entity, dl.num_relation, dl.num_edge, params()).cuda()
+    opt2 = k.ClipAdam(m2.parameters(), lr=1e-3, max_norm=1.0)
+    assert k.load_checkpoint(os.path.join(d, 'last.ckpt'), m2, opt2) == {'mrr': 0.5}
+    for (n1, a), (n2, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert n1 == n2 and b.is_cuda and torch.equal(a, b), n1
+    s1, s2 = opt.state_dict()['state'], opt2.state_dict()['state']
+    assert s1.keys() == s2.keys()
+    for i in s1:
+        assert torch.equal(s1[i]['exp_avg'].cpu(), s2[i]['exp_avg'].cpu()) and torch.equal(s1[i]['exp_avg_sq'].cpu(), s2[i]['exp_avg_sq'].cpu())

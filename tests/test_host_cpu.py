@@ -439,3 +439,57 @@ def test_gather_segments_edge_cases():
     assert p.tolist() == [0, 0, 0] and v.shape == (0,)
     p, v = _gather_segments(ptr, idx, [3, 1, 1, 0])
     assert p.tolist() == [0, 1, 4, 7, 7] and v.tolist() == [5, 7, 8, 9, 7, 8, 9] and v.dtype == np.int32
+
+
+def test_checkpoint_interchanges_with_the_reference(tmp_path):
+    """utils.save_checkpoint / load_checkpoint (reference utils.py:121-155): same files both ways - what ours writes the
+    reference's own loader reads (oracle/_ref, when built) and vice versa; best.ckpt follows is_best; the returned measure;
+    a missing file raises; last.ckpt is replaced atomically."""
+    import sys
+    import kgc_gcn_b200 as k
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import build_ref
+    ref = build_ref.load_reference()
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model(torch.randn(4, 7)).sum().backward()
+    opt.step()
+    state = {'epoch': 3, 'state_dict': model.state_dict(), 'optim_dict': opt.state_dict(), 'measure': {'mrr': 0.25}}
+    d = str(tmp_path / 'ckpt')
+    k.save_checkpoint(state, False, d)
+    assert os.path.exists(os.path.join(d, 'last.ckpt')) and not os.path.exists(os.path.join(d, 'best.ckpt'))
+    k.save_checkpoint(state, True, d)
+    assert os.path.samefile(os.path.join(d, 'last.ckpt'), os.path.join(d, 'best.ckpt'))       # a link, not a second copy
+    state2 = dict(state, epoch=4)
+    k.save_checkpoint(state2, False, d)                                  # best.ckpt keeps the epoch-3 file
+    assert torch.load(os.path.join(d, 'best.ckpt'), weights_only=False)['epoch'] == 3
+    assert torch.load(os.path.join(d, 'last.ckpt'), weights_only=False)['epoch'] == 4
+    assert not [f for f in os.listdir(d) if f.endswith('.tmp')]
+
+    def fresh():
+        m = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5))
+        return m, torch.optim.Adam(m.parameters(), lr=1e-3)
+
+    def same(m, o):
+        for a, b in zip(m.state_dict().values(), model.state_dict().values()):
+            assert torch.equal(a, b)
+        sa, sb = o.state_dict()['state'], opt.state_dict()['state']
+        assert sa.keys() == sb.keys() and all(torch.equal(sa[i]['exp_avg'], sb[i]['exp_avg']) for i in sa)
+
+    m, o = fresh()
+    assert k.load_checkpoint(os.path.join(d, 'last.ckpt'), m, o) == {'mrr': 0.25}
+    same(m, o)
+    with pytest.raises(FileNotFoundError):
+        k.load_checkpoint(os.path.join(d, 'nope.ckpt'), m)
+    if ref is None:
+        pytest.skip('oracle/_ref not built (no /root/reference on this box): interchange with the reference not checked')
+    ref_utils = sys.modules['utils']
+    m, o = fresh()
+    assert ref_utils.load_checkpoint(os.path.join(d, 'best.ckpt'), m, o) == {'mrr': 0.25}     # ours -> reference
+    same(m, o)
+    d2 = str(tmp_path / 'ckpt_ref')
+    ref_utils.save_checkpoint(state, True, d2)                                                # reference -> ours
+    m, o = fresh()
+    assert k.load_checkpoint(os.path.join(d2, 'best.ckpt'), m, o) == {'mrr': 0.25}
+    same(m, o)
