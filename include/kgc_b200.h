@@ -128,7 +128,11 @@ int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
  * counter-based Philox4x32-10 stream keyed by *seed (device int64), counter = (float4 index, plane): the forward
  * and the backward regenerate the same mask, nothing is stored.  keep_scale = 1/(1-p).  kgc_dropout_mask writes
  * the mask of one plane (0 = in, 1 = out) for inspection.
- *   kgc_tail_fwd           writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares; fp64)
+ *   kgc_tail_fwd           writes pre[n_rows,Dout] and per-block column partials (sum, sum of squares; fp64) and, when keep
+ *                          is given (uint8 [n_rows, kgc_keep_pitch()], Dout <= 256), the keep flags it used: byte c of a
+ *                          row = columns 4c..4c+3, low nibble = in half, high nibble = out half.  The backward GEMMs
+ *                          apply them to ONE upstream plane while splitting it (kgc_gemm_nt_batch_masked,
+ *                          kgc_gemm_tn_tc_batch_masked): no mask is regenerated, no masked plane is written.
  *   kgc_colsum_finalize    reduces the partials in a fixed order into sums[2,Dout] (fp64).  A partitioned
  *                          graph all-reduces these 2*Dout doubles across ranks here.
  *   kgc_colstats_from_sums stats[0]=mean, [1]=biased var, [2]=rstd=1/sqrt(var+eps) over n_rows (GLOBAL) rows
@@ -136,9 +140,10 @@ int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
  *   kgc_tail_apply         all_ent = tanh((pre - mean) * rstd * gamma + beta) */
 int64_t kgc_tail_num_blocks(int64_t n_rows);
 int kgc_dropout_mask(const int64_t* seed, int32_t plane, float drop_p, int64_t n_elem, uint8_t* mask, void* stream);
+int32_t kgc_keep_pitch(void);
 int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, const int64_t* seed, float drop_p,
                  float keep_scale, const float* bias, int64_t n_rows, int32_t Dout, float* pre, double* partials,
-                 void* stream);
+                 uint8_t* keep, void* stream);
 int kgc_colsum_finalize(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, void* stream);
 int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_t Dout, float eps, int32_t training,
                            const float* running_mean, const float* running_var, float* stats, void* stream);
@@ -153,16 +158,18 @@ int kgc_colsum_finalize2(const double* partials, int64_t n_blocks, int32_t Dout,
                          void* stream);
 int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
                    int64_t n_rows, int32_t Dout, float* all_ent, void* stream);
-/* Backward of the tail.  kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and
- * dz*xhat; kgc_colsum_finalize -> sums[0] = sum dz (= d beta), sums[1] = sum dz*xhat (= d gamma), all-reduced
- * by a partitioned caller; kgc_tail_bwd_apply: d_pre (BatchNorm backward over n_rows_global rows when
- * training) spread to the three planes d_res3[3,n_rows,Dout] with the dropout masks and the 1/3. */
-int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
+/* Backward of the tail.  all_ent = tanh(BatchNorm(pre)) is recomputed from pre (one plane less to read).
+ * kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and dz*xhat; kgc_colsum_finalize -> sums[0] =
+ * sum dz (= d beta), sums[1] = sum dz*xhat (= d gamma), all-reduced by a partitioned caller; kgc_tail_bwd_apply:
+ * d_out[n_rows,Dout] = d_pre / 3 (BatchNorm backward over n_rows_global rows when training) - ONE plane: the self-loop
+ * transform's upstream gradient as it is, the in / out halves' after the keep flags x 1/(1-p): applied by the GEMMs
+ * (d_res2 NULL), or written here as two more planes d_res2[2,n_rows,Dout] from kgc_tail_fwd's keep flags (keep NULL: no
+ * dropout, both planes = d_out). */
+int kgc_tail_bwd_reduce(const float* g_ent, const float* pre, const float* stats, const float* gamma, const float* beta,
                         int64_t n_rows, int32_t Dout, double* partials, void* stream);
-int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
-                       const float* gamma, const double* sums, const uint8_t* mask_in, const uint8_t* mask_out,
-                       const int64_t* seed, float drop_p, float keep_scale, int32_t training, int64_t n_rows,
-                       int64_t n_rows_global, int32_t Dout, float* d_res3, void* stream);
+int kgc_tail_bwd_apply(const float* g_ent, const float* pre, const float* stats, const float* gamma, const float* beta,
+                       const double* sums, int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout,
+                       float* d_out, const uint8_t* keep, float keep_scale, float* d_res2, void* stream);
 
 /* ---- K0: parameter-side work of one layer step, batched --------------------------------------------------
  * kgc_conv_prep (forward): relp = cat(rels, loop_rel) (model.py:86); all_rel = relp @ w_rel (model.py:107, all
@@ -204,6 +211,13 @@ int kgc_gemm_nt(const float* A, int64_t M, int32_t K, int64_t lda, const float* 
  * A[i], packed_b[i], C[i] are HOST arrays of device pointers.  The CTAs are dealt to (problem, column tile) groups. */
 int kgc_gemm_nt_batch(int32_t n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda,
                       const float* const* packed_b, int32_t N, float* const* C, int64_t ldc, void* stream);
+/* The same with dropout applied to the streamed operand while it is split (backward of the layer tail, model.py:103):
+ * keep = kgc_tail_fwd's packed keep flags (byte c of row m = columns 4c..4c+3; problem 0 reads the low nibble, problem 1
+ * the high nibble, problem 2 takes the operand as it is); a kept element is multiplied by keep_scale, a dropped one is 0.
+ * The three problems may (and in the layer do) stream the SAME plane A[0] = A[1] = A[2]. */
+int kgc_gemm_nt_batch_masked(int32_t n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda,
+                             const float* const* packed_b, int32_t N, float* const* C, int64_t ldc, const uint8_t* keep,
+                             int32_t keep_pitch, float keep_scale, void* stream);
 /* Same kernel with the streamed operand AND the result transposed in memory (the long dimension M contiguous):
  *   Ct[n, m] = sum_k At[k, m] * Bt[n, k],  At: [K, M] row-major, pitch ldat;  Ct: [N, M] row-major, pitch ldct.
  * M % 32 == 0.  Used for the autograd of ConvE's fc layer (model.py:173): d_W[out, flat] = d_y^T @ x_flat and
@@ -241,6 +255,11 @@ int kgc_gemm_nt_splitk(const float* A, int64_t lda, const float* Bt, int64_t ldb
 int kgc_gemm_tn_tc_batch(int32_t n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb,
                          int64_t M, int32_t Ka, int32_t Nb, float* const* C, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* The same with the keep flags applied to the B operand (the upstream plane) while it is split: see
+ * kgc_gemm_nt_batch_masked. */
+int kgc_gemm_tn_tc_batch_masked(int32_t n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb,
+                                int64_t M, int32_t Ka, int32_t Nb, float* const* C, void* workspace, size_t workspace_bytes,
+                                const uint8_t* keep, int32_t keep_pitch, float keep_scale, void* stream);
 
 /* ---- K5: label / batch builder ---------------------------------------------------------------------
  * Replaces KBDataset.get_label + label smoothing + collate (data_loader.py:25-51): for the batch's

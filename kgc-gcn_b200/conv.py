@@ -11,6 +11,8 @@ arithmetic runs in libkgc_b200.so (K1-K4) plus plain fp32 GEMMs (TF32 off, like 
 (aggregate-then-transform is exact algebra because the message transform is linear).
 Backward is hand-derived and runs K3/K4-backward; it is deterministic.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -54,9 +56,10 @@ def gemm_nt(a, b_kn, out, plan=None, tag='b', packed=None):
     return out
 
 
-def gemm_nt_batch(a_list, packed_list, out_list):
+def gemm_nt_batch(a_list, packed_list, out_list, keep=None, keep_scale=1.0):
     """Up to three products out_i = a_i @ B_i of identical shape in ONE launch (K4b); ``packed_list`` holds the split small
-    operands (kgc_conv_prep / kgc_gemm_pack_b)."""
+    operands (kgc_conv_prep / kgc_gemm_pack_b).  ``keep`` (uint8 [M, pitch], kgc_tail_fwd's packed keep flags): dropout of
+    the streamed operand while it is split - problem 0 by the low nibbles, problem 1 by the high nibbles, problem 2 as it is."""
     import ctypes
     n = len(a_list)
     M, K = a_list[0].shape
@@ -66,11 +69,15 @@ def gemm_nt_batch(a_list, packed_list, out_list):
         if a.shape != (M, K) or o.shape != (M, N) or a.stride() != (lda, 1) or o.stride() != (ldc, 1):
             raise ValueError('gemm_nt_batch needs operands of identical shape and strides')
     arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])       # noqa: E731
-    _lib.call('kgc_gemm_nt_batch', n, arr(a_list), M, K, lda, arr(packed_list), N, arr(out_list), ldc, _lib.stream())
+    if keep is not None:
+        _lib.call('kgc_gemm_nt_batch_masked', n, arr(a_list), M, K, lda, arr(packed_list), N, arr(out_list), ldc,
+                  _lib.ptr(keep), keep.stride(0), float(keep_scale), _lib.stream())
+    else:
+        _lib.call('kgc_gemm_nt_batch', n, arr(a_list), M, K, lda, arr(packed_list), N, arr(out_list), ldc, _lib.stream())
     return out_list
 
 
-def gemm_tn_batch(a_list, b_list, out_list, plan=None):
+def gemm_tn_batch(a_list, b_list, out_list, plan=None, keep=None, keep_scale=1.0):
     """Up to three weight-gradient reductions out_i = a_i^T @ b_i of identical shape in ONE launch (K4c on the tensor
     cores; Ka <= 128, Nb <= 224 - wider shapes go through gemm_tn one by one)."""
     import ctypes
@@ -81,6 +88,8 @@ def gemm_tn_batch(a_list, b_list, out_list, plan=None):
     same = all(a.shape == (M, Ka) and b.shape == (M, Nb) and a.stride() == (lda, 1) and b.stride() == (ldb, 1)
                and o.is_contiguous() for a, b, o in zip(a_list, b_list, out_list))
     if not same or Ka > 128 or Nb > 224:
+        if keep is not None:
+            raise ValueError('gemm_tn_batch: the masked form needs Ka <= 128, Nb <= 224 and operands of identical shape')
         for a, b, o in zip(a_list, b_list, out_list):
             gemm_tn(a, b, o, plan)
         return out_list
@@ -88,8 +97,12 @@ def gemm_tn_batch(a_list, b_list, out_list, plan=None):
     ws = plan.scratch('kgc_gemm_tn_tc_ws', (nbytes // 4,)) if plan is not None else \
         torch.empty((nbytes // 4,), dtype=torch.float32, device=a_list[0].device)
     arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])       # noqa: E731
-    _lib.call('kgc_gemm_tn_tc_batch', n, arr(a_list), lda, arr(b_list), ldb, M, Ka, Nb, arr(out_list), _lib.ptr(ws), nbytes,
-              _lib.stream())
+    if keep is not None:
+        _lib.call('kgc_gemm_tn_tc_batch_masked', n, arr(a_list), lda, arr(b_list), ldb, M, Ka, Nb, arr(out_list), _lib.ptr(ws),
+                  nbytes, _lib.ptr(keep), keep.stride(0), float(keep_scale), _lib.stream())
+    else:
+        _lib.call('kgc_gemm_tn_tc_batch', n, arr(a_list), lda, arr(b_list), ldb, M, Ka, Nb, arr(out_list), _lib.ptr(ws), nbytes,
+                  _lib.stream())
     return out_list
 
 
@@ -382,8 +395,12 @@ class _ConvFn(torch.autograd.Function):
         pre = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
         stats = torch.empty((3, Dout), dtype=torch.float32, device=x.device)
         all_ent = torch.empty((Nl, Dout), dtype=torch.float32, device=x.device)
+        # keep flags of the two dropped planes, one byte per four columns: the backward GEMMs apply them while they split the
+        # ONE upstream plane (no masked planes are written, nothing is regenerated)
+        dropping = (mask_in is not None or seed is not None) and drop_p > 0.0
+        keep = torch.empty((Nl, int(_lib.lib().kgc_keep_pitch())), dtype=torch.uint8, device=x.device) if dropping else None
         _lib.call('kgc_tail_fwd', p(res3), p(mask_in), p(mask_out), p(seed), float(drop_p), float(keep_scale), p(bias),
-                  Nl, Dout, p(pre), p(partials), st())
+                  Nl, Dout, p(pre), p(partials), p(keep), st())
         if training and coll is None:
             # one GPU: column sums -> batch statistics -> nn.BatchNorm1d's running-statistics bookkeeping in ONE launch
             # (bn_track = (momentum, num_batches_tracked) when the module tracks running statistics)
@@ -403,15 +420,15 @@ class _ConvFn(torch.autograd.Function):
         ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias, ctx.coll = plan, bool(training), float(keep_scale), \
             bias is not None, coll
         ctx.drop_p = float(drop_p)
-        ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre,
-                              all_ent, stats, mask_in, mask_out, packed_b, seed)
+        ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, agg, pre,
+                              all_ent, stats, keep, packed_b)
         ctx.mark_non_differentiable(stats)
         return all_ent, all_rel, stats
 
     @staticmethod
     def backward(ctx, g_ent, g_rel, _g_stats):
-        (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, agg, pre, all_ent, stats, mask_in,
-         mask_out, packed_b, seed) = ctx.saved_tensors
+        (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, agg, pre, all_ent, stats, keep,
+         packed_b) = ctx.saved_tensors
         plan, coll = ctx.plan, ctx.coll
         Nl, D = x.shape
         n_global = Nl if coll is None else coll.n_global      # BatchNorm rows (real nodes of all ranks)
@@ -430,8 +447,8 @@ class _ConvFn(torch.autograd.Function):
         nb = int(_lib.lib().kgc_tail_num_blocks(Nl))
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
         sums = torch.empty((2, Dout), dtype=torch.float64, device=dev)
-        d_res3 = plan.scratch('d_res3', (3, Nl, Dout))
-        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(all_ent), p(pre), p(stats), Nl, Dout, p(partials), st())
+        d_out = plan.scratch('d_out', (Nl, Dout))          # ONE upstream plane (d out / 3); the GEMMs apply the keep flags
+        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(partials), st())
         if coll is None:
             sums32 = torch.empty((2, Dout), dtype=torch.float32, device=dev)
             _lib.call('kgc_colsum_finalize2', p(partials), nb, Dout, p(sums), p(sums32), st())
@@ -439,8 +456,18 @@ class _ConvFn(torch.autograd.Function):
             _lib.call('kgc_colsum_finalize', p(partials), nb, Dout, p(sums), st())
             coll.all_reduce(sums, 'bn_b')
             sums32 = sums.float()
-        _lib.call('kgc_tail_bwd_apply', p(g_ent), p(all_ent), p(pre), p(stats), p(gamma), p(sums), p(mask_in),
-                  p(mask_out), p(seed), ctx.drop_p, ctx.keep_scale, int(ctx.training), Nl, n_global, Dout, p(d_res3), st())
+        # the in / out halves' upstream planes = d_out x keep flags x 1 / (1 - p): either written by the tail kernel as two
+        # more planes, or applied by the GEMMs while they split the ONE plane.  Measured (graph-timed layer step, B200):
+        # Wikidata5M shape 49.7 vs 50.5 ms, WN18RR 0.387 vs 0.400 ms - the operand splitters are the busier side of K4b /
+        # K4c (+1.9 / +1.0 ms against -2.5 ms of tail traffic) - but FB15k-237 0.462 vs 0.411 ms: when the planes stay in
+        # L2 the extra writes are what costs.  Default by size; KGC_TAIL_PLANES=1|3 overrides.
+        mode = os.environ.get('KGC_TAIL_PLANES', '')
+        three = (3 * Nl * Dout * 4 > (48 << 20)) if mode not in ('1', '3') else mode == '3'
+        d_res2 = plan.scratch('d_res2', (2, Nl, Dout)) if three else None
+        _lib.call('kgc_tail_bwd_apply', p(g_ent), p(pre), p(stats), p(gamma), p(beta), p(sums), int(ctx.training), Nl,
+                  n_global, Dout, p(d_out), p(keep), ctx.keep_scale, p(d_res2), st())
+        ups = [d_res2[0], d_res2[1], d_out] if three else [d_out, d_out, d_out]
+        gkeep = None if three else keep
         d_beta, d_gamma = sums32[0], sums32[1]
 
         # replicated-parameter gradients: one flat buffer so that a partitioned run needs ONE all-reduce
@@ -453,15 +480,16 @@ class _ConvFn(torch.autograd.Function):
         main, side = torch.cuda.current_stream(), plan.side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], [d_res3[0], d_res3[1], d_res3[2]], [d_w_in, d_w_out, m_loop], plan)   # [D, Dout] each
+            gemm_tn_batch([agg[0, :Nl], agg[1, :Nl], x], ups, [d_w_in, d_w_out, m_loop], plan,
+                          keep=gkeep, keep_scale=ctx.keep_scale)                                         # [D, Dout] each
             if ctx.has_bias:
-                torch.sum(d_res3[2], 0, out=flat[3 * D * Dout + T * D:])
+                torch.sum(d_out, 0, out=flat[3 * D * Dout + T * D:])
 
         # ---- d(agg) = d_res @ W^T on the tensor cores (3xTF32), main stream
         hybrid = coll is not None and coll.p2p is not None and coll.p2p.hybrid
         g3 = coll.p2p.g3_planes() if hybrid else plan.scratch('g3', (3, Nb, D))
-        gemm_nt_batch([d_res3[0], d_res3[1], d_res3[2]], [packed_b[0], packed_b[1], packed_b[2]],
-                      [g3[0, :Nl], g3[1, :Nl], g3[2, :Nl]])
+        gemm_nt_batch(ups, [packed_b[0], packed_b[1], packed_b[2]],
+                      [g3[0, :Nl], g3[1, :Nl], g3[2, :Nl]], keep=gkeep, keep_scale=ctx.keep_scale)
         if n_hub:
             coll.spread_hub_rows(g3, 2, n_loc)                       # the virtual rows see their hub's upstream gradient
         if hybrid:

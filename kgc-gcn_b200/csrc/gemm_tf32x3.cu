@@ -188,6 +188,12 @@ struct GemmParams {
   int32_t act;             // 0: identity, 1: logistic sigmoid
   int32_t trans_c;         // store C transposed: Ct[n, m] (the tensor maps then describe Ct)
   int32_t trans_a;         // A is given transposed, At[K, M] row-major (M % 32 == 0): tiles land as [m group][k][32 m]
+  // optional dropout of the streamed operand while it is split (backward of the layer tail): keep[m * keep_pitch + c] holds
+  // the keep flags of columns 4c..4c+3 of row m, low nibble for problem 0, high nibble for problem 1; problem 2 is taken
+  // as it is.  A kept element is multiplied by keep_scale = 1 / (1 - p), a dropped one becomes 0.
+  const uint8_t* keep;
+  int32_t keep_pitch;
+  float keep_scale;
   long long* dbg;     // optional timeline of CTA 0: [role][event] clock64 stamps (debug aid)
 };
 
@@ -291,8 +297,41 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmParams P) {
     const int r = quarter * 32 + lane;
     int stage = 0, ts = 0;
     uint32_t phase = 0, tphase = 0;
+    // dropout of the streamed operand (P.keep): the 64 keep bytes of this thread's row cover all K blocks of a tile; they
+    // are loaded ONE TILE AHEAD (a global load inside the per-K-block chain costs its full latency every block: measured
+    // +2.2 ms per launch at the Wikidata5M shape) and this thread's word of a K block is picked with a select chain
+    // (a runtime index into the register array would send it to local memory)
+    const bool masked = P.keep != nullptr && prob < 2 && !P.trans_a;
+    uint32_t kcur[kMaxKB], knxt[kMaxKB];
+#pragma unroll
+    for (int j = 0; j < kMaxKB; ++j) kcur[j] = knxt[j] = 0u;
+    auto load_keep = [&](int mt_, uint32_t (&w)[kMaxKB]) {
+      const int64_t grow = (int64_t)mt_ * kBM + r;
+      if (mt_ < P.n_mtiles && grow < P.M) {
+        const uint4* kp = reinterpret_cast<const uint4*>(P.keep + grow * P.keep_pitch);
+#pragma unroll
+        for (int q = 0; q < kMaxKB / 2; ++q) {                     // 16 bytes = K blocks 2q, 2q + 1: words (kb, half 0), (kb, half 1)
+          const uint4 t4 = __ldg(kp + q);
+          w[2 * q] = half ? t4.y : t4.x;
+          w[2 * q + 1] = half ? t4.w : t4.z;
+        }
+      }
+    };
+    if (masked) load_keep(first, knxt);
     for (int mt = first; mt < P.n_mtiles; mt += step) {
+      if (masked) {
+#pragma unroll
+        for (int j = 0; j < kMaxKB; ++j) kcur[j] = knxt[j];
+        load_keep(mt + step, knxt);
+      }
       for (int kb = 0; kb < P.n_kb; ++kb) {
+        uint32_t kw = 0;                                           // keep flags of this thread's 16 columns (4 bytes)
+        if (masked) {
+#pragma unroll
+          for (int j = 0; j < kMaxKB; ++j)
+            if (kb == j) kw = kcur[j];
+          if (prob == 1) kw >>= 4;
+        }
         mb_wait(raw_full + stage, phase);
         if (warp == 2 && lane == 0) KGC_DBG(1);
         uint32_t h[16], l[16];
@@ -311,6 +350,16 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmParams P) {
           uint4 v[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(row + (((half * 4 + i) ^ (r & 7)) << 4));
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t nb = kw >> (8 * i);
+              v[i].x = (nb & 1u) ? __float_as_uint(__uint_as_float(v[i].x) * P.keep_scale) : 0u;
+              v[i].y = (nb & 2u) ? __float_as_uint(__uint_as_float(v[i].y) * P.keep_scale) : 0u;
+              v[i].z = (nb & 4u) ? __float_as_uint(__uint_as_float(v[i].z) * P.keep_scale) : 0u;
+              v[i].w = (nb & 8u) ? __float_as_uint(__uint_as_float(v[i].w) * P.keep_scale) : 0u;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // hi = nearest TF32, lo = nearest TF32 of (v - hi): measurably tighter than truncation at K = 200
@@ -723,6 +772,7 @@ constexpr int kTnRows = 32;                      // node rows per K block
 constexpr int kTnBox = kTnRows * 128;            // one 32-column x 32-row box: 4 KB
 constexpr int kTnStages = 3;
 constexpr int kTnLoStages = 2;
+constexpr int kTnMaxGb = 7;                      // 32-column groups of B: Nb <= 224
 
 struct GemmTnMaps {                              // per problem of a batched launch
   CUtensorMap a[kMaxBatch], b[kMaxBatch], a3[kMaxBatch], b3[kMaxBatch], p[kMaxBatch];
@@ -736,6 +786,9 @@ struct GemmTnParams {
   int32_t kmajor;                                // split-K product of K-major operands (see kgc_gemm_nt_splitk)
   int64_t rows_per_cta;
   float* partial;                                // [grid][Ka][Nb]
+  const uint8_t* keep;                           // optional dropout of the B operand while it is split (see GemmParams::keep)
+  int32_t keep_pitch;
+  float keep_scale;
   long long* dbg;                                // optional timeline of CTA 0 (debug aid, see kgc_gemm_set_debug)
 };
 
@@ -843,6 +896,18 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmTnMaps maps, const GemmTnParams P)
     int stage = 0, ls = 0;
     uint32_t phase = 0, lphase = 0;
     const int n_vec = stage_bytes / 16;
+    const bool masked = P.keep != nullptr && prob < 2 && !P.kmajor;
+    const int brow_t = (t & 255) >> 3;                                            // this thread's row inside every box
+    const int c16_t = ((((t & 7) >> 1) ^ (brow_t & 3)) << 1) | (t & 1);           // ... and its 16-byte column chunk
+    uint32_t nbn[kTnMaxGb];
+#pragma unroll
+    for (int g = 0; g < kTnMaxGb; ++g) nbn[g] = 0u;
+    if (masked && n_kb > 0 && m0 + brow_t < m1) {
+      const uint8_t* kp = P.keep + (m0 + brow_t) * P.keep_pitch + c16_t;
+#pragma unroll
+      for (int g = 0; g < kTnMaxGb; ++g)
+        if (g < P.gb) nbn[g] = (uint32_t)__ldg(kp + g * 8);
+    }
     for (int kb = 0; kb < n_kb; ++kb) {
       mb_wait(raw_full + stage, phase);
       if (t == 0) KGC_DBG(1);
@@ -853,6 +918,45 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmTnMaps maps, const GemmTnParams P)
       // rows of this K block that lie past the CTA's slab must not contribute: a 16-byte vector v of a box belongs to
       // box row (v % 256) / 8  (32 rows x 8 vectors per box; the swizzle permutes vectors only inside a row)
       const int rows_valid = P.kmajor ? kTnRows : (int)min((int64_t)kTnRows, m1 - (m0 + (int64_t)kb * kTnRows));
+      if (masked) {
+        // B operand = the upstream plane, dropped while it is split.  With 256 splitter threads the k-th trip of a thread
+        // handles box k: boxes 0..3 = A, box 4 + g = 32-column group g of B; the thread's position inside a box is fixed:
+        // row brow = t / 8, and (un-swizzling: the 32-byte chunks of a 128-byte row are XOR-ed with row % 4, layout
+        // SWIZZLE_128B_BASE32B; the 16-byte half is kept) 16-byte column chunk c16 -> ONE keep byte per trip.  The bytes
+        // of the NEXT K block are loaded before this one is processed (see the K4b splitter).
+        uint32_t nbc[kTnMaxGb];
+#pragma unroll
+        for (int g = 0; g < kTnMaxGb; ++g) nbc[g] = nbn[g];
+        if (kb + 1 < n_kb) {
+          const uint8_t* kp = P.keep + (m0 + (int64_t)(kb + 1) * kTnRows + brow_t) * P.keep_pitch + c16_t;
+          const bool ok = m0 + (int64_t)(kb + 1) * kTnRows + brow_t < m1;
+#pragma unroll
+          for (int g = 0; g < kTnMaxGb; ++g) nbn[g] = (ok && g < P.gb) ? (uint32_t)__ldg(kp + g * 8) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4 + kTnMaxGb; ++k) {
+          if (k < 4 + P.gb) {
+            const int v = t + k * kSplitThreads;
+            uint4 x = hi[v];
+            if (brow_t >= rows_valid) x = make_uint4(0u, 0u, 0u, 0u);
+            else if (k >= 4) {
+              uint32_t nb = nbc[k >= 4 ? k - 4 : 0];
+              if (prob == 1) nb >>= 4;
+              x.x = (nb & 1u) ? __float_as_uint(__uint_as_float(x.x) * P.keep_scale) : 0u;
+              x.y = (nb & 2u) ? __float_as_uint(__uint_as_float(x.y) * P.keep_scale) : 0u;
+              x.z = (nb & 4u) ? __float_as_uint(__uint_as_float(x.z) * P.keep_scale) : 0u;
+              x.w = (nb & 8u) ? __float_as_uint(__uint_as_float(x.w) * P.keep_scale) : 0u;
+            }
+            uint4 h, l;
+            split_tf32(x.x, h.x, l.x);
+            split_tf32(x.y, h.y, l.y);
+            split_tf32(x.z, h.z, l.z);
+            split_tf32(x.w, h.w, l.w);
+            hi[v] = h;
+            lo[v] = l;
+          }
+        }
+      } else
       for (int v = t; v < n_vec; v += kSplitThreads) {
         uint4 x = hi[v];
         if (((v & 255) >> 3) >= rows_valid) x = make_uint4(0u, 0u, 0u, 0u);
@@ -1072,7 +1176,8 @@ extern "C" void kgc_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }   // de
 // fills the 148 SMs with whole row-tile rounds where a single N x 100 x 200 product leaves a 14% tail
 static int launch_gemm_nt(int n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda, const float* const* packed_b,
                           int32_t N, float* const* C, int64_t ldc, const float* row_bias, int32_t act, int32_t trans_c,
-                          int32_t trans_a, void* stream) {
+                          int32_t trans_a, void* stream, const uint8_t* keep = nullptr, int32_t keep_pitch = 0,
+                          float keep_scale = 1.f) {
   Tiling t;
   KGC_REQUIRE(n_prob >= 1 && n_prob <= kMaxBatch, "1..3 problems per launch");
   KGC_REQUIRE(make_tiling(N, K, &t) == 0, "unsupported GEMM shape (K <= 256, N <= 1024)");
@@ -1104,6 +1209,9 @@ static int launch_gemm_nt(int n_prob, const float* const* A, int64_t M, int32_t 
   P.n_kb = t.n_kb; P.ksteps = t.ksteps; P.NT = t.NT; P.n_ntiles = t.n_ntiles;
   P.n_mtiles = (int32_t)ceil_div(M, kBM);
   P.C = C[0]; P.ldc = ldc; P.row_bias = row_bias; P.act = act; P.trans_c = trans_c; P.trans_a = trans_a; P.dbg = g_gemm_dbg;
+  KGC_REQUIRE(keep == nullptr || (!trans_a && keep_pitch % 16 == 0 && keep_pitch >= 8 * kMaxKB && (reinterpret_cast<uintptr_t>(keep) & 15) == 0),
+              "keep flags: one byte per 4 columns, 16-byte aligned rows of at least 64 bytes");
+  P.keep = keep; P.keep_pitch = keep_pitch; P.keep_scale = keep_scale;
   const int tile_b_al = (t.NT * kBK * 4 + 1023) & ~1023;
   const size_t fixed = (size_t)2 * t.n_kb * tile_b_al + kEpiStage + 512 + 1024;
   int stages = (int)((226 * 1024 - fixed) / kTileA);
@@ -1136,6 +1244,13 @@ extern "C" int kgc_gemm_nt_batch(int32_t n_prob, const float* const* A, int64_t 
 
 // Ct[N, M] = (A @ Bt^T)^T with A given transposed, At[K, M] row-major: the long dimension M is contiguous in BOTH the
 // streamed operand and the result (a [K, M] weight or activation matrix and a gradient of the same shape)
+extern "C" int kgc_gemm_nt_batch_masked(int32_t n_prob, const float* const* A, int64_t M, int32_t K, int64_t lda,
+                                        const float* const* packed_b, int32_t N, float* const* C, int64_t ldc,
+                                        const uint8_t* keep, int32_t keep_pitch, float keep_scale, void* stream) {
+  KGC_REQUIRE(A && packed_b && C, "null pointer table");
+  return launch_gemm_nt(n_prob, A, M, K, lda, packed_b, N, C, ldc, nullptr, 0, 0, 0, stream, keep, keep_pitch, keep_scale);
+}
+
 extern "C" int kgc_gemm_nt_trans(const float* At, int64_t M, int32_t K, int64_t ldat, const float* packed_b, int32_t N,
                                  float* Ct, int64_t ldct, void* stream) {
   return launch_gemm_nt(1, &At, M, K, ldat, &packed_b, N, &Ct, ldct, nullptr, 0, 1, 1, stream);
@@ -1194,7 +1309,7 @@ extern "C" size_t kgc_gemm_tn_tc_workspace_bytes(int64_t M, int32_t Ka, int32_t 
 // C[Ka, Nb] = A[M, Ka]^T @ B[M, Nb] on the tensor cores (3xTF32).  Ka <= 128, Nb <= 224, multiples of 4.
 static int launch_gemm_tn_tc(int n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb, int64_t M,
                              int32_t Ka, int32_t Nb, float* const* C, void* workspace, size_t workspace_bytes, int32_t kmajor,
-                             void* stream) {
+                             void* stream, const uint8_t* keep = nullptr, int32_t keep_pitch = 0, float keep_scale = 1.f) {
   KGC_REQUIRE(n_prob >= 1 && n_prob <= kMaxBatch, "1..3 problems per launch");
   KGC_REQUIRE(M > 0 && Ka > 0 && Nb > 0 && Ka <= 128 && Nb <= 224, "supported: Ka <= 128, Nb <= 224");
   KGC_REQUIRE(Nb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && (kmajor || Ka % 4 == 0), "dimensions and leading dimensions must be multiples of 4");
@@ -1211,6 +1326,8 @@ static int launch_gemm_tn_tc(int n_prob, const float* const* A, int64_t lda, con
   P.n_slabs = slabs;
   P.partial = static_cast<float*>(workspace);
   P.dbg = g_gemm_dbg;
+  KGC_REQUIRE(keep == nullptr || (!kmajor && keep_pitch >= 8 * P.gb), "keep flags: one byte per 4 columns of B, rows that cover the padded width");
+  P.keep = keep; P.keep_pitch = keep_pitch; P.keep_scale = keep_scale;
   P.ga_full = kmajor ? 0 : Ka / 32;
   P.gb_full = kmajor ? 0 : Nb / 32;
   GemmTnMaps maps;
@@ -1251,6 +1368,15 @@ extern "C" int kgc_gemm_tn_tc_batch(int32_t n_prob, const float* const* A, int64
                                     size_t workspace_bytes, void* stream) {
   KGC_REQUIRE(A && B && C, "null pointer table");
   return launch_gemm_tn_tc(n_prob, A, lda, B, ldb, M, Ka, Nb, C, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int kgc_gemm_tn_tc_batch_masked(int32_t n_prob, const float* const* A, int64_t lda, const float* const* B, int64_t ldb,
+                                           int64_t M, int32_t Ka, int32_t Nb, float* const* C, void* workspace,
+                                           size_t workspace_bytes, const uint8_t* keep, int32_t keep_pitch, float keep_scale,
+                                           void* stream) {
+  KGC_REQUIRE(A && B && C, "null pointer table");
+  return launch_gemm_tn_tc(n_prob, A, lda, B, ldb, M, Ka, Nb, C, workspace, workspace_bytes, 0, stream, keep, keep_pitch,
+                           keep_scale);
 }
 
 // C[Ma, Nb] = A[Ma, K] @ Bt[Nb, K]^T with a LONG contraction (K >> Ma, Nb): the K range is cut into per-CTA slabs, both

@@ -26,6 +26,11 @@ __device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t idx4, float s)
   return make_float4(v.x ? s : 0.f, v.y ? s : 0.f, v.z ? s : 0.f, v.w ? s : 0.f);
 }
 
+constexpr int kKeepPitch = 64;            // bytes per row of the packed keep flags: one byte per float4 column (Dout <= 256)
+__device__ __forceinline__ uint32_t nibble(const float4& m) {
+  return (m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u);
+}
+
 struct DropCfg {
   const uint8_t* mask_in;     // injected keep masks (tests / replay of recorded draws) ...
   const uint8_t* mask_out;
@@ -66,7 +71,8 @@ __device__ __forceinline__ void block_store_partials(double4 a, double4 b, int r
 
 __global__ void __launch_bounds__(kThreads)
 tail_fwd_kernel(const float4* __restrict__ res3, const DropCfg drop, const float4* __restrict__ bias,
-                int64_t n_rows, int Do4, float4* __restrict__ pre, double* __restrict__ partials) {
+                int64_t n_rows, int Do4, float4* __restrict__ pre, double* __restrict__ partials,
+                uint8_t* __restrict__ keep) {
   extern __shared__ double4 sm[];
   const int RL = kThreads / Do4;
   const int rl = threadIdx.x / Do4, c = threadIdx.x % Do4;
@@ -79,8 +85,13 @@ tail_fwd_kernel(const float4* __restrict__ res3, const DropCfg drop, const float
       const int64_t i = r * Do4 + c;
       float4 a = __ldg(res3 + i), b = __ldg(res3 + plane + i);
       const float4 l = __ldg(res3 + 2 * plane + i);
-      { const float4 m = drop_scale4(drop, 0, i); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; }
-      { const float4 m = drop_scale4(drop, 1, i); b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w; }
+      uint32_t kb = 0;
+      { const float4 m = drop_scale4(drop, 0, i); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; kb |= nibble(m); }
+      { const float4 m = drop_scale4(drop, 1, i); b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w; kb |= nibble(m) << 4; }
+      // the keep flags of the four columns, both planes, in one byte: the backward GEMMs apply them to the single
+      // upstream plane while they split it (kgc_gemm_nt_batch / kgc_gemm_tn_tc_batch), nothing is regenerated or stored
+      // per plane
+      if (keep != nullptr) keep[r * kKeepPitch + c] = (uint8_t)kb;
       float4 o;   // (drop(in) + drop(out) + loop) / 3 [+ bias]   (model.py:103-105)
       o.x = (a.x + b.x + l.x) / 3.0f + bv.x;
       o.y = (a.y + b.y + l.y) / 3.0f + bv.y;
@@ -218,8 +229,8 @@ tail_apply_kernel(const float4* __restrict__ pre, const float4* __restrict__ sta
 }
 
 __global__ void __launch_bounds__(kThreads)
-tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
-                       const float4* __restrict__ pre, const float4* __restrict__ stats, int64_t n_rows, int Do4,
+tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ pre, const float4* __restrict__ stats,
+                       const float4* __restrict__ gamma, const float4* __restrict__ beta, int64_t n_rows, int Do4,
                        double* __restrict__ partials) {
   extern __shared__ double4 sm[];
   const int RL = kThreads / Do4;
@@ -227,33 +238,40 @@ tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restric
   const Stripe s = block_stripe(n_rows);
   double4 s1 = make_double4(0, 0, 0, 0), s2 = make_double4(0, 0, 0, 0);
   if (rl < RL) {
-    const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c);
+    // all_ent = tanh(BatchNorm(pre)) is recomputed from pre (one plane less to read; the tail is HBM-bound)
+    const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
     for (int64_t r = s.row_beg + rl; r < s.row_end; r += RL) {
       const int64_t i = r * Do4 + c;
-      const float4 g = __ldg(g_ent + i), t = __ldg(all_ent + i), v = __ldg(pre + i);
+      const float4 g = __ldg(g_ent + i), v = __ldg(pre + i);
+      const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
+      const float4 t = make_float4(tanhf(xh.x * ga.x + be.x), tanhf(xh.y * ga.y + be.y), tanhf(xh.z * ga.z + be.z),
+                                   tanhf(xh.w * ga.w + be.w));
       const float dzx = g.x * (1.f - t.x * t.x), dzy = g.y * (1.f - t.y * t.y);
       const float dzz = g.z * (1.f - t.z * t.z), dzw = g.w * (1.f - t.w * t.w);
       s1.x += dzx; s1.y += dzy; s1.z += dzz; s1.w += dzw;
-      s2.x += (double)dzx * ((v.x - m.x) * rs.x);
-      s2.y += (double)dzy * ((v.y - m.y) * rs.y);
-      s2.z += (double)dzz * ((v.z - m.z) * rs.z);
-      s2.w += (double)dzw * ((v.w - m.w) * rs.w);
+      s2.x += (double)dzx * xh.x;
+      s2.y += (double)dzy * xh.y;
+      s2.z += (double)dzz * xh.z;
+      s2.w += (double)dzw * xh.w;
     }
   }
   block_store_partials(s1, s2, rl, c, RL, Do4, partials, sm);
 }
 
 __global__ void __launch_bounds__(kThreads)
-tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ all_ent,
-                      const float4* __restrict__ pre, const float4* __restrict__ stats,
-                      const float4* __restrict__ gamma, const double* __restrict__ sums, const DropCfg drop,
-                      int training, int64_t n_rows, int64_t n_rows_global, int Do4, float4* __restrict__ d_res3) {
+tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ pre, const float4* __restrict__ stats,
+                      const float4* __restrict__ gamma, const float4* __restrict__ beta, const double* __restrict__ sums,
+                      int training, int64_t n_rows, int64_t n_rows_global, int Do4, float4* __restrict__ d_out,
+                      const uint8_t* __restrict__ keep, float keep_scale, float4* __restrict__ d_res2) {
   const int64_t n4 = n_rows * (int64_t)Do4;
   const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)(i % Do4);
-  const float4 g = __ldg(g_ent + i), t = __ldg(all_ent + i), v = __ldg(pre + i);
-  const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c);
+  const float4 g = __ldg(g_ent + i), v = __ldg(pre + i);
+  const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
+  const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
+  const float4 t = make_float4(tanhf(xh.x * ga.x + be.x), tanhf(xh.y * ga.y + be.y), tanhf(xh.z * ga.z + be.z),
+                               tanhf(xh.w * ga.w + be.w));
   float4 dz = make_float4(g.x * (1.f - t.x * t.x), g.y * (1.f - t.y * t.y), g.z * (1.f - t.z * t.z),
                           g.w * (1.f - t.w * t.w));
   float4 dp;
@@ -263,20 +281,27 @@ tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict
     const double* sq = sums + 4 * (Do4 + c);
     const float4 s1 = make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]);
     const float4 s2 = make_float4((float)sq[0], (float)sq[1], (float)sq[2], (float)sq[3]);
-    dp.x = ga.x * rs.x * (dz.x - s1.x * inv_n - (v.x - m.x) * rs.x * s2.x * inv_n);
-    dp.y = ga.y * rs.y * (dz.y - s1.y * inv_n - (v.y - m.y) * rs.y * s2.y * inv_n);
-    dp.z = ga.z * rs.z * (dz.z - s1.z * inv_n - (v.z - m.z) * rs.z * s2.z * inv_n);
-    dp.w = ga.w * rs.w * (dz.w - s1.w * inv_n - (v.w - m.w) * rs.w * s2.w * inv_n);
+    dp.x = ga.x * rs.x * (dz.x - s1.x * inv_n - xh.x * s2.x * inv_n);
+    dp.y = ga.y * rs.y * (dz.y - s1.y * inv_n - xh.y * s2.y * inv_n);
+    dp.z = ga.z * rs.z * (dz.z - s1.z * inv_n - xh.z * s2.z * inv_n);
+    dp.w = ga.w * rs.w * (dz.w - s1.w * inv_n - xh.w * s2.w * inv_n);
   } else {
     dp = make_float4(ga.x * rs.x * dz.x, ga.y * rs.y * dz.y, ga.z * rs.z * dz.z, ga.w * rs.w * dz.w);
   }
+  // ONE upstream plane: d out / 3.  The self-loop transform takes it as it is; the in / out halves are this plane times
+  // their keep flags x 1 / (1 - p), applied by the GEMM kernels while they split the operand (tail_fwd's packed flags)
   const float4 third = make_float4(dp.x / 3.0f, dp.y / 3.0f, dp.z / 3.0f, dp.w / 3.0f);
-  float4 a = third, b = third;
-  { const float4 k = drop_scale4(drop, 0, i); a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w; }
-  { const float4 k = drop_scale4(drop, 1, i); b.x *= k.x; b.y *= k.y; b.z *= k.z; b.w *= k.w; }
-  d_res3[i] = a;
-  d_res3[n4 + i] = b;
-  d_res3[2 * n4 + i] = third;
+  d_out[i] = third;
+  if (d_res2 != nullptr) {
+    // three-plane form: the dropped in / out planes are written here (tail_fwd's keep flags, nothing regenerated) and the
+    // GEMMs stream them as they are - their operand splitters are the busier side of those kernels
+    const uint32_t kb = keep != nullptr ? keep[(i / Do4) * kKeepPitch + c] : 0xFFu;
+    const float s = keep != nullptr ? keep_scale : 1.f;
+    d_res2[i] = make_float4((kb & 1u) ? third.x * s : 0.f, (kb & 2u) ? third.y * s : 0.f, (kb & 4u) ? third.z * s : 0.f,
+                            (kb & 8u) ? third.w * s : 0.f);
+    d_res2[n4 + i] = make_float4((kb & 16u) ? third.x * s : 0.f, (kb & 32u) ? third.y * s : 0.f, (kb & 64u) ? third.z * s : 0.f,
+                                 (kb & 128u) ? third.w * s : 0.f);
+  }
 }
 
 inline int check_dout(int32_t Dout) { return (Dout <= 0 || Dout % 4 != 0 || Dout > 1024) ? 1 : 0; }
@@ -323,16 +348,19 @@ extern "C" int kgc_dropout_mask(const int64_t* seed, int32_t plane, float drop_p
   return 0;
 }
 
+extern "C" int32_t kgc_keep_pitch() { return kKeepPitch; }
+
 extern "C" int kgc_tail_fwd(const float* res3, const uint8_t* mask_in, const uint8_t* mask_out, const int64_t* seed,
                             float drop_p, float keep_scale, const float* bias, int64_t n_rows, int32_t Dout, float* pre,
-                            double* partials, void* stream) {
+                            double* partials, uint8_t* keep, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
+  KGC_REQUIRE(keep == nullptr || Dout <= 4 * kKeepPitch, "packed keep flags need Dout <= 256");
   KGC_REQUIRE(n_rows > 0, "n_rows must be positive");
   const int Do4 = Dout / 4;
   const size_t smem = partial_smem(Do4);   // <= 16 KB
   tail_fwd_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
       (const float4*)res3, make_drop(mask_in, mask_out, seed, drop_p, keep_scale), (const float4*)bias, n_rows, Do4,
-      (float4*)pre, partials);
+      (float4*)pre, partials, keep);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -389,28 +417,28 @@ extern "C" int kgc_tail_apply(const float* pre, const float* stats, const float*
   return 0;
 }
 
-extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
-                                   int64_t n_rows, int32_t Dout, double* partials, void* stream) {
+extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* pre, const float* stats, const float* gamma,
+                                   const float* beta, int64_t n_rows, int32_t Dout, double* partials, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const size_t smem = partial_smem(Do4);   // <= 16 KB
   tail_bwd_reduce_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
-      (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, n_rows, Do4, partials);
+      (const float4*)g_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, n_rows, Do4,
+      partials);
   KGC_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* all_ent, const float* pre, const float* stats,
-                                  const float* gamma, const double* sums, const uint8_t* mask_in,
-                                  const uint8_t* mask_out, const int64_t* seed, float drop_p, float keep_scale,
-                                  int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout, float* d_res3,
-                                  void* stream) {
+extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* pre, const float* stats, const float* gamma,
+                                  const float* beta, const double* sums, int32_t training, int64_t n_rows,
+                                  int64_t n_rows_global, int32_t Dout, float* d_out, const uint8_t* keep, float keep_scale,
+                                  float* d_res2, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const int64_t n4 = n_rows * Do4;
   tail_bwd_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
-      (const float4*)g_ent, (const float4*)all_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma,
-      sums, make_drop(mask_in, mask_out, seed, drop_p, keep_scale), training, n_rows, n_rows_global, Do4, (float4*)d_res3);
+      (const float4*)g_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, sums,
+      training, n_rows, n_rows_global, Do4, (float4*)d_out, keep, keep_scale, (float4*)d_res2);
   KGC_LAUNCH_CHECK();
   return 0;
 }
