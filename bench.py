@@ -671,7 +671,8 @@ def kernel_rooflines(case, flush):
     xd, eed = case.x.detach(), case.ee.detach()
     agg = torch.empty((2, N, D), device=dev)
     g3 = synth_rows(torch.arange(3 * N, dtype=torch.int64, device=dev), D, 1.0, 21).view(3, N, D)
-    d_ee, d_x, d_rel = torch.empty_like(eed), torch.empty((N, D), device=dev), torch.empty((T, D), device=dev)
+    d_ee, d_x, d_rel = torch.empty_like(eed), torch.empty((N, D), device=dev), torch.empty((plan.num_type_rows, D), device=dev)
+    d_rel_sum = torch.empty((T, D), device=dev)
     sf, ss, sr = plan.fwd, plan.bwd_src, plan.bwd_rel
 
     def l0_fwd(sp, out_final, carry):
@@ -694,7 +695,7 @@ def kernel_rooflines(case, flush):
 
     def pass_bwd():
         plan.run_reduction(ss, l0_src, d_x, D, addend=g3[2], tag='rf_s')
-        plan.run_reduction(sr, l0_rel, d_rel, D, tag='rf_r')
+        plan.run_rel_reduction(l0_rel, d_rel_sum, D, tag='rf_r')
     row = 4 * D
     fwd_b, bwd_b = algorithmic_bytes(N, R, E)
     n_ch = (2 * E + 31) // 32

@@ -21,7 +21,9 @@ SIGNATURES = {
     'kgc_abi_version': (ctypes.c_int, []),
     'kgc_csr_workspace_bytes': (_sz, [_i64, _i64, _i64]),
     'kgc_csr_build': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    'kgc_csr_type_rows': (_i64, [_i64, _i64, _i64]),
+    'kgc_block_sum': (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     'kgc_agg_fwd': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_fill': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),

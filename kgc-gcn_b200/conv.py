@@ -532,7 +532,7 @@ class _ConvFn(torch.autograd.Function):
         def level0_rel(sp, out_final, carry):
             _lib.call('kgc_agg_bwd_rel', p(x_full), p(ee), p(g3), p(plan.rec_type), p(sp.rowflags), p(sp.chunks), sp.n_rec,
                       plan.num_dst_rows, plan.num_edges_in, p(out_final), p(carry), D, st())
-        plan.run_reduction(plan.bwd_rel, level0_rel, d_relp, D, tag='r')
+        plan.run_rel_reduction(level0_rel, d_relp, D)
 
         main.wait_stream(side)                                        # the weight gradients are part of `flat`
         if coll is None:

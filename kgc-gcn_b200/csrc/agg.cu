@@ -574,6 +574,22 @@ extern "C" int kgc_agg_bwd_rel(const float* x, const float* ee, const float* g3,
   return launch_stream<kBwdRel>(A, as_stream(stream));
 }
 
+__global__ void block_sum_kernel(const float4* __restrict__ in, int64_t n_blocks, int64_t n4, float4* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = __ldg(in + i);
+  for (int64_t b = 1; b < n_blocks; ++b) add4(acc, __ldg(in + b * n4 + i));
+  out[i] = acc;
+}
+
+extern "C" int kgc_block_sum(const float* in, int64_t n_blocks, int64_t n, float* out, void* stream) {
+  KGC_REQUIRE(in && out && n_blocks >= 1 && n > 0 && n % 4 == 0, "bad arguments");
+  block_sum_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)in, n_blocks, n / 4,
+                                                                               (float4*)out);
+  KGC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int kgc_rows_fill(const int32_t* rows, int64_t n_rows, const float* addend, float* out, int32_t D,
                              void* stream) {
   int D4, nf;

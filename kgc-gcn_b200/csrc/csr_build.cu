@@ -102,6 +102,18 @@ __global__ void add_rows(const int32_t* __restrict__ a, const int32_t* __restric
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// key of the type-sorted pass when it is blocked by subject: (block of the edge's subject row) * n_types + type.  The
+// subject (src of an in-half edge, dst of its reverse) is the endpoint whose row the d_rel pass gathers at random - the
+// object side of a knowledge graph is hub-heavy and stays in L2 by itself.  Inside one block the gathered x / g rows
+// (2 * block_rows * 4 D bytes) are L2-resident; the per-(block, type) partial rows are summed afterwards (kgc_block_sum).
+__global__ void type_block_key(const int32_t* __restrict__ src32, const int32_t* __restrict__ dst32, int32_t* __restrict__ type32,
+                               int64_t n2, int64_t n_in, int32_t n_types, int32_t block_rows) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const int32_t subj = i < n_in ? src32[i] : dst32[i];
+  type32[i] = (subj / block_rows) * n_types + type32[i];
+}
+
 __global__ void gather_records(const int32_t* __restrict__ perm, const int32_t* __restrict__ a32,
                                const int32_t* __restrict__ b32, const float* __restrict__ norm, int64_t n2,
                                kgc_edge_rec_t* __restrict__ rec) {
@@ -139,6 +151,10 @@ int sorted_csr(const int32_t* key32, int64_t n2, int64_t n_rows, const int32_t* 
 
 using namespace kgc;
 
+extern "C" int64_t kgc_csr_type_rows(int64_t n_nodes, int64_t n_types, int64_t type_block_rows) {
+  return type_block_rows > 0 ? ceil_div(n_nodes, type_block_rows) * n_types : n_types;
+}
+
 extern "C" size_t kgc_csr_workspace_bytes(int64_t n_edges2, int64_t n_nodes, int64_t n_types) {
   size_t cub_bytes = 0;
   if (cub_temp_bytes(n_edges2, n_nodes > n_types ? n_nodes : n_types, &cub_bytes) != cudaSuccess) {
@@ -153,15 +169,19 @@ extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64
                              int32_t deg_given, int32_t* deg, float* norm, int32_t* perm_dst, int32_t* rowptr_dst,
                              int32_t* rowmid_dst, kgc_edge_rec_t* rec_dst, int32_t* perm_src, int32_t* rowptr_src,
                              kgc_edge_rec_t* rec_src, int32_t* perm_type, int32_t* rowptr_type, kgc_edge_rec_t* rec_type,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             int64_t type_block_rows, void* workspace, size_t workspace_bytes, void* stream) {
   KGC_REQUIRE(n2 >= 0 && n_in >= 0 && n_in <= n2, "n_edges_in must lie in [0, n_edges2] (in half first, model.py:84-90)");
   KGC_REQUIRE(n_nodes > 0 && n_types > 0 && n_dst_rows > 0, "empty node or type set");
   KGC_REQUIRE(dst_offset >= 0 && dst_offset + n_dst_rows <= n_nodes, "destination range must lie inside the node set");
   KGC_REQUIRE(n2 < (int64_t(1) << 31) && n_nodes < (int64_t(1) << 31) && n_types < (int64_t(1) << 31),
               "ids must fit int32");
+  // type rows of the (optionally subject-blocked) type sort: kgc_csr_type_rows(n_nodes, n_types, type_block_rows)
+  KGC_REQUIRE(type_block_rows >= 0, "type_block_rows must be >= 0");
+  const int64_t n_type_rows = type_block_rows > 0 ? ceil_div(n_nodes, type_block_rows) * n_types : n_types;
+  KGC_REQUIRE(n_type_rows < (int64_t(1) << 30), "too many (block, type) rows");
   size_t cub_bytes = 0;
-  KGC_CUDA_TRY(cub_temp_bytes(n2, n_nodes > n_types ? n_nodes : n_types, &cub_bytes));
-  const Layout L = make_layout(n2, n_nodes, n_types, cub_bytes);
+  KGC_CUDA_TRY(cub_temp_bytes(n2, n_nodes > n_type_rows ? n_nodes : n_type_rows, &cub_bytes));
+  const Layout L = make_layout(n2, n_nodes, n_type_rows, cub_bytes);
   KGC_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, "workspace too small");
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
@@ -216,8 +236,12 @@ extern "C" int kgc_csr_build(const int64_t* src, const int64_t* dst, const int64
     gather_records<<<grid, kThreads, 0, st>>>(perm_src, dst32, type32, norm, n2, rec_src);
     KGC_LAUNCH_CHECK();
   }
-  // type-sorted (backward d_rel)
-  if (sorted_csr(type32, n2, n_types, iota, key_sorted, perm_type, rowptr_type, cnt, cub_ws, cub_bytes, st)) return 1;
+  // type-sorted (backward d_rel), optionally blocked by subject row
+  if (type_block_rows > 0 && n2 > 0) {
+    type_block_key<<<grid, kThreads, 0, st>>>(src32, dst32, type32, n2, n_in, (int32_t)n_types, (int32_t)type_block_rows);
+    KGC_LAUNCH_CHECK();
+  }
+  if (sorted_csr(type32, n2, n_type_rows, iota, key_sorted, perm_type, rowptr_type, cnt, cub_ws, cub_bytes, st)) return 1;
   if (n2 > 0) {
     gather_records<<<grid, kThreads, 0, st>>>(perm_type, src32, dst32, norm, n2, rec_type);
     KGC_LAUNCH_CHECK();

@@ -4,11 +4,14 @@ deterministic segmented reductions of K2/K3.
 The plan is built once per graph (the reference re-derives degrees, norms and gather/scatter
 indices on every step: model.py:96-101) and cached on the identity of the edge tensors.
 """
+import os
+
 import numpy as np
 import torch
 
 from . import _lib
 
+TYPE_BLOCK_ROWS = 65536   # subject rows per block of the blocked d_rel pass (GraphPlan.type_block_rows)
 CHUNK0 = 32      # build_levels default fan-in of the first level
 CHUNK1 = 2048    # carry / partial rows per item on the fix-up levels (one 1024-thread block): a 38k-edge hub row
                  # (1,187 carry rows) is one item and ONE launch; a 9M-edge hub needs two levels
@@ -141,7 +144,7 @@ class GraphPlan(object):
     """
 
     def __init__(self, edge_index, edge_type, num_nodes, num_types, n_edges_in=None, n_dst_rows=None, dst_offset=0,
-                 deg=None):
+                 deg=None, type_block_rows=None):
         """Single GPU: edge_index [2, 2E] with the in half first (defaults).  Partitioned: only the
         edges this rank owns, ``n_edges_in`` in-half edges first, src = global ids, dst = LOCAL row ids in
         [0, n_dst_rows) (global id = dst + dst_offset) and ``deg`` = the GLOBAL per-half degrees [2, num_nodes] int32."""
@@ -169,11 +172,19 @@ class GraphPlan(object):
         self.norm = torch.empty((n2,), dtype=torch.float32, device=dev)
         self.perm_dst, self.perm_src, self.perm_type = (torch.empty((n2,), **i32) for _ in range(3))
         self.rowptr_dst, self.rowptr_src = torch.empty((Nd + 1,), **i32), torch.empty((N + 1,), **i32)
-        self.rowptr_type = torch.empty((T + 1,), **i32)
+        # the d_rel pass blocked by subject row (kgc_csr_build): node tables far beyond L2 only.  65,536 rows = 26 MB of x
+        # + 26 MB of g per block at D = 100; KGC_TYPE_BLOCK_ROWS overrides (0 = plain type sort)
+        if type_block_rows is None:
+            env = os.environ.get('KGC_TYPE_BLOCK_ROWS', '')
+            type_block_rows = int(env) if env else (TYPE_BLOCK_ROWS if N >= 4 * TYPE_BLOCK_ROWS else 0)
+        self.type_block_rows = int(type_block_rows)
+        Tr = int(_lib.lib().kgc_csr_type_rows(N, T, self.type_block_rows))
+        self.num_type_rows, self.num_type_blocks = Tr, Tr // T
+        self.rowptr_type = torch.empty((Tr + 1,), **i32)
         self.rowmid_dst = torch.empty((Nd,), **i32)
         self.rec_dst, self.rec_src, self.rec_type = (torch.empty((n2, 4), **i32) for _ in range(3))
         h = _lib.lib()
-        ws_bytes = int(h.kgc_csr_workspace_bytes(n2, N, T))
+        ws_bytes = int(h.kgc_csr_workspace_bytes(n2, N, Tr))
         if ws_bytes == 0:
             raise RuntimeError('kgc_csr_workspace_bytes failed: ' + h.kgc_last_error().decode())
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
@@ -183,7 +194,7 @@ class GraphPlan(object):
                   0 if deg is None else 1, p(self.deg), p(self.norm),
                   p(self.perm_dst), p(self.rowptr_dst), p(self.rowmid_dst), p(self.rec_dst),
                   p(self.perm_src), p(self.rowptr_src), p(self.rec_src),
-                  p(self.perm_type), p(self.rowptr_type), p(self.rec_type), p(ws), ws_bytes, _lib.stream())
+                  p(self.perm_type), p(self.rowptr_type), p(self.rec_type), self.type_block_rows, p(ws), ws_bytes, _lib.stream())
         del ws
         # ---- reduction plans (host integer scheduling over the row pointers)
         rp_dst = self.rowptr_dst.cpu().numpy().astype(np.int64)
@@ -198,7 +209,7 @@ class GraphPlan(object):
         fr = np.stack([drows, drows + Nd], 1).reshape(-1)
         self.fwd = StreamPlan(build_stream_plan(fb, fe, fr, n2), n2, dev)
         self.bwd_src = StreamPlan(build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2), n2, dev)
-        self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(T, dtype=np.int64), n2), n2, dev)
+        self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(Tr, dtype=np.int64), n2), n2, dev)
         self._scratch = {}
 
     def side_stream(self):
@@ -215,6 +226,15 @@ class GraphPlan(object):
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._scratch[key] = t
         return t
+
+    def run_rel_reduction(self, level0, d_relp, D, tag='r'):
+        """The d_rel pass: the type-sorted reduction into d_relp [num_types, D]; when the sort is blocked by subject row the
+        pass yields one partial row per (block, type) and kgc_block_sum adds the blocks in ascending order."""
+        if self.num_type_blocks == 1:
+            return self.run_reduction(self.bwd_rel, level0, d_relp, D, tag=tag)
+        part = self.scratch(tag + 'blocks', (self.num_type_rows, D))
+        self.run_reduction(self.bwd_rel, level0, part, D, tag=tag)
+        _lib.call('kgc_block_sum', _lib.ptr(part), self.num_type_blocks, self.num_types * D, _lib.ptr(d_relp), _lib.stream())
 
     def run_reduction(self, sp, level0, out_final, D, addend=None, tag=''):
         """Launch the streaming kernel through ``level0(sp, out_final, carry)``, fill the rows without records and

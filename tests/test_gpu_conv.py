@@ -168,6 +168,48 @@ def test_csr_build_bit_exact(k):
     np.testing.assert_array_equal(rec[:, 3].view(np.float32), plan.norm.cpu().numpy()[perm])
 
 
+def test_type_sort_blocked_by_subject(k, monkeypatch):
+    """The d_rel pass blocked by subject row (kgc_csr_build type_block_rows): the permutation is the stable sort by
+    (block of the subject, type) bit for bit; the layer's outputs and gradients with the blocked pass equal the plain
+    pass (d_rel within float tolerance: the partial rows are added block by block; everything else bit for bit)."""
+    N, R, E = 1500, 9, 20000
+    tri = orc.synthetic_triples(N, R, E, 51)
+    g = orc.build_graph(tri, N, R)
+    ei = torch.from_numpy(g['edge_index']).cuda()
+    et = torch.from_numpy(g['edge_attr'][0]).cuda()
+    T, BR = 2 * R + 1, 256
+    plan = k.GraphPlan(ei, et, N, T, type_block_rows=BR)
+    src, dst, typ = g['edge_index'][0], g['edge_index'][1], g['edge_attr'][0]
+    subj = np.concatenate([src[:E], dst[E:]])
+    n_blocks = -(-N // BR)
+    assert plan.num_type_blocks == n_blocks and plan.num_type_rows == n_blocks * T
+    perm, rowptr = orc.stable_csr((subj // BR) * T + typ, n_blocks * T)
+    np.testing.assert_array_equal(plan.perm_type.cpu().numpy(), perm)
+    np.testing.assert_array_equal(plan.rowptr_type.cpu().numpy(), rowptr)
+    rec = plan.rec_type.cpu().numpy()
+    np.testing.assert_array_equal(rec[:, 0], perm)
+    np.testing.assert_array_equal(rec[:, 1], src[perm])
+    np.testing.assert_array_equal(rec[:, 2], dst[perm])
+    # the other two sorts are untouched
+    for key, perm_t in ((dst, plan.perm_dst), (src, plan.perm_src)):
+        np.testing.assert_array_equal(perm_t.cpu().numpy(), orc.stable_csr(key, N)[0])
+    z, _ = synth_case(2000, 5, 12000, 100, 200, 43)
+    res = {}
+    for br in ('0', '128'):
+        monkeypatch.setenv('KGC_TYPE_BLOCK_ROWS', br)
+        k.plan._PLAN_CACHE.clear()
+        _, ent, rel, grads = run_case(k, z)
+        res[br] = (ent, rel, grads)
+    k.plan._PLAN_CACHE.clear()
+    assert torch.equal(res['0'][0], res['128'][0]) and torch.equal(res['0'][1], res['128'][1])
+    for name in res['0'][2]:
+        a, b = res['0'][2][name], res['128'][2][name]
+        if torch.equal(a, b):
+            continue
+        assert name in ('rels', 'w.loop_rel'), name
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-12, name
+
+
 def test_csr_toy_known_answers(k, golden_dir):
     import json
     with open(os.path.join(golden_dir, 'toy_loader.json')) as f:
