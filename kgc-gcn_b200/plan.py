@@ -109,7 +109,7 @@ def build_stream_plan(seg_beg, seg_end, seg_row, n_rec, chunk=CHUNK_EDGES, fan_i
 class StreamPlan(object):
     """Device copy of one streaming-aggregation schedule (see build_stream_plan)."""
 
-    def __init__(self, sp, n_rec, device):
+    def __init__(self, sp, n_rec, device, prefill_ranges=None):
         self.n_rec = int(n_rec)
         self.rowflags = torch.from_numpy(sp['rowflags'].view(np.int32)).to(device)
         self.chunks = torch.from_numpy(np.ascontiguousarray(sp['chunks'])).to(device)
@@ -118,6 +118,21 @@ class StreamPlan(object):
         self.n_fill = int(sp['fill_rows'].shape[0])
         self.levels = []
         levels = list(sp['levels'])
+        # Rows without records.  A knowledge graph's in-half plane is mostly such rows (few entities are ever an object:
+        # 4.4 M of 4.6 M rows at the Wikidata5M shape): when a contiguous row range is >= 3/4 empty and large, the range
+        # is zero-filled by one memset before the streaming kernel (0.3 ms) instead of one 8-lane work item per row (0.87 ms);
+        # the remaining empty rows ride in the first fix-up launch as before
+        self.prefill = []
+        fr_all = sp['fill_rows'].astype(np.int64)
+        for lo, hi in (prefill_ranges or ()):
+            inside = (fr_all >= lo) & (fr_all < hi)
+            n_in = int(inside.sum())
+            if n_in >= (1 << 18) and n_in >= 0.75 * (hi - lo):
+                self.prefill.append((int(lo), int(hi)))
+                fr_all = fr_all[~inside]
+        if self.prefill:
+            sp = dict(sp, fill_rows=fr_all.astype(np.int32))
+            self.n_fill = int(fr_all.shape[0])
         if self.n_fill:
             # rows without any record ride along in the first fix-up launch as EMPTY final items (out = addend or 0):
             # one launch less per aggregation than a separate kgc_rows_fill
@@ -207,7 +222,7 @@ class GraphPlan(object):
         fe = np.stack([rm_dst, rp_dst[1:]], 1).reshape(-1)
         drows = np.arange(Nd, dtype=np.int64)
         fr = np.stack([drows, drows + Nd], 1).reshape(-1)
-        self.fwd = StreamPlan(build_stream_plan(fb, fe, fr, n2), n2, dev)
+        self.fwd = StreamPlan(build_stream_plan(fb, fe, fr, n2), n2, dev, prefill_ranges=[(0, Nd), (Nd, 2 * Nd)])   # per plane
         self.bwd_src = StreamPlan(build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2), n2, dev)
         self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(Tr, dtype=np.int64), n2), n2, dev)
         self._scratch = {}
@@ -240,6 +255,11 @@ class GraphPlan(object):
         """Launch the streaming kernel through ``level0(sp, out_final, carry)``, fill the rows without records and
         reduce the carry rows of chunk-spanning rows through kgc_rows_reduce (fixed order, deterministic)."""
         carry = self.scratch(tag + 'carry', (max(sp.n_carry, 1), D))
+        if addend is None:
+            for lo, hi in getattr(sp, 'prefill', ()):
+                out_final.view(-1, D)[lo:hi].zero_()
+        elif getattr(sp, 'prefill', ()):
+            raise ValueError('a pre-filled plan cannot take an addend')
         level0(sp, out_final, carry)
         if sp.n_fill:
             _lib.call('kgc_rows_fill', _lib.ptr(sp.fill_rows), sp.n_fill, _lib.ptr(addend), _lib.ptr(out_final), D,
