@@ -305,6 +305,78 @@ def test_partitions_with_uneven_node_counts(world):
         np.testing.assert_allclose(pulled, full[p['owned_nodes']], rtol=1e-10, atol=1e-11)
 
 
+@pytest.mark.parametrize('world', [2, 3, 4, 8])
+def test_hybrid_cut_all_ranks(world):
+    """partition_edges_hybrid on the hub-heavy generator, every rank emulated in numpy (node counts not a multiple of the
+    rank count): every edge and node owned once, edge-balanced without split rows, far fewer remote rows than the
+    destination partition's halo, and the four exchanges (x rows in, partial aggregates to their owners through
+    peer_dst_idx, upstream rows in, partial d_x to their owners through peer_idx) reproduce the global aggregation and the
+    global source-row gradients; the sparse tables (sparse_peer_table) list exactly the rows other ranks contribute to."""
+    from kgc_gcn_b200.partition import partition_edges_hybrid, partition_edges_balanced, sparse_peer_table
+    N, R, E, D = 256 * world + 3, 3, 2000 * world, 4
+    tri = orc.synthetic_triples(N, R, E, 17)
+    g = orc.build_graph(tri, N, R)
+    ei, et = g['edge_index'], g['edge_attr'][0]
+    rng = np.random.default_rng(2)
+    x, ee, rel = rng.standard_normal((N, D)), rng.standard_normal((2 * E, D)), rng.standard_normal((2 * R + 1, D))
+    g_in, g_out = rng.standard_normal((N, D)), rng.standard_normal((N, D))
+    glob = [_agg_numpy(x, rel, ee[h], ei[0, h], ei[1, h], et[h], np.ones(E), N) for h in (slice(0, E), slice(E, 2 * E))]
+    full = np.zeros((N, D))
+    np.add.at(full, ei[0, :E], g_in[ei[1, :E]] * rel[et[:E]] * ee[:E])
+    np.add.at(full, ei[0, E:], g_out[ei[1, E:]] * rel[et[E:]] * ee[E:])
+    parts = [partition_edges_hybrid(ei, et, N, world, r) for r in range(world)]
+    assert sorted(np.concatenate([p['owned_eids'] for p in parts]).tolist()) == list(range(2 * E))
+    assert sorted(np.concatenate([p['owned_nodes'] for p in parts]).tolist()) == list(range(N))
+    assert max(p['owned_eids'].shape[0] for p in parts) <= 1.1 * 2 * E / world
+    halo_dst = sum(partition_edges_balanced(ei, et, N, world, r, hub_fraction=0.1)['n_halo'] for r in range(world))
+    assert sum(p['n_halo'] for p in parts) < 0.5 * halo_dst
+    n_loc = parts[0]['n_loc']
+    rows_max = n_loc + max(p['n_halo'] for p in parts)
+    aggs, dxs = [], []
+    for r, p in enumerate(parts):
+        assert p['n_loc'] == n_loc == -(-N // world) and p['block'] == n_loc and p['n_hub'] == 0
+        assert [int(v) for v in p['n_remote_all']] == [q['n_halo'] for q in parts] and p['n_halo_max'] == rows_max - n_loc
+        rows = n_loc + p['n_halo']
+        comp = np.concatenate([np.arange(r * n_loc, (r + 1) * n_loc), p['halo_rows'].astype(np.int64)])
+        old = np.full(world * n_loc, -1)
+        old[p['newid']] = np.arange(N)
+        valid = old[comp] >= 0
+        assert valid[p['src']].all() and valid[p['dst']].all() and (p['src'] < rows).all() and (p['dst'] < rows).all()
+        xt, gi, go = np.zeros((rows, D)), np.zeros((rows, D)), np.zeros((rows, D))
+        xt[valid], gi[valid], go[valid] = x[old[comp][valid]], g_in[old[comp][valid]], g_out[old[comp][valid]]   # pulled rows
+        n_in, own = p['n_edges_in'], p['owned_eids']
+        agg = np.zeros((2, rows_max, D))
+        agg[0, :rows] = _agg_numpy(xt, rel, ee[own[:n_in]], p['src'][:n_in], p['dst'][:n_in], p['type'][:n_in], np.ones(n_in), rows)
+        agg[1, :rows] = _agg_numpy(xt, rel, ee[own[n_in:]], p['src'][n_in:], p['dst'][n_in:], p['type'][n_in:],
+                                   np.ones(own.shape[0] - n_in), rows)
+        aggs.append(agg)
+        dx = np.zeros((rows_max, D))
+        np.add.at(dx, p['src'][:n_in], gi[p['dst'][:n_in]] * rel[p['type'][:n_in]] * ee[own[:n_in]])
+        np.add.at(dx, p['src'][n_in:], go[p['dst'][n_in:]] * rel[p['type'][n_in:]] * ee[own[n_in:]])
+        dxs.append(dx)
+    for r, p in enumerate(parts):
+        nr = p['n_real']
+        for h in (0, 1):
+            tot = np.zeros((nr, D))
+            for q in range(world):
+                at = p['peer_dst_idx'][q]
+                tot[at >= 0] += aggs[q][h][at[at >= 0]]
+            np.testing.assert_allclose(tot, glob[h][p['owned_nodes']], rtol=1e-10, atol=1e-11)
+        tot = np.zeros((nr, D))
+        for q in range(world):
+            at = p['peer_idx'][q]
+            tot[at >= 0] += dxs[q][at[at >= 0]]
+        np.testing.assert_allclose(tot, full[p['owned_nodes']], rtol=1e-10, atol=1e-11)
+        # the sparse form used on the device: own value in place, only the listed rows get the other ranks' partial rows
+        for table, mine, want in ((p['peer_dst_idx'], aggs[r][0][:nr].copy(), glob[0][p['owned_nodes']]),):
+            rows_l, idx_l = (a.numpy() for a in sparse_peer_table(table, r))
+            assert (idx_l[r] == -1).all() and idx_l.shape == (world, rows_l.shape[0])
+            for q in range(world):
+                at = idx_l[q]
+                mine[rows_l[at >= 0]] += aggs[q][0][at[at >= 0]]
+            np.testing.assert_allclose(mine, want, rtol=1e-10, atol=1e-11)
+
+
 @pytest.mark.parametrize('world', [2, 4, 8])
 def test_balanced_partition_properties(world):
     """Host logic of the edge-balanced partition (partition.py) on the hub-heavy generator of SURVEY.md 8(d): equal node
