@@ -89,6 +89,15 @@ int64_t kgc_csr_type_rows(int64_t n_nodes, int64_t n_types, int64_t type_block_r
 /* out[i] = sum over b < n_blocks (ascending) of in[b * n + i], i < n (n a multiple of 4). */
 int kgc_block_sum(const float* in, int64_t n_blocks, int64_t n, float* out, void* stream);
 
+/* Streaming schedules of K2/K3 on the device.  The sorted records of an aggregation are cut into chunks of `chunk` (32)
+ * records, one warp each; segments [seg_beg[s], seg_end[s]) tile the record array in order (empty segments allowed) and
+ * reduce into output row seg_row[s].  Writes rowflags[p] = row | first-record-of-its-segment << 30 | last << 31,
+ * rec_seg[p] = the segment of record p (scratch), and per chunk c inter[2c] / inter[2c + 1] = 1 when the chunk needs a
+ * head / tail carry row (its first segment began in an earlier chunk and ends here / its last segment continues).
+ * Slot numbers = exclusive prefix sum of inter.  Bit-exact against plan.build_stream_plan (numpy). */
+int kgc_stream_plan_flags(const int32_t* seg_beg, const int32_t* seg_end, const int32_t* seg_row, int64_t n_seg,
+                          int64_t n_rec, int32_t chunk, uint32_t* rowflags, int32_t* rec_seg, int32_t* inter, void* stream);
+
 /* ---- K2: aggregation forward -----------------------------------------------------------------
  * Replaces the gather + MGCNConv.message product + norm + scatter-add of the "in" and "out"
  * propagations (model.py:99-100,111-118) in the aggregate-then-transform order:

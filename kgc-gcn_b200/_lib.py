@@ -24,6 +24,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     'kgc_csr_type_rows': (_i64, [_i64, _i64, _i64]),
     'kgc_block_sum': (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    'kgc_stream_plan_flags': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     'kgc_agg_fwd': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_fill': (ctypes.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
     'kgc_rows_reduce': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),

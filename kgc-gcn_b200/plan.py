@@ -106,13 +106,51 @@ def build_stream_plan(seg_beg, seg_end, seg_row, n_rec, chunk=CHUNK_EDGES, fan_i
             'levels': levels}
 
 
+def build_stream_plan_device(seg_beg, seg_end, seg_row, n_rec, chunk=CHUNK_EDGES, fan_in=CHUNK1):
+    """The same schedule as build_stream_plan with the O(n_rec) part on the GPU (kgc_stream_plan_flags: row + first / last
+    flags per record by binary search over the segment starts, head / tail carry flags per chunk); slot numbers are a prefix
+    sum on the device; only the rows that span chunks (a few per mille of the records) come to the host for the fix-up
+    levels.  ``seg_*``: int32 CUDA tensors.  Returns the build_stream_plan dict with ``rowflags`` / ``chunks`` as CUDA tensors
+    (int32 views) - bit-identical contents (tests/test_gpu_conv.py::test_stream_plan_on_device)."""
+    dev = seg_beg.device
+    n_seg = int(seg_beg.numel())
+    n_chunks = -(-n_rec // chunk) if n_rec else 0
+    rowflags = torch.empty((n_rec,), dtype=torch.int32, device=dev)
+    inter = torch.zeros((2 * n_chunks,), dtype=torch.int32, device=dev)
+    if n_rec:
+        rec_seg = torch.empty((n_rec,), dtype=torch.int32, device=dev)
+        _lib.call('kgc_stream_plan_flags', _lib.ptr(seg_beg), _lib.ptr(seg_end), _lib.ptr(seg_row), n_seg, n_rec, chunk,
+                  _lib.ptr(rowflags), _lib.ptr(rec_seg), _lib.ptr(inter), _lib.stream())
+        del rec_seg
+    slot = torch.cumsum(inter, 0, dtype=torch.int64) - 1
+    slots = torch.where(inter != 0, slot, torch.full_like(slot, -1)).to(torch.int32).view(-1, 2).contiguous()
+    n_carry = int(inter.sum())
+    beg, end = seg_beg.to(torch.int64), seg_end.to(torch.int64)
+    nz = end > beg
+    c_first = torch.div(beg, chunk, rounding_mode='floor')
+    c_last = torch.div(end - 1, chunk, rounding_mode='floor')
+    span = nz & (c_last > c_first)
+    fill_rows = seg_row[~nz].to(torch.int32).cpu().numpy()
+    if bool(span.any()):
+        s_beg = slots[c_first[span], 1].to(torch.int64)
+        s_end = slots[c_last[span], 0].to(torch.int64) + 1
+        host = torch.stack([s_beg, s_end, seg_row[span].to(torch.int64)]).cpu().numpy()
+        levels = build_levels(host[0], host[1], host[2], fan_in, fan_in)
+    else:
+        levels = []
+    return {'rowflags': rowflags, 'chunks': slots, 'n_carry': n_carry, 'fill_rows': fill_rows, 'levels': levels}
+
+
 class StreamPlan(object):
     """Device copy of one streaming-aggregation schedule (see build_stream_plan)."""
 
     def __init__(self, sp, n_rec, device, prefill_ranges=None):
         self.n_rec = int(n_rec)
-        self.rowflags = torch.from_numpy(sp['rowflags'].view(np.int32)).to(device)
-        self.chunks = torch.from_numpy(np.ascontiguousarray(sp['chunks'])).to(device)
+        if torch.is_tensor(sp['rowflags']):                         # built on the device (build_stream_plan_device)
+            self.rowflags, self.chunks = sp['rowflags'], sp['chunks']
+        else:
+            self.rowflags = torch.from_numpy(sp['rowflags'].view(np.int32)).to(device)
+            self.chunks = torch.from_numpy(np.ascontiguousarray(sp['chunks'])).to(device)
         self.n_carry = sp['n_carry']
         self.fill_rows = torch.from_numpy(sp['fill_rows']).to(device)
         self.n_fill = int(sp['fill_rows'].shape[0])
@@ -211,20 +249,37 @@ class GraphPlan(object):
                   p(self.perm_src), p(self.rowptr_src), p(self.rec_src),
                   p(self.perm_type), p(self.rowptr_type), p(self.rec_type), self.type_block_rows, p(ws), ws_bytes, _lib.stream())
         del ws
-        # ---- reduction plans (host integer scheduling over the row pointers)
-        rp_dst = self.rowptr_dst.cpu().numpy().astype(np.int64)
-        rm_dst = self.rowmid_dst.cpu().numpy().astype(np.int64)
-        rp_src = self.rowptr_src.cpu().numpy().astype(np.int64)
-        rp_typ = self.rowptr_type.cpu().numpy().astype(np.int64)
-        # forward: records of dst row i = [rowptr[i], rowmid[i]) (in half, output row i) then [rowmid[i], rowptr[i+1])
-        # (out half, output row Nd + i): 2 * Nd segments in record order
-        fb = np.stack([rp_dst[:-1], rm_dst], 1).reshape(-1)
-        fe = np.stack([rm_dst, rp_dst[1:]], 1).reshape(-1)
-        drows = np.arange(Nd, dtype=np.int64)
-        fr = np.stack([drows, drows + Nd], 1).reshape(-1)
-        self.fwd = StreamPlan(build_stream_plan(fb, fe, fr, n2), n2, dev, prefill_ranges=[(0, Nd), (Nd, 2 * Nd)])   # per plane
-        self.bwd_src = StreamPlan(build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2), n2, dev)
-        self.bwd_rel = StreamPlan(build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(Tr, dtype=np.int64), n2), n2, dev)
+        # ---- reduction plans: the per-record / per-chunk tables are built on the device from the row pointers
+        # (KGC_PLAN_HOST=1: the numpy restatement, kept as the tested reference of the same tables)
+        if os.environ.get('KGC_PLAN_HOST', '0') not in ('', '0'):
+            rp_dst = self.rowptr_dst.cpu().numpy().astype(np.int64)
+            rm_dst = self.rowmid_dst.cpu().numpy().astype(np.int64)
+            rp_src = self.rowptr_src.cpu().numpy().astype(np.int64)
+            rp_typ = self.rowptr_type.cpu().numpy().astype(np.int64)
+            # forward: records of dst row i = [rowptr[i], rowmid[i]) (in half, output row i) then [rowmid[i], rowptr[i+1])
+            # (out half, output row Nd + i): 2 * Nd segments in record order
+            fb = np.stack([rp_dst[:-1], rm_dst], 1).reshape(-1)
+            fe = np.stack([rm_dst, rp_dst[1:]], 1).reshape(-1)
+            drows = np.arange(Nd, dtype=np.int64)
+            fr = np.stack([drows, drows + Nd], 1).reshape(-1)
+            sp_f = build_stream_plan(fb, fe, fr, n2)
+            sp_s = build_stream_plan(rp_src[:-1], rp_src[1:], np.arange(N, dtype=np.int64), n2)
+            sp_r = build_stream_plan(rp_typ[:-1], rp_typ[1:], np.arange(Tr, dtype=np.int64), n2)
+        else:
+            rp, rm = self.rowptr_dst, self.rowmid_dst
+            drows = torch.arange(Nd, dtype=torch.int32, device=dev)
+            fb = torch.stack([rp[:-1], rm], 1).reshape(-1).contiguous()
+            fe = torch.stack([rm, rp[1:]], 1).reshape(-1).contiguous()
+            fr = torch.stack([drows, drows + Nd], 1).reshape(-1).contiguous()
+            sp_f = build_stream_plan_device(fb, fe, fr, n2)
+            del fb, fe, fr
+            sp_s = build_stream_plan_device(self.rowptr_src[:-1].contiguous(), self.rowptr_src[1:].contiguous(),
+                                            torch.arange(N, dtype=torch.int32, device=dev), n2)
+            sp_r = build_stream_plan_device(self.rowptr_type[:-1].contiguous(), self.rowptr_type[1:].contiguous(),
+                                            torch.arange(Tr, dtype=torch.int32, device=dev), n2)
+        self.fwd = StreamPlan(sp_f, n2, dev, prefill_ranges=[(0, Nd), (Nd, 2 * Nd)])     # per plane; no addend in the forward
+        self.bwd_src = StreamPlan(sp_s, n2, dev)
+        self.bwd_rel = StreamPlan(sp_r, n2, dev)
         self._scratch = {}
 
     def side_stream(self):

@@ -168,6 +168,52 @@ def test_csr_build_bit_exact(k):
     np.testing.assert_array_equal(rec[:, 3].view(np.float32), plan.norm.cpu().numpy()[perm])
 
 
+def test_stream_plan_on_device(k, monkeypatch):
+    """kgc_stream_plan_flags + the device-side slot numbering (plan.build_stream_plan_device) against the numpy
+    restatement (plan.build_stream_plan): rowflags, chunk carry slots, carry count, empty rows and fix-up levels bit for
+    bit - random segment sets with empty segments, rows spanning many chunks, a partial last chunk; then whole GraphPlans
+    built both ways."""
+    from kgc_gcn_b200.plan import build_stream_plan, build_stream_plan_device
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        n_seg = int(rng.integers(1, 400))
+        length = rng.integers(0, 6, n_seg) * (rng.random(n_seg) < 0.7)
+        hubs = rng.integers(0, n_seg, 3)
+        length[hubs] += rng.integers(40, 5000, 3)                       # rows that span many chunks (several fix-up levels)
+        if trial == 0:
+            length[:] = 0
+            length[n_seg // 2] = 7
+        end = np.cumsum(length)
+        beg = end - length
+        row = rng.permutation(n_seg + 50)[:n_seg]
+        n_rec = int(end[-1])
+        want = build_stream_plan(beg, end, row, n_rec, fan_in=64)
+        dev_args = [torch.from_numpy(a.astype(np.int32)).cuda() for a in (beg, end, row)]
+        got = build_stream_plan_device(*dev_args, n_rec, fan_in=64)
+        np.testing.assert_array_equal(got['rowflags'].cpu().numpy().view(np.uint32), want['rowflags'])
+        np.testing.assert_array_equal(got['chunks'].cpu().numpy(), want['chunks'])
+        assert got['n_carry'] == want['n_carry']
+        np.testing.assert_array_equal(got['fill_rows'], want['fill_rows'])
+        assert len(got['levels']) == len(want['levels'])
+        for (ia, pa), (ib, pb) in zip(got['levels'], want['levels']):
+            np.testing.assert_array_equal(ia, ib)
+            assert pa == pb
+    N, R, E = 3000, 7, 40000
+    tri = orc.synthetic_triples(N, R, E, 5)
+    g = orc.build_graph(tri, N, R)
+    ei, et = torch.from_numpy(g['edge_index']).cuda(), torch.from_numpy(g['edge_attr'][0]).cuda()
+    plans = {}
+    for host in ('1', '0'):
+        monkeypatch.setenv('KGC_PLAN_HOST', host)
+        plans[host] = k.GraphPlan(ei, et, N, 2 * R + 1, type_block_rows=512)
+    for name in ('fwd', 'bwd_src', 'bwd_rel'):
+        a, b = getattr(plans['1'], name), getattr(plans['0'], name)
+        assert torch.equal(a.rowflags, b.rowflags) and torch.equal(a.chunks, b.chunks) and a.n_carry == b.n_carry
+        assert len(a.levels) == len(b.levels) and a.prefill == b.prefill
+        for la, lb in zip(a.levels, b.levels):
+            assert torch.equal(la[0], lb[0]) and la[1:] == lb[1:]
+
+
 def test_type_sort_blocked_by_subject(k, monkeypatch):
     """The d_rel pass blocked by subject row (kgc_csr_build type_block_rows): the permutation is the stable sort by
     (block of the subject, type) bit for bit; the layer's outputs and gradients with the blocked pass equal the plain
