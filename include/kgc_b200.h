@@ -438,6 +438,19 @@ int kgc_label_mask_build(const int64_t* qid, int64_t B, const int64_t* triples, 
 int kgc_bce_1n_bwd_logit(const float* pred, int64_t ld_p, const uint32_t* mask, int64_t n_ent, int32_t B, int32_t ldt,
                          float pos, float add, float* d_logitT, float* d_bias, double* loss_partial, float* loss,
                          void* stream);
+/* Entity-major form of the same three steps (round 2): kgc_score_1n_fwd_t stores predT[n, b] (rows of ldt >= B floats,
+ * ldt % 4 == 0) - the scorer's natural orientation; kgc_label_mask_t_build keeps the positives as bits per ENTITY
+ * (mask_t [n_entity, ceil(B / 32)] uint32, zeroed by the call); kgc_bce_1n_bwd_logit_t makes one row-wise pass that
+ * OVERWRITES pred_t with the transposed logit gradient (pad columns [B, ldt) = 0), writes d_bias and the mean loss
+ * (loss_partial: kgc_bce_1n_t_blocks(n_ent) doubles).  [B, N] row pitches of 4 N bytes made the batch-major kernels move
+ * their 2.35 GB in 128-byte pieces, one per DRAM page (3.4 ms each at N = 4.6 M). */
+int kgc_score_1n_fwd_t(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                       const float* bias, float* pred_t, int64_t ld_t, void* stream);
+int64_t kgc_bce_1n_t_blocks(int64_t n_ent);
+int kgc_label_mask_t_build(const int64_t* qid, int64_t B, const int64_t* ptr, const int32_t* idx, int64_t n_entity,
+                           uint32_t* mask_t, void* stream);
+int kgc_bce_1n_bwd_logit_t(float* pred_t, const uint32_t* mask_t, int64_t n_ent, int32_t B, int32_t ldt, float pos, float add,
+                           float* d_bias, double* loss_partial, float* loss, void* stream);
 
 /* ---- K6: fused 1-N scoring + filter + rank (tcgen05 / TMA) --------------------------------------------
  * Replaces model.py:177-178 (X @ all_ent^T + bias) and main.py:122-126 (filter, rank) without

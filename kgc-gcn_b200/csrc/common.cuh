@@ -90,4 +90,15 @@ __device__ __forceinline__ float4 philox_mask4(int64_t idx4, uint32_t plane, uin
                      r.w >= drop_thr ? s : 0.f);
 }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it needs a context current on the calling thread.  A thread that has
+// made no runtime call yet (autograd's backward thread when the first thing it runs is one of the GEMM launchers) has
+// none and the encode fails with CUDA_ERROR_INVALID_CONTEXT (201); one runtime call per thread binds the primary context.
+inline void ensure_thread_context() {
+  static thread_local bool done = false;
+  if (!done) {
+    cudaFree(nullptr);
+    done = true;
+  }
+}
+
 }  // namespace kgc

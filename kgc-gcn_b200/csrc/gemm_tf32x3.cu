@@ -675,6 +675,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int encode_fn(EncodeTiledFn* out) {
+  ensure_thread_context();
   static EncodeTiledFn cached = nullptr;
   if (!cached) {
     void* fn = nullptr;
@@ -1287,6 +1288,14 @@ static int64_t tn_slabs(int64_t M, int n_prob) {
   const int64_t need = ceil_div(M, tn_max_slab_rows());
   if (slabs < need) slabs = ceil_div(need, per_wave) * per_wave;      // whole waves
   return slabs < 1 ? 1 : slabs;
+}
+
+// Entity-major form for the fused loss: predT[n, b] = sigmoid(E[n, :] . X[b, :] + bias[n]), rows of ld_t >= B floats - the
+// kernel's natural orientation (contiguous 128-byte row pieces 4 B bytes apart instead of 4 N bytes apart)
+extern "C" int kgc_score_1n_fwd_t(const float* ent, int64_t n_ent, int32_t D, int64_t ld_ent, const float* packed_x, int32_t B,
+                                  const float* bias, float* pred_t, int64_t ld_t, void* stream) {
+  KGC_REQUIRE(bias != nullptr, "bias is required");
+  return launch_gemm_nt(1, &ent, n_ent, D, ld_ent, &packed_x, B, &pred_t, ld_t, bias, 1, 0, 0, stream);
 }
 
 // The same product WITHOUT the sigmoid: logit[b, n] = X[b, :] . E[n, :] + bias[n] (fp32-grade, 3xTF32) - the exact-mode

@@ -491,6 +491,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int get_encode_fn(EncodeTiledFn* out) {
+  ensure_thread_context();
   static EncodeTiledFn cached = nullptr;
   if (!cached) {
     void* fn = nullptr;

@@ -95,20 +95,21 @@ class _Score1NBCE(torch.autograd.Function):
         N = int(ent.shape[0])
         if int(qid.numel()) != B:
             raise ValueError('qid has {} entries for {} queries'.format(int(qid.numel()), B))
-        ldp, ldt = (N + 3) // 4 * 4, (B + 3) // 4 * 4
+        ldt = (B + 3) // 4 * 4
         p, dev = _lib.ptr, x.device
         packed = torch.empty((int(_lib.lib().kgc_gemm_packed_b_bytes(B, D)) // 4,), dtype=torch.float32, device=dev)
-        pred = torch.empty((B, ldp), dtype=torch.float32, device=dev)
-        _lib.call('kgc_gemm_pack_b', p(x), x.stride(1), x.stride(0), B, D, p(packed), _lib.stream())
-        _lib.call('kgc_score_1n_fwd', p(ent), N, D, ent.stride(0), p(packed), B, p(bias_), p(pred), ldp, _lib.stream())
-        words = int(_lib.lib().kgc_label_mask_words(N))
-        mask = torch.empty((B, words), dtype=torch.int32, device=dev)            # uint32 bits; zeroed by the call
-        _lib.call('kgc_label_mask_build', p(qid), B, None, p(ptr), p(idx), N, p(mask), None, _lib.stream())
+        # entity-major throughout: the scorer stores predT [N, ldt] (its natural orientation), the positives are bits per
+        # entity, and the loss pass overwrites predT with the logit gradient in place (the [N, ldt] operand of both
+        # gradient GEMMs) - no [B, N]-pitched buffer, no transpose
         d_logit_t = torch.empty((N, ldt), dtype=torch.float32, device=dev)
+        _lib.call('kgc_gemm_pack_b', p(x), x.stride(1), x.stride(0), B, D, p(packed), _lib.stream())
+        _lib.call('kgc_score_1n_fwd_t', p(ent), N, D, ent.stride(0), p(packed), B, p(bias_), p(d_logit_t), ldt, _lib.stream())
+        mask_t = torch.empty((N, (B + 31) // 32), dtype=torch.int32, device=dev)          # uint32 bits; zeroed by the call
+        _lib.call('kgc_label_mask_t_build', p(qid), B, p(ptr), p(idx), N, p(mask_t), _lib.stream())
         d_bias = torch.empty((N,), dtype=torch.float32, device=dev)
-        partial = torch.empty((words,), dtype=torch.float64, device=dev)
+        partial = torch.empty((int(_lib.lib().kgc_bce_1n_t_blocks(N)),), dtype=torch.float64, device=dev)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
-        _lib.call('kgc_bce_1n_bwd_logit', p(pred), ldp, p(mask), N, B, ldt, float(pos), float(add), p(d_logit_t), p(d_bias),
+        _lib.call('kgc_bce_1n_bwd_logit_t', p(d_logit_t), p(mask_t), N, B, ldt, float(pos), float(add), p(d_bias),
                   p(partial), p(loss), _lib.stream())
         ctx.save_for_backward(x, ent, d_logit_t, d_bias)
         return loss[0]

@@ -327,3 +327,27 @@ def test_checkpoint_round_trip_from_the_device(toy, tmp_path, monkeypatch):
     assert s1.keys() == s2.keys()
     for i in s1:
         assert torch.equal(s1[i]['exp_avg'].cpu(), s2[i]['exp_avg'].cpu()) and torch.equal(s1[i]['exp_avg_sq'].cpu(), s2[i]['exp_avg_sq'].cpu())
+
+
+def test_tensor_map_encode_on_a_thread_without_a_context():
+    """cuTensorMapEncodeTiled is a driver entry point: autograd's backward thread has no current context when the first
+    thing it runs is one of the GEMM launchers (CUDA_ERROR_INVALID_CONTEXT, seen in a training step whose backward starts
+    with the scorer's gradient GEMM).  Fresh process: forward on the main thread, backward of the tensor-core fc layer
+    (two tensor-map encodes) as the backward thread's first CUDA work."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ('import sys, torch\n'
+            'sys.path.insert(0, %r)\n'
+            'import kgc_gcn_b200 as k\n'
+            'x = torch.randn(64, 4096, device="cuda", requires_grad=True)\n'
+            'w = torch.randn(200, 4096, device="cuda", requires_grad=True)\n'
+            'assert k.linear_tc_supported(x, w)\n'
+            'y = k.linear_tc(x, w)\n'
+            'y.backward(torch.ones_like(y))\n'
+            'torch.cuda.synchronize()\n'
+            'ref = torch.ones(64, 200, device="cuda") @ w.detach()\n'
+            'assert float((x.grad - ref).abs().max()) < 1e-3 * float(ref.abs().max())\n'
+            'print("ENCODE_OK")\n') % root
+    p = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and 'ENCODE_OK' in p.stdout, p.stdout[-3000:]

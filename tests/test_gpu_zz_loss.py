@@ -79,6 +79,31 @@ def test_sparse_bce_kernels_match_oracle(B, N, smooth):
     assert float((d_logit_t[:, :B].double() - o_dl.t()).abs().max()) <= 2e-6 * scale
     assert float((d_bias.double() - o_db).abs().max()) <= 2e-6 * scale * max(1.0, B ** 0.5)
     assert float(d_logit_t[:, B:].abs().sum()) == 0.0
+    # ---- the entity-major kernels (round 2): bits per entity, the loss pass overwrites predT [N, ldt] in place
+    outs_t = []
+    for _ in range(2):
+        mask_t = torch.full((N, (B + 31) // 32), -1, dtype=torch.int32, **dev)       # the call zeroes it
+        buf = torch.full((N, ldt), float('nan'), **dev)
+        buf[:, :B] = pred[:, :N].t()
+        d_bias_t = torch.full((N,), float('nan'), **dev)
+        partial_t = torch.empty((int(L.lib().kgc_bce_1n_t_blocks(N)),), dtype=torch.float64, **dev)
+        loss_t = torch.empty((1,), **dev)
+        L.call('kgc_label_mask_t_build', p(qid_d), B, p(ptr_d), p(idx_d), N, p(mask_t), L.stream())
+        L.call('kgc_bce_1n_bwd_logit_t', p(buf), p(mask_t), N, B, ldt, pos, add, p(d_bias_t), p(partial_t), p(loss_t), L.stream())
+        torch.cuda.synchronize()
+        outs_t.append((mask_t.cpu(), buf.cpu(), d_bias_t.cpu(), loss_t.cpu()))
+    for a, b in zip(*outs_t):
+        assert torch.equal(a, b)
+    mask_t, buf, d_bias_t, loss_t = outs_t[0]
+    bits = orc.label_mask(ptr, idx, qid, N)                                          # [B, words] bits over entities
+    dense = ((bits[:, np.arange(N) >> 5] >> (np.arange(N) & 31).astype(np.uint32)) & 1).astype(bool)     # [B, N]
+    got_t = mask_t.numpy().view(np.uint32)
+    dense_t = ((got_t[:, np.arange(B) >> 5] >> (np.arange(B) & 31).astype(np.uint32)) & 1).astype(bool)  # [N, B]
+    assert np.array_equal(dense_t, dense.T)
+    assert abs(float(loss_t) - float(o_loss)) <= 2e-6 * abs(float(o_loss))
+    assert torch.equal(buf[:, :B], d_logit_t[:, :B])                 # the same per-element arithmetic, bit for bit
+    assert float(buf[:, B:].abs().sum()) == 0.0
+    assert float((d_bias_t.double() - o_db).abs().max()) <= 2e-6 * scale * max(1.0, B ** 0.5)
 
 
 def _params(**kw):

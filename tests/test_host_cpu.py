@@ -493,3 +493,20 @@ def test_checkpoint_interchanges_with_the_reference(tmp_path):
     m, o = fresh()
     assert k.load_checkpoint(os.path.join(d2, 'best.ckpt'), m, o) == {'mrr': 0.25}
     same(m, o)
+
+
+def test_rows_and_table_gradient_matches_autograd():
+    """model._RowsAndTable: (table[idx], table) whose backward adds the rows' gradient INTO the dense table gradient - same
+    gradients as index_select + plain use of the table, with duplicate indices, with and without a dense gradient."""
+    from kgc_gcn_b200.model import _RowsAndTable
+    torch.manual_seed(0)
+    t = torch.randn(50, 8, dtype=torch.float64, requires_grad=True)
+    idx = torch.tensor([3, 7, 3, 49, 0, 7, 7])
+    w1, w2 = torch.randn(7, 8, dtype=torch.float64), torch.randn(50, 8, dtype=torch.float64)
+    for use_table in (True, False):
+        r, tt = _RowsAndTable.apply(t, idx)
+        ((r * w1).sum() + ((tt * w2).sum() if use_table else 0)).backward()
+        got, t.grad = t.grad.clone(), None
+        ((t.index_select(0, idx) * w1).sum() + ((t * w2).sum() if use_table else 0)).backward()
+        want, t.grad = t.grad.clone(), None
+        assert torch.allclose(got, want, rtol=0, atol=1e-14)
