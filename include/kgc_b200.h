@@ -175,8 +175,12 @@ int kgc_colstats_finalize(const double* partials, int64_t n_blocks, int64_t n_ro
                           double* sums, float* stats, void* stream);
 int kgc_colsum_finalize2(const double* partials, int64_t n_blocks, int32_t Dout, double* sums, float* sums32,
                          void* stream);
+/* out_seed != NULL and out_drop_p > 0: dropout of the OUTPUT in the same pass (MGCN.forward's F.dropout(all_ent, gcn_drop),
+ * model.py:34): Philox stream of *out_seed, plane 2 (kgc_dropout_mask(seed, 2, p) shows the mask), kept values x 1/(1-p);
+ * the keep flags go to out_keep [n_rows, kgc_keep_pitch()] (low nibble of byte c = columns 4c..4c+3) for the backward. */
 int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
-                   int64_t n_rows, int32_t Dout, float* all_ent, void* stream);
+                   int64_t n_rows, int32_t Dout, float* all_ent, const int64_t* out_seed, float out_drop_p,
+                   uint8_t* out_keep, void* stream);
 /* Backward of the tail.  all_ent = tanh(BatchNorm(pre)) is recomputed from pre (one plane less to read).
  * kgc_tail_bwd_reduce: partial column sums of dz = g_ent*(1-all_ent^2) and dz*xhat; kgc_colsum_finalize -> sums[0] =
  * sum dz (= d beta), sums[1] = sum dz*xhat (= d gamma), all-reduced by a partitioned caller; kgc_tail_bwd_apply:
@@ -184,11 +188,14 @@ int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, con
  * transform's upstream gradient as it is, the in / out halves' after the keep flags x 1/(1-p): applied by the GEMMs
  * (d_res2 NULL), or written here as two more planes d_res2[2,n_rows,Dout] from kgc_tail_fwd's keep flags (keep NULL: no
  * dropout, both planes = d_out). */
+/* out_keep != NULL: the forward dropped its output (kgc_tail_apply): g_ent is taken x keep flag x out_scale = 1/(1-p). */
 int kgc_tail_bwd_reduce(const float* g_ent, const float* pre, const float* stats, const float* gamma, const float* beta,
-                        int64_t n_rows, int32_t Dout, double* partials, void* stream);
+                        int64_t n_rows, int32_t Dout, double* partials, const uint8_t* out_keep, float out_scale,
+                        void* stream);
 int kgc_tail_bwd_apply(const float* g_ent, const float* pre, const float* stats, const float* gamma, const float* beta,
                        const double* sums, int32_t training, int64_t n_rows, int64_t n_rows_global, int32_t Dout,
-                       float* d_out, const uint8_t* keep, float keep_scale, float* d_res2, void* stream);
+                       float* d_out, const uint8_t* keep, float keep_scale, float* d_res2, const uint8_t* out_keep,
+                       float out_scale, void* stream);
 
 /* ---- K0: parameter-side work of one layer step, batched --------------------------------------------------
  * kgc_conv_prep (forward): relp = cat(rels, loop_rel) (model.py:86); all_rel = relp @ w_rel (model.py:107, all

@@ -304,7 +304,7 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, rels, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, bias,
                 plan, mask_in, mask_out, keep_scale, training, running_mean, running_var, eps, coll, seed, drop_p,
-                bn_track=None):
+                bn_track=None, out_drop=None):
         # x: this rank's node rows [Nl, D] (all rows on one GPU); ee: the rows of the edges this rank owns
         Nl, D = x.shape
         Dout = w_in.shape[1]
@@ -414,21 +414,26 @@ class _ConvFn(torch.autograd.Function):
                 coll.all_reduce(sums, 'bn_f')                        # BatchNorm statistics over ALL node rows
             _lib.call('kgc_colstats_from_sums', p(sums), n_global, Dout, float(eps), int(training), p(running_mean),
                       p(running_var), p(stats), st())
-        _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), st())
+        # out_drop = (p, seed): MGCN.encode's F.dropout(all_ent, gcn_drop) (model.py:34) in the same pass
+        out_p, out_seed = out_drop if out_drop is not None else (0.0, None)
+        out_keep = torch.empty((Nl, int(_lib.lib().kgc_keep_pitch())), dtype=torch.uint8, device=x.device) if out_seed is not None else None
+        _lib.call('kgc_tail_apply', p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(all_ent), p(out_seed), float(out_p),
+                  p(out_keep), st())
+        ctx.out_scale = 1.0 / (1.0 - float(out_p)) if out_seed is not None else 1.0
         all_rel = all_rel_pad[:-1]
 
         ctx.plan, ctx.training, ctx.keep_scale, ctx.has_bias, ctx.coll = plan, bool(training), float(keep_scale), \
             bias is not None, coll
         ctx.drop_p = float(drop_p)
         ctx.save_for_backward(x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, agg, pre,
-                              all_ent, stats, keep, packed_b)
+                              all_ent, stats, keep, packed_b, out_keep)
         ctx.mark_non_differentiable(stats)
         return all_ent, all_rel, stats
 
     @staticmethod
     def backward(ctx, g_ent, g_rel, _g_stats):
         (x, x_full, relp, ee, w_in, w_out, w_loop, w_rel, loop_rel, loop_edge, gamma, beta, agg, pre, all_ent, stats, keep,
-         packed_b) = ctx.saved_tensors
+         packed_b, out_keep) = ctx.saved_tensors
         plan, coll = ctx.plan, ctx.coll
         Nl, D = x.shape
         n_global = Nl if coll is None else coll.n_global      # BatchNorm rows (real nodes of all ranks)
@@ -448,7 +453,8 @@ class _ConvFn(torch.autograd.Function):
         partials = plan.scratch('colpart', (nb, 2, Dout), torch.float64)
         sums = torch.empty((2, Dout), dtype=torch.float64, device=dev)
         d_out = plan.scratch('d_out', (Nl, Dout))          # ONE upstream plane (d out / 3); the GEMMs apply the keep flags
-        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(partials), st())
+        _lib.call('kgc_tail_bwd_reduce', p(g_ent), p(pre), p(stats), p(gamma), p(beta), Nl, Dout, p(partials), p(out_keep),
+                  ctx.out_scale, st())
         if coll is None:
             sums32 = torch.empty((2, Dout), dtype=torch.float32, device=dev)
             _lib.call('kgc_colsum_finalize2', p(partials), nb, Dout, p(sums), p(sums32), st())
@@ -465,7 +471,7 @@ class _ConvFn(torch.autograd.Function):
         three = (3 * Nl * Dout * 4 > (48 << 20)) if mode not in ('1', '3') else mode == '3'
         d_res2 = plan.scratch('d_res2', (2, Nl, Dout)) if three else None
         _lib.call('kgc_tail_bwd_apply', p(g_ent), p(pre), p(stats), p(gamma), p(beta), p(sums), int(ctx.training), Nl,
-                  n_global, Dout, p(d_out), p(keep), ctx.keep_scale, p(d_res2), st())
+                  n_global, Dout, p(d_out), p(keep), ctx.keep_scale, p(d_res2), p(out_keep), ctx.out_scale, st())
         ups = [d_res2[0], d_res2[1], d_out] if three else [d_out, d_out, d_out]
         gkeep = None if three else keep
         d_beta, d_gamma = sums32[0], sums32[1]
@@ -564,7 +570,7 @@ class _ConvFn(torch.autograd.Function):
                   p(relp), p(w_rel.detach().contiguous()), p(g_rel_c), p(d_relp), T - 1, D, Dout, p(d_w_loop), p(d_loop_rel),
                   p(d_loop_edge), p(d_rels), p(d_w_rel), p(rel_add), st())
         return (d_x, d_rels, d_ee, d_w_in, d_w_out, d_w_loop, d_w_rel, d_loop_rel, d_loop_edge, d_gamma, d_beta, d_bias,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class MGCNConv(nn.Module):
@@ -626,6 +632,20 @@ class MGCNConv(nn.Module):
         self._drop_seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)     # new stream every step (device op: graph-capturable)
         return None, None, 1.0 / (1.0 - p), self._drop_seed.clone(), p
 
+    def _out_drop_cfg(self, p, seed):
+        """(p, seed) of the output dropout of this forward, or None.  It shares the tail's Philox seed (plane 2); when the
+        tail itself does not draw (p = 0 or injected masks) the seed counter is advanced here."""
+        if not self.training or not p or p <= 0.0:
+            return None
+        if seed is None:
+            if not self._drop_seeded:
+                self._drop_seed.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+                self._drop_seeded = True
+            self._drop_seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+            seed = self._drop_seed.clone()
+        self._last_out_seed = seed
+        return float(p), seed
+
     def dropout_masks(self, seed, n_rows):
         """The two keep masks [n_rows, Dout] the tail kernels derive from ``seed`` (int64 device tensor): for tests."""
         out = []
@@ -635,8 +655,9 @@ class MGCNConv(nn.Module):
             out.append(m)
         return out
 
-    def forward(self, x, edge_index, edge_type, edge_norm, edge_embs, rels_embs, size=None):
-        # edge_norm and size are accepted and ignored, exactly as the reference does (model.py:82)
+    def forward(self, x, edge_index, edge_type, edge_norm, edge_embs, rels_embs, size=None, _out_drop=0.0):
+        # edge_norm and size are accepted and ignored, exactly as the reference does (model.py:82).
+        # _out_drop (private, used by MGCN.encode): dropout probability applied to all_ent inside the tail kernel
         num_ent = x.size(0)
         plan = get_plan(edge_index, edge_type, num_ent, rels_embs.size(0) + 1)
         m_in, m_out, keep_scale, seed, drop_p = self._masks(num_ent, x.device)
@@ -650,7 +671,7 @@ class MGCNConv(nn.Module):
             x, rels_embs, edge_embs, self.in_weight, self.out_weight, self.loop_weight, self.rels_weight,
             self.loop_rel, self.loop_edge, bn.weight, bn.bias, self.bias, plan, m_in, m_out, keep_scale,
             use_batch_stats, bn.running_mean, bn.running_var, bn.eps, None, seed, drop_p,
-            (float(bn.momentum), bn.num_batches_tracked) if fused else None)
+            (float(bn.momentum), bn.num_batches_tracked) if fused else None, self._out_drop_cfg(_out_drop, seed))
         if track and not fused:
             self._update_running_stats(stats, num_ent)
         return all_ent, all_rel

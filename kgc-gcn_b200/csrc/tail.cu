@@ -31,6 +31,10 @@ __device__ __forceinline__ uint32_t nibble(const float4& m) {
   return (m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u);
 }
 
+__device__ __forceinline__ float4 keep4(const float4& g, uint32_t nb, float s) {
+  return make_float4((nb & 1u) ? g.x * s : 0.f, (nb & 2u) ? g.y * s : 0.f, (nb & 4u) ? g.z * s : 0.f, (nb & 8u) ? g.w * s : 0.f);
+}
+
 struct DropCfg {
   const uint8_t* mask_in;     // injected keep masks (tests / replay of recorded draws) ...
   const uint8_t* mask_out;
@@ -212,9 +216,19 @@ __global__ void colstats_from_sums_kernel(const double* __restrict__ sums, int64
   stats[2 * Dout + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Optional dropout of the OUTPUT (MGCN.encode applies F.dropout(all_ent, gcn_drop) right after the layer, model.py:34: a
+// read + write + mask pass over [N, Dout] each way): the same Philox stream as the tail's own masks, plane 2; the keep
+// flags go to out_keep (low nibble of byte c of a row = columns 4c..4c+3) for the backward.
+struct OutDrop {
+  const int64_t* seed;        // NULL: no output dropout
+  uint32_t drop_thr;
+  float keep_scale;
+  uint8_t* keep;              // written by the forward / read by the backward
+};
+
 __global__ void __launch_bounds__(kThreads)
 tail_apply_kernel(const float4* __restrict__ pre, const float4* __restrict__ stats, const float4* __restrict__ gamma,
-                  const float4* __restrict__ beta, int64_t n4, int Do4, float4* __restrict__ all_ent) {
+                  const float4* __restrict__ beta, int64_t n4, int Do4, float4* __restrict__ all_ent, const OutDrop od) {
   const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)(i % Do4);
@@ -225,13 +239,18 @@ tail_apply_kernel(const float4* __restrict__ pre, const float4* __restrict__ sta
   o.y = tanhf((v.y - m.y) * rs.y * ga.y + be.y);
   o.z = tanhf((v.z - m.z) * rs.z * ga.z + be.z);
   o.w = tanhf((v.w - m.w) * rs.w * ga.w + be.w);
+  if (od.seed != nullptr) {
+    const float4 k = philox_mask4(i, 2u, (uint64_t)__ldg(od.seed), od.drop_thr, od.keep_scale);
+    o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+    od.keep[(i / Do4) * kKeepPitch + c] = (uint8_t)nibble(k);
+  }
   all_ent[i] = o;
 }
 
 __global__ void __launch_bounds__(kThreads)
 tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ pre, const float4* __restrict__ stats,
                        const float4* __restrict__ gamma, const float4* __restrict__ beta, int64_t n_rows, int Do4,
-                       double* __restrict__ partials) {
+                       double* __restrict__ partials, const uint8_t* __restrict__ out_keep, float out_scale) {
   extern __shared__ double4 sm[];
   const int RL = kThreads / Do4;
   const int rl = threadIdx.x / Do4, c = threadIdx.x % Do4;
@@ -242,7 +261,9 @@ tail_bwd_reduce_kernel(const float4* __restrict__ g_ent, const float4* __restric
     const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
     for (int64_t r = s.row_beg + rl; r < s.row_end; r += RL) {
       const int64_t i = r * Do4 + c;
-      const float4 g = __ldg(g_ent + i), v = __ldg(pre + i);
+      float4 g = __ldg(g_ent + i);
+      const float4 v = __ldg(pre + i);
+      if (out_keep != nullptr) g = keep4(g, out_keep[r * kKeepPitch + c], out_scale);
       const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
       const float4 t = make_float4(tanhf(xh.x * ga.x + be.x), tanhf(xh.y * ga.y + be.y), tanhf(xh.z * ga.z + be.z),
                                    tanhf(xh.w * ga.w + be.w));
@@ -262,12 +283,15 @@ __global__ void __launch_bounds__(kThreads)
 tail_bwd_apply_kernel(const float4* __restrict__ g_ent, const float4* __restrict__ pre, const float4* __restrict__ stats,
                       const float4* __restrict__ gamma, const float4* __restrict__ beta, const double* __restrict__ sums,
                       int training, int64_t n_rows, int64_t n_rows_global, int Do4, float4* __restrict__ d_out,
-                      const uint8_t* __restrict__ keep, float keep_scale, float4* __restrict__ d_res2) {
+                      const uint8_t* __restrict__ keep, float keep_scale, float4* __restrict__ d_res2,
+                      const uint8_t* __restrict__ out_keep, float out_scale) {
   const int64_t n4 = n_rows * (int64_t)Do4;
   const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)(i % Do4);
-  const float4 g = __ldg(g_ent + i), v = __ldg(pre + i);
+  float4 g = __ldg(g_ent + i);
+  const float4 v = __ldg(pre + i);
+  if (out_keep != nullptr) g = keep4(g, out_keep[(i / Do4) * kKeepPitch + c], out_scale);
   const float4 m = __ldg(stats + c), rs = __ldg(stats + 2 * Do4 + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
   const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
   const float4 t = make_float4(tanhf(xh.x * ga.x + be.x), tanhf(xh.y * ga.y + be.y), tanhf(xh.z * ga.z + be.z),
@@ -407,24 +431,34 @@ extern "C" int kgc_colstats_from_sums(const double* sums, int64_t n_rows, int32_
 }
 
 extern "C" int kgc_tail_apply(const float* pre, const float* stats, const float* gamma, const float* beta,
-                              int64_t n_rows, int32_t Dout, float* all_ent, void* stream) {
+                              int64_t n_rows, int32_t Dout, float* all_ent, const int64_t* out_seed, float out_drop_p,
+                              uint8_t* out_keep, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const int64_t n4 = n_rows * Do4;
+  OutDrop od;
+  od.seed = (out_seed != nullptr && out_drop_p > 0.f) ? out_seed : nullptr;
+  KGC_REQUIRE(od.seed == nullptr || (out_keep != nullptr && Dout <= 4 * kKeepPitch && out_drop_p < 1.f),
+              "output dropout needs a keep-flag buffer, Dout <= 256 and p < 1");
+  const DropCfg d = make_drop(nullptr, nullptr, out_seed, out_drop_p, 1.f);
+  od.drop_thr = d.drop_thr;
+  od.keep_scale = 1.f / (1.f - out_drop_p);
+  od.keep = out_keep;
   tail_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
-      (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, n4, Do4, (float4*)all_ent);
+      (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, n4, Do4, (float4*)all_ent, od);
   KGC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* pre, const float* stats, const float* gamma,
-                                   const float* beta, int64_t n_rows, int32_t Dout, double* partials, void* stream) {
+                                   const float* beta, int64_t n_rows, int32_t Dout, double* partials, const uint8_t* out_keep,
+                                   float out_scale, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const size_t smem = partial_smem(Do4);   // <= 16 KB
   tail_bwd_reduce_kernel<<<(unsigned)kgc_tail_num_blocks(n_rows), kThreads, smem, as_stream(stream)>>>(
       (const float4*)g_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, n_rows, Do4,
-      partials);
+      partials, out_keep, out_scale);
   KGC_LAUNCH_CHECK();
   return 0;
 }
@@ -432,13 +466,13 @@ extern "C" int kgc_tail_bwd_reduce(const float* g_ent, const float* pre, const f
 extern "C" int kgc_tail_bwd_apply(const float* g_ent, const float* pre, const float* stats, const float* gamma,
                                   const float* beta, const double* sums, int32_t training, int64_t n_rows,
                                   int64_t n_rows_global, int32_t Dout, float* d_out, const uint8_t* keep, float keep_scale,
-                                  float* d_res2, void* stream) {
+                                  float* d_res2, const uint8_t* out_keep, float out_scale, void* stream) {
   KGC_REQUIRE(check_dout(Dout) == 0, "Dout must be a multiple of 4 and <= 1024");
   const int Do4 = Dout / 4;
   const int64_t n4 = n_rows * Do4;
   tail_bwd_apply_kernel<<<(unsigned)ceil_div(n4, kThreads), kThreads, 0, as_stream(stream)>>>(
       (const float4*)g_ent, (const float4*)pre, (const float4*)stats, (const float4*)gamma, (const float4*)beta, sums,
-      training, n_rows, n_rows_global, Do4, (float4*)d_out, keep, keep_scale, (float4*)d_res2);
+      training, n_rows, n_rows_global, Do4, (float4*)d_out, keep, keep_scale, (float4*)d_res2, out_keep, out_scale);
   KGC_LAUNCH_CHECK();
   return 0;
 }

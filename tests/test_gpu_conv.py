@@ -168,6 +168,42 @@ def test_csr_build_bit_exact(k):
     np.testing.assert_array_equal(rec[:, 3].view(np.float32), plan.norm.cpu().numpy()[perm])
 
 
+def test_output_dropout_inside_the_tail(k):
+    """MGCNConv(..., _out_drop=p) (what MGCN.encode uses for F.dropout(all_ent, gcn_drop), model.py:34): the output equals
+    the undropped output x the Philox mask of plane 2 x 1/(1-p) bit for bit, and every gradient equals autograd through
+    that explicit product (the layer's own dropout replayed with injected masks so both runs draw the same)."""
+    z, masks = synth_case(1200, 4, 7000, 100, 200, 47), None
+    z = z[0]
+    d_in, d_out, R = z['x'].shape[1], z['g_ent'].shape[1], int(z['R'])
+    rng = np.random.default_rng(3)
+    m_in = torch.from_numpy((rng.random((z['x'].shape[0], d_out)) > 0.1).astype(np.uint8))
+    m_out = torch.from_numpy((rng.random((z['x'].shape[0], d_out)) > 0.1).astype(np.uint8))
+    p_out = 0.3
+    res = {}
+    for fused in (True, False):
+        conv = make_conv(k, z, d_in, d_out, R, 0.1).train()
+        conv.set_dropout_masks(m_in, m_out)
+        x = torch.from_numpy(z['x']).cuda().requires_grad_(True)
+        ee = torch.from_numpy(z['edge_embs']).cuda().requires_grad_(True)
+        rl = torch.from_numpy(z['rels']).cuda().requires_grad_(True)
+        ei, et = torch.from_numpy(z['edge_index']).cuda(), torch.from_numpy(z['edge_type']).cuda()
+        g_ent, g_rel = torch.from_numpy(z['g_ent']).cuda(), torch.from_numpy(z['g_rel']).cuda()
+        if fused:
+            ent, rel = conv(x, ei, et, None, ee, rl, _out_drop=p_out)
+            seed = conv._last_out_seed.clone()
+        else:
+            ent0, rel = conv(x, ei, et, None, ee, rl)
+            mask = torch.empty(ent0.shape, dtype=torch.uint8, device='cuda')
+            k._lib.call('kgc_dropout_mask', k._lib.ptr(seed), 2, p_out, mask.numel(), k._lib.ptr(mask), k._lib.stream())
+            assert 0.6 < float(mask.float().mean()) < 0.8
+            ent = ent0 * (mask.float() * np.float32(1.0 / (1.0 - p_out)))
+        torch.autograd.backward([ent, rel], [g_ent, g_rel])
+        res[fused] = [ent.detach(), rel.detach(), x.grad, ee.grad, rl.grad] + [p_.grad for p_ in conv.parameters()]
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    for a, b in zip(res[True][2:], res[False][2:]):
+        assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-12
+
+
 def test_stream_plan_on_device(k, monkeypatch):
     """kgc_stream_plan_flags + the device-side slot numbering (plan.build_stream_plan_device) against the numpy
     restatement (plan.build_stream_plan): rowflags, chunk carry slots, carry count, empty rows and fix-up levels bit for
