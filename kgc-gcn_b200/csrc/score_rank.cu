@@ -24,6 +24,8 @@
 // diagonal: the target score thr[q] and the scores of the filtered positives come from the SAME
 // instruction path as the sweep, so the filter correction is bit-consistent.
 #include <cuda.h>
+
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -100,6 +102,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load delivered to the same shared-memory offset (and the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], "
+      "[%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -126,6 +146,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // all tcgen05.mma issued so far by this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// the same arrival on the mbarrier at this offset in every CTA of cta_mask (the B stage is shared by a CTA pair)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -198,20 +225,29 @@ struct ScoreParams {
   int64_t n_pairs;
 };
 
-template <bool kPairs, bool kCountEq>
+// kCluster: launched as clusters of TWO CTAs that sweep the same entity tiles for different query tiles.  Each CTA of the
+// pair fetches HALF of every B stage (64 entity rows) and the TMA multicasts it into both CTAs' shared memory: every byte
+// of the entity table crosses L2 -> SM once per 512 queries instead of once per 256.  (Measured: no gain - the sweep is
+// not bound by the 4.3 TB/s it pulls out of L2; opt-in.)  A stage's `full` barrier collects both halves (its own TMA and
+// the peer's), its `empty` barrier the retired MMAs of BOTH CTAs (tcgen05.commit multicast) - a slot is rewritten by the
+// peer's TMA as well.
+template <bool kPairs, bool kCountEq, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
-score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ScoreParams P) {
+score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             const __grid_constant__ CUtensorMap map_bh, const ScoreParams P) {
   extern __shared__ uint8_t smem_raw[];
   const SharedLayout S = carve(smem_raw);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   constexpr int kNumM = kPairs ? 1 : kMTiles;
+  static_assert(!(kPairs && kCluster), "pairs mode runs single CTAs");
+  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < kStagesB; ++i) {
       mbar_init(S.full + i, 1);
-      mbar_init(S.empty + i, 1);
+      mbar_init(S.empty + i, kCluster ? 2 : 1);
     }
     mbar_init(S.a_full, 1);
     mbar_init(S.a_empty, 1);
@@ -226,6 +262,7 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (kCluster) cluster_sync_all();                            // the peer's barriers exist before anything targets them
   const uint32_t tmem_base = *S.tmem_slot;
 
   if (warp == 0) {
@@ -248,7 +285,11 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           for (int kb = 0; kb < P.n_kblocks; ++kb) {
             mbar_wait(S.empty + stage, phase ^ 1);
             mbar_expect_tx(S.full + stage, kTileBytes);
-            tma_load_2d(S.b + stage * kTileBytes, &map_b, S.full + stage, kb * kBlockK, t * kBlockN);
+            if (kCluster)                                          // my half of the stage, into both CTAs
+              tma_load_2d_mc(S.b + stage * kTileBytes + cta_rank * (kTileBytes / 2), &map_bh, S.full + stage, kb * kBlockK,
+                             t * kBlockN + (int)cta_rank * (kBlockN / 2), (uint16_t)3);
+            else
+              tma_load_2d(S.b + stage * kTileBytes, &map_b, S.full + stage, kb * kBlockK, t * kBlockN);
             if (++stage == kStagesB) { stage = 0; phase ^= 1; }
           }
         }
@@ -279,13 +320,19 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const uint64_t adesc1 = make_sw128_desc(a_base + (kMaxKBlocks + kb) * kTileBytes);
             const uint32_t d0 = tmem_base + acc * (kMTiles * kBlockN);
             if (elect_one()) {
-              for (int k = 0; k < nk; ++k) {
-                // + k * 32 bytes along K inside the swizzle row: descriptor start address is in 16-byte units
-                const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-                umma_bf16(d0, adesc0 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
-                if (kNumM == 2) umma_bf16(d0 + kBlockN, adesc1 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
+              // straight-line issue: with a runtime trip count the loop carried three R2UR moves and ~20 uniform-datapath
+              // instructions per pair of MMAs (SASS) - about the 64 cycles the tensor pipe needs for one of them
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                if (k < nk) {
+                  // + k * 32 bytes along K inside the swizzle row: descriptor start address is in 16-byte units
+                  const uint32_t accum = (k != 0 || kb != 0) ? 1u : 0u;
+                  umma_bf16(d0, adesc0 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
+                  if (kNumM == 2) umma_bf16(d0 + kBlockN, adesc1 + 2 * k, bdesc + 2 * k, kInstrDesc, accum);
+                }
               }
-              umma_commit(S.empty + stage);                    // B stage is free once these MMAs retire
+              if (kCluster) umma_commit_mc(S.empty + stage, (uint16_t)3);   // ... in BOTH CTAs: the slot is shared
+              else umma_commit(S.empty + stage);               // B stage is free once these MMAs retire
               if (kb == P.n_kblocks - 1) {
                 umma_commit(S.acc_full + acc);                 // accumulators of this entity tile are complete
                 if (t == t1 - 1) umma_commit(S.a_empty);       // A tiles may be overwritten
@@ -330,12 +377,17 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j == row) diag = __uint_as_float(v[c & 1][j]);
           } else if (valid == kBlockN) {
+            // four independent counters: one counter made a serial chain of 128 dependent (add, select) pairs per tile -
+            // about as long as the tile's MMAs
+            int g4[4] = {0, 0, 0, 0}, e4[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float s = __uint_as_float(v[c & 1][j]);
-              gt += (s > thr) ? 1 : 0;
-              if (kCountEq) eq += (s == thr) ? 1 : 0;
+              if (s > thr) ++g4[j & 3];
+              if (kCountEq && s == thr) ++e4[j & 3];
             }
+            gt += (g4[0] + g4[1]) + (g4[2] + g4[3]);
+            if (kCountEq) eq += (e4[0] + e4[1]) + (e4[2] + e4[3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -361,6 +413,7 @@ score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();                            // no CTA leaves while the peer may still write or signal into it
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -505,13 +558,13 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // bf16 [rows, kpad] row-major -> boxes of 64 (K) x 128 (rows), 128-byte swizzle, zero fill out of bounds
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int kpad) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int kpad, int box_rows = kBlockM) {
   EncodeTiledFn enc;
   if (get_encode_fn(&enc)) return 1;
   KGC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "bf16 table must be 16-byte aligned");
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -524,12 +577,37 @@ inline int check_kpad(int kpad) { return (kpad < 16 || kpad % 16 != 0 || kpad > 
 
 template <bool kPairs, bool kCountEq>
 int launch_score(const CUtensorMap& ma, const CUtensorMap& mb, const ScoreParams& P, cudaStream_t st) {
-  auto kern = score_kernel<kPairs, kCountEq>;
+  auto kern = score_kernel<kPairs, kCountEq, false>;
   static SmemAttrCache attr;                           // one per <kPairs, kCountEq> instantiation
   KGC_CUDA_TRY(attr.ensure(kern, (size_t)kSmemBytes));
   const int grid = P.n_items < kNumSMs ? P.n_items : kNumSMs;
-  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, P);
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mb, P);
   KGC_LAUNCH_CHECK();
+  return 0;
+}
+
+// sweep as clusters of two CTAs (see score_kernel): n_items and the grid are even, item 2i / 2i + 1 share an entity chunk
+template <bool kCountEq>
+int launch_score_pairs_of_ctas(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbh, const ScoreParams& P,
+                               cudaStream_t st) {
+  auto kern = score_kernel<false, kCountEq, true>;
+  static SmemAttrCache attr;
+  KGC_CUDA_TRY(attr.ensure(kern, (size_t)kSmemBytes));
+  int grid = P.n_items < kNumSMs ? P.n_items : kNumSMs;
+  grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  KGC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbh, P));
   return 0;
 }
 
@@ -612,6 +690,13 @@ extern "C" int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, in
   P.ksteps = kpad / kUmmaK;
   P.n_kblocks = (kpad + kBlockK - 1) / kBlockK;
   P.n_mp = (int32_t)ceil_div(b, kMTiles * kBlockM);
+  // CTA pairs that share their B stages (TMA multicast), KGC_SCORE_CLUSTER=1.  Built to test whether the sweep is bound by
+  // L2 -> SM traffic: it is not - 104.4 ms against 104.7 ms with single CTAs (65,536 x 4.59 M, B200 under its power cap) -
+  // so single CTAs stay the default.  The pair needs an even number of query-tile pairs (a padding pair has no valid
+  // query: its rows never count)
+  static const bool cluster_ok = [] { const char* e = getenv("KGC_SCORE_CLUSTER"); return e && e[0] == '1'; }();
+  const bool cluster = cluster_ok && P.n_mp >= 2;
+  if (cluster) P.n_mp = (P.n_mp + 1) & ~1;
   P.n_tiles = (int32_t)ceil_div(n, kBlockN);
   // entity chunks: enough work items to balance 148 persistent CTAs, chunk small enough to stay in L2
   // (<= ~48 MB of bf16 rows) so that the CTAs sweeping one chunk share its tiles.
@@ -632,6 +717,12 @@ extern "C" int kgc_score_rank(const uint16_t* q_bf16, const uint16_t* e_bf16, in
   P.thr = thr;
   P.count_gt = count_gt;
   P.count_eq = count_eq;
+  if (cluster) {
+    CUtensorMap mbh;
+    if (make_map(&mbh, e_bf16, n, kpad, kBlockN / 2)) return 1;
+    if (count_eq) return launch_score_pairs_of_ctas<true>(ma, mb, mbh, P, st);
+    return launch_score_pairs_of_ctas<false>(ma, mb, mbh, P, st);
+  }
   if (count_eq) return launch_score<false, true>(ma, mb, P, st);
   return launch_score<false, false>(ma, mb, P, st);
 }
