@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libkgc_b200.so')
+LIB_PATH = os.environ.get('KGC_LIB_PATH') or os.path.join(_HERE, 'libkgc_b200.so')     # KGC_LIB_PATH: A/B runs of two builds
 _LIB = None
 
 _vp, _i64, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t

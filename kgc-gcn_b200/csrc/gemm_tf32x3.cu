@@ -407,10 +407,15 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmParams P) {
           const uint64_t b_hi = sw128_desc(s_u32(s_bhi + kb * tile_b_al));
           const uint64_t b_lo = sw128_desc(s_u32(s_blo + kb * tile_b_al));
           if (elect_one()) {
-            for (int k = 0; k < nk; ++k) {                         // + 8 TMEM columns / + 32 bytes (2 descriptor units) along K
-              umma_tf32_ts(d_addr, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
-              umma_tf32_ts(d_addr, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
-              umma_tf32_ts(d_addr, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+            // straight-line issue (a runtime trip count makes the loop carry R2UR moves and ~20 uniform-datapath
+            // instructions per step: measured on the K6 scorer, +6%)
+#pragma unroll
+            for (int k = 0; k < kBK / kUK; ++k) {                  // + 8 TMEM columns / + 32 bytes (2 descriptor units) along K
+              if (k < nk) {
+                umma_tf32_ts(d_addr, a_lo + 8 * k, b_hi + 2 * k, idesc, (k != 0 || kb != 0) ? 1u : 0u);    // small terms first
+                umma_tf32_ts(d_addr, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+                umma_tf32_ts(d_addr, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+              }
             }
             umma_commit_g(split_empty + ts);
             if (kb == P.n_kb - 1) umma_commit_g(acc_full + acc);
