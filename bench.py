@@ -452,9 +452,16 @@ class LayerCase(object):
             self.edge_ids = torch.arange(2 * E, dtype=torch.int64, device=dev)
         else:
             p2p_on = os.environ.get('KGC_P2P', '1') != '0'
+            balance = os.environ.get('KGC_BALANCE', 'hybrid' if p2p_on else 'edges')
             self.part = k.GraphPartition(self.g['edge_index'], self.g['edge_attr'][0], N, 2 * R + 1, world, rank, dev,
-                                         balance=os.environ.get('KGC_BALANCE', 'hybrid' if p2p_on else 'edges'),
-                                         p2p='auto' if p2p_on else False)
+                                         balance=balance, p2p='auto' if p2p_on else False)
+            if balance == 'hybrid':
+                try:                                       # peer memory is decided collectively: all ranks or none
+                    self.part.p2p(D_IN)
+                except RuntimeError as exc:
+                    sys.stderr.write('hybrid cut unavailable ({}): destination partition instead\n'.format(exc))
+                    self.part = k.GraphPartition(self.g['edge_index'], self.g['edge_attr'][0], N, 2 * R + 1, world, rank, dev,
+                                                 balance='edges', p2p='auto')
             self.node_ids, self.edge_ids = self.part.owned_nodes, self.part.owned_eids
         self.x = self.rows('x', self.node_ids).requires_grad_(True)
         self.ee = self.rows('ee', self.edge_ids).requires_grad_(True)

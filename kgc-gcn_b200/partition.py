@@ -369,17 +369,22 @@ class GraphPartition(object):
         if self.hybrid and not self._p2p_mode:
             raise RuntimeError("balance='hybrid' exchanges partial aggregates over peer memory (K10): it needs p2p")
         if self._p2p_mode and self.balance in ('edges', 'hybrid') and self.world > 1 and self.world <= 8 and self.device.type == 'cuda':
+            err = None
             try:
                 ctx = _P2PContext(self, D)
-            except Exception:                                   # pragma: no cover (depends on the box)
-                if self._p2p_mode is True or self.hybrid:
-                    raise
-                ctx = None
+            except Exception as exc:                            # pragma: no cover (depends on the box)
+                err, ctx = exc, None
+            # all ranks or none - and every rank reaches this all-reduce, whatever happened on it
             ok = torch.tensor([1 if ctx is not None else 0], device=self.device)
             import torch.distributed as dist
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
             if int(ok) == 0:
                 ctx = None
+                if self._p2p_mode is True or self.hybrid:
+                    raise RuntimeError('peer-memory exchange (symmetric memory) is not available on every rank'
+                                       + ('' if err is None else ': {!r}'.format(err)))
+        elif self.hybrid:
+            raise RuntimeError("balance='hybrid' needs 2..8 CUDA ranks with peer memory")
         self._p2p[D] = ctx
         return ctx
 
