@@ -1,15 +1,19 @@
 """MGCNConv: the relation-aware graph convolution (reference model.py:47-127), B200 path.
 
-Same constructor, parameter names, forward signature and return values as the reference class; the
-arithmetic runs in libkgc_b200.so (K1-K4) plus plain fp32 GEMMs (TF32 off, like the reference gets):
+Same constructor, parameter names, forward signature and return values as the reference class; the arithmetic runs in
+libkgc_b200.so: K1 (sorted CSRs, norms, schedules), K2 / K3 (streaming aggregation, forward and backward), K4b / K4c (the
+dense transforms on tcgen05 with fp32-grade accuracy, 3xTF32), K4 (dropout, /3, BatchNorm1d, tanh), K0 (parameter-side
+kernels):
 
     agg_h[i]  = sum_{e in half h, dst_e = i} norm_e * x[src_e] (.) rel+[type_e] (.) ee[e]     K2
-    res_h     = agg_h @ W_h ; res_loop = x @ (diag(loop_rel (.) loop_edge) W_loop)               GEMM
+    res_h     = agg_h @ W_h ; res_loop = x @ (diag(loop_rel (.) loop_edge) W_loop)               K4b
     all_ent   = tanh(BN((drop(res_in) + drop(res_out) + res_loop) / 3 [+ bias]))                  K4
-    all_rel   = (rel+ @ W_rel)[:-1]
+    all_rel   = (rel+ @ W_rel)[:-1]                                                              K0
 
 (aggregate-then-transform is exact algebra because the message transform is linear).
-Backward is hand-derived and runs K3/K4-backward; it is deterministic.
+Backward is hand-derived and runs K3 / K4-backward / K4b / K4c; it is deterministic.
+``forward_partitioned`` is the same layer on a partitioned graph (partition.py): one process per GPU, exchanges over
+NVLink peer memory (K10).
 """
 import os
 

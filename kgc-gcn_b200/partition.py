@@ -257,6 +257,109 @@ def partition_edges_hybrid(edge_index, edge_type, num_nodes, world, rank):
             'peer_idx': peer_src, 'peer_dst_idx': peer_dst}
 
 
+def _balanced_assignment_t(w, num_nodes, world, n_greedy=8192):
+    """balanced_assignment(weights=w) with torch tensors on w's device (the O(N) parts; the LPT loop over the n_greedy
+    heaviest nodes runs on the host over copies of their weights).  Same integers as the numpy function."""
+    dev = w.device
+    base, rem = divmod(num_nodes, world)
+    cap_all = base + (torch.arange(world, dtype=torch.int64) < rem).to(torch.int64)          # host
+    n_loc = int(cap_all.max())
+    order = torch.sort(-w, stable=True).indices
+    k = min(num_nodes, n_greedy)
+    head = order[:k].cpu().numpy()
+    w_head = w[order[:k]].cpu().numpy()
+    cap_np = cap_all.numpy()
+    load = np.zeros(world, dtype=np.int64)
+    count = np.zeros(world, dtype=np.int64)
+    own_head = np.empty(k, dtype=np.int64)
+    big = np.iinfo(np.int64).max
+    for i in range(k):                                        # LPT over the heavy head
+        r = int(np.argmin(np.where(count < cap_np, load, big)))
+        own_head[i] = r
+        load[r] += w_head[i]
+        count[r] += 1
+    owner = torch.empty(num_nodes, dtype=torch.int64, device=dev)
+    owner[order[:k]] = torch.from_numpy(own_head).to(dev)
+    rest = order[k:]
+    cap = cap_np - count
+    m = int(cap.min())
+    j = torch.arange(m * world, dtype=torch.int64, device=dev)
+    rnd, pos = torch.div(j, world, rounding_mode='floor'), j % world
+    owner[rest[:m * world]] = torch.where(rnd % 2 == 0, pos, world - 1 - pos)    # snake: 0..W-1, W-1..0, ...
+    owner[rest[m * world:]] = torch.repeat_interleave(torch.arange(world, dtype=torch.int64, device=dev),
+                                                      torch.from_numpy(cap - m).to(dev))
+    slot = torch.empty(num_nodes, dtype=torch.int64, device=dev)
+    by_rank = torch.sort(owner[order], stable=True).indices    # per rank, nodes in decreasing weight
+    first = (torch.cumsum(cap_all, 0) - cap_all).to(dev)
+    slot[order[by_rank]] = torch.arange(num_nodes, dtype=torch.int64, device=dev) - torch.repeat_interleave(first, cap_all.to(dev))
+    return {'owner': owner, 'slot': slot, 'n_loc': n_loc, 'count': cap_np}
+
+
+def partition_edges_hybrid_device(edge_index, edge_type, num_nodes, world, rank):
+    """partition_edges_hybrid on the device of ``edge_index`` (torch ops: histograms, stable sorts, boolean scatters; the
+    numpy function needs ~8 s per rank at the Wikidata5M shape, all of it host work outside every timed region).  Returns the
+    same dict with torch tensors on that device in place of the numpy arrays ('count' / 'n_remote_all' stay host arrays);
+    bit-identical contents (tests/test_gpu_conv.py::test_hybrid_partition_on_device)."""
+    ei = edge_index.to(torch.int64)
+    et = edge_type.to(torch.int64)
+    dev = ei.device
+    n2 = int(ei.shape[1])
+    if n2 % 2 != 0:
+        raise ValueError('edge list must hold an in half and an out half of equal size')
+    E = n2 // 2
+    src, dst = ei[0], ei[1]
+    tot = torch.bincount(src, minlength=num_nodes) + torch.bincount(dst, minlength=num_nodes)
+    anchor = torch.where(tot[src] < tot[dst], src, dst)
+    w = torch.bincount(anchor, minlength=num_nodes)
+    a = _balanced_assignment_t(w, num_nodes, world)
+    owner, slot, n_loc = a['owner'], a['slot'], a['n_loc']
+    block = n_loc
+    newid = owner * block + slot
+    edge_rank = owner[anchor]
+    owned = torch.nonzero(edge_rank == rank).squeeze(1)
+    n_in = int(torch.searchsorted(owned, torch.tensor([E], device=dev, dtype=torch.int64)))
+    src_new, dst_new = newid[src], newid[dst]
+    n_real = int(a['count'][rank])
+    mine = torch.nonzero(owner == rank).squeeze(1)
+    owned_nodes = mine[torch.sort(slot[mine], stable=True).indices]
+    my_ids = torch.arange(rank * block, rank * block + n_real, dtype=torch.int64, device=dev)
+    ids = torch.arange(world * block, dtype=torch.int64, device=dev)
+    peer_src = torch.full((world, n_real), -1, dtype=torch.int32, device=dev)
+    peer_dst = torch.full((world, n_real), -1, dtype=torch.int32, device=dev)
+    n_remote_all = np.zeros(world, dtype=np.int64)
+    remote_mine = cmap = None
+    for r in range(world):
+        sel = edge_rank == r
+        seen_s = torch.zeros(world * block, dtype=torch.bool, device=dev)
+        seen_d = torch.zeros(world * block, dtype=torch.bool, device=dev)
+        seen_s[src_new[sel]] = True
+        seen_d[dst_new[sel]] = True
+        outside = (ids < r * block) | (ids >= (r + 1) * block)
+        remote = torch.nonzero((seen_s | seen_d) & outside).squeeze(1)
+        n_remote_all[r] = int(remote.numel())
+        pos = torch.full((world * block,), -1, dtype=torch.int64, device=dev)
+        pos[remote] = block + torch.arange(remote.numel(), dtype=torch.int64, device=dev)
+        if r == rank:
+            own = torch.arange(n_real, dtype=torch.int32, device=dev)
+            peer_src[r], peer_dst[r] = own, own
+            remote_mine = remote
+            cmap = pos
+            cmap[r * block:(r + 1) * block] = torch.arange(block, dtype=torch.int64, device=dev)
+        else:
+            peer_src[r] = torch.where(seen_s[my_ids], pos[my_ids], torch.full_like(my_ids, -1)).to(torch.int32)
+            peer_dst[r] = torch.where(seen_d[my_ids], pos[my_ids], torch.full_like(my_ids, -1)).to(torch.int32)
+    deg = torch.stack([torch.bincount(src[:E], minlength=num_nodes), torch.bincount(src[E:], minlength=num_nodes)]).to(torch.int32)
+    deg_ext = torch.zeros((2, world * block), dtype=torch.int32, device=dev)
+    deg_ext[:, newid] = deg
+    comp_ids = torch.cat([torch.arange(rank * block, (rank + 1) * block, dtype=torch.int64, device=dev), remote_mine])
+    return {'n_loc': n_loc, 'n_real': n_real, 'n_hub': 0, 'block': block, 'owned_nodes': owned_nodes,
+            'hubs': np.zeros((0,), dtype=np.int64), 'owned_eids': owned, 'n_edges_in': n_in,
+            'src': cmap[src_new[owned]], 'dst': cmap[dst_new[owned]], 'type': et[owned],
+            'deg': deg_ext[:, comp_ids].contiguous(), 'newid': newid, 'halo_rows': remote_mine.to(torch.int32),
+            'n_halo': int(remote_mine.numel()), 'n_halo_max': int(n_remote_all.max()), 'n_remote_all': n_remote_all,
+            'peer_idx': peer_src, 'peer_dst_idx': peer_dst}
+
+
 def sparse_peer_table(peer, rank):
     """[world, n_real] table of partial-row positions (-1: none) -> (rows [n_list] int32: the own rows some OTHER rank holds
     a partial row for, idx [world, n_list] int32: the table restricted to them, this rank's own line set to -1)."""
@@ -327,35 +430,48 @@ class GraphPartition(object):
             self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
         elif balance == 'hybrid':
             # an edge lives with its lower-degree endpoint (partition_edges_hybrid): remote rows are few; they are read as
-            # sources AND written as destinations (partial aggregates the owners add up), one compact numbering for both
-            info = partition_edges_hybrid(ei, et, num_nodes, world, rank)
+            # sources AND written as destinations (partial aggregates the owners add up), one compact numbering for both.
+            # On a CUDA device the partition itself is computed there (same integers; KGC_PARTITION_HOST=1: numpy)
+            on_dev = self.device.type == 'cuda' and os.environ.get('KGC_PARTITION_HOST', '0') in ('', '0')
+            if on_dev:
+                ei_d = (edge_index if torch.is_tensor(edge_index) else torch.from_numpy(np.asarray(edge_index))).to(self.device)
+                et_d = (edge_type if torch.is_tensor(edge_type) else torch.from_numpy(np.asarray(edge_type))).to(self.device)
+                info = partition_edges_hybrid_device(ei_d, et_d, num_nodes, world, rank)
+                del ei_d, et_d
+            else:
+                info = partition_edges_hybrid(ei, et, num_nodes, world, rank)
+            tt = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a))).to(device)      # noqa: E731
+            nn_ = lambda a: a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)                       # noqa: E731
             self.lo = self.hi = None
             self.n_loc, self.n_hub, self.block, self.n_real = info['n_loc'], 0, info['block'], info['n_real']
-            self.owned_nodes = torch.from_numpy(info['owned_nodes']).to(device)
+            self.owned_nodes = tt(info['owned_nodes'])
             ext_nodes, offset = self.block + info['n_halo'], 0
             self.hub_idx_mine = self.hub_rows_mine = None
             self.hubs = info['hubs']
-            self.halo_rows = torch.from_numpy(info['halo_rows']).to(device)
+            self.halo_rows = tt(info['halo_rows'])
             self.halo_rows64 = self.halo_rows.to(torch.int64)
-            self.halo_order = torch.from_numpy(halo_pull_order(info['halo_rows'], self.block, rank, world)).to(device)
+            self.halo_order = torch.from_numpy(halo_pull_order(nn_(info['halo_rows']), self.block, rank, world)).to(device)
             self.n_halo, self.n_halo_max = info['n_halo'], info['n_halo_max']
             self.n_remote_all = [int(v) for v in info['n_remote_all']]
-            self.peer_idx = torch.from_numpy(info['peer_idx']).to(device)
-            self.peer_dst_idx = torch.from_numpy(info['peer_dst_idx']).to(device)
+            self.peer_idx = tt(info['peer_idx'])
+            self.peer_dst_idx = tt(info['peer_dst_idx'])
             # only the rows OTHER ranks contributed to take part in the two reductions: (row list, [world, n_list] index
             # table with -1 in this rank's own line - its own value is already in place)
-            self.sparse_src = tuple(t.to(device) for t in sparse_peer_table(info['peer_idx'], rank))
-            self.sparse_dst = tuple(t.to(device) for t in sparse_peer_table(info['peer_dst_idx'], rank))
+            self.sparse_src = tuple(t.to(device) for t in sparse_peer_table(nn_(info['peer_idx']), rank))
+            self.sparse_dst = tuple(t.to(device) for t in sparse_peer_table(nn_(info['peer_dst_idx']), rank))
+            info = dict(info, owned_eids=tt(info['owned_eids']), src=tt(info['src']), dst=tt(info['dst']), type=tt(info['type']),
+                        deg=tt(info['deg']))
         else:
             raise ValueError("balance must be 'hybrid', 'edges' or 'range'")
         self.hybrid = balance == 'hybrid'
-        self.owned_eids = torch.from_numpy(info['owned_eids']).to(device)
+        as_t = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(a)).to(device)                     # noqa: E731
+        self.owned_eids = as_t(info['owned_eids'])
         self.n_edges_in = info['n_edges_in']
-        self.edge_index = torch.from_numpy(np.stack([info['src'], info['dst']])).to(device)
-        self.edge_type = torch.from_numpy(info['type']).to(device)
+        self.edge_index = torch.stack([as_t(info['src']), as_t(info['dst'])])
+        self.edge_type = as_t(info['type'])
         self.plan = GraphPlan(self.edge_index, self.edge_type, ext_nodes, num_types, n_edges_in=self.n_edges_in,
                               n_dst_rows=ext_nodes if self.hybrid else self.block, dst_offset=offset,
-                              deg=torch.from_numpy(info['deg']).to(device))
+                              deg=as_t(info['deg']))
 
     # ------------------------------------------------------------------ peer-memory halo exchange (K10)
     def p2p(self, D):

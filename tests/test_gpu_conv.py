@@ -204,6 +204,25 @@ def test_output_dropout_inside_the_tail(k):
         assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-12
 
 
+def test_hybrid_partition_on_device(k):
+    """partition.partition_edges_hybrid_device (torch ops on the GPU) == partition_edges_hybrid (numpy), every field, for
+    2 / 3 / 8 ranks on a hub-heavy graph whose node count is not a multiple of the rank count."""
+    from kgc_gcn_b200.partition import partition_edges_hybrid, partition_edges_hybrid_device
+    N, R, E = 30001, 7, 160000
+    tri = orc.synthetic_triples(N, R, E, 4)
+    g = orc.build_graph(tri, N, R)
+    ei, et = g['edge_index'], g['edge_attr'][0]
+    ei_d, et_d = torch.from_numpy(ei).cuda(), torch.from_numpy(et).cuda()
+    for world in (2, 3, 8):
+        for rank in (0, world - 1):
+            a = partition_edges_hybrid(ei, et, N, world, rank)
+            b = partition_edges_hybrid_device(ei_d, et_d, N, world, rank)
+            assert set(a) == set(b)
+            for key in a:
+                got = b[key].cpu().numpy() if torch.is_tensor(b[key]) else b[key]
+                assert np.array_equal(np.asarray(a[key]), np.asarray(got)), (world, rank, key)
+
+
 def test_stream_plan_on_device(k, monkeypatch):
     """kgc_stream_plan_flags + the device-side slot numbering (plan.build_stream_plan_device) against the numpy
     restatement (plan.build_stream_plan): rowflags, chunk carry slots, carry count, empty rows and fix-up levels bit for
