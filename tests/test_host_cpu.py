@@ -510,3 +510,33 @@ def test_rows_and_table_gradient_matches_autograd():
         ((t.index_select(0, idx) * w1).sum() + ((t * w2).sum() if use_table else 0)).backward()
         want, t.grad = t.grad.clone(), None
         assert torch.allclose(got, want, rtol=0, atol=1e-14)
+
+
+def test_stream_plan_prefill_of_mostly_empty_planes():
+    """plan.StreamPlan(prefill_ranges=...): a plane that is >= 3/4 rows without records (and large) is zero-filled by a
+    memset - its empty rows leave the fix-up items - while a dense plane keeps its few empty rows as items; small plans
+    never pre-fill.  Host logic only (CPU tensors)."""
+    from kgc_gcn_b200.plan import build_stream_plan, StreamPlan
+    rng = np.random.default_rng(0)
+    Nd = 400000
+    deg = np.zeros(2 * Nd, dtype=np.int64)
+    deg[rng.choice(Nd, 20000, replace=False)] = rng.integers(1, 50, 20000)        # plane 0: 95% of the rows are empty
+    deg[Nd:] = rng.integers(1, 5, Nd)                                             # plane 1: dense ...
+    hole = Nd + rng.choice(Nd, 1000, replace=False)
+    deg[hole] = 0                                                                 # ... but for 1,000 empty rows
+    end = np.cumsum(deg)
+    beg = end - deg
+    sp = build_stream_plan(beg, end, np.arange(2 * Nd), int(end[-1]))
+    n_empty = int((deg == 0).sum())
+    assert sp['fill_rows'].shape[0] == n_empty
+    plain = StreamPlan(sp, int(end[-1]), 'cpu')
+    pre = StreamPlan(sp, int(end[-1]), 'cpu', prefill_ranges=[(0, Nd), (Nd, 2 * Nd)])
+    assert plain.prefill == [] and pre.prefill == [(0, Nd)]
+    items_plain = sum(l[1] for l in plain.levels)
+    items_pre = sum(l[1] for l in pre.levels)
+    assert items_plain - items_pre == int((deg[:Nd] == 0).sum())                  # plane 0's empty rows left the items
+    first = pre.levels[0][0].numpy()
+    empties = first[(first[:, 0] == 0) & (first[:, 1] == 0) & ((first[:, 3] & 1) == 1)]
+    assert sorted(empties[:, 2].tolist()) == sorted(hole.tolist())                # plane 1's empty rows are still items
+    small = build_stream_plan(beg[:2000], np.minimum(end[:2000], end[1999]), np.arange(2000), int(end[1999]))
+    assert StreamPlan(small, int(end[1999]), 'cpu', prefill_ranges=[(0, 1000), (1000, 2000)]).prefill == []
