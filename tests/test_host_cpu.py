@@ -291,6 +291,26 @@ def test_cpu_tensors_fail_loudly():
     ei = torch.tensor([[0, 1], [1, 0]])
     with pytest.raises(RuntimeError, match='CUDA'):
         conv(torch.zeros(2, 8), ei, torch.tensor([0, 2]), None, torch.zeros(2, 8), torch.zeros(4, 8))
+    # the sampler extensions: GPU only, no CPU fallback either
+    kb = k.KBDataset([{'triple': (0, 0, -1), 'label': [1, 2]}], 5, None)
+    with pytest.raises(RuntimeError, match='GPU only'):
+        kb.negatives([0], 2, device='cpu')
+    dl = k.DataLoader.__new__(k.DataLoader)
+    dl.num_edge, dl.num_relation = 1, 2
+    dl.graph = k.GraphData(edge_index=ei, edge_attr=torch.tensor([[0, 2], [0, 1]]))
+    with pytest.raises(RuntimeError, match='GPU only'):
+        dl.sample_edges(1)
+
+
+def test_uint32_draws_as_int32_bits():
+    """data_loader._u32_bits: the samplers take uint32 draws as any integer tensor; the C ABI reads int32 bit patterns."""
+    from kgc_gcn_b200.data_loader import _u32_bits
+    vals = [0, 1, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1, 2 ** 32 + 5]
+    got = _u32_bits(torch.tensor(vals, dtype=torch.int64))
+    assert got.dtype == torch.int32
+    assert (got.numpy().view(np.uint32) == np.array([v % 2 ** 32 for v in vals], dtype=np.uint32)).all()
+    same = torch.tensor([-1, 7], dtype=torch.int32)
+    assert _u32_bits(same) is same or torch.equal(_u32_bits(same), same)
 
 
 def _write_dataset(root, name, files):
